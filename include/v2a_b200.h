@@ -1,0 +1,188 @@
+/* v2a_b200 — C ABI of the B200-native hot paths of video-to-action-release.
+ *
+ * The reference (pure Python/PyTorch) has no FFI of its own; its "operator
+ * interface" for the two hot paths is the nn.Module call surface listed in
+ * SURVEY.md §8(b).  This header is the boundary our Python host modules bind
+ * with ctypes.  Each entry point cites the reference code it replaces
+ * (paths relative to the reference checkout).
+ *
+ * Conventions
+ *  - plain C, raw device pointers, sizes as int / int64_t; no torch types.
+ *  - the caller allocates every buffer; nothing here mallocs device memory
+ *    or synchronises.  Work is enqueued on `stream` (a cudaStream_t passed as
+ *    void*), so calls are CUDA-graph capturable.
+ *  - return 0 on success; non-zero on failure, message via v2a_last_error().
+ *  - activations are channels-last.  "hl" tensors are two bf16 planes
+ *    (hi, lo) with x ~= hi + lo: the operand format of every tensor-core
+ *    contraction (3-pass bf16 split product, fp32 accumulate in TMEM).
+ */
+#ifndef V2A_B200_H
+#define V2A_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define V2A_MAX_SRC 2
+#define V2A_MAX_TAPS 16
+
+const char* v2a_last_error(void);
+int v2a_version(void);
+
+/* ------------------------------------------------------------------------
+ * Implicit-GEMM convolution / linear on tcgen05 tensor cores.
+ *
+ * out[row, n] = sum_taps sum_c A_src[pixel(row) + tap.d, c] * W[n, k(tap, c)]
+ *
+ * replaces, depending on the tap program:
+ *   nn.Conv2d 3x3 (spatial_conv)         guided_diffusion/nn.py:45,66
+ *   nn.Conv1d k3 over frames (temporal)  guided_diffusion/nn.py:46,76-85
+ *   1x1 skip_connection                  guided_diffusion/unet.py:225
+ *   AttentionBlock qkv / proj_out        guided_diffusion/unet.py:290,298
+ *   Conv1d k5/k3/k1, Linear (policy)     diffusion_policy/model/conv1d_components.py:7-40
+ * ---------------------------------------------------------------------- */
+typedef struct v2a_igemm_src {
+    const void* hi;   /* bf16 [X3][X2][X1][X0][C] */
+    const void* lo;   /* bf16 same shape (ignored when passes == 1) */
+    int channels;     /* C, multiple of 8 */
+    int dims[4];      /* X0..X3, X0 fastest */
+} v2a_igemm_src;
+
+typedef struct v2a_igemm_tap {
+    int src;      /* index into desc.src */
+    int d[4];     /* coordinate offset of this tap in X0..X3 (may be negative: zero padding) */
+    int nchunks;  /* ceil(C / 64) K-chunks taken from this tap */
+} v2a_igemm_tap;
+
+typedef struct v2a_igemm_desc {
+    v2a_igemm_src src[V2A_MAX_SRC];
+    int nsrc;
+    v2a_igemm_tap taps[V2A_MAX_TAPS];
+    int ntaps;
+    const void* w_hi;  /* bf16 [wrows][ktot], K-major; k runs tap-major, 64 per chunk */
+    const void* w_lo;
+    int wrows;         /* rows present in the weight matrix (>= cout) */
+    int ktot;          /* 64 * sum(nchunks) */
+    int out_dims[4];   /* output pixel grid D0..D3 (D0 fastest); rows = prod */
+    int tile_log2[4];  /* log2 of the 128-row tile box along D0..D3 (sums to 7) */
+    int block_n;       /* N tile: multiple of 16, <= 256 */
+    int passes;        /* 3 = hi*hi + hi*lo + lo*hi (fp32-class); 1 = bf16 only */
+    int cout;          /* valid output channels */
+    int ldc;           /* output row pitch in elements, multiple of 16 and >= cout rounded up to 16 */
+    float* out_f32;    /* [rows][ldc] or NULL */
+    void* out_hi;      /* bf16 [rows][ldc] or NULL */
+    void* out_lo;
+    const float* bias;      /* [cout] or NULL */
+    const float* rowvec;    /* per-row-group additive vector [groups][ld_rowvec] or NULL */
+    int ld_rowvec;
+    int rowvec_mul[4];      /* group = sum coord[d] * rowvec_mul[d] */
+    const float* residual;  /* fp32 [rows][ld_res] added to the output, or NULL */
+    int ld_res;
+    double* stats;          /* per (instance, channel) {sum, sumsq} of the written fp32 value, or NULL */
+    int stats_mul[4];       /* instance = sum coord[d] * stats_mul[d] */
+    int stats_ld;           /* channels per instance in the stats buffer */
+} v2a_igemm_desc;
+
+int v2a_igemm_plan_create(const v2a_igemm_desc* desc, void** plan_out);
+int v2a_igemm_plan_run(void* plan, void* stream);
+void v2a_igemm_plan_destroy(void* plan);
+/* kernel launches performed by v2a_* calls since process start */
+int64_t v2a_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * GroupNorm statistics + apply (HBM-bound elementwise).
+ * replaces GroupNorm32 / SiLU / th.cat / F.interpolate(nearest) / the two
+ * rearranges of Conv3d            guided_diffusion/nn.py:26-28,76,85
+ *                                 guided_diffusion/unet.py:107-114,239-260,681
+ * and Conv1dBlock's GroupNorm+Mish + FiLM
+ *                                 diffusion_policy/model/conv1d_components.py:23-40
+ *                                 diffusion_policy/model/conditional_unet1d.py:55-61
+ * ---------------------------------------------------------------------- */
+/* stats[(inst*C + c)*2 + {0,1}] += {sum, sumsq} over the pixels of instance */
+int v2a_channel_stats(const float* x, int64_t instances, int64_t pixels_per_instance, int C,
+                      double* stats, void* stream);
+
+typedef struct v2a_prep_desc {
+    const float* x0;        /* fp32 [P][C0] */
+    const float* x1;        /* fp32 [P][C1] or NULL (channel concat) */
+    int C0, C1;
+    const double* stats0;   /* per (inst, channel) sums for x0 (NULL: no normalisation) */
+    const double* stats1;
+    int64_t pixels_per_inst;     /* pixels in one stats instance */
+    int inst_per_group;          /* consecutive instances pooled into one GroupNorm sample */
+    int groups;                  /* GroupNorm groups over C0+C1 */
+    float eps;
+    float* gn_scratch;      /* fp32 [samples*groups*2] mean/rstd table written by this call */
+    const float* gamma;     /* [C0+C1] */
+    const float* beta;
+    int act;                /* 0 none, 1 SiLU, 2 Mish */
+    const float* film;      /* policy FiLM [B][2*C]: out = scale*act(gn) + bias, or NULL */
+    int64_t pixels_per_film;     /* pixels sharing one FiLM row */
+    int mode;               /* 0 same grid, 1 nearest x2 upsample (H,W), 2 stride-2 phase split */
+    int H, W;               /* input grid (mode 1/2); images = P / (H*W) */
+    int64_t P;              /* input pixels */
+    void* out_hi;           /* bf16 [P'][C0+C1] */
+    void* out_lo;
+    float* out_f32;         /* optional fp32 copy of the result (policy autograd) */
+    void* raw_hi;           /* optional: hi/lo split of the un-normalised concat (1x1 skip operand) */
+    void* raw_lo;
+} v2a_prep_desc;
+int v2a_prep(const v2a_prep_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Per-frame spatial self-attention, legacy head order.
+ * replaces QKVAttentionLegacy.forward      guided_diffusion/unet.py:341-358
+ * qkv fp32 [N][L][3*C] with channel = head*96 + {q:0..31, k:32..63, v:64..95};
+ * writes a = softmax(q k^T / sqrt(32)) v as hl planes [N][L][C].
+ * ---------------------------------------------------------------------- */
+int v2a_attention(const float* qkv, int N, int L, int heads, void* out_hi, void* out_lo,
+                  void* stream);
+
+/* ------------------------------------------------------------------------
+ * Small dense layers (batch <= a few hundred, fp32 CUDA cores).
+ * y[b][o] = act_out( sum_i act_in(x[b][i]) * W[o][i] + bias[o] ) (+ add[b][o])
+ * replaces time_embed / emb_layers / diffusion_step_encoder linears
+ *   guided_diffusion/unet.py:204-210,482-486; conditional_unet1d.py:87-93
+ * act codes: 0 none, 1 SiLU, 2 Mish
+ * ---------------------------------------------------------------------- */
+int v2a_linear(const float* x, int ldx, const float* W, const float* bias, const float* add,
+               int ld_add, float* y, int ldy, int B, int IN, int OUT, int act_in, int act_out,
+               void* stream);
+/* sinusoidal embeddings: mode 0 = video [cos|sin], freq exp(-ln(1e4) i/half)
+ *   (guided_diffusion/nn.py:171-189); mode 1 = policy [sin|cos], freq
+ *   exp(-ln(1e4) i/(half-1)) (diffusion_policy/model/positional_embedding.py:5-17) */
+int v2a_timestep_embedding(const int64_t* t, int B, int dim, int mode, float* out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Video UNet boundary layout kernels.  Unet_Libero.forward rearranges
+ *   flowdiffusion/unet.py:216-222
+ * ---------------------------------------------------------------------- */
+/* x [B][3F][H][W] fp32, cond [B][3][H][W] -> im2col'd first-conv operand
+ * hl [B*F][H][W][64], k = tap*6 + c (c<3 frame rgb, c>=3 cond rgb), 54 used */
+int v2a_unet_input_pack(const float* x, const float* cond, int B, int F, int H, int W,
+                        void* out_hi, void* out_lo, void* stream);
+/* y fp32 [B][F][H][W][ldy] (3 used) -> temporal Conv1d(3,3,k3)+bias -> out [B][3F][H][W] */
+int v2a_unet_output_head(const float* y, int ldy, const float* wt, const float* bt, int B, int F,
+                         int H, int W, float* out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Sampler steps.  replaces p_sample / ddim_sample elementwise chains
+ *   flowdiffusion/goal_diffusion.py:484-497,561-580,601-641
+ * coef (device, fp32[8]) = {sqrt_ac, sqrt_1m_ac, c1, c2, sigma, -, -, -} for DDPM,
+ *        {sqrt_ac, sqrt_1m_ac, sqrt_recip_ac, sqrt_recipm1_ac, sqrt_ac_next, c, sigma, last} for DDIM
+ * ---------------------------------------------------------------------- */
+int v2a_ddpm_step(float* x, const float* v, const float* noise, const float* coef, int64_t n,
+                  void* stream);
+int v2a_ddim_step(float* x, const float* v, const float* noise, const float* coef, int64_t n,
+                  void* stream);
+/* out = clamp((x + 1) / 2, 0, 1)   goal_diffusion.py:598,650 */
+int v2a_unnormalize_clamp(const float* x, float* out, int64_t n, void* stream);
+
+/* fp32 -> (hi, lo) bf16 planes, optional [rows][cols] row-padding to ld */
+int v2a_split_hl(const float* x, int64_t rows, int cols, int ld_out, void* out_hi, void* out_lo,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

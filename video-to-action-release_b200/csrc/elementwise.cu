@@ -1,0 +1,486 @@
+// HBM-bound kernels around the tensor-core contractions: GroupNorm statistics
+// and apply (+SiLU/Mish, concat, nearest upsample, stride-2 phase split, FiLM,
+// bf16 hi/lo split), boundary layout packs, small dense layers, sampler steps.
+// All loads/stores are 16-byte vectors over the contiguous channel axis.
+#include "common.cuh"
+#include "../../include/v2a_b200.h"
+
+#include <atomic>
+
+namespace v2a {
+extern std::atomic<int64_t> g_launches;
+
+#define V2A_LAUNCH_OK()                      \
+    do {                                     \
+        V2A_CUDA_OK(cudaGetLastError());     \
+        v2a::g_launches.fetch_add(1);        \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// per-(instance, channel) sum / sum of squares
+// ---------------------------------------------------------------------------
+// grid (chunks, instances); block = (C/4 quads) x pixel lanes
+__global__ void channel_stats_kernel(const float* __restrict__ x, int64_t ppi, int C, int pix_per_block,
+                                     double* __restrict__ stats) {
+    extern __shared__ float sh[];  // [2*C]
+    const int quads = C >> 2;
+    const int lanes = blockDim.x / quads;
+    const int q = threadIdx.x % quads;
+    const int pl = threadIdx.x / quads;
+    const int64_t inst = blockIdx.y;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.0f;
+    __syncthreads();
+    float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+    if (pl < lanes) {
+        const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
+        int64_t p1 = p0 + pix_per_block;
+        if (p1 > ppi) p1 = ppi;
+        const float4* base = reinterpret_cast<const float4*>(x + (inst * ppi) * C) + q;
+        for (int64_t p = p0 + pl; p < p1; p += lanes) {
+            float4 v = __ldg(base + p * quads);
+            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+            ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&sh[(4 * q + j) * 2], s[j]);
+            atomicAdd(&sh[(4 * q + j) * 2 + 1], ss[j]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x)
+        atomicAdd(&stats[inst * 2 * C + i], (double)sh[i]);
+}
+
+// (sample, group) -> mean, rstd from per-channel sums of up to two concat sources
+__global__ void gn_finalize_kernel(const double* __restrict__ st0, const double* __restrict__ st1,
+                                   int C0, int C1, int groups, int inst_per_group, double count,
+                                   float eps, float2* __restrict__ mr, int samples) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= samples * groups) return;
+    const int g = idx % groups, smp = idx / groups;
+    const int cpg = (C0 + C1) / groups;
+    double s = 0.0, ss = 0.0;
+    for (int i = 0; i < inst_per_group; ++i) {
+        const int64_t inst = (int64_t)smp * inst_per_group + i;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            const double* p = c < C0 ? st0 + (inst * C0 + c) * 2 : st1 + (inst * C1 + (c - C0)) * 2;
+            s += p[0];
+            ss += p[1];
+        }
+    }
+    const double mean = s / count;
+    double var = ss / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mr[idx] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+}
+
+struct PrepParams {
+    const float* x0; const float* x1;
+    int C0, C1;
+    const float2* mr;          // [samples][groups] or null
+    int64_t pixels_per_sample; // pixels sharing one GroupNorm sample
+    int groups;
+    const float* gamma; const float* beta;
+    int act;
+    const float* film; int64_t pixels_per_film;
+    int mode, H, W;
+    int64_t P;
+    __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; float* out_f32;
+    __nv_bfloat16* raw_hi; __nv_bfloat16* raw_lo;
+};
+
+// one thread = 8 channels of one OUTPUT pixel
+__global__ void __launch_bounds__(256) prep_kernel(const PrepParams p, int64_t total_out_pix) {
+    const int C = p.C0 + p.C1;
+    const int oct = C >> 3;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total_out_pix * oct) return;
+    const int o8 = (int)(gid % oct);
+    const int64_t op = gid / oct;
+    const int c = o8 * 8;
+    // output pixel -> input pixel
+    int64_t ip = op;
+    int64_t out_index = op;
+    if (p.mode == 1) {
+        const int W2 = p.W * 2, H2 = p.H * 2;
+        const int w = (int)(op % W2);
+        const int h = (int)((op / W2) % H2);
+        const int64_t img = op / ((int64_t)W2 * H2);
+        ip = (img * p.H + (h >> 1)) * p.W + (w >> 1);
+    } else if (p.mode == 2) {
+        // iterate input pixels, scatter to [img][ph*2+pw][H/2][W/2]
+        const int w = (int)(op % p.W);
+        const int h = (int)((op / p.W) % p.H);
+        const int64_t img = op / ((int64_t)p.W * p.H);
+        const int Hh = p.H >> 1, Wh = p.W >> 1;
+        out_index = ((img * 4 + (h & 1) * 2 + (w & 1)) * Hh + (h >> 1)) * Wh + (w >> 1);
+    }
+    float v[8];
+    {
+        const float* src = c < p.C0 ? p.x0 + ip * p.C0 + c : p.x1 + ip * p.C1 + (c - p.C0);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    if (p.raw_hi) {
+        uint4 h, l;
+        split8(v, h, l);
+        *reinterpret_cast<uint4*>(p.raw_hi + out_index * C + c) = h;
+        *reinterpret_cast<uint4*>(p.raw_lo + out_index * C + c) = l;
+    }
+    if (p.mr) {
+        const int64_t smp = ip / p.pixels_per_sample;
+        const int cpg = C / p.groups;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float2 m = __ldg(&p.mr[smp * p.groups + (c + j) / cpg]);
+            v[j] = (v[j] - m.x) * m.y * __ldg(&p.gamma[c + j]) + __ldg(&p.beta[c + j]);
+        }
+    }
+    if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+    } else if (p.act == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = mish_f(v[j]);
+    }
+    if (p.film) {
+        const float* f = p.film + (ip / p.pixels_per_film) * (2 * C);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(&f[c + j]) * v[j] + __ldg(&f[C + c + j]);
+    }
+    if (p.out_hi) {
+        uint4 h, l;
+        split8(v, h, l);
+        *reinterpret_cast<uint4*>(p.out_hi + out_index * C + c) = h;
+        *reinterpret_cast<uint4*>(p.out_lo + out_index * C + c) = l;
+    }
+    if (p.out_f32) {
+        float4* o = reinterpret_cast<float4*>(p.out_f32 + out_index * C + c);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// small dense layer: one warp per output feature, batch tiled by 8
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float act_f(float x, int a) {
+    return a == 1 ? silu_f(x) : (a == 2 ? mish_f(x) : x);
+}
+__global__ void linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W,
+                              const float* __restrict__ bias, const float* __restrict__ add, int ld_add,
+                              float* __restrict__ y, int ldy, int B, int IN, int OUT, int act_in,
+                              int act_out) {
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (o >= OUT) return;
+    const float* w = W + (int64_t)o * IN;
+    for (int b0 = blockIdx.y * 8; b0 < B; b0 += gridDim.y * 8) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = lane; i < IN; i += 32) {
+            const float wv = __ldg(&w[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (b0 + j < B) acc[j] += act_f(__ldg(&x[(int64_t)(b0 + j) * ldx + i]), act_in) * wv;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+        }
+        if (lane < 8 && b0 + lane < B) {
+            float r = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (lane == j) r = acc[j];
+            if (bias) r += bias[o];
+            r = act_f(r, act_out);
+            if (add) r += add[(int64_t)(b0 + lane) * ld_add + o];
+            y[(int64_t)(b0 + lane) * ldy + o] = r;
+        }
+    }
+}
+
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, int B, int dim, int mode,
+                                          float* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int half = dim / 2;
+    if (idx >= B * half) return;
+    const int b = idx / half, i = idx % half;
+    const float tv = (float)t[b];
+    // reference computes freqs in fp32: exp(-ln(1e4) * i / denom)
+    float freq;
+    if (mode == 0)  // th.exp(-log(1e4) * arange(half, fp32) / half)
+        freq = expf(-9.210340371976184f * (float)i / (float)half);
+    else            // th.exp(arange(half) * -(log(1e4) / (half - 1))), scalar rounded from double
+        freq = expf((float)i * (float)(-(9.210340371976184 / (double)(half - 1))));
+    const float a = tv * freq;
+    if (mode == 0) {
+        out[(int64_t)b * dim + i] = cosf(a);
+        out[(int64_t)b * dim + half + i] = sinf(a);
+    } else {
+        out[(int64_t)b * dim + i] = sinf(a);
+        out[(int64_t)b * dim + half + i] = cosf(a);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// UNet boundary packs
+// ---------------------------------------------------------------------------
+// one thread = one (image n=b*F+f, h, w, tap): writes 8 channels (6 used)
+__global__ void unet_input_pack_kernel(const float* __restrict__ x, const float* __restrict__ cond,
+                                       int B, int F, int H, int W, __nv_bfloat16* __restrict__ ohi,
+                                       __nv_bfloat16* __restrict__ olo) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t npix = (int64_t)B * F * H * W;
+    if (gid >= npix * 8) return;
+    const int oc = (int)(gid & 7);  // which 8-channel octet of the 64
+    const int64_t pix = gid >> 3;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int f = (int)((pix / ((int64_t)W * H)) % F);
+    const int b = (int)(pix / ((int64_t)W * H * F));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = oc * 8 + j;
+        float val = 0.0f;
+        if (k < 54) {
+            const int tap = k / 6, c = k % 6;
+            const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                val = c < 3 ? __ldg(&x[(((int64_t)b * 3 * F + f * 3 + c) * H + hh) * W + ww])
+                            : __ldg(&cond[(((int64_t)b * 3 + (c - 3)) * H + hh) * W + ww]);
+            }
+        }
+        v[j] = val;
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    *reinterpret_cast<uint4*>(ohi + pix * 64 + oc * 8) = hi;
+    *reinterpret_cast<uint4*>(olo + pix * 64 + oc * 8) = lo;
+}
+
+// temporal Conv1d(3,3,k=3, zero pad) over frames + NHWC -> [B][(f c)][H][W]
+__global__ void unet_output_head_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ wt,
+                                        const float* __restrict__ bt, int B, int F, int H, int W,
+                                        float* __restrict__ out) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t HW = (int64_t)H * W;
+    if (gid >= (int64_t)B * F * HW) return;
+    const int64_t hw = gid % HW;
+    const int f = (int)((gid / HW) % F);
+    const int b = (int)(gid / (HW * F));
+    float acc[3] = {bt[0], bt[1], bt[2]};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int ff = f + k - 1;
+        if (ff < 0 || ff >= F) continue;
+        const float* yp = y + (((int64_t)b * F + ff) * HW + hw) * ldy;
+        const float y0 = yp[0], y1 = yp[1], y2 = yp[2];
+#pragma unroll
+        for (int co = 0; co < 3; ++co)  // weight [co][ci][k]
+            acc[co] += wt[(co * 3 + 0) * 3 + k] * y0 + wt[(co * 3 + 1) * 3 + k] * y1 +
+                       wt[(co * 3 + 2) * 3 + k] * y2;
+    }
+#pragma unroll
+    for (int co = 0; co < 3; ++co) out[((int64_t)b * 3 * F + f * 3 + co) * HW + hw] = acc[co];
+}
+
+// ---------------------------------------------------------------------------
+// sampler steps (operation order follows the reference's fp32 op chain)
+// ---------------------------------------------------------------------------
+__global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ v,
+                                 const float* __restrict__ noise, const float* __restrict__ coef,
+                                 int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float sa = coef[0], s1 = coef[1], c1 = coef[2], c2 = coef[3], sigma = coef[4], vt = coef[5];
+    const float xt = x[i];
+    float x0 = __fsub_rn(__fmul_rn(sa, xt), __fmul_rn(s1, v[i]));  // predict_start_from_v
+    x0 = fminf(fmaxf(x0, -1.0f), 1.0f);                            // clamp_(-1, 1)
+    const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xt));  // q_posterior mean
+    const float nz = noise ? __fmul_rn(noise[i], vt) : 0.0f;
+    x[i] = __fadd_rn(mean, __fmul_rn(sigma, nz));
+}
+
+__global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict__ v,
+                                 const float* __restrict__ noise, const float* __restrict__ coef,
+                                 int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float sa = coef[0], s1 = coef[1], sr = coef[2], srm1 = coef[3];
+    const float san = coef[4], cc = coef[5], sigma = coef[6], last = coef[7];
+    const float xt = x[i];
+    const float x0 = __fsub_rn(__fmul_rn(sa, xt), __fmul_rn(s1, v[i]));
+    if (last != 0.0f) {
+        x[i] = x0;
+        return;
+    }
+    const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(sr, xt), x0), srm1);  // predict_noise_from_start
+    const float nz = noise ? noise[i] : 0.0f;
+    // x0 * sqrt(a_next) + c * eps + sigma * noise, left to right
+    x[i] = __fadd_rn(__fadd_rn(__fmul_rn(x0, san), __fmul_rn(cc, eps)), __fmul_rn(sigma, nz));
+}
+
+__global__ void unnormalize_clamp_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float u = __fmul_rn(__fadd_rn(x[i], 1.0f), 0.5f);
+    out[i] = fminf(fmaxf(u, 0.0f), 1.0f);
+}
+
+__global__ void split_hl_kernel(const float* __restrict__ x, int64_t rows, int cols, int ld,
+                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * ld) return;
+    const int c = (int)(i % ld);
+    const int64_t r = i / ld;
+    const float v = c < cols ? x[r * cols + c] : 0.0f;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    lo[i] = l;
+}
+
+}  // namespace v2a
+
+using namespace v2a;
+
+extern "C" {
+
+int v2a_channel_stats(const float* x, int64_t instances, int64_t ppi, int C, double* stats,
+                      void* stream) {
+    V2A_REQUIRE(C % 4 == 0 && C >= 4 && C / 4 <= 1024, "channel_stats: C %d unsupported", C);
+    const int quads = C / 4;
+    int threads = quads >= 256 ? quads : (256 / quads) * quads;
+    if (threads > 1024) threads = quads;
+    const int lanes = threads / quads;
+    // ~512 pixels per lane-row keeps fp32 partial sums short
+    int64_t pix_per_block = (int64_t)lanes * 128;
+    if (pix_per_block > ppi) pix_per_block = ppi;
+    const int64_t chunks = (ppi + pix_per_block - 1) / pix_per_block;
+    V2A_REQUIRE(instances <= 65535, "channel_stats: too many instances");
+    dim3 grid((unsigned)chunks, (unsigned)instances);
+    channel_stats_kernel<<<grid, threads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+        x, ppi, C, (int)pix_per_block, stats);
+    V2A_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_prep(const v2a_prep_desc* d, void* stream) {
+    const int C = d->C0 + d->C1;
+    V2A_REQUIRE(C % 8 == 0 && d->C0 % 8 == 0, "prep: channel counts must be multiples of 8");
+    V2A_REQUIRE(d->out_hi || d->out_f32 || d->raw_hi, "prep: no output");
+    PrepParams p;
+    p.x0 = d->x0; p.x1 = d->x1; p.C0 = d->C0; p.C1 = d->C1;
+    p.mr = nullptr;
+    p.groups = d->groups > 0 ? d->groups : 1;
+    p.pixels_per_sample = d->pixels_per_inst * (d->inst_per_group > 0 ? d->inst_per_group : 1);
+    p.gamma = d->gamma; p.beta = d->beta; p.act = d->act;
+    p.film = d->film; p.pixels_per_film = d->pixels_per_film > 0 ? d->pixels_per_film : 1;
+    p.mode = d->mode; p.H = d->H; p.W = d->W; p.P = d->P;
+    p.out_hi = (__nv_bfloat16*)d->out_hi; p.out_lo = (__nv_bfloat16*)d->out_lo;
+    p.out_f32 = d->out_f32;
+    p.raw_hi = (__nv_bfloat16*)d->raw_hi; p.raw_lo = (__nv_bfloat16*)d->raw_lo;
+    if (d->stats0) {
+        V2A_REQUIRE(d->gamma && d->beta, "prep: GroupNorm needs gamma/beta");
+        V2A_REQUIRE(C % d->groups == 0, "prep: C %d not divisible by groups %d", C, d->groups);
+        V2A_REQUIRE(d->C1 == 0 || d->stats1, "prep: second source needs stats");
+        V2A_REQUIRE(d->P % p.pixels_per_sample == 0, "prep: P not a multiple of the GroupNorm sample size");
+        V2A_REQUIRE(d->gn_scratch != nullptr, "prep: gn_scratch missing");
+        const int64_t inst = d->P / d->pixels_per_inst;
+        const int samples = (int)(inst / d->inst_per_group);
+        float2* mr = reinterpret_cast<float2*>(d->gn_scratch);
+        const double count = (double)p.pixels_per_sample * (double)(C / d->groups);
+        const int n = samples * d->groups;
+        gn_finalize_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(
+            d->stats0, d->stats1, d->C0, d->C1, d->groups, d->inst_per_group, count, d->eps, mr, samples);
+        V2A_LAUNCH_OK();
+        p.mr = mr;
+    }
+    int64_t out_pix = d->P;
+    if (d->mode == 1) out_pix = d->P * 4;
+    if (d->mode == 1 || d->mode == 2)
+        V2A_REQUIRE(d->H > 0 && d->W > 0 && d->P % ((int64_t)d->H * d->W) == 0 &&
+                        (d->mode == 1 || (d->H % 2 == 0 && d->W % 2 == 0)),
+                    "prep: bad H/W for resampling mode");
+    const int64_t total = out_pix * (C / 8);
+    prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, out_pix);
+    V2A_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_linear(const float* x, int ldx, const float* W, const float* bias, const float* add, int ld_add,
+               float* y, int ldy, int B, int IN, int OUT, int act_in, int act_out, void* stream) {
+    V2A_REQUIRE(B >= 1 && IN >= 1 && OUT >= 1, "linear: bad shape");
+    const int warps = 4;
+    int by = ceil_div(B, 8);
+    if (by > 64) by = 64;
+    dim3 grid(ceil_div(OUT, warps), by);
+    linear_kernel<<<grid, warps * 32, 0, (cudaStream_t)stream>>>(x, ldx, W, bias, add, ld_add, y, ldy, B,
+                                                                 IN, OUT, act_in, act_out);
+    V2A_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_timestep_embedding(const int64_t* t, int B, int dim, int mode, float* out, void* stream) {
+    V2A_REQUIRE(dim % 2 == 0 && dim >= 4, "timestep_embedding: dim must be even");
+    const int n = B * dim / 2;
+    timestep_embedding_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(t, B, dim, mode, out);
+    V2A_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_unet_input_pack(const float* x, const float* cond, int B, int F, int H, int W, void* out_hi,
+                        void* out_lo, void* stream) {
+    const int64_t total = (int64_t)B * F * H * W * 8;
+    unet_input_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x, cond, B, F, H, W, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+    V2A_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_unet_output_head(const float* y, int ldy, const float* wt, const float* bt, int B, int F, int H,
+                         int W, float* out, void* stream) {
+    const int64_t total = (int64_t)B * F * H * W;
+    unet_output_head_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        y, ldy, wt, bt, B, F, H, W, out);
+    V2A_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_ddpm_step(float* x, const float* v, const float* noise, const float* coef, int64_t n,
+                  void* stream) {
+    ddpm_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, v, noise, coef, n);
+    V2A_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_ddim_step(float* x, const float* v, const float* noise, const float* coef, int64_t n,
+                  void* stream) {
+    ddim_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, v, noise, coef, n);
+    V2A_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_unnormalize_clamp(const float* x, float* out, int64_t n, void* stream) {
+    unnormalize_clamp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, n);
+    V2A_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_split_hl(const float* x, int64_t rows, int cols, int ld_out, void* out_hi, void* out_lo,
+                 void* stream) {
+    V2A_REQUIRE(ld_out >= cols, "split_hl: ld_out < cols");
+    const int64_t total = rows * ld_out;
+    split_hl_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x, rows, cols, ld_out, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+    V2A_LAUNCH_OK();
+    return 0;
+}
+
+}  // extern "C"

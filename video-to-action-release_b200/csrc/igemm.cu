@@ -1,0 +1,580 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// One persistent, warp-specialised kernel serves every dense contraction of the
+// two hot paths: 3x3 spatial conv, temporal Conv1d k3 (+ fused 1x1 skip conv as
+// extra K), 1x1 qkv / proj, and the policy's Conv1d k5/k3/k1 and Linear layers.
+//
+//   rows (M)  = 128 output pixels: a 4-D box of the channels-last output grid
+//   cols (N)  = block_n output channels
+//   K         = a "tap program": for each tap (source tensor, coordinate
+//               offset) a run of 64-channel chunks.  The A tile of one K step
+//               is ONE TMA box load at (pixel box + tap offset): out-of-bounds
+//               coordinates are zero-filled by the TMA unit, which is exactly
+//               the convolution's zero padding, so no im2col buffer exists.
+//
+// Precision: operands are stored as bf16 (hi, lo) pairs; each K step issues
+// hi*hi + lo*hi + hi*lo into the same fp32 TMEM accumulator (error ~2^-16,
+// i.e. fp32-class; see DESIGN.md "precision").  passes==1 keeps only hi*hi.
+//
+// Pipeline (per CTA, 256 threads):
+//   warp 0 lane 0 : TMA producer  (smem ring: full/empty mbarriers)
+//   warp 1 lane 0 : tcgen05.mma issuer, accumulators double-buffered in TMEM
+//   warp 2        : TMEM alloc / dealloc
+//   warps 4..7    : epilogue (tcgen05.ld -> bias/rowvec/residual -> global,
+//                   optional hi/lo split output, optional GroupNorm partial sums)
+#include "common.cuh"
+#include "../../include/v2a_b200.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+namespace v2a {
+
+// ---------------------------------------------------------------------------
+// host error state
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+const char* get_error() { return g_err.c_str(); }
+std::atomic<int64_t> g_launches{0};
+
+// ---------------------------------------------------------------------------
+// kernel parameters
+// ---------------------------------------------------------------------------
+constexpr int kThreads = 256;
+constexpr int kTileM = 128;
+constexpr int kChunkK = 64;                                 // bf16 elements per K step (128 B rows)
+constexpr int kATileBytes = kTileM * kChunkK * 2;           // 16 KB
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;                             // TMEM columns per accumulator stage
+
+struct alignas(64) IgemmParams {
+    CUtensorMap a_hi[V2A_MAX_SRC];
+    CUtensorMap a_lo[V2A_MAX_SRC];
+    CUtensorMap b_hi;
+    CUtensorMap b_lo;
+    int tap_src[V2A_MAX_TAPS];
+    int tap_d[V2A_MAX_TAPS][4];
+    int tap_chunks[V2A_MAX_TAPS];
+    int ntaps;
+    int k_iters;          // sum of tap_chunks
+    int tile_log2[4];
+    int out_dims[4];
+    int ntile[4];         // tiles along each output dim
+    int num_m_tiles, num_n_tiles;
+    int block_n, passes, stages;
+    uint32_t stage_bytes, b_tile_bytes;
+    int cout, ldc;
+    float* out_f32;
+    __nv_bfloat16* out_hi;
+    __nv_bfloat16* out_lo;
+    const float* bias;
+    const float* rowvec;
+    int ld_rowvec;
+    int rowvec_mul[4];
+    const float* residual;
+    int ld_res;
+    double* stats;
+    int stats_mul[4];
+    int stats_ld;
+};
+
+__device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int& n_idx, int o[4]) {
+    n_idx = tile % p.num_n_tiles;
+    int m = tile / p.num_n_tiles;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        int j = m % p.ntile[d];
+        m /= p.ntile[d];
+        o[d] = j << p.tile_log2[d];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int S = p.stages;
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * p.stage_bytes);
+    uint64_t* full_bar = bars;             // [S]
+    uint64_t* empty_bar = bars + S;        // [S]
+    uint64_t* tfull_bar = bars + 2 * S;    // [2]
+    uint64_t* tempty_bar = bars + 2 * S + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 128);
+        }
+        fence_mbar_init();
+    } else if (warp == 1 && lane == 0) {
+        tma_prefetch_desc(&p.a_hi[0]);
+        tma_prefetch_desc(&p.b_hi);
+        if (p.passes == 3) {
+            tma_prefetch_desc(&p.a_lo[0]);
+            tma_prefetch_desc(&p.b_lo);
+        }
+    } else if (warp == 2) {
+        tmem_alloc(tmem_slot, kTmemCols);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int n_idx, o[4];
+            decode_tile(p, tile, n_idx, o);
+            const int n0 = n_idx * p.block_n;
+            int kit = 0;
+            for (int e = 0; e < p.ntaps; ++e) {
+                const int src = p.tap_src[e];
+                const int c1 = o[0] + p.tap_d[e][0], c2 = o[1] + p.tap_d[e][1];
+                const int c3 = o[2] + p.tap_d[e][2], c4 = o[3] + p.tap_d[e][3];
+                for (int ch = 0; ch < p.tap_chunks[e]; ++ch, ++kit) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+                    uint8_t* st = smem + (size_t)stage * p.stage_bytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], p.stage_bytes);
+                    if (p.passes == 3) {
+                        tma_load_5d(st, &p.a_hi[src], &full_bar[stage], ch * kChunkK, c1, c2, c3, c4);
+                        tma_load_5d(st + kATileBytes, &p.a_lo[src], &full_bar[stage], ch * kChunkK,
+                                    c1, c2, c3, c4);
+                        uint8_t* sb = st + 2 * kATileBytes;
+                        tma_load_2d(sb, &p.b_hi, &full_bar[stage], kit * kChunkK, n0);
+                        tma_load_2d(sb + p.b_tile_bytes, &p.b_lo, &full_bar[stage], kit * kChunkK, n0);
+                    } else {
+                        tma_load_5d(st, &p.a_hi[src], &full_bar[stage], ch * kChunkK, c1, c2, c3, c4);
+                        tma_load_2d(st + kATileBytes, &p.b_hi, &full_bar[stage], kit * kChunkK, n0);
+                    }
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = umma_idesc_bf16(kTileM, p.block_n);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * kAccStride;
+            for (int kit = 0; kit < p.k_iters; ++kit) {
+                mbar_wait(&full_bar[stage], phase, 300 + stage);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+                if (p.passes == 3) {
+                    const uint64_t a_hi = umma_desc_sw128(sa);
+                    const uint64_t a_lo = umma_desc_sw128(sa + kATileBytes);
+                    const uint64_t b_hi = umma_desc_sw128(sa + 2 * kATileBytes);
+                    const uint64_t b_lo = umma_desc_sw128(sa + 2 * kATileBytes + p.b_tile_bytes);
+                    // small cross terms first, dominant hi*hi last
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, (kit | k) != 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
+                } else {
+                    const uint64_t a_hi = umma_desc_sw128(sa);
+                    const uint64_t b_hi = umma_desc_sw128(sa + kATileBytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kit | k) != 0);
+                }
+                umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                if (kit == p.k_iters - 1) umma_commit(&tfull_bar[acc]);
+                if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int quad = warp & 3;            // TMEM lane quarter this warp may read
+        const int row = quad * 32 + lane;     // row of the 128-row tile
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            int n_idx, o[4];
+            decode_tile(p, tile, n_idx, o);
+            const int n0 = n_idx * p.block_n;
+            // row -> output pixel
+            int r = row, coord[4];
+            bool valid = true;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                coord[d] = o[d] + (r & ((1 << p.tile_log2[d]) - 1));
+                r >>= p.tile_log2[d];
+                valid = valid && (coord[d] < p.out_dims[d]);
+            }
+            const int64_t pix =
+                ((int64_t)(coord[3] * p.out_dims[2] + coord[2]) * p.out_dims[1] + coord[1]) *
+                    p.out_dims[0] + coord[0];
+            int rv = 0, inst = 0;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                rv += coord[d] * p.rowvec_mul[d];
+                inst += coord[d] * p.stats_mul[d];
+            }
+            bool inst_uniform = true;
+            if (p.stats) {
+                const int inst0 = __shfl_sync(0xffffffffu, valid ? inst : -1, 0);
+                inst_uniform = __all_sync(0xffffffffu, !valid || inst == inst0) && inst0 >= 0;
+                // a warp whose lane 0 is invalid but others are valid takes the slow path
+                if (!inst_uniform) inst_uniform = false;
+            }
+
+            mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kAccStride;
+            for (int c = 0; c < p.block_n; c += 16) {
+                uint32_t raw[16];
+                tmem_ld16(t_row + c, raw);
+                tmem_ld_wait();
+                const int n = n0 + c;
+                if (n >= p.cout) continue;  // warp-uniform
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+                if (valid) {
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n + j < p.cout) v[j] += __ldg(&p.bias[n + j]);
+                    }
+                    if (p.rowvec) {
+                        const float* rp = p.rowvec + (int64_t)rv * p.ld_rowvec + n;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n + j < p.cout) v[j] += __ldg(&rp[j]);
+                    }
+                    if (p.residual) {
+                        const float4* rp =
+                            reinterpret_cast<const float4*>(p.residual + pix * p.ld_res + n);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float4 t = __ldg(&rp[q]);
+                            v[4 * q + 0] += t.x; v[4 * q + 1] += t.y;
+                            v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                        }
+                    }
+                    if (p.out_f32) {
+                        float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * p.ldc + n);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                    if (p.out_hi) {
+                        uint4 h0, l0, h1, l1;
+                        split8(v, h0, l0);
+                        split8(v + 8, h1, l1);
+                        uint4* hp = reinterpret_cast<uint4*>(p.out_hi + pix * p.ldc + n);
+                        uint4* lp = reinterpret_cast<uint4*>(p.out_lo + pix * p.ldc + n);
+                        hp[0] = h0; hp[1] = h1;
+                        lp[0] = l0; lp[1] = l1;
+                    }
+                }
+                if (p.stats) {
+                    if (inst_uniform) {
+                        // butterfly-reduce 16 sums + 16 sums of squares over the warp's 32 rows
+                        float s[16], q[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float x = (valid && n + j < p.cout) ? v[j] : 0.0f;
+                            s[j] = x; q[j] = x * x;
+                        }
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                s[j] += __shfl_xor_sync(0xffffffffu, s[j], off);
+                                q[j] += __shfl_xor_sync(0xffffffffu, q[j], off);
+                            }
+                        }
+                        const int inst0 = __shfl_sync(0xffffffffu, inst, 0);
+                        // lane j (<16) publishes sum of column j, lane 16+j its sum of squares
+                        float mine = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (lane == j) mine = s[j];
+                            if (lane == 16 + j) mine = q[j];
+                        }
+                        const int col = n + (lane & 15);
+                        if (col < p.cout)
+                            atomicAdd(&p.stats[((int64_t)inst0 * p.stats_ld + col) * 2 + (lane >> 4)],
+                                      (double)mine);
+                    } else if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n + j < p.cout) {
+                                double* sp = &p.stats[((int64_t)inst * p.stats_ld + n + j) * 2];
+                                atomicAdd(sp, (double)v[j]);
+                                atomicAdd(sp + 1, (double)v[j] * (double)v[j]);
+                            }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side: tensor maps + plan
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+                cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// bf16 tensor, dims[0] innermost (contiguous); box[0] must be 64 (128 B rows)
+static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                    const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    V2A_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    cuuint64_t gdim[5];
+    cuuint64_t gstride[4];
+    cuuint32_t bdim[5], estr[5];
+    uint64_t stride = 2;  // bytes
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        stride *= dims[i];
+        if (i < rank - 1) gstride[i] = stride;
+    }
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                    gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    V2A_REQUIRE(r == CUDA_SUCCESS,
+                "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box "
+                "[%u %u %u %u %u] base %p",
+                (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0,
+                rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0, base);
+    return 0;
+}
+
+struct IgemmPlan {
+    IgemmParams p;
+    int grid;
+    size_t smem;
+};
+
+static int g_num_sms = 0;
+static int g_max_smem = 0;
+
+static int device_props() {
+    if (g_num_sms) return 0;
+    int dev = 0;
+    V2A_CUDA_OK(cudaGetDevice(&dev));
+    V2A_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    V2A_CUDA_OK(cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    return 0;
+}
+
+static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
+    if (int rc = device_props()) return rc;
+    V2A_REQUIRE(d->nsrc >= 1 && d->nsrc <= V2A_MAX_SRC, "igemm: nsrc %d out of range", d->nsrc);
+    V2A_REQUIRE(d->ntaps >= 1 && d->ntaps <= V2A_MAX_TAPS, "igemm: ntaps %d out of range", d->ntaps);
+    V2A_REQUIRE(d->passes == 1 || d->passes == 3, "igemm: passes must be 1 or 3");
+    V2A_REQUIRE(d->block_n >= 16 && d->block_n <= 256 && d->block_n % 16 == 0,
+                "igemm: block_n %d must be a multiple of 16 in [16,256]", d->block_n);
+    V2A_REQUIRE(d->ldc % 16 == 0 && d->ldc >= d->cout, "igemm: ldc %d must be a multiple of 16 >= cout %d",
+                d->ldc, d->cout);
+    V2A_REQUIRE(d->out_f32 || d->out_hi, "igemm: no output tensor");
+    V2A_REQUIRE(!d->out_hi || d->out_lo, "igemm: out_hi without out_lo");
+    V2A_REQUIRE(!d->residual || d->ld_res % 4 == 0, "igemm: ld_res must be a multiple of 4");
+    int tl = 0;
+    for (int i = 0; i < 4; ++i) {
+        V2A_REQUIRE(d->tile_log2[i] >= 0 && d->tile_log2[i] <= 7, "igemm: bad tile_log2");
+        V2A_REQUIRE(d->out_dims[i] >= 1, "igemm: bad out_dims");
+        tl += d->tile_log2[i];
+    }
+    V2A_REQUIRE(tl == 7, "igemm: tile box must hold 128 rows (sum tile_log2 = %d)", tl);
+
+    IgemmPlan* pl = new IgemmPlan();
+    memset(&pl->p, 0, sizeof(pl->p));
+    IgemmParams& p = pl->p;
+    int k_iters = 0;
+    for (int e = 0; e < d->ntaps; ++e) {
+        const v2a_igemm_tap& t = d->taps[e];
+        if (!(t.src >= 0 && t.src < d->nsrc && t.nchunks >= 1)) {
+            delete pl;
+            V2A_REQUIRE(false, "igemm: bad tap %d", e);
+        }
+        p.tap_src[e] = t.src;
+        for (int i = 0; i < 4; ++i) p.tap_d[e][i] = t.d[i];
+        p.tap_chunks[e] = t.nchunks;
+        k_iters += t.nchunks;
+    }
+    if (k_iters * kChunkK != d->ktot) {
+        delete pl;
+        V2A_REQUIRE(false, "igemm: ktot %d != 64 * sum(nchunks) %d", d->ktot, k_iters * kChunkK);
+    }
+    p.ntaps = d->ntaps;
+    p.k_iters = k_iters;
+    p.num_m_tiles = 1;
+    for (int i = 0; i < 4; ++i) {
+        p.tile_log2[i] = d->tile_log2[i];
+        p.out_dims[i] = d->out_dims[i];
+        p.ntile[i] = ceil_div(d->out_dims[i], 1 << d->tile_log2[i]);
+        p.num_m_tiles *= p.ntile[i];
+        p.rowvec_mul[i] = d->rowvec_mul[i];
+        p.stats_mul[i] = d->stats_mul[i];
+    }
+    p.num_n_tiles = ceil_div(d->cout, d->block_n);
+    p.block_n = d->block_n;
+    p.passes = d->passes;
+    p.b_tile_bytes = (uint32_t)d->block_n * kChunkK * 2;
+    p.stage_bytes = (uint32_t)d->passes == 3 ? 2 * (kATileBytes + p.b_tile_bytes)
+                                             : (kATileBytes + p.b_tile_bytes);
+    const size_t overhead = 1024 /*align*/ + 256 /*barriers*/;
+    int stages = (int)((g_max_smem - overhead) / p.stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 2) {
+        delete pl;
+        V2A_REQUIRE(false, "igemm: block_n %d leaves room for %d pipeline stages", d->block_n, stages);
+    }
+    p.stages = stages;
+    pl->smem = (size_t)stages * p.stage_bytes + overhead;
+    p.cout = d->cout;
+    p.ldc = d->ldc;
+    p.out_f32 = d->out_f32;
+    p.out_hi = reinterpret_cast<__nv_bfloat16*>(d->out_hi);
+    p.out_lo = reinterpret_cast<__nv_bfloat16*>(d->out_lo);
+    p.bias = d->bias;
+    p.rowvec = d->rowvec;
+    p.ld_rowvec = d->ld_rowvec;
+    p.residual = d->residual;
+    p.ld_res = d->ld_res;
+    p.stats = d->stats;
+    p.stats_ld = d->stats_ld;
+
+    // tensor maps: A boxes follow the output tile box; every source shares it
+    int rc = 0;
+    for (int s = 0; s < d->nsrc && !rc; ++s) {
+        const v2a_igemm_src& src = d->src[s];
+        if (src.channels % 8 != 0 || !src.hi || (d->passes == 3 && !src.lo)) {
+            set_error("igemm: source %d needs channels %% 8 == 0 and hi/lo planes", s);
+            rc = 2;
+            break;
+        }
+        uint64_t dims[5] = {(uint64_t)src.channels, (uint64_t)src.dims[0], (uint64_t)src.dims[1],
+                            (uint64_t)src.dims[2], (uint64_t)src.dims[3]};
+        uint32_t box[5] = {kChunkK, 1u << d->tile_log2[0], 1u << d->tile_log2[1],
+                           1u << d->tile_log2[2], 1u << d->tile_log2[3]};
+        rc = make_map(&p.a_hi[s], src.hi, 5, dims, box);
+        if (!rc && d->passes == 3) rc = make_map(&p.a_lo[s], src.lo, 5, dims, box);
+    }
+    if (!rc) {
+        uint64_t dims[2] = {(uint64_t)d->ktot, (uint64_t)d->wrows};
+        uint32_t box[2] = {kChunkK, (uint32_t)d->block_n};
+        if (!d->w_hi || (d->passes == 3 && !d->w_lo)) {
+            set_error("igemm: missing weight planes");
+            rc = 2;
+        }
+        if (!rc) rc = make_map(&p.b_hi, d->w_hi, 2, dims, box);
+        if (!rc && d->passes == 3) rc = make_map(&p.b_lo, d->w_lo, 2, dims, box);
+    }
+    if (rc) {
+        delete pl;
+        return rc;
+    }
+    const int total = p.num_m_tiles * p.num_n_tiles;
+    pl->grid = total < g_num_sms ? total : g_num_sms;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             g_max_smem);
+        if (e != cudaSuccess) {
+            delete pl;
+            V2A_CUDA_OK(e);
+        }
+        attr_set = true;
+    }
+    *out = pl;
+    return 0;
+}
+
+}  // namespace v2a
+
+extern "C" {
+
+const char* v2a_last_error(void) { return v2a::get_error(); }
+int v2a_version(void) { return 100; }
+int64_t v2a_launch_count(void) { return v2a::g_launches.load(); }
+
+int v2a_igemm_plan_create(const v2a_igemm_desc* desc, void** plan_out) {
+    v2a::IgemmPlan* pl = nullptr;
+    int rc = v2a::plan_create(desc, &pl);
+    if (rc) return rc;
+    *plan_out = pl;
+    return 0;
+}
+
+int v2a_igemm_plan_run(void* plan, void* stream) {
+    v2a::IgemmPlan* pl = reinterpret_cast<v2a::IgemmPlan*>(plan);
+    v2a::igemm_kernel<<<pl->grid, v2a::kThreads, pl->smem, (cudaStream_t)stream>>>(pl->p);
+    V2A_CUDA_OK(cudaGetLastError());
+    v2a::g_launches.fetch_add(1);
+    return 0;
+}
+
+void v2a_igemm_plan_destroy(void* plan) { delete reinterpret_cast<v2a::IgemmPlan*>(plan); }
+
+}  // extern "C"

@@ -1,0 +1,309 @@
+"""Thin Python wrappers over the C ABI: torch tensors in, raw pointers out.
+
+PyTorch is used for device memory and streams only.  Every function here
+launches hand-written CUDA through libv2a_b200.so and raises if it cannot.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+CHUNK_K = 64
+ACT_NONE, ACT_SILU, ACT_MISH = 0, 1, 2
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("v2a_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+@dataclass
+class HL:
+    """bf16 (hi, lo) planes of an fp32 tensor: x ~= hi + lo."""
+
+    hi: torch.Tensor
+    lo: torch.Tensor
+
+    @staticmethod
+    def empty(rows: int, cols: int, device) -> "HL":
+        return HL(torch.empty(rows, cols, dtype=torch.bfloat16, device=device),
+                  torch.empty(rows, cols, dtype=torch.bfloat16, device=device))
+
+    def float(self) -> torch.Tensor:
+        return self.hi.float() + self.lo.float()
+
+
+def split_hl_torch(x: torch.Tensor) -> HL:
+    """Weight-time split with torch ops (one-off packing; same RN rounding as the kernels)."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return HL(hi.contiguous(), lo.contiguous())
+
+
+def split_hl(x: torch.Tensor, ld: Optional[int] = None) -> HL:
+    """fp32 [rows, cols] -> HL [rows, ld] (zero padded) on the GPU kernel."""
+    _require_cuda(x)
+    x = x.contiguous()
+    rows, cols = x.shape
+    ld = ld or cols
+    out = HL.empty(rows, ld, x.device)
+    _lib.check(_lib.load().v2a_split_hl(x.data_ptr(), rows, cols, ld, out.hi.data_ptr(),
+                                        out.lo.data_ptr(), _stream()), "split_hl")
+    return out
+
+
+# ---------------------------------------------------------------------------
+# tile / block heuristics (host logic, unit-tested on CPU)
+# ---------------------------------------------------------------------------
+def choose_tile(out_dims: Sequence[int]) -> tuple[int, int, int, int]:
+    """log2 of the 128-row tile box along D0..D3 minimising padded rows.
+
+    Ties prefer boxes that are long in the fastest dims (contiguous TMA rows).
+    """
+    best = None
+    for l in itertools.product(range(8), repeat=4):
+        if sum(l) != 7:
+            continue
+        rows = 1
+        over = 0
+        for d, ld in zip(out_dims, l):
+            t = 1 << ld
+            rows *= -(-d // t) * t
+            if t > d:
+                over += 1
+        key = (rows, over, tuple(-x for x in l))
+        if best is None or key < best[0]:
+            best = (key, l)
+    return best[1]
+
+
+def choose_block_n(cout: int) -> int:
+    """N tile (multiple of 16, <= 256): least padding, then the widest."""
+    best = None
+    for n in range(16, 257, 16):
+        tiles = -(-cout // n)
+        key = (tiles * n - cout, -n)
+        if best is None or key < best[0]:
+            best = (key, n)
+    return best[1]
+
+
+def nchunks(c: int) -> int:
+    return -(-c // CHUNK_K)
+
+
+def pack_weight_taps(per_tap: Sequence[torch.Tensor]) -> torch.Tensor:
+    """[Cout, Cin_t] per tap -> [Cout, sum 64*ceil(Cin_t/64)] K-major, zero padded per tap."""
+    cols = []
+    for w in per_tap:
+        cout, cin = w.shape
+        pad = nchunks(cin) * CHUNK_K - cin
+        cols.append(torch.nn.functional.pad(w, (0, pad)) if pad else w)
+    return torch.cat(cols, dim=1).contiguous()
+
+
+# ---------------------------------------------------------------------------
+# implicit GEMM plan
+# ---------------------------------------------------------------------------
+class Igemm:
+    """One planned tcgen05 implicit-GEMM launch (TMA descriptors built once)."""
+
+    def __init__(self, *, srcs, taps, w: HL, out_dims, cout, ldc=None, out_f32=None, out_hl=None,
+                 bias=None, rowvec=None, rowvec_mul=(0, 0, 0, 0), residual=None, stats=None,
+                 stats_mul=(0, 0, 0, 0), block_n=None, passes=3, tile_log2=None):
+        lib = _lib.load()
+        d = _lib.IgemmDesc()
+        self._keep = [srcs, w, out_f32, out_hl, bias, rowvec, residual, stats]
+        assert 1 <= len(srcs) <= _lib.V2A_MAX_SRC
+        for i, (hl, channels, dims) in enumerate(srcs):
+            _require_cuda(hl.hi, hl.lo)
+            dims = list(dims) + [1] * (4 - len(dims))
+            need = channels * dims[0] * dims[1] * dims[2] * dims[3]
+            assert hl.hi.numel() == need, f"src {i}: {hl.hi.numel()} elements, dims say {need}"
+            d.src[i].hi = hl.hi.data_ptr()
+            d.src[i].lo = hl.lo.data_ptr()
+            d.src[i].channels = channels
+            for k in range(4):
+                d.src[i].dims[k] = dims[k]
+        d.nsrc = len(srcs)
+        assert 1 <= len(taps) <= _lib.V2A_MAX_TAPS
+        ktot = 0
+        for i, (src, off, nch) in enumerate(taps):
+            off = list(off) + [0] * (4 - len(off))
+            d.taps[i].src = src
+            for k in range(4):
+                d.taps[i].d[k] = off[k]
+            d.taps[i].nchunks = nch
+            ktot += nch * CHUNK_K
+        d.ntaps = len(taps)
+        assert w.hi.shape[1] == ktot, f"weight K {w.hi.shape[1]} != tap program K {ktot}"
+        d.w_hi, d.w_lo = w.hi.data_ptr(), w.lo.data_ptr()
+        d.wrows = w.hi.shape[0]
+        d.ktot = ktot
+        out_dims = list(out_dims) + [1] * (4 - len(out_dims))
+        tile_log2 = tile_log2 or choose_tile(out_dims)
+        for k in range(4):
+            d.out_dims[k] = out_dims[k]
+            d.tile_log2[k] = tile_log2[k]
+            d.rowvec_mul[k] = rowvec_mul[k]
+            d.stats_mul[k] = stats_mul[k]
+        d.block_n = block_n or choose_block_n(cout)
+        d.passes = passes
+        d.cout = cout
+        ldc = ldc or -(-cout // 16) * 16
+        d.ldc = ldc
+        rows = out_dims[0] * out_dims[1] * out_dims[2] * out_dims[3]
+        self.rows, self.cout, self.ldc, self.ktot = rows, cout, ldc, ktot
+        if out_f32 is not None:
+            assert out_f32.dtype == torch.float32 and out_f32.numel() == rows * ldc
+            d.out_f32 = out_f32.data_ptr()
+        if out_hl is not None:
+            assert out_hl.hi.numel() == rows * ldc
+            d.out_hi, d.out_lo = out_hl.hi.data_ptr(), out_hl.lo.data_ptr()
+        if bias is not None:
+            assert bias.dtype == torch.float32 and bias.numel() >= cout
+            d.bias = bias.data_ptr()
+        if rowvec is not None:
+            assert rowvec.dtype == torch.float32 and rowvec.dim() == 2
+            d.rowvec = rowvec.data_ptr()
+            d.ld_rowvec = rowvec.stride(0)
+        if residual is not None:
+            assert residual.dtype == torch.float32
+            d.residual = residual.data_ptr()
+            d.ld_res = residual.shape[-1]
+        if stats is not None:
+            assert stats.dtype == torch.float64
+            d.stats = stats.data_ptr()
+            d.stats_ld = stats.shape[-2]
+        self.desc = d
+        self.flops = 2.0 * rows * cout * sum(nch * CHUNK_K for _, _, nch in taps)
+        plan = C.c_void_p()
+        _lib.check(lib.v2a_igemm_plan_create(C.byref(d), C.byref(plan)), "igemm_plan_create")
+        self._plan = plan
+        self._lib = lib
+
+    def run(self) -> None:
+        _lib.check(self._lib.v2a_igemm_plan_run(self._plan, _stream()), "igemm_plan_run")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None):
+                self._lib.v2a_igemm_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------
+# elementwise wrappers
+# ---------------------------------------------------------------------------
+def channel_stats(x: torch.Tensor, instances: int, stats: torch.Tensor) -> None:
+    """x fp32 [instances*ppi, C]; stats float64 [instances, C, 2] accumulated in place."""
+    _require_cuda(x, stats)
+    rows, Cc = x.shape
+    _lib.check(_lib.load().v2a_channel_stats(x.data_ptr(), instances, rows // instances, Cc,
+                                             stats.data_ptr(), _stream()), "channel_stats")
+
+
+class Prep:
+    """Planned GroupNorm-apply / activation / concat / resample / split launch."""
+
+    def __init__(self, *, x0, x1=None, stats0=None, stats1=None, pixels_per_inst=1, inst_per_group=1,
+                 groups=32, eps=1e-5, gamma=None, beta=None, act=ACT_NONE, film=None, pixels_per_film=1,
+                 mode=0, H=0, W=0, out_hl=None, out_f32=None, raw_hl=None):
+        _require_cuda(x0)
+        d = _lib.PrepDesc()
+        P, C0 = x0.shape
+        C1 = 0 if x1 is None else x1.shape[1]
+        d.x0, d.x1, d.C0, d.C1 = x0.data_ptr(), _ptr(x1), C0, C1
+        d.stats0, d.stats1 = _ptr(stats0), _ptr(stats1)
+        d.pixels_per_inst, d.inst_per_group, d.groups, d.eps = pixels_per_inst, inst_per_group, groups, eps
+        self.scratch = None
+        if stats0 is not None:
+            samples = P // (pixels_per_inst * inst_per_group)
+            self.scratch = torch.empty(samples * groups * 2, dtype=torch.float32, device=x0.device)
+            d.gn_scratch = self.scratch.data_ptr()
+        d.gamma, d.beta, d.act = _ptr(gamma), _ptr(beta), act
+        d.film, d.pixels_per_film = _ptr(film), pixels_per_film
+        d.mode, d.H, d.W, d.P = mode, H, W, P
+        if out_hl is not None:
+            d.out_hi, d.out_lo = out_hl.hi.data_ptr(), out_hl.lo.data_ptr()
+        d.out_f32 = _ptr(out_f32)
+        if raw_hl is not None:
+            d.raw_hi, d.raw_lo = raw_hl.hi.data_ptr(), raw_hl.lo.data_ptr()
+        self.desc = d
+        self._keep = [x0, x1, stats0, stats1, gamma, beta, film, out_hl, out_f32, raw_hl]
+        self._lib = _lib.load()
+
+    def run(self) -> None:
+        _lib.check(self._lib.v2a_prep(C.byref(self.desc), _stream()), "prep")
+
+
+def attention(qkv: torch.Tensor, N: int, L: int, heads: int, out: HL) -> None:
+    _require_cuda(qkv)
+    _lib.check(_lib.load().v2a_attention(qkv.data_ptr(), N, L, heads, out.hi.data_ptr(),
+                                         out.lo.data_ptr(), _stream()), "attention")
+
+
+def linear(x, W, bias, y, *, add=None, act_in=ACT_NONE, act_out=ACT_NONE) -> None:
+    """y[b, o] = act_out(act_in(x[b]) . W[o] + bias[o]) (+ add[b, o]); fp32, small batch."""
+    _require_cuda(x, W, y)
+    B, IN = x.shape
+    OUT = W.shape[0]
+    assert W.shape[1] == IN and W.is_contiguous() and y.shape[0] == B and y.shape[1] >= OUT
+    _lib.check(_lib.load().v2a_linear(x.data_ptr(), x.stride(0), W.data_ptr(), _ptr(bias), _ptr(add),
+                                      0 if add is None else add.stride(0), y.data_ptr(), y.stride(0),
+                                      B, IN, OUT, act_in, act_out, _stream()), "linear")
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, mode: int, out: torch.Tensor) -> None:
+    _require_cuda(t, out)
+    assert t.dtype == torch.int64
+    _lib.check(_lib.load().v2a_timestep_embedding(t.data_ptr(), t.numel(), dim, mode, out.data_ptr(),
+                                                  _stream()), "timestep_embedding")
+
+
+def unet_input_pack(x, cond, B, F, H, W, out: HL) -> None:
+    _lib.check(_lib.load().v2a_unet_input_pack(x.data_ptr(), cond.data_ptr(), B, F, H, W,
+                                               out.hi.data_ptr(), out.lo.data_ptr(), _stream()),
+               "unet_input_pack")
+
+
+def unet_output_head(y, ldy, wt, bt, B, F, H, W, out) -> None:
+    _lib.check(_lib.load().v2a_unet_output_head(y.data_ptr(), ldy, wt.data_ptr(), bt.data_ptr(), B, F,
+                                                H, W, out.data_ptr(), _stream()), "unet_output_head")
+
+
+def ddpm_step(x, v, noise, coef) -> None:
+    _lib.check(_lib.load().v2a_ddpm_step(x.data_ptr(), v.data_ptr(), _ptr(noise), coef.data_ptr(),
+                                         x.numel(), _stream()), "ddpm_step")
+
+
+def ddim_step(x, v, noise, coef) -> None:
+    _lib.check(_lib.load().v2a_ddim_step(x.data_ptr(), v.data_ptr(), _ptr(noise), coef.data_ptr(),
+                                         x.numel(), _stream()), "ddim_step")
+
+
+def unnormalize_clamp(x, out) -> None:
+    _lib.check(_lib.load().v2a_unnormalize_clamp(x.data_ptr(), out.data_ptr(), x.numel(), _stream()),
+               "unnormalize_clamp")
+
+
+def launch_count() -> int:
+    return int(_lib.load().v2a_launch_count())
