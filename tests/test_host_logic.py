@@ -1,0 +1,103 @@
+"""CPU tests of the host-side conv programs (tap offsets, packing, phase split)
+replayed through tests/emulator.py and compared with torch's own convolutions."""
+import torch
+import torch.nn.functional as F
+
+from tests.emulator import as5d, emulate
+from v2a_b200 import convs, ops
+
+torch.manual_seed(0)
+D = torch.float64
+
+
+def _nhwc(x):  # [N, C, H, W] -> [N*H*W, C]
+    return x.permute(0, 2, 3, 1).reshape(-1, x.shape[1])
+
+
+def test_spatial3x3_matches_conv2d():
+    N, Ci, Co, H, W = 3, 72, 40, 8, 16
+    x = torch.randn(N, Ci, H, W, dtype=D)
+    w = torch.randn(Co, Ci, 3, 3, dtype=D)
+    prog = convs.spatial3x3(Ci, N, H, W)
+    out = emulate(prog, [as5d(_nhwc(x), Ci, prog.src_dims[0])], convs.spatial3x3_weight(w), Co)
+    ref = _nhwc(F.conv2d(x, w, padding=1))
+    assert prog.ktot == 9 * 128
+    torch.testing.assert_close(out, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_spatial3x3_stride2_phase_split():
+    N, Ci, Co, H, W = 2, 16, 24, 8, 12
+    x = torch.randn(N, Ci, H, W, dtype=D)
+    w = torch.randn(Co, Ci, 3, 3, dtype=D)
+    # phase split exactly as prep mode 2 lays it out: [img][ph*2+pw][H/2][W/2][C]
+    xp = x.permute(0, 2, 3, 1).reshape(N, H // 2, 2, W // 2, 2, Ci).permute(0, 2, 4, 1, 3, 5)
+    xp = xp.reshape(N, 4, H // 2, W // 2, Ci)
+    prog = convs.spatial3x3_s2(Ci, N, H, W)
+    out = emulate(prog, [xp], convs.spatial3x3_weight(w), Co)
+    ref = _nhwc(F.conv2d(x, w, padding=1, stride=2))
+    torch.testing.assert_close(out, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_temporal_with_skip_matches_conv1d_plus_1x1():
+    B, Fr, HW, C, Cx = 2, 7, 6, 24, 40
+    y = torch.randn(B, Fr, HW, C, dtype=D)
+    xs = torch.randn(B, Fr, HW, Cx, dtype=D)
+    wt = torch.randn(C, C, 3, dtype=D)
+    ws = torch.randn(C, Cx, 1, 1, dtype=D)
+    prog = convs.temporal3(C, B, Fr, HW, skip_channels=Cx)
+    # src layout [X3=1][X2=B][X1=F][X0=HW][C]
+    out = emulate(prog, [y[None], xs[None]], convs.temporal3_weight(wt, ws), C)
+    # reference: '(b h w) c f' conv1d with zero padding 1 (guided_diffusion/nn.py:76-85)
+    yy = y.permute(0, 2, 3, 1).reshape(B * HW, C, Fr)
+    ref_t = F.conv1d(F.pad(yy, (1, 1)), wt).reshape(B, HW, C, Fr).permute(0, 3, 1, 2)
+    ref_s = torch.einsum("bfpc,oc->bfpo", xs, ws[:, :, 0, 0])
+    ref = (ref_t + ref_s).reshape(-1, C)
+    torch.testing.assert_close(out, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_conv1d_k5_and_dgrad_weights():
+    B, T, Ci, Co = 3, 8, 24, 16
+    x = torch.randn(B, Ci, T, dtype=D, requires_grad=True)
+    w = torch.randn(Co, Ci, 5, dtype=D)
+    y = F.conv1d(x, w, padding=2)
+    prog = convs.conv1d(Ci, B, T, 5, 2)
+    xl = x.detach().permute(0, 2, 1).reshape(1, 1, B, T, Ci)
+    out = emulate(prog, [xl], convs.conv1d_weight(w), Co)
+    torch.testing.assert_close(out, y.detach().permute(0, 2, 1).reshape(-1, Co), rtol=1e-12, atol=1e-12)
+    # data gradient = same program over dy with flipped / transposed weights
+    dy = torch.randn_like(y)
+    (dx,) = torch.autograd.grad(y, x, dy)
+    progb = convs.conv1d(Co, B, T, 5, 2)
+    dyl = dy.permute(0, 2, 1).reshape(1, 1, B, T, Co)
+    outb = emulate(progb, [dyl], convs.conv1d_dgrad_weight(w), Ci)
+    torch.testing.assert_close(outb, dx.permute(0, 2, 1).reshape(-1, Ci), rtol=1e-12, atol=1e-12)
+
+
+def test_input_conv_weight_matches_im2col():
+    Co, H, W = 8, 5, 6
+    x = torch.randn(1, 6, H, W, dtype=D)
+    w = torch.randn(Co, 6, 3, 3, dtype=D)
+    cols = F.unfold(x, 3, padding=1)  # [1, 6*9, H*W], index c*9 + tap
+    cols = cols.reshape(6, 9, H * W).permute(2, 1, 0).reshape(H * W, 54)  # k = tap*6 + c
+    out = F.pad(cols, (0, 10)) @ convs.input_conv_weight(w).t()
+    ref = _nhwc(F.conv2d(x, w, padding=1))
+    torch.testing.assert_close(out, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_choose_tile_and_block_n():
+    for dims in [(16384, 7, 16, 1), (64, 7, 16, 1), (8, 8, 112, 1), (16, 256, 1, 1), (4, 256, 1, 1), (1, 1, 1, 1)]:
+        t = ops.choose_tile(dims)
+        assert sum(t) == 7
+    assert ops.choose_tile((16384, 7, 16, 1)) == (7, 0, 0, 0)
+    # 8x8 frames: pair two batch elements rather than padding 7 frames to 8
+    assert ops.choose_tile((64, 7, 16, 1)) == (6, 0, 1, 0)
+    assert ops.choose_block_n(128) == 128 and ops.choose_block_n(512) == 256
+    assert ops.choose_block_n(384) == 192 and ops.choose_block_n(640) == 160
+    assert ops.choose_block_n(3) == 16
+
+
+def test_bf16_split_error_bound():
+    x = torch.randn(4096) * torch.logspace(-3, 3, 4096)
+    hl = ops.split_hl_torch(x)
+    err = (hl.float() - x).abs() / x.abs().clamp_min(1e-30)
+    assert err.max() < 2.0 ** -16
