@@ -157,13 +157,18 @@ int v2a_timestep_embedding(const int64_t* t, int B, int dim, int mode, float* ou
  * Video UNet boundary layout kernels.  Unet_Libero.forward rearranges
  *   flowdiffusion/unet.py:216-222
  * ---------------------------------------------------------------------- */
-/* x [B][3F][H][W] fp32, cond [B][3][H][W] -> im2col'd first-conv operand
- * hl [B*F][H][W][64], k = tap*6 + c (c<3 frame rgb, c>=3 cond rgb), 54 used */
-int v2a_unet_input_pack(const float* x, const float* cond, int B, int F, int H, int W,
-                        void* out_hi, void* out_lo, void* stream);
-/* y fp32 [B][F][H][W][ldy] (3 used) -> temporal Conv1d(3,3,k3)+bias -> out [B][3F][H][W] */
+/* First-conv operand: hl [B*F][H][W][64], k = tap*6 + c (c<3 frame rgb from `x`, c>=3
+ * conditioning rgb from `cond`), 54 of 64 used.  Each source is addressed as
+ * base[b*s[0] + f*s[1] + c*s[2] + h*W + w] (element strides), which covers both the
+ * packed [B][(f c)+3][H][W] tensor (cond frame stride 0 = broadcast over frames) and
+ * UNetModel's 5-D [B][6][F][H][W] input. */
+int v2a_unet_input_pack(const float* x, const int64_t* x_strides, const float* cond,
+                        const int64_t* cond_strides, int B, int F, int H, int W, void* out_hi,
+                        void* out_lo, void* stream);
+/* y fp32 [B][F][H][W][ldy] (3 used) -> temporal Conv1d(3,3,k3)+bias ->
+ * out[b*s[0] + f*s[1] + c*s[2] + h*W + w] */
 int v2a_unet_output_head(const float* y, int ldy, const float* wt, const float* bt, int B, int F,
-                         int H, int W, float* out, void* stream);
+                         int H, int W, float* out, const int64_t* out_strides, void* stream);
 
 /* ------------------------------------------------------------------------
  * Sampler steps.  replaces p_sample / ddim_sample elementwise chains

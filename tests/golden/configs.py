@@ -1,0 +1,28 @@
+"""Shared seeded inputs / configs of the golden fixtures (used by make_golden.py and the tests)."""
+import torch
+
+# small UNetModel with every block kind: skip convs, identity skips, both attention
+# resolutions, down/up-sampling, concat seams that straddle GroupNorm groups (128+64=192 -> 6/group)
+TINY_UNET = dict(image_size=(16, 16), in_channels=6, model_channels=64, out_channels=3, num_res_blocks=2,
+                 attention_resolutions=(2, 4), dropout=0, channel_mult=(1, 2, 3), conv_resample=True, dims=3,
+                 num_classes=None, task_tokens=True, task_token_channels=512, use_checkpoint=False,
+                 use_fp16=False, num_head_channels=32)
+
+
+def tiny_inputs():
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(2, 9, 16, 16, generator=g)
+    t = torch.tensor([3, 1], dtype=torch.long)
+    x_cond = torch.rand(2, 3, 16, 16, generator=g)
+    te = torch.randn(2, 6, 512, generator=g)
+    return x, t, x_cond, te
+
+
+def config1_inputs():
+    """BASELINE.json configs[0]: Unet_Libero, 64x64, 4 frames, batch 1."""
+    g = torch.Generator().manual_seed(123)
+    x = torch.randn(1, 12, 64, 64, generator=g)
+    t = torch.tensor([57], dtype=torch.long)
+    x_cond = torch.rand(1, 3, 64, 64, generator=g)
+    te = torch.randn(1, 8, 512, generator=g)
+    return x, t, x_cond, te

@@ -258,7 +258,7 @@ def test_unet_boundary_packs_and_sampler_steps():
     x = torch.randn(B, 3 * Fr, H, W, device=DEV)
     cond = torch.rand(B, 3, H, W, device=DEV)
     packed = ops.HL.empty(B * Fr * H * W, 64, DEV)
-    ops.unet_input_pack(x, cond, B, Fr, H, W, packed)
+    ops.unet_input_pack(x, (3 * Fr * H * W, 3 * H * W, H * W), cond, (3 * H * W, 0, H * W), B, Fr, H, W, packed)
     # reference rearrange of Unet_Libero.forward (flowdiffusion/unet.py:216-222) + 3x3 conv
     xin = torch.cat([x.reshape(B, Fr, 3, H, W), cond[:, None].expand(B, Fr, 3, H, W)], 2).reshape(B * Fr, 6, H, W)
     w = torch.randn(32, 6, 3, 3, device=DEV)
@@ -269,7 +269,7 @@ def test_unet_boundary_packs_and_sampler_steps():
     y = torch.randn(B * Fr * H * W, 16, device=DEV)
     wt, bt = torch.randn(3, 3, 3, device=DEV), torch.randn(3, device=DEV)
     out = torch.empty(B, 3 * Fr, H, W, device=DEV)
-    ops.unet_output_head(y, 16, wt, bt, B, Fr, H, W, out)
+    ops.unet_output_head(y, 16, wt, bt, B, Fr, H, W, out, (3 * Fr * H * W, 3 * H * W, H * W))
     yy = y[:, :3].reshape(B, Fr, H * W, 3).permute(0, 2, 3, 1).reshape(B * H * W, 3, Fr)
     r = F.conv1d(F.pad(yy, (1, 1)), wt, bt).reshape(B, H, W, 3, Fr).permute(0, 4, 3, 1, 2).reshape(B, 3 * Fr, H, W)
     assert _rel(out, r) < 1e-5

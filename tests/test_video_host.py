@@ -1,0 +1,80 @@
+"""CPU tests of the video-path host modules: reference-identical state_dict layout,
+bit-exact schedule buffers, deepcopy/strict-load mechanics, loud failure without CUDA,
+and that the C-ABI library exports every symbol include/v2a_b200.h declares."""
+import copy
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from v2a_b200 import _lib
+from v2a_b200.goal_diffusion import GoalGaussianDiffusion
+from v2a_b200.unet import UNetModel, Unet_Libero
+from tests.golden.configs import TINY_UNET
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _load(name):
+    with open(os.path.join(HERE, "golden", name)) as f:
+        return json.load(f)
+
+
+def _libero_diffusion():
+    return GoalGaussianDiffusion(Unet_Libero(), image_size=(128, 128), channels=21, timesteps=100,
+                                 sampling_timesteps=100, loss_type="l2", objective="pred_v",
+                                 beta_schedule="cosine", min_snr_loss_weight=True, guidance_weight=0)
+
+
+def test_state_dict_layout_equals_reference():
+    lay = _load("goal_diffusion_state_dict_layout.json")
+    sd = _libero_diffusion().state_dict()
+    assert list(sd.keys()) == list(lay.keys())
+    assert all(list(sd[k].shape) == lay[k] for k in lay)
+    tiny = _load("tiny_unet_state_dict_layout.json")
+    net = Unet_Libero.__new__(Unet_Libero)
+    torch.nn.Module.__init__(net)
+    net.unet = UNetModel(**TINY_UNET)
+    assert {k: list(v.shape) for k, v in net.state_dict().items()} == tiny
+
+
+def test_schedule_buffers_bit_exact_vs_reference_golden():
+    gold = torch.load(os.path.join(HERE, "golden", "video_golden.pt"))
+    sd = _libero_diffusion().state_dict()
+    bufs = [k for k in sd if not k.startswith("model.")]
+    assert len(bufs) == 13
+    for k in bufs:
+        assert torch.equal(sd[k], gold["buf100." + k]), k
+
+
+def test_reference_default_init_and_ema_mechanics():
+    d = _libero_diffusion()
+    # temporal convs start as identity (dirac) with zero bias, like gd/nn.py:49-51
+    w = d.model.unet.input_blocks[1][0].in_layers[2].temporal_conv.weight
+    assert torch.equal(w[:, :, 1], torch.eye(w.shape[0])) and w[:, :, 0].abs().sum() == 0
+    d2 = copy.deepcopy(d)  # ema_pytorch.EMA deep-copies the module
+    d2.load_state_dict(d.state_dict(), strict=True)
+    assert d.is_ddim_sampling is False and d.num_timesteps == 100
+    d.sampling_timesteps, d.is_ddim_sampling, d.var_temp, d.guidance_weight = 10, True, 0.5, 0.0  # attribute pokes
+
+
+def test_sample_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    d = GoalGaussianDiffusion(Unet_Libero(), image_size=(16, 16), channels=9, timesteps=4, sampling_timesteps=4,
+                              objective="pred_v", beta_schedule="cosine", guidance_weight=0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        d.sample(torch.rand(1, 3, 16, 16), torch.randn(1, 4, 512), batch_size=1)
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "v2a_b200.h")).read()
+    declared = set(re.findall(r"\b(v2a_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()  # builds with nvcc if needed; raises if missing
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.v2a_version() >= 100

@@ -1,0 +1,67 @@
+"""Developer timing probe (not the contract bench): UNet forward time + per-launch breakdown.
+
+usage: python tools/quick_bench.py [B] [--layers]
+"""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from v2a_b200 import ops  # noqa: E402
+from v2a_b200.unet import Unet_Libero  # noqa: E402
+
+
+def timed(fn, n=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 2
+    Fr, H, W = 7, 128, 128
+    torch.manual_seed(0)
+    net = Unet_Libero().cuda()
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() > 1:
+                p.add_(0.02 * torch.randn_like(p))
+    x = torch.randn(B, 3 * Fr + 3, H, W, device="cuda")
+    t = torch.full((B,), 50, device="cuda")
+    te = torch.randn(B, 12, 512, device="cuda")
+    t0 = time.time()
+    net(x, t, te)
+    torch.cuda.synchronize()
+    print(f"first forward (plan build + pack) {time.time() - t0:.2f}s")
+    ms = timed(lambda: net(x, t, te))
+    eng = net.unet.engine(B, Fr, H, W, "cuda")
+    print(f"B={B} forward {ms:.2f} ms  igemm-flops {eng.flops / 1e12:.3f} TF -> {eng.flops / ms / 1e9:.1f} TFLOP/s "
+          f"(algorithmic; x{eng.passes} MMA passes)  launches/forward {len(eng.steps)}  arena {eng.pool.total / 1e9:.2f} GB")
+    print(f"torch mem allocated {torch.cuda.memory_allocated() / 1e9:.2f} GB")
+    if "--layers" in sys.argv:
+        rows = []
+        tot = 0.0
+        for i, g in enumerate(eng.igemms):
+            m = timed(g.run, n=3, warm=1)
+            tot += m
+            d = g.desc
+            rows.append((m, i, g.rows, g.cout, g.ktot, d.block_n, g.flops / m / 1e9))
+        print(f"sum of igemm launches {tot:.2f} ms ({len(eng.igemms)} launches)")
+        for m, i, r, c, k, bn, tf in sorted(rows, reverse=True)[:40]:
+            print(f"  #{i:3d} rows {r:8d} cout {c:5d} K {k:6d} bn {bn:3d}  {m:7.3f} ms  {tf:7.1f} TFLOP/s")
+        # non-igemm remainder
+        other = [s for s in eng.steps]
+        print(f"non-igemm share ~ {ms - tot:.2f} ms")
+
+
+if __name__ == "__main__":
+    main()

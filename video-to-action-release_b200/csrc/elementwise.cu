@@ -230,8 +230,12 @@ __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, int B, 
 // ---------------------------------------------------------------------------
 // UNet boundary packs
 // ---------------------------------------------------------------------------
-// one thread = one (image n=b*F+f, h, w, tap): writes 8 channels (6 used)
-__global__ void unet_input_pack_kernel(const float* __restrict__ x, const float* __restrict__ cond,
+// one thread = 8 of the 64 im2col channels of one pixel.  Sources are addressed
+// through (batch, frame, channel) element strides so both the packed
+// [B][(f c)][H][W] (+ broadcast cond frame) and the 5-D [B][6][F][H][W] layouts work.
+struct PackStrides { int64_t b, f, c; };
+__global__ void unet_input_pack_kernel(const float* __restrict__ x, PackStrides xs,
+                                       const float* __restrict__ cond, PackStrides cs,
                                        int B, int F, int H, int W, __nv_bfloat16* __restrict__ ohi,
                                        __nv_bfloat16* __restrict__ olo) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -252,8 +256,8 @@ __global__ void unet_input_pack_kernel(const float* __restrict__ x, const float*
             const int tap = k / 6, c = k % 6;
             const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
             if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-                val = c < 3 ? __ldg(&x[(((int64_t)b * 3 * F + f * 3 + c) * H + hh) * W + ww])
-                            : __ldg(&cond[(((int64_t)b * 3 + (c - 3)) * H + hh) * W + ww]);
+                val = c < 3 ? __ldg(&x[b * xs.b + f * xs.f + c * xs.c + (int64_t)hh * W + ww])
+                            : __ldg(&cond[b * cs.b + f * cs.f + (c - 3) * cs.c + (int64_t)hh * W + ww]);
             }
         }
         v[j] = val;
@@ -264,10 +268,10 @@ __global__ void unet_input_pack_kernel(const float* __restrict__ x, const float*
     *reinterpret_cast<uint4*>(olo + pix * 64 + oc * 8) = lo;
 }
 
-// temporal Conv1d(3,3,k=3, zero pad) over frames + NHWC -> [B][(f c)][H][W]
+// temporal Conv1d(3,3,k=3, zero pad) over frames + NHWC -> strided (b, f, c) output
 __global__ void unet_output_head_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ wt,
                                         const float* __restrict__ bt, int B, int F, int H, int W,
-                                        float* __restrict__ out) {
+                                        float* __restrict__ out, PackStrides os) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t HW = (int64_t)H * W;
     if (gid >= (int64_t)B * F * HW) return;
@@ -287,7 +291,7 @@ __global__ void unet_output_head_kernel(const float* __restrict__ y, int ldy, co
                        wt[(co * 3 + 2) * 3 + k] * y2;
     }
 #pragma unroll
-    for (int co = 0; co < 3; ++co) out[((int64_t)b * 3 * F + f * 3 + co) * HW + hw] = acc[co];
+    for (int co = 0; co < 3; ++co) out[b * os.b + f * os.f + co * os.c + hw] = acc[co];
 }
 
 // ---------------------------------------------------------------------------
@@ -435,20 +439,24 @@ int v2a_timestep_embedding(const int64_t* t, int B, int dim, int mode, float* ou
     return 0;
 }
 
-int v2a_unet_input_pack(const float* x, const float* cond, int B, int F, int H, int W, void* out_hi,
+int v2a_unet_input_pack(const float* x, const int64_t* x_strides, const float* cond,
+                        const int64_t* cond_strides, int B, int F, int H, int W, void* out_hi,
                         void* out_lo, void* stream) {
     const int64_t total = (int64_t)B * F * H * W * 8;
+    PackStrides xs{x_strides[0], x_strides[1], x_strides[2]};
+    PackStrides cs{cond_strides[0], cond_strides[1], cond_strides[2]};
     unet_input_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        x, cond, B, F, H, W, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+        x, xs, cond, cs, B, F, H, W, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
     V2A_LAUNCH_OK();
     return 0;
 }
 
 int v2a_unet_output_head(const float* y, int ldy, const float* wt, const float* bt, int B, int F, int H,
-                         int W, float* out, void* stream) {
+                         int W, float* out, const int64_t* out_strides, void* stream) {
     const int64_t total = (int64_t)B * F * H * W;
+    PackStrides os{out_strides[0], out_strides[1], out_strides[2]};
     unet_output_head_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        y, ldy, wt, bt, B, F, H, W, out);
+        y, ldy, wt, bt, B, F, H, W, out, os);
     V2A_LAUNCH_OK();
     return 0;
 }

@@ -279,15 +279,23 @@ def timestep_embedding(t: torch.Tensor, dim: int, mode: int, out: torch.Tensor) 
                                                   _stream()), "timestep_embedding")
 
 
-def unet_input_pack(x, cond, B, F, H, W, out: HL) -> None:
-    _lib.check(_lib.load().v2a_unet_input_pack(x.data_ptr(), cond.data_ptr(), B, F, H, W,
+def _i64x3(v):
+    return (C.c_int64 * 3)(*[int(i) for i in v])
+
+
+def unet_input_pack(x, x_strides, cond, cond_strides, B, F, H, W, out: HL) -> None:
+    """x / cond are device pointers (ints) or tensors; strides are (batch, frame, channel) in elements."""
+    xp = x if isinstance(x, int) else x.data_ptr()
+    cp = cond if isinstance(cond, int) else cond.data_ptr()
+    _lib.check(_lib.load().v2a_unet_input_pack(xp, _i64x3(x_strides), cp, _i64x3(cond_strides), B, F, H, W,
                                                out.hi.data_ptr(), out.lo.data_ptr(), _stream()),
                "unet_input_pack")
 
 
-def unet_output_head(y, ldy, wt, bt, B, F, H, W, out) -> None:
+def unet_output_head(y, ldy, wt, bt, B, F, H, W, out, out_strides) -> None:
     _lib.check(_lib.load().v2a_unet_output_head(y.data_ptr(), ldy, wt.data_ptr(), bt.data_ptr(), B, F,
-                                                H, W, out.data_ptr(), _stream()), "unet_output_head")
+                                                H, W, out.data_ptr(), _i64x3(out_strides), _stream()),
+               "unet_output_head")
 
 
 def ddpm_step(x, v, noise, coef) -> None:

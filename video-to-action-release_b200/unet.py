@@ -1,0 +1,681 @@
+"""B200-native video UNet behind the reference's module surface.
+
+Mirrors (names, constructor arguments, ``state_dict`` keys and shapes):
+  * ``UNetModel``    flowdiffusion/flowdiffusion/guided_diffusion/guided_diffusion/unet.py:400-684
+  * ``Unet_Libero``  flowdiffusion/flowdiffusion/unet.py:195-222
+so reference checkpoints load with ``strict=True`` and ``ema_pytorch.EMA`` can
+deep-copy the module.  The ``nn.Module`` tree below only HOLDS parameters (the
+stock torch layer classes give the reference's initialisation for free); none
+of their ``forward`` methods is ever called.  ``forward`` runs a planned list
+of hand-written CUDA launches (``_UNetEngine``) through the C ABI:
+
+  prep (GroupNorm-apply + SiLU + concat/upsample/phase-split + bf16 hi/lo split)
+    -> tcgen05 implicit-GEMM 3x3 conv -> tcgen05 temporal conv (+1x1 skip as extra K,
+       + bias + timestep-embedding add + residual + GroupNorm partial sums in the epilogue)
+  per-frame attention: prep -> qkv GEMM -> fused softmax(QK)V -> proj GEMM (+residual, +sums)
+
+Engines (TMA descriptors, packed weights, activation arena, CUDA graph) live in a
+process-global registry keyed by module, never on the module itself.
+"""
+from __future__ import annotations
+
+import math
+import os
+import weakref
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import convs, ops
+from .ops import HL
+
+# ---------------------------------------------------------------------------
+# parameter holders (reference-identical names)
+# ---------------------------------------------------------------------------
+
+
+class Conv3d(nn.Module):
+    """Pseudo-3D conv parameters: spatial Conv2d + temporal Conv1d (gd/nn.py:30-51)."""
+
+    def __init__(self, dim, dim_out=None, kernel_size=3, stride=(1, 1, 1), padding=None):
+        super().__init__()
+        dim_out = dim_out or dim
+        self.spatial_conv = nn.Conv2d(dim, dim_out, kernel_size, padding=kernel_size // 2, stride=tuple(stride[1:]))
+        self.temporal_conv = nn.Conv1d(dim_out, dim_out, kernel_size) if kernel_size > 1 else None
+        self.kernel_size = kernel_size
+        self.stride = tuple(stride)
+        if self.temporal_conv is not None:
+            nn.init.dirac_(self.temporal_conv.weight.data)
+            nn.init.zeros_(self.temporal_conv.bias.data)
+
+
+class ResBlock(nn.Module):
+    def __init__(self, channels, emb_channels, dropout, out_channels=None):
+        super().__init__()
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.in_layers = nn.Sequential(nn.GroupNorm(32, channels), nn.SiLU(), Conv3d(channels, self.out_channels, 3))
+        self.h_upd = self.x_upd = nn.Identity()
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, self.out_channels))
+        self.out_layers = nn.Sequential(nn.GroupNorm(32, self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
+                                        Conv3d(self.out_channels, self.out_channels, 3))
+        if self.out_channels == channels:
+            self.skip_connection = nn.Identity()
+        else:
+            self.skip_connection = Conv3d(channels, self.out_channels, 1)
+
+
+class AttentionBlock(nn.Module):
+    def __init__(self, channels, num_heads=1, num_head_channels=-1):
+        super().__init__()
+        self.channels = channels
+        if num_head_channels == -1:
+            self.num_heads = num_heads
+        else:
+            assert channels % num_head_channels == 0, (
+                f"q,k,v channels {channels} is not divisible by num_head_channels {num_head_channels}")
+            self.num_heads = channels // num_head_channels
+        self.norm = nn.GroupNorm(32, channels)
+        self.qkv = nn.Conv1d(channels, channels * 3, 1)
+        self.attention = nn.Identity()  # QKVAttentionLegacy has no parameters
+        self.proj_out = nn.Conv1d(channels, channels, 1)
+
+
+class Downsample(nn.Module):
+    def __init__(self, channels, out_channels=None):
+        super().__init__()
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.op = Conv3d(channels, self.out_channels, 3, stride=(1, 2, 2))
+
+
+class Upsample(nn.Module):
+    def __init__(self, channels, out_channels=None):
+        super().__init__()
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.conv = Conv3d(channels, self.out_channels, 3)
+
+
+class _GainLayerNorm(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.g = nn.Parameter(torch.ones(dim))
+
+
+class PerceiverAttention(nn.Module):
+    def __init__(self, *, dim, dim_head=64, heads=8, scale=8):
+        super().__init__()
+        self.scale, self.heads = scale, heads
+        inner = dim_head * heads
+        self.norm = nn.LayerNorm(dim)
+        self.norm_latents = nn.LayerNorm(dim)
+        self.to_q = nn.Linear(dim, inner, bias=False)
+        self.to_kv = nn.Linear(dim, inner * 2, bias=False)
+        self.q_scale = nn.Parameter(torch.ones(dim_head))
+        self.k_scale = nn.Parameter(torch.ones(dim_head))
+        self.to_out = nn.Sequential(nn.Linear(inner, dim, bias=False), nn.LayerNorm(dim))
+
+
+class PerceiverResampler(nn.Module):
+    def __init__(self, *, dim, depth, dim_head=64, heads=8, num_latents=64, num_latents_mean_pooled=4,
+                 max_seq_len=512, ff_mult=4):
+        super().__init__()
+        self.pos_emb = nn.Embedding(max_seq_len, dim)
+        self.latents = nn.Parameter(torch.randn(num_latents, dim))
+        self.to_latents_from_mean_pooled_seq = None
+        if num_latents_mean_pooled > 0:
+            self.to_latents_from_mean_pooled_seq = nn.Sequential(
+                _GainLayerNorm(dim), nn.Linear(dim, dim * num_latents_mean_pooled), nn.Identity())
+        self.layers = nn.ModuleList([])
+        hidden = int(dim * ff_mult)
+        for _ in range(depth):
+            ff = nn.Sequential(_GainLayerNorm(dim), nn.Linear(dim, hidden, bias=False), nn.GELU(),
+                               _GainLayerNorm(hidden), nn.Linear(hidden, dim, bias=False))
+            self.layers.append(nn.ModuleList([PerceiverAttention(dim=dim, dim_head=dim_head, heads=heads), ff]))
+
+
+class TimestepEmbedSequential(nn.Sequential):
+    pass
+
+
+# ---------------------------------------------------------------------------
+# engine registry
+# ---------------------------------------------------------------------------
+_ENGINES: "weakref.WeakKeyDictionary[nn.Module, Dict[tuple, _UNetEngine]]" = weakref.WeakKeyDictionary()
+
+
+def _engine_for(model: "UNetModel", B: int, Fr: int, H: int, W: int, device) -> "_UNetEngine":
+    per_model = _ENGINES.setdefault(model, {})
+    key = (B, Fr, H, W, str(device))
+    eng = per_model.get(key)
+    if eng is None:
+        if len(per_model) >= 4:  # bound memory: drop the oldest shape
+            per_model.pop(next(iter(per_model)))
+        eng = _UNetEngine(model, B, Fr, H, W, device)
+        per_model[key] = eng
+    return eng
+
+
+class UNetModel(nn.Module):
+    """Parameter layout of the reference UNetModel (dims=3 pseudo-3D variant)."""
+
+    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks,
+                 attention_resolutions, dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2,
+                 num_classes=None, task_tokens=True, task_token_channels=512, use_checkpoint=False,
+                 use_fp16=False, num_heads=1, num_head_channels=-1, num_heads_upsample=-1,
+                 use_scale_shift_norm=False, resblock_updown=False, use_new_attention_order=False):
+        super().__init__()
+        if dims != 3 or num_classes is not None or not task_tokens or use_scale_shift_norm or \
+                resblock_updown or use_new_attention_order or not conv_resample or use_fp16 or in_channels != 6 \
+                or out_channels != 3:
+            raise NotImplementedError(
+                "v2a_b200.UNetModel implements the configuration family the Libero video path uses "
+                "(dims=3, task tokens, 6->3 channels, conv resample, legacy attention order)")
+        if num_heads_upsample == -1:
+            num_heads_upsample = num_heads
+        self.image_size, self.in_channels, self.model_channels = image_size, in_channels, model_channels
+        self.out_channels, self.num_res_blocks = out_channels, num_res_blocks
+        self.attention_resolutions, self.dropout, self.channel_mult = attention_resolutions, dropout, channel_mult
+        self.conv_resample, self.num_classes, self.task_tokens = conv_resample, num_classes, task_tokens
+        self.use_checkpoint, self.dtype = use_checkpoint, torch.float32
+        self.num_heads, self.num_head_channels, self.num_heads_upsample = num_heads, num_head_channels, num_heads_upsample
+
+        ted = model_channels * 4
+        self.time_embed = nn.Sequential(nn.Linear(model_channels, ted), nn.SiLU(), nn.Linear(ted, ted))
+        self.task_attnpool = nn.Sequential(PerceiverResampler(dim=task_token_channels, depth=2),
+                                           nn.Linear(task_token_channels, ted))
+        ch = input_ch = int(channel_mult[0] * model_channels)
+        self.input_blocks = nn.ModuleList([TimestepEmbedSequential(Conv3d(in_channels, ch, 3))])
+        chans = [ch]
+        ds = 1
+        attn = lambda c, nh: AttentionBlock(c, num_heads=nh, num_head_channels=num_head_channels)
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                layers = [ResBlock(ch, ted, dropout, out_channels=int(mult * model_channels))]
+                ch = int(mult * model_channels)
+                if ds in attention_resolutions:
+                    layers.append(attn(ch, num_heads))
+                self.input_blocks.append(TimestepEmbedSequential(*layers))
+                chans.append(ch)
+            if level != len(channel_mult) - 1:
+                self.input_blocks.append(TimestepEmbedSequential(Downsample(ch, out_channels=ch)))
+                chans.append(ch)
+                ds *= 2
+        self.middle_block = TimestepEmbedSequential(ResBlock(ch, ted, dropout), attn(ch, num_heads),
+                                                    ResBlock(ch, ted, dropout))
+        self.output_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                ich = chans.pop()
+                layers = [ResBlock(ch + ich, ted, dropout, out_channels=int(model_channels * mult))]
+                ch = int(model_channels * mult)
+                if ds in attention_resolutions:
+                    layers.append(attn(ch, num_heads_upsample))
+                if level and i == num_res_blocks:
+                    layers.append(Upsample(ch, out_channels=ch))
+                    ds //= 2
+                self.output_blocks.append(TimestepEmbedSequential(*layers))
+        self.out = nn.Sequential(nn.GroupNorm(32, ch), nn.SiLU(), Conv3d(input_ch, out_channels, 3))
+
+    # -- reference signature: x [B, 6, F, H, W] -> [B, 3, F, H, W] (gd/unet.py:650-684)
+    def forward(self, x, timesteps, y=None):
+        assert y is not None, "must specify y if and only if the model is class-conditional"
+        B, C, Fr, H, W = x.shape
+        assert C == 6
+        x = x.contiguous().float()
+        eng = _engine_for(self, B, Fr, H, W, x.device)
+        out = torch.empty(B, 3, Fr, H, W, device=x.device, dtype=torch.float32)
+        HW = H * W
+        eng.forward(x.data_ptr(), (6 * Fr * HW, HW, Fr * HW), x.data_ptr() + 4 * 3 * Fr * HW,
+                    (6 * Fr * HW, HW, Fr * HW), timesteps, y, out, (3 * Fr * HW, HW, Fr * HW), keep=[x])
+        return out
+
+    # -- packed layout used by Unet_Libero / the sampler: x [B, 3F, H, W] + cond [B, 3, H, W]
+    def forward_packed(self, x, cond, timesteps, y, out=None):
+        B, C3, H, W = x.shape
+        Fr = C3 // 3
+        HW = H * W
+        eng = _engine_for(self, B, Fr, H, W, x.device)
+        if out is None:
+            out = torch.empty(B, 3 * Fr, H, W, device=x.device, dtype=torch.float32)
+        eng.forward(x.data_ptr(), (x.stride(0), 3 * HW, HW), cond.data_ptr(), (cond.stride(0), 0, HW),
+                    timesteps, y, out, (3 * Fr * HW, 3 * HW, HW), keep=[x, cond])
+        return out
+
+    def engine(self, B, Fr, H, W, device) -> "_UNetEngine":
+        return _engine_for(self, B, Fr, H, W, torch.device(device))
+
+
+class Unet_Libero(nn.Module):
+    """flowdiffusion/flowdiffusion/unet.py:195-222 (same constructor, same state_dict)."""
+
+    def __init__(self):
+        super().__init__()
+        self.unet = UNetModel(image_size=(128, 128), in_channels=6, model_channels=128, out_channels=3,
+                              num_res_blocks=2, attention_resolutions=(8, 16), dropout=0,
+                              channel_mult=(1, 2, 3, 4, 5), conv_resample=True, dims=3, num_classes=None,
+                              task_tokens=True, task_token_channels=512, use_checkpoint=False, use_fp16=False,
+                              num_head_channels=32)
+
+    def forward(self, x, t, task_embed=None, **kwargs):
+        # x: [B, 3F + 3, H, W]; last 3 channels = conditioning frame broadcast over frames
+        x = x.contiguous().float()
+        return self.unet.forward_packed(x[:, :-3], x[:, -3:], t, task_embed)
+
+
+# ---------------------------------------------------------------------------
+# the engine
+# ---------------------------------------------------------------------------
+class _Pool:
+    """Exact-size free lists so per-block scratch is reused across the forward."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free: Dict[int, List[torch.Tensor]] = {}
+        self.total = 0
+
+    def get(self, nbytes: int) -> torch.Tensor:
+        lst = self.free.get(nbytes)
+        if lst:
+            return lst.pop()
+        self.total += nbytes
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+
+    def put(self, t: torch.Tensor) -> None:
+        self.free.setdefault(t.numel(), []).append(t)
+
+
+class _Act:
+    """fp32 channels-last activation [N*H*W, C] + its per-(image, channel) GroupNorm sums."""
+
+    def __init__(self, eng: "_UNetEngine", N, H, W, C):
+        self.N, self.H, self.W, self.C = N, H, W, C
+        self.rows = N * H * W
+        self._raw_store = eng.pool.get(self.rows * C * 4)
+        self.raw = self._raw_store.view(torch.float32).view(self.rows, C)
+        self.stats = eng.take_stats(N, C)
+        self.refs = 1
+
+
+class _UNetEngine:
+    def __init__(self, model: UNetModel, B, Fr, H, W, device):
+        if device.type != "cuda":
+            raise RuntimeError("v2a_b200 UNet runs on CUDA only (no CPU fallback)")
+        self.model_ref = weakref.ref(model)
+        self.B, self.Fr, self.H, self.W, self.device = B, Fr, H, W, device
+        self.N = B * Fr
+        self.passes = int(os.environ.get("V2A_PASSES", "3"))
+        self.pool = _Pool(device)
+        self.steps: List = []          # callables, in launch order
+        self.igemms: List[ops.Igemm] = []
+        self.packers: List = []        # (fn(model) -> fp32 tensor, HL destination)
+        self.bias_packers: List = []
+        self._stats_chunks: List[Tuple[int, int]] = []
+        self._stats_total = 0
+        self._stats_views: List = []
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._wkey = None
+        self._task_key = None
+        mc = model.model_channels
+        self.mc, self.ted = mc, mc * 4
+        f32 = dict(dtype=torch.float32, device=device)
+        self.t_buf = torch.zeros(B, dtype=torch.int64, device=device)
+        self.temb = torch.empty(B, mc, **f32)
+        self.temb_h = torch.empty(B, self.ted, **f32)
+        self.task_emb = torch.zeros(B, self.ted, **f32)
+        self.emb = torch.empty(B, self.ted, **f32)
+        # static I/O for graph replay
+        self.io = None
+        self._build(model)
+        self.stats_arena = torch.zeros(self._stats_total, dtype=torch.float64, device=device)
+        for (off, n, shape), holder in zip(self._stats_chunks, self._stats_views):
+            holder.append(self.stats_arena[off:off + n].view(*shape))
+        self._finalize_plans()
+
+    # ---- buffers -----------------------------------------------------------
+    def take_stats(self, N, C):
+        """Reserve [N, C, 2] float64 in the stats arena (bound after the plan is known)."""
+        holder: List[torch.Tensor] = []
+        self._stats_chunks.append((self._stats_total, N * C * 2, (N, C, 2)))
+        self._stats_views.append(holder)
+        self._stats_total += N * C * 2
+        return holder
+
+    def hl(self, rows, cols) -> Tuple[HL, List[torch.Tensor]]:
+        a, b = self.pool.get(rows * cols * 2), self.pool.get(rows * cols * 2)
+        return HL(a.view(torch.bfloat16).view(rows, cols), b.view(torch.bfloat16).view(rows, cols)), [a, b]
+
+    def release(self, stores) -> None:
+        for s in stores:
+            self.pool.put(s)
+
+    def free_act(self, a: _Act) -> None:
+        a.refs -= 1
+        if a.refs == 0:
+            self.pool.put(a._raw_store)
+
+    # ---- weights -----------------------------------------------------------
+    def weight(self, fn, rows, cols) -> HL:
+        hl = HL.empty(rows, cols, self.device)
+        self.packers.append((fn, hl))
+        return hl
+
+    def vec(self, fn, n) -> torch.Tensor:
+        v = torch.empty(n, dtype=torch.float32, device=self.device)
+        self.bias_packers.append((fn, v))
+        return v
+
+    def refresh_weights(self, model: UNetModel, force=False) -> None:
+        key = tuple((p.data_ptr(), p._version) for p in model.parameters())
+        if not force and key == self._wkey:
+            return
+        with torch.no_grad():
+            for fn, hl in self.packers:
+                w = fn().detach().to(self.device, torch.float32)
+                hi = w.to(torch.bfloat16)
+                hl.hi.copy_(hi)
+                hl.lo.copy_((w - hi.float()).to(torch.bfloat16))
+            for fn, v in self.bias_packers:
+                v.copy_(fn().detach().to(self.device, torch.float32).reshape(-1))
+        self._wkey = key
+        self._task_key = None
+
+    # ---- deferred plan creation (stats views exist only after _build) -------
+    def add_igemm(self, **kw):
+        self._pending = getattr(self, "_pending", [])
+        slot = [None]
+        self._pending.append((slot, kw))
+        self.steps.append(lambda s=slot: s[0].run())
+        return slot
+
+    def add_prep(self, **kw):
+        self._pending = getattr(self, "_pending", [])
+        slot = [None]
+        self._pending.append((slot, ("prep", kw)))
+        self.steps.append(lambda s=slot: s[0].run())
+        return slot
+
+    def _finalize_plans(self):
+        def res(v):
+            return v[0] if isinstance(v, list) and len(v) == 1 and isinstance(v[0], torch.Tensor) else v
+        for slot, kw in self._pending:
+            if isinstance(kw, tuple):
+                args = {k: res(v) for k, v in kw[1].items()}
+                slot[0] = ops.Prep(**args)
+            else:
+                args = {k: res(v) for k, v in kw.items()}
+                g = ops.Igemm(passes=self.passes, **args)
+                slot[0] = g
+                self.igemms.append(g)
+        self._pending = []
+        self.flops = sum(g.flops for g in self.igemms)
+
+    # ---- building blocks ---------------------------------------------------
+    def conv3d(self, m: Conv3d, a_hl: HL, cin, N, H, W, *, stride2=False, rowvec=None, residual=None,
+               skip=None, extra_bias=None) -> _Act:
+        """spatial 3x3 (TMA zero-padded taps) -> hl y -> temporal k3 (+skip K) -> fp32 raw + sums."""
+        B, Fr = self.B, self.Fr
+        cout = m.spatial_conv.out_channels
+        Ho, Wo = (H // 2, W // 2) if stride2 else (H, W)
+        prog = convs.spatial3x3_s2(cin, N, H, W) if stride2 else convs.spatial3x3(cin, N, H, W)
+        w_s = self.weight(lambda: convs.spatial3x3_weight(m.spatial_conv.weight), cout, prog.ktot)
+        b_s = self.vec(lambda: m.spatial_conv.bias, cout)
+        y_hl, y_st = self.hl(N * Ho * Wo, cout)
+        self.add_igemm(srcs=[(a_hl, cin, prog.src_dims[0])], taps=prog.taps, w=w_s, out_dims=prog.out_dims,
+                       cout=cout, out_hl=y_hl, bias=b_s)
+        out = _Act(self, N, Ho, Wo, cout)
+        HW = Ho * Wo
+        srcs = [(y_hl, cout, (HW, Fr, B, 1))]
+        if skip is not None:
+            x_hl, cx, mskip = skip
+            progt = convs.temporal3(cout, B, Fr, HW, skip_channels=cx)
+            srcs.append((x_hl, cx, (HW, Fr, B, 1)))
+            w_t = self.weight(lambda: convs.temporal3_weight(m.temporal_conv.weight, mskip.spatial_conv.weight),
+                              cout, progt.ktot)
+            b_t = self.vec(lambda: m.temporal_conv.bias + mskip.spatial_conv.bias, cout)
+        else:
+            progt = convs.temporal3(cout, B, Fr, HW)
+            w_t = self.weight(lambda: convs.temporal3_weight(m.temporal_conv.weight), cout, progt.ktot)
+            b_t = self.vec(lambda: m.temporal_conv.bias, cout)
+        self.add_igemm(srcs=srcs, taps=progt.taps, w=w_t, out_dims=progt.out_dims, cout=cout, out_f32=out.raw,
+                       bias=b_t, rowvec=rowvec, rowvec_mul=(0, 0, 1, 0), residual=residual, stats=out.stats,
+                       stats_mul=(0, 1, Fr, 0))
+        self.release(y_st)
+        return out
+
+    def gn_prep(self, parts: List[_Act], norm: nn.GroupNorm, *, per_frame, act, want_raw=False, mode=0):
+        x0 = parts[0]
+        x1 = parts[1] if len(parts) > 1 else None
+        C = x0.C + (x1.C if x1 else 0)
+        rows_out = x0.rows * (4 if mode == 1 else 1)
+        a_hl, a_st = self.hl(rows_out, C)
+        raw_hl, raw_st = (self.hl(rows_out, C) if want_raw else (None, []))
+        gamma = self.vec(lambda: norm.weight, C)
+        beta = self.vec(lambda: norm.bias, C)
+        self.add_prep(x0=x0.raw, x1=None if x1 is None else x1.raw, stats0=x0.stats,
+                      stats1=None if x1 is None else x1.stats, pixels_per_inst=x0.H * x0.W,
+                      inst_per_group=1 if per_frame else self.Fr, groups=norm.num_groups, eps=norm.eps,
+                      gamma=gamma, beta=beta, act=act, mode=mode, H=x0.H, W=x0.W, out_hl=a_hl, raw_hl=raw_hl)
+        return a_hl, a_st, raw_hl, raw_st, C
+
+    def res_block(self, m: ResBlock, parts: List[_Act], emb_slice) -> _Act:
+        x0 = parts[0]
+        N, H, W = x0.N, x0.H, x0.W
+        has_skip = not isinstance(m.skip_connection, nn.Identity)
+        a1, a1_st, x_hl, x_st, cin = self.gn_prep(parts, m.in_layers[0], per_frame=False, act=ops.ACT_SILU,
+                                                  want_raw=has_skip)
+        assert cin == m.channels
+        h1 = self.conv3d(m.in_layers[2], a1, cin, N, H, W, rowvec=emb_slice)
+        self.release(a1_st)
+        a2, a2_st, _, _, _ = self.gn_prep([h1], m.out_layers[0], per_frame=False, act=ops.ACT_SILU)
+        if has_skip:
+            out = self.conv3d(m.out_layers[3], a2, m.out_channels, N, H, W, skip=(x_hl, cin, m.skip_connection))
+        else:
+            out = self.conv3d(m.out_layers[3], a2, m.out_channels, N, H, W, residual=x0.raw)
+        self.release(a2_st)
+        self.release(x_st)
+        self.free_act(h1)
+        for p in parts:
+            self.free_act(p)
+        return out
+
+    def attn_block(self, m: AttentionBlock, x: _Act) -> _Act:
+        N, H, W, C = x.N, x.H, x.W, x.C
+        L = H * W
+        assert C // m.num_heads == 32, "attention kernel is specialised for 32-channel heads"
+        a, a_st, _, _, _ = self.gn_prep([x], m.norm, per_frame=True, act=ops.ACT_NONE)
+        qkv_store = self.pool.get(x.rows * 3 * C * 4)
+        qkv = qkv_store.view(torch.float32).view(x.rows, 3 * C)
+        prog = convs.pointwise(C, (x.rows,))
+        w_qkv = self.weight(lambda: convs.pointwise_weight(m.qkv.weight), 3 * C, prog.ktot)
+        b_qkv = self.vec(lambda: m.qkv.bias, 3 * C)
+        self.add_igemm(srcs=[(a, C, prog.src_dims[0])], taps=prog.taps, w=w_qkv, out_dims=prog.out_dims,
+                       cout=3 * C, out_f32=qkv, bias=b_qkv)
+        h_hl, h_st = self.hl(x.rows, C)
+        heads = m.num_heads
+        self.steps.append(lambda: ops.attention(qkv, N, L, heads, h_hl))
+        out = _Act(self, N, H, W, C)
+        prog2 = convs.pointwise(C, (L, N))
+        w_p = self.weight(lambda: convs.pointwise_weight(m.proj_out.weight), C, prog2.ktot)
+        b_p = self.vec(lambda: m.proj_out.bias, C)
+        self.add_igemm(srcs=[(h_hl, C, prog2.src_dims[0])], taps=prog2.taps, w=w_p, out_dims=prog2.out_dims,
+                       cout=C, out_f32=out.raw, bias=b_p, residual=x.raw, stats=out.stats, stats_mul=(0, 1, 0, 0))
+        self.release(a_st)
+        self.release(h_st)
+        self.pool.put(qkv_store)
+        self.free_act(x)
+        return out
+
+    def resample(self, conv: Conv3d, x: _Act, *, down: bool) -> _Act:
+        rows_out = x.rows * (1 if down else 4)
+        s_hl, s_st = self.hl(rows_out, x.C)
+        self.add_prep(x0=x.raw, mode=2 if down else 1, H=x.H, W=x.W, out_hl=s_hl)
+        if down:
+            out = self.conv3d(conv, s_hl, x.C, x.N, x.H, x.W, stride2=True)
+        else:
+            out = self.conv3d(conv, s_hl, x.C, x.N, 2 * x.H, 2 * x.W)
+        self.release(s_st)
+        self.free_act(x)
+        return out
+
+    def run_block(self, block: nn.Sequential, parts: List[_Act]) -> _Act:
+        h = None
+        for layer in block:
+            if isinstance(layer, ResBlock):
+                h = self.res_block(layer, parts if h is None else [h], self.emb_slices[id(layer)])
+            elif isinstance(layer, AttentionBlock):
+                h = self.attn_block(layer, h)
+            elif isinstance(layer, Downsample):
+                h = self.resample(layer.op, parts[0] if h is None else h, down=True)
+            elif isinstance(layer, Upsample):
+                h = self.resample(layer.conv, h, down=False)
+            else:
+                raise RuntimeError(f"unexpected layer {type(layer).__name__}")
+        return h
+
+    # ---- whole-network plan ------------------------------------------------
+    def _build(self, model: UNetModel) -> None:
+        B, Fr, H, W, N = self.B, self.Fr, self.H, self.W, self.N
+        dev = self.device
+        # timestep embedding MLP + all ResBlock emb_layers as ONE concatenated linear
+        res_blocks = [m for m in model.modules() if isinstance(m, ResBlock)]
+        tot = sum(m.out_channels for m in res_blocks)
+        self.emb_all = torch.empty(B, tot, dtype=torch.float32, device=dev)
+        self.emb_slices, off = {}, 0
+        for m in res_blocks:
+            self.emb_slices[id(m)] = self.emb_all[:, off:off + m.out_channels]
+            off += m.out_channels
+        te0, te2 = model.time_embed[0], model.time_embed[2]
+        self.w_te0 = self.vec(lambda: te0.weight, te0.weight.numel()).view(te0.weight.shape)
+        self.b_te0 = self.vec(lambda: te0.bias, te0.bias.numel())
+        self.w_te2 = self.vec(lambda: te2.weight, te2.weight.numel()).view(te2.weight.shape)
+        self.b_te2 = self.vec(lambda: te2.bias, te2.bias.numel())
+        self.w_emb = self.vec(lambda: torch.cat([m.emb_layers[1].weight for m in res_blocks], 0),
+                              tot * self.ted).view(tot, self.ted)
+        self.b_emb = self.vec(lambda: torch.cat([m.emb_layers[1].bias for m in res_blocks], 0), tot)
+
+        def emb_path():
+            ops.timestep_embedding(self.t_buf, self.mc, 0, self.temb)
+            ops.linear(self.temb, self.w_te0, self.b_te0, self.temb_h, act_out=ops.ACT_SILU)
+            ops.linear(self.temb_h, self.w_te2, self.b_te2, self.emb, add=self.task_emb)
+            ops.linear(self.emb, self.w_emb, self.b_emb, self.emb_all, act_in=ops.ACT_SILU)
+        self.steps.append(emb_path)
+
+        # input conv: im2col'd 6-channel 3x3 (K = 54 -> one 64-wide chunk)
+        conv0: Conv3d = model.input_blocks[0][0]
+        c0 = conv0.spatial_conv.out_channels
+        self.in_hl, _ = self.hl(N * H * W, 64)
+        self.steps.append(lambda: ops.unet_input_pack(self.io["x"], self.io["xs"], self.io["c"], self.io["cs"],
+                                                      B, Fr, H, W, self.in_hl))
+        prog = convs.pointwise(64, (N * H * W,))
+        w0 = self.weight(lambda: convs.input_conv_weight(conv0.spatial_conv.weight), c0, 64)
+        b0 = self.vec(lambda: conv0.spatial_conv.bias, c0)
+        y0, y0_st = self.hl(N * H * W, c0)
+        self.add_igemm(srcs=[(self.in_hl, 64, prog.src_dims[0])], taps=prog.taps, w=w0, out_dims=prog.out_dims,
+                       cout=c0, out_hl=y0, bias=b0)
+        h = _Act(self, N, H, W, c0)
+        progt = convs.temporal3(c0, B, Fr, H * W)
+        wt0 = self.weight(lambda: convs.temporal3_weight(conv0.temporal_conv.weight), c0, progt.ktot)
+        bt0 = self.vec(lambda: conv0.temporal_conv.bias, c0)
+        self.add_igemm(srcs=[(y0, c0, progt.src_dims[0])], taps=progt.taps, w=wt0, out_dims=progt.out_dims,
+                       cout=c0, out_f32=h.raw, bias=bt0, stats=h.stats, stats_mul=(0, 1, Fr, 0))
+        self.release(y0_st)
+
+        hs = [h]
+        h.refs += 1
+        for block in list(model.input_blocks)[1:]:
+            h = self.run_block(block, [h])
+            hs.append(h)
+            h.refs += 1
+        h = self.run_block(model.middle_block, [h])
+        for block in model.output_blocks:
+            h = self.run_block(block, [h, hs.pop()])
+        # out head: GN -> SiLU -> 3x3 conv to 3 channels (N tile 16) -> temporal conv + layout kernel
+        a, a_st, _, _, C = self.gn_prep([h], model.out[0], per_frame=False, act=ops.ACT_SILU)
+        convo: Conv3d = model.out[2]
+        prog = convs.spatial3x3(C, N, H, W)
+        wo = self.weight(lambda: convs.spatial3x3_weight(convo.spatial_conv.weight), 3, prog.ktot)
+        bo = self.vec(lambda: convo.spatial_conv.bias, 3)
+        self.y_out = torch.empty(N * H * W, 16, dtype=torch.float32, device=dev)
+        self.add_igemm(srcs=[(a, C, prog.src_dims[0])], taps=prog.taps, w=wo, out_dims=prog.out_dims, cout=3,
+                       ldc=16, out_f32=self.y_out, bias=bo)
+        self.wt_out = self.vec(lambda: convo.temporal_conv.weight, 27)
+        self.bt_out = self.vec(lambda: convo.temporal_conv.bias, 3)
+        self.steps.append(lambda: ops.unet_output_head(self.y_out, 16, self.wt_out, self.bt_out, B, Fr, H, W,
+                                                       self.io["o"], self.io["os"]))
+        self.release(a_st)
+        self.free_act(h)
+
+    # ---- conditioning (step-invariant): PerceiverResampler on the text tokens ---
+    def set_task_embed(self, model: UNetModel, y: torch.Tensor) -> None:
+        key = (y.data_ptr(), y._version, tuple(y.shape))
+        if key == self._task_key:
+            return
+        with torch.no_grad(), torch.autocast("cuda", enabled=False):
+            self.task_emb.copy_(_task_pool(model.task_attnpool, y.float()))
+        self._task_key = key
+
+    # ---- execution ---------------------------------------------------------
+    def _launch_all(self) -> None:
+        self.stats_arena.zero_()
+        for s in self.steps:
+            s()
+
+    def forward(self, x_ptr, xs, c_ptr, cs, timesteps, y, out, os_, keep=()):
+        model = self.model_ref()
+        self.refresh_weights(model)
+        self.set_task_embed(model, y)
+        t = timesteps if torch.is_tensor(timesteps) else torch.tensor([timesteps], device=self.device)
+        self.t_buf.copy_(t.to(self.device, torch.int64).expand(self.B))
+        self.io = dict(x=x_ptr, xs=xs, c=c_ptr, cs=cs, o=out, os=os_)
+        self._launch_all()
+
+    # static-buffer interface for the sampler (CUDA-graph capturable)
+    def bind_static(self, x, cond, out):
+        HW = self.H * self.W
+        self.io = dict(x=x.data_ptr(), xs=(x.stride(0), 3 * HW, HW), c=cond.data_ptr(), cs=(cond.stride(0), 0, HW),
+                       o=out, os=(3 * self.Fr * HW, 3 * HW, HW))
+        self._static = (x, cond, out)
+
+    def run_static(self):
+        self._launch_all()
+
+
+def _task_pool(seq: nn.Sequential, y: torch.Tensor) -> torch.Tensor:
+    """task_attnpool(y).mean(1) (gd/unet.py:491-494,671; gd/imagen.py:254-372).
+
+    Step-invariant conditioning: evaluated ONCE per sample() call (0.92 GFLOP vs
+    2.1 TFLOP per denoise step), with stock torch ops on the parameter tensors.
+    """
+    pr: PerceiverResampler = seq[0]
+    B, n, D = y.shape
+    xp = y + pr.pos_emb.weight[:n]
+    lat = pr.latents.unsqueeze(0).expand(B, -1, -1)
+
+    def gln(x, g):
+        var = x.var(dim=-1, unbiased=False, keepdim=True)
+        return (x - x.mean(dim=-1, keepdim=True)) * (var + 1e-5).rsqrt() * g
+    if pr.to_latents_from_mean_pooled_seq is not None:
+        mp = pr.to_latents_from_mean_pooled_seq
+        pooled = F.linear(gln(y.mean(dim=1), mp[0].g), mp[1].weight, mp[1].bias)
+        lat = torch.cat([pooled.reshape(B, -1, D), lat], dim=1)
+    for attn, ff in pr.layers:
+        h = attn.heads
+        xn = F.layer_norm(xp, (D,), attn.norm.weight, attn.norm.bias)
+        ln = F.layer_norm(lat, (D,), attn.norm_latents.weight, attn.norm_latents.bias)
+        q = F.linear(ln, attn.to_q.weight)
+        k, v = F.linear(torch.cat([xn, ln], dim=1), attn.to_kv.weight).chunk(2, dim=-1)
+        sp = lambda t: t.reshape(B, t.shape[1], h, -1).permute(0, 2, 1, 3)
+        q, k, v = sp(q), sp(k), sp(v)
+        q = F.normalize(q, dim=-1) * attn.q_scale
+        k = F.normalize(k, dim=-1) * attn.k_scale
+        att = (torch.einsum("bhid,bhjd->bhij", q, k) * attn.scale).softmax(dim=-1)
+        o = torch.einsum("bhij,bhjd->bhid", att, v).permute(0, 2, 1, 3).reshape(B, lat.shape[1], -1)
+        o = F.layer_norm(F.linear(o, attn.to_out[0].weight), (D,), attn.to_out[1].weight, attn.to_out[1].bias)
+        lat = o + lat
+        hdn = F.linear(gln(lat, ff[0].g), ff[1].weight)
+        lat = F.linear(gln(F.gelu(hdn), ff[3].g), ff[4].weight) + lat
+    return F.linear(lat, seq[1].weight, seq[1].bias).mean(dim=1)
