@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Headline benchmark: Libero goal-video synthesis, 128x128, 7 generated + 1 conditioning frame,
+100 denoise steps (the shipped config runs DDPM ancestral sampling), batch 16 per GPU.
+
+  python bench.py --gpus N --steps K --warmup W          # our arm (one rank per GPU under torchrun for N>1)
+  python bench.py --impl reference --steps K --warmup W  # the reference algorithm on the host CPU cores
+
+One "step" = one GoalGaussianDiffusion.sample() call (100 UNet forwards + sampler updates) on one
+batch of synthetic prompts.  Prints ONE JSON line (contract in the task statement / DESIGN.md §6).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "video frames/s (128x128, 7 generated + 1 cond frame, 100 denoise steps)"
+UNIT = "frames/s"
+FRAMES = 7
+H = W = 128
+DENOISE_STEPS = 100
+TOKENS = 12
+FLOP_PER_VIDEO_STEP = 2132.6e9  # algorithmic GFLOP per (video, denoise step)
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_state_dict():
+    """Random-init weights of the Unet_Libero architecture (no checkpoints offline), deterministic."""
+    from oracle.video_oracle import seeded_state_dict  # weight recipe shared with the tests
+    with open(os.path.join(ROOT, "tests", "golden", "goal_diffusion_state_dict_layout.json")) as f:
+        lay = json.load(f)
+    shapes = {k[len("model."):]: tuple(v) for k, v in lay.items() if k.startswith("model.")}
+    return seeded_state_dict(shapes, 2)
+
+
+def cpu_reference_step(sd, threads: int):
+    """One denoise step of the reference algorithm (CPU oracle port), B=1, full Libero size."""
+    from oracle import video_oracle as VO
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 3 * FRAMES, H, W, generator=g)
+    cond = torch.rand(1, 3, H, W, generator=g)
+    te = torch.randn(1, TOKENS, 512, generator=g)
+    t = torch.tensor([50])
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        VO.unet_libero_forward(sd, torch.cat([x, cond], 1), t, te)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sd = synthetic_state_dict()
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step(sd, threads)
+    k = max(1, min(args.steps, 3))
+    ts = [cpu_reference_step(sd, threads) for _ in range(k)]
+    step_s = sum(ts) / len(ts)
+    fps = FRAMES / (step_s * DENOISE_STEPS)  # one video = 100 such steps; throughput is per-video on CPU
+    sample = f"{k} timed UNet denoise steps at B=1, 128x128x7 (a full step is 100 of these x B=16); linear extrapolation"
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
+            "warmup": min(args.warmup, 1), "ms_per_step": step_s * DENOISE_STEPS * 16 * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus, 16),
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus, batch):
+    return {"workload": "Libero goal-video synthesis 128x128x8 (7 generated + 1 cond), 100 denoise steps "
+                        "(DDPM ancestral = the shipped config), Unet_Libero 201M params",
+            "global_batch": batch * n_gpus, "batch_per_gpu": batch, "frames": FRAMES, "denoise_steps": DENOISE_STEPS,
+            "parallelism": f"dp{n_gpus}", "precision": "bf16x3 split product, fp32 accumulate (fp32-class, <=1e-3)",
+            "l2": "working set per denoise step (>1.8 GB/sample) exceeds the 126 MB L2; no explicit flush"}
+
+
+def measure_kernel_roofline(diff, batch, peaks):
+    """Per-launch CUDA-event timing of the dominant kernel (igemm) over one eager denoise step."""
+    eng = diff.model.unet.engine(batch, FRAMES, H, W, "cuda")
+    ig = set(id(g) for g in eng.igemms)
+    evs = []
+    eng.stats_arena.zero_()
+    from v2a_b200 import ops
+    orig_run = ops.Igemm.run
+
+    def timed_run(self):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_run(self)
+        e1.record()
+        evs.append((self, e0, e1))
+    ops.Igemm.run = timed_run
+    try:
+        for _ in range(2):
+            evs.clear()
+            eng.run_static()
+            torch.cuda.synchronize()
+    finally:
+        ops.Igemm.run = orig_run
+    tot_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in evs)
+    flops = sum(g.flops for g, _, _ in evs)
+    n = len(evs)
+    achieved = flops / (tot_ms * 1e-3) / 1e12
+    peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    return {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv)", "achieved": achieved,
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "launches_per_denoise_step": n, "avg_launch_ms": tot_ms / n, "flop_per_launch": flops / n,
+            "mma_passes": eng.passes, "tensor_pipe_tflops": achieved * eng.passes,
+            "tensor_pipe_frac": achieved * eng.passes / peak, "kernel_ms_per_denoise_step": tot_ms}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from v2a_b200 import ops
+    from v2a_b200.goal_diffusion import GoalGaussianDiffusion
+    from v2a_b200.unet import Unet_Libero
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the v2a_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+    peaks, peak_src = read_peaks()
+
+    sd = synthetic_state_dict()
+    net = Unet_Libero()
+    net.load_state_dict(sd, strict=True)
+    diff = GoalGaussianDiffusion(net, image_size=(H, W), channels=3 * FRAMES, timesteps=DENOISE_STEPS,
+                                 sampling_timesteps=DENOISE_STEPS, loss_type="l2", objective="pred_v",
+                                 beta_schedule="cosine", min_snr_loss_weight=True, guidance_weight=0).cuda()
+    g = torch.Generator().manual_seed(1000 + rank)
+    cond_host = torch.rand(B, 3, H, W, generator=g).pin_memory()
+    te_host = torch.randn(B, TOKENS, 512, generator=g).pin_memory()
+    out_host = torch.empty(B, 3 * FRAMES, H, W).pin_memory()
+    cond_dev, te_dev = cond_host.cuda(), te_host.cuda()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    torch.manual_seed(1234 + rank)
+    launches0 = ops.launch_count()
+    for _ in range(args.warmup):
+        diff.sample(cond_dev, te_dev, batch_size=B)
+    launches_capture = ops.launch_count() - launches0
+
+    # ---- timed: device-resident inputs ----
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    e0.record()
+    for _ in range(args.steps):
+        res = diff.sample(cond_dev, te_dev, batch_size=B)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    frames = args.steps * B * FRAMES * world
+    value = frames / (ms * 1e-3)
+
+    # ---- timed: end to end through the public API with host buffers ----
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e2.record()
+    for _ in range(args.steps):
+        c = cond_host.to("cuda", non_blocking=True)
+        te = te_host.to("cuda", non_blocking=True)
+        r = diff.sample(c, te, batch_size=B)
+        out_host.copy_(r, non_blocking=True)
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    e2e_value = frames / (ms_e2e * 1e-3)
+
+    eng = net.unet.engine(B, FRAMES, H, W, "cuda")
+    launches_per_denoise = len(eng.steps) + 3  # + emb-path extra launches + sampler update
+    if rank == 0:
+        roof = measure_kernel_roofline(diff, B, peaks)
+        roof["peak_source"] = peak_src
+        cpu = None
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cpu_reference_step(sd, threads)
+            ts = cpu_reference_step(sd, threads)
+            cpu = {"value": FRAMES / (ts * DENOISE_STEPS), "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "1 timed UNet denoise step at B=1, 128x128x7 after 1 warm-up (a bench step is "
+                             "100 of these x 16 videos); linear extrapolation"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16x3->f32", "data": "synthetic (seeded random-init Unet_Libero weights, "
+                "random prompts)", "config": workload_config(world, B),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cond_host.numel() * 4 + te_host.numel() * 4,
+                        "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(args.steps * DENOISE_STEPS * roof["launches_per_denoise_step"]),
+                "gpu_launches_all_kernels": int(args.steps * (DENOISE_STEPS * eng_launches_per_step(eng) + 1)),
+                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "videos_per_s": value / FRAMES, "frames_per_s_counting_cond_frame": value * 8 / 7,
+                "algorithmic_tflops_whole_step": args.steps * B * world * DENOISE_STEPS * FLOP_PER_VIDEO_STEP / (ms * 1e-3) / 1e12,
+                "out_checksum": float(res.double().mean().item())}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def eng_launches_per_step(eng):
+    """Kernel launches of ours per denoise step: every planned step (prep = 2 kernels when it normalises),
+    4 launches of the embedding path (counted as one step entry) and the sampler update."""
+    n = 0
+    for s in eng.steps:
+        n += 1
+    return n + 3 + 1
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="videos per GPU (configs[1]: 16)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -162,7 +162,8 @@ def test_full_size_libero_properties():
     assert o.shape == (2, 21, 128, 128) and torch.isfinite(o).all()
     # each batch element is independent of its neighbour (GroupNorm / attention never cross the batch)
     o0 = net(x[:1].contiguous(), t[:1], te[:1].contiguous())
-    assert rel_l2(o0, o[:1]) < 1e-5
+    # (different batch -> different tile shapes / summation order: equal to split-product rounding)
+    assert rel_l2(o0, o[:1]) < 1e-4
     assert rel_l2(net(x, t, te), o) < 1e-6
     d = _diffusion(net, 21, (128, 128), 100, 100)
     d.sampling_timesteps, d.is_ddim_sampling = 3, True  # the eval helper's attribute pokes
