@@ -146,7 +146,8 @@ def workload_config(n_gpus, batch):
 def measure_kernel_roofline(diff, batch, peaks):
     """Per-launch CUDA-event timing of the dominant kernel (igemm) over one eager denoise step."""
     eng = diff.model.unet.engine(batch, FRAMES, H, W, "cuda")
-    ig = set(id(g) for g in eng.igemms)
+    st = eng._sampler
+    eng.bind_static(st["x"], st["cond"], st["v"])
     evs = []
     eng.stats_arena.zero_()
     from v2a_b200 import ops

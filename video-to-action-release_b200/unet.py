@@ -149,6 +149,9 @@ _ENGINES: "weakref.WeakKeyDictionary[nn.Module, Dict[tuple, _UNetEngine]]" = wea
 
 def _engine_for(model: "UNetModel", B: int, Fr: int, H: int, W: int, device) -> "_UNetEngine":
     per_model = _ENGINES.setdefault(model, {})
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
     key = (B, Fr, H, W, str(device))
     eng = per_model.get(key)
     if eng is None:
