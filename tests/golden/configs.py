@@ -26,3 +26,28 @@ def config1_inputs():
     x_cond = torch.rand(1, 3, 64, 64, generator=g)
     te = torch.randn(1, 8, 512, generator=g)
     return x, t, x_cond, te
+
+
+# ---- policy (ConditionalUnet1D) ----
+POLICY_LIBERO = dict(input_dim=7, local_cond_dim=None, global_cond_dim=128, diffusion_step_embed_dim=128,
+                     down_dims=[256, 512, 1024], kernel_size=5, n_groups=8, cond_predict_scale=True)
+POLICY_TINY = dict(input_dim=7, local_cond_dim=None, global_cond_dim=32, diffusion_step_embed_dim=32,
+                   down_dims=[64, 128], kernel_size=5, n_groups=8, cond_predict_scale=True)
+
+
+def policy_inputs(B, cfg, seed=0, T=16):
+    g = torch.Generator().manual_seed(seed)
+    traj = torch.rand(B, T, cfg["input_dim"], generator=g) * 2 - 1
+    noise = torch.randn(B, T, cfg["input_dim"], generator=g)
+    t = torch.randint(0, 100, (B,), generator=g)
+    gc = torch.randn(B, cfg["global_cond_dim"], generator=g)
+    return traj, noise, t, gc
+
+
+def grad_fingerprint(name, grad):
+    """(L2 norm, projection on a seeded random direction) of one gradient tensor."""
+    import zlib
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+    r = torch.randn(grad.shape, generator=g, dtype=torch.float64)
+    gd = grad.detach().double().cpu()
+    return [gd.norm().item(), (gd * r).sum().item()]
