@@ -187,6 +187,64 @@ int v2a_unnormalize_clamp(const float* x, float* out, int64_t n, void* stream);
 int v2a_split_hl(const float* x, int64_t rows, int cols, int ld_out, void* out_hi, void* out_lo,
                  void* stream);
 
+/* ------------------------------------------------------------------------
+ * Policy path (ConditionalUnet1D forward / backward).  One CTA per batch sample.
+ * replaces Conv1dBlock's GroupNorm -> Mish (conv1d_components.py:23-40), the FiLM
+ * modulation and residual add of ConditionalResidualBlock1D.forward
+ * (conditional_unet1d.py:46-66) and their autograd backward.
+ * ---------------------------------------------------------------------- */
+typedef struct v2a_policy_gn_desc {
+    int B, T, C, groups;
+    float eps;
+    const float* y;          /* conv output fp32 [B][T][C] */
+    const float* gamma;      /* [C] */
+    const float* beta;
+    const float* film;       /* [B][ld_film]: scale = film[b][c], bias = film[b][C + c]; or NULL */
+    int ld_film;
+    const float* addend;     /* fwd: fp32 [B][T][ld_add] added to the result (identity residual) or NULL */
+    int ld_add;
+    float* out_f32;          /* fwd: [B][T][ld_out] or NULL */
+    int ld_out;
+    void* out_hi;            /* fwd: bf16 planes [B][T][ld_hl] or NULL */
+    void* out_lo;
+    int ld_hl;
+    float* mean_rstd;        /* [B][groups][2]: written by fwd, read by bwd */
+    /* backward */
+    const float* dout;       /* grad wrt the block output, fp32 [B][T][ld_dout] */
+    int ld_dout;
+    void* dy_hi;             /* grad wrt y as bf16 planes [B][T][C] (operand of the data-gradient GEMM) */
+    void* dy_lo;
+    void* dyT_hi;            /* same, transposed [C][B*T] (operand of the weight-gradient GEMM) */
+    void* dyT_lo;
+    float* dy_f32;           /* optional fp32 copy */
+    float* dbias;            /* [C] += sum_{b,t} dy   (conv bias grad) or NULL */
+    float* dgamma;           /* [C] += ... */
+    float* dbeta;
+    float* dfilm;            /* [B][ld_dfilm] += (d scale | d bias) */
+    int ld_dfilm;
+} v2a_policy_gn_desc;
+int v2a_policy_gn_act_fwd(const v2a_policy_gn_desc* d, void* stream);
+int v2a_policy_gn_act_bwd(const v2a_policy_gn_desc* d, void* stream);
+
+/* transposed im2col of a bf16 hi/lo activation x [B][Tin][ld_x] (channels c_off..c_off+C):
+ * out[(c*ntaps + k)][b*Tout + o] = x[b][stride*o + offsets[k]][c] (0 outside) — the K-major
+ * operand of the weight-gradient GEMM dW[co][ci][k] = sum dy[b,o,co] x[b, s*o+off_k, ci] */
+int v2a_policy_im2col_t(const void* x_hi, const void* x_lo, int ld_x, int c_off, int B, int Tin, int Tout,
+                        int C, int ntaps, int stride, const int* offsets, void* out_hi, void* out_lo,
+                        void* stream);
+/* dy fp32 [rows][ld] (C used) -> hl [rows][ld_hl] (zero padded), hl^T [C][rows], colsum[C] += */
+int v2a_grad_prep(const float* dy, int64_t rows, int C, int ld, void* hi, void* lo, int ld_hl, void* t_hi,
+                  void* t_lo, float* colsum, void* stream);
+/* dx = dy * act'(x), act 1 SiLU / 2 Mish; optional fp32 and hi/lo outputs */
+int v2a_act_bwd(const float* x, const float* dy, float* dx, void* hi, void* lo, int64_t n, int act,
+                void* stream);
+/* optimiser tail of the train step (lb_online_trainer_v7.py:608-624): global grad-norm clip,
+ * AdamW, EMA; out[0] += sum g^2 */
+int v2a_grad_sumsq(const float* g, int64_t n, double* out, void* stream);
+int v2a_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n,
+                       const double* grad_sumsq, float max_norm, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int step, float ema_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,25 @@ class PrepDesc(C.Structure):
     ]
 
 
+class PolicyGnDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("T", C.c_int), ("C", C.c_int), ("groups", C.c_int),
+        ("eps", C.c_float),
+        ("y", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("film", C.c_void_p), ("ld_film", C.c_int),
+        ("addend", C.c_void_p), ("ld_add", C.c_int),
+        ("out_f32", C.c_void_p), ("ld_out", C.c_int),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ld_hl", C.c_int),
+        ("mean_rstd", C.c_void_p),
+        ("dout", C.c_void_p), ("ld_dout", C.c_int),
+        ("dy_hi", C.c_void_p), ("dy_lo", C.c_void_p),
+        ("dyT_hi", C.c_void_p), ("dyT_lo", C.c_void_p),
+        ("dy_f32", C.c_void_p),
+        ("dbias", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+        ("dfilm", C.c_void_p), ("ld_dfilm", C.c_int),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/v2a_b200.h declares
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
@@ -103,6 +122,13 @@ SIGNATURES = {
     "v2a_ddim_step": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "v2a_unnormalize_clamp": (_i, [_vp, _vp, _i64, _vp]),
     "v2a_split_hl": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "v2a_policy_gn_act_fwd": (_i, [C.POINTER(PolicyGnDesc), _vp]),
+    "v2a_policy_gn_act_bwd": (_i, [C.POINTER(PolicyGnDesc), _vp]),
+    "v2a_policy_im2col_t": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _vp, _vp, _vp]),
+    "v2a_grad_prep": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "v2a_act_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    "v2a_grad_sumsq": (_i, [_vp, _i64, _vp, _vp]),
+    "v2a_adamw_ema_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _f, _i, _f, _vp]),
 }
 
 _lib = None

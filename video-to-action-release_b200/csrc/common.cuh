@@ -196,6 +196,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
         : "r"(taddr)
         : "memory");
 }
+// Wait for outstanding tcgen05.ld; the loaded registers are tied to the asm ("+r") so the
+// compiler cannot schedule their uses above the wait.
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),
+                   "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]),
+                   "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }

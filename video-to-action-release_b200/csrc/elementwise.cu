@@ -53,26 +53,35 @@ __global__ void channel_stats_kernel(const float* __restrict__ x, int64_t ppi, i
 }
 
 // (sample, group) -> mean, rstd from per-channel sums of up to two concat sources
+// one warp per (sample, group): lanes stride over the (instance, channel) sums
 __global__ void gn_finalize_kernel(const double* __restrict__ st0, const double* __restrict__ st1,
                                    int C0, int C1, int groups, int inst_per_group, double count,
                                    float eps, float2* __restrict__ mr, int samples) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (idx >= samples * groups) return;
     const int g = idx % groups, smp = idx / groups;
     const int cpg = (C0 + C1) / groups;
     double s = 0.0, ss = 0.0;
-    for (int i = 0; i < inst_per_group; ++i) {
-        const int64_t inst = (int64_t)smp * inst_per_group + i;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-            const double* p = c < C0 ? st0 + (inst * C0 + c) * 2 : st1 + (inst * C1 + (c - C0)) * 2;
-            s += p[0];
-            ss += p[1];
-        }
+    for (int e = lane; e < inst_per_group * cpg; e += 32) {
+        const int64_t inst = (int64_t)smp * inst_per_group + e / cpg;
+        const int c = g * cpg + e % cpg;
+        const double2 v = c < C0 ? *reinterpret_cast<const double2*>(st0 + (inst * C0 + c) * 2)
+                                 : *reinterpret_cast<const double2*>(st1 + (inst * C1 + (c - C0)) * 2);
+        s += v.x;
+        ss += v.y;
     }
-    const double mean = s / count;
-    double var = ss / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    mr[idx] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    }
+    if (lane == 0) {
+        const double mean = s / count;
+        double var = ss / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        mr[idx] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
 }
 
 struct PrepParams {
@@ -133,15 +142,29 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepParams p, int64_t t
     if (p.mr) {
         const int64_t smp = ip / p.pixels_per_sample;
         const int cpg = C / p.groups;
+        int g = c / cpg, rem = c - g * cpg;   // walk the (at most 8) groups without divisions
+        const float2* mrp = p.mr + smp * p.groups;
+        float2 m = __ldg(&mrp[g]);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + c) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + c));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + c) + 1);
+        const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float2 m = __ldg(&p.mr[smp * p.groups + (c + j) / cpg]);
-            v[j] = (v[j] - m.x) * m.y * __ldg(&p.gamma[c + j]) + __ldg(&p.beta[c + j]);
+            v[j] = (v[j] - m.x) * m.y * ga[j] + be[j];
+            if (++rem == cpg && j < 7) {
+                rem = 0;
+                m = __ldg(&mrp[++g]);
+            }
         }
     }
     if (p.act == 1) {
+        // SiLU with the fast exp / divide intrinsics (rel. error ~2^-21, far below the 2^-17 of the
+        // bf16 hi/lo split the result is stored in)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+        for (int j = 0; j < 8; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
     } else if (p.act == 2) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = mish_f(v[j]);
@@ -401,7 +424,7 @@ int v2a_prep(const v2a_prep_desc* d, void* stream) {
         float2* mr = reinterpret_cast<float2*>(d->gn_scratch);
         const double count = (double)p.pixels_per_sample * (double)(C / d->groups);
         const int n = samples * d->groups;
-        gn_finalize_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(
+        gn_finalize_kernel<<<ceil_div(n * 32, 128), 128, 0, (cudaStream_t)stream>>>(
             d->stats0, d->stats1, d->C0, d->C1, d->groups, d->inst_per_group, count, d->eps, mr, samples);
         V2A_LAUNCH_OK();
         p.mr = mr;

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     uint64_t* tfull_bar = bars + 2 * S;    // [2]
     uint64_t* tempty_bar = bars + 2 * S + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+    float* warp_add = reinterpret_cast<float*>(bars) + 64;  // 4 epilogue warps x 256 floats, after the 256 B barrier block
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         // ===================== epilogue =====================
         const int quad = warp & 3;            // TMEM lane quarter this warp may read
         const int row = quad * 32 + lane;     // row of the 128-row tile
+        float* addv = warp_add + quad * 256;  // this warp's private bias(+rowvec) staging
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -247,46 +249,57 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 rv += coord[d] * p.rowvec_mul[d];
                 inst += coord[d] * p.stats_mul[d];
             }
-            bool inst_uniform = true;
-            if (p.stats) {
-                const int inst0 = __shfl_sync(0xffffffffu, valid ? inst : -1, 0);
-                inst_uniform = __all_sync(0xffffffffu, !valid || inst == inst0) && inst0 >= 0;
-                // a warp whose lane 0 is invalid but others are valid takes the slow path
-                if (!inst_uniform) inst_uniform = false;
+            // warp-uniform row group / stats instance?  (true for every large layer)
+            const int rv0 = __shfl_sync(0xffffffffu, rv, 0);
+            const bool rv_uniform = p.rowvec == nullptr || __all_sync(0xffffffffu, !valid || rv == rv0);
+            const int inst0 = __shfl_sync(0xffffffffu, valid ? inst : -1, 0);
+            const bool inst_uniform =
+                p.stats != nullptr && __all_sync(0xffffffffu, !valid || inst == inst0) && inst0 >= 0;
+            // stage bias (+ the shared rowvec row) for this N tile: overlaps the tile's MMAs
+            __syncwarp();
+            for (int c = lane; c < p.block_n; c += 32) {
+                float a = 0.0f;
+                if (n0 + c < p.cout) {
+                    if (p.bias) a = __ldg(&p.bias[n0 + c]);
+                    if (p.rowvec && rv_uniform) a += __ldg(&p.rowvec[(int64_t)rv0 * p.ld_rowvec + n0 + c]);
+                }
+                addv[c] = a;
+            }
+            __syncwarp();
+            const float* res_row = p.residual ? p.residual + pix * p.ld_res + n0 : nullptr;
+            float4 res_next[4];
+            if (res_row && valid) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) res_next[q] = __ldg(reinterpret_cast<const float4*>(res_row) + q);
             }
 
             mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kAccStride;
-            for (int c = 0; c < p.block_n; c += 16) {
-                uint32_t raw[16];
-                tmem_ld16(t_row + c, raw);
-                tmem_ld_wait();
+
+            auto process = [&](uint32_t (&raw)[16], int c) {
                 const int n = n0 + c;
-                if (n >= p.cout) continue;  // warp-uniform
+                if (n >= p.cout) return;  // warp-uniform
                 float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) + addv[c + j];
                 if (valid) {
-                    if (p.bias) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (n + j < p.cout) v[j] += __ldg(&p.bias[n + j]);
-                    }
-                    if (p.rowvec) {
+                    if (p.rowvec && !rv_uniform) {
                         const float* rp = p.rowvec + (int64_t)rv * p.ld_rowvec + n;
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             if (n + j < p.cout) v[j] += __ldg(&rp[j]);
                     }
-                    if (p.residual) {
-                        const float4* rp =
-                            reinterpret_cast<const float4*>(p.residual + pix * p.ld_res + n);
+                    if (res_row) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            float4 t = __ldg(&rp[q]);
-                            v[4 * q + 0] += t.x; v[4 * q + 1] += t.y;
-                            v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                            v[4 * q + 0] += res_next[q].x; v[4 * q + 1] += res_next[q].y;
+                            v[4 * q + 2] += res_next[q].z; v[4 * q + 3] += res_next[q].w;
+                        }
+                        if (c + 16 < p.block_n && n + 16 < p.cout) {  // prefetch the next chunk's residual
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                res_next[q] = __ldg(reinterpret_cast<const float4*>(res_row + c + 16) + q);
                         }
                     }
                     if (p.out_f32) {
@@ -307,33 +320,29 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 }
                 if (p.stats) {
                     if (inst_uniform) {
-                        // butterfly-reduce 16 sums + 16 sums of squares over the warp's 32 rows
-                        float s[16], q[16];
+                        // 32 quantities (16 column sums, 16 sums of squares) over 32 rows:
+                        // recursive halving, 31 shuffles; lane L ends with the total of quantity L
+                        float w[32];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float x = (valid && n + j < p.cout) ? v[j] : 0.0f;
-                            s[j] = x; q[j] = x * x;
+                            w[j] = x;
+                            w[16 + j] = x * x;
                         }
 #pragma unroll
                         for (int off = 16; off > 0; off >>= 1) {
+                            const bool up = (lane & off) != 0;
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                s[j] += __shfl_xor_sync(0xffffffffu, s[j], off);
-                                q[j] += __shfl_xor_sync(0xffffffffu, q[j], off);
+                            for (int j = 0; j < off; ++j) {
+                                const float send = up ? w[j] : w[j + off];
+                                const float keep = up ? w[j + off] : w[j];
+                                w[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                             }
-                        }
-                        const int inst0 = __shfl_sync(0xffffffffu, inst, 0);
-                        // lane j (<16) publishes sum of column j, lane 16+j its sum of squares
-                        float mine = 0.0f;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (lane == j) mine = s[j];
-                            if (lane == 16 + j) mine = q[j];
                         }
                         const int col = n + (lane & 15);
                         if (col < p.cout)
                             atomicAdd(&p.stats[((int64_t)inst0 * p.stats_ld + col) * 2 + (lane >> 4)],
-                                      (double)mine);
+                                      (double)w[0]);
                     } else if (valid) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
@@ -343,6 +352,20 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                                 atomicAdd(sp + 1, (double)v[j] * (double)v[j]);
                             }
                     }
+                }
+            };
+
+            // TMEM loads are software pipelined: chunk c+16 is in flight while chunk c is processed
+            uint32_t ra[16], rb[16];
+            tmem_ld16(t_row, ra);
+            for (int c = 0; c < p.block_n; c += 32) {
+                tmem_ld_wait16(ra);
+                if (c + 16 < p.block_n) tmem_ld16(t_row + c + 16, rb);
+                process(ra, c);
+                if (c + 16 < p.block_n) {
+                    tmem_ld_wait16(rb);
+                    if (c + 32 < p.block_n) tmem_ld16(t_row + c + 32, ra);
+                    process(rb, c + 16);
                 }
             }
             tc_fence_before();
@@ -483,7 +506,7 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
     p.b_tile_bytes = (uint32_t)d->block_n * kChunkK * 2;
     p.stage_bytes = (uint32_t)d->passes == 3 ? 2 * (kATileBytes + p.b_tile_bytes)
                                              : (kATileBytes + p.b_tile_bytes);
-    const size_t overhead = 1024 /*align*/ + 256 /*barriers*/;
+    const size_t overhead = 1024 /*align*/ + 256 /*barriers*/ + 4096 /*epilogue bias staging*/;
     int stages = (int)((g_max_smem - overhead) / p.stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) {

@@ -1,0 +1,482 @@
+// Policy-path kernels around the tensor-core contractions of ConditionalUnet1D
+// (diffuser/diffusion_policy/model/conditional_unet1d.py, conv1d_components.py).
+//
+// One sample of the policy UNet is tiny (T*C = 16*256 = 8*512 = 4*1024 = 4096 values per
+// conv output), so GroupNorm + Mish + FiLM forward AND backward each run as ONE CTA per
+// batch sample with the whole sample in registers: exact two-pass statistics, no atomics
+// on the activation path, and the backward emits everything the conv gradients need in
+// one pass (dy as bf16 hi/lo planes for the data-gradient GEMM, dy^T for the
+// weight-gradient GEMM, bias / gamma / beta / FiLM gradients).
+#include "common.cuh"
+#include "../../include/v2a_b200.h"
+
+#include <atomic>
+
+namespace v2a {
+extern std::atomic<int64_t> g_launches;
+
+constexpr int kPolThreads = 256;
+constexpr int kMaxOct = 8;  // 8-channel octets per thread (T*C <= 256*8*8 = 16384)
+
+struct GnActParams {
+    const float* y;        // [B][T][C] conv output
+    int T, C, groups;
+    float eps;
+    const float* gamma; const float* beta;
+    const float* film; int ld_film;       // [B][2C] scale|bias or null
+    const float* addend; int ld_add;      // [B][T][ld_add] identity residual or null
+    float* out_f32; int ld_out;           // [B][T][ld_out] or null
+    __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int ld_hl;
+    float* mean_rstd;                     // [B][groups][2]
+    // backward only
+    const float* dout; int ld_dout;       // [B][T][ld_dout]
+    __nv_bfloat16* dy_hi; __nv_bfloat16* dy_lo;     // [B][T][C]
+    __nv_bfloat16* dyT_hi; __nv_bfloat16* dyT_lo;   // [C][B*T]
+    float* dy_f32;                        // optional [B][T][C]
+    float* dbias; float* dgamma; float* dbeta;      // [C] accumulated with atomics over samples
+    float* dfilm; int ld_dfilm;           // [B][2C] written
+    int B;
+};
+
+// thread -> (octet of 8 channels, lane over t); values of a thread share one group
+__device__ __forceinline__ void thread_map(int C, int& octs, int& tl, int& oc, int& tlane) {
+    octs = C >> 3;
+    tl = kPolThreads / octs;
+    if (tl < 1) tl = 1;
+    oc = threadIdx.x % octs;
+    tlane = threadIdx.x / octs;
+}
+
+__device__ __forceinline__ void load8(const float* p, float* v) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(float* p, const float* v) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// block-wide per-group reduction of one float per thread (thread's group = g); result broadcast
+__device__ __forceinline__ float group_sum(float v, int g, float* sh, int groups) {
+    __syncthreads();
+    if (threadIdx.x < groups) sh[threadIdx.x] = 0.0f;
+    __syncthreads();
+    atomicAdd(&sh[g], v);
+    __syncthreads();
+    return sh[g];
+}
+
+__global__ void __launch_bounds__(kPolThreads) gn_act_fwd_kernel(const GnActParams p) {
+    __shared__ float sh[64];
+    const int b = blockIdx.x;
+    int octs, tl, oc, tlane;
+    thread_map(p.C, octs, tl, oc, tlane);
+    const bool active = tlane < tl && oc < octs;
+    const int c0 = oc * 8;
+    const int cpg = p.C / p.groups;
+    const int g = active ? c0 / cpg : 0;
+    float v[kMaxOct][8];
+    int nt = 0;
+    float s = 0.0f;
+    if (active)
+        for (int t = tlane; t < p.T; t += tl, ++nt) {
+            load8(p.y + ((int64_t)b * p.T + t) * p.C + c0, v[nt]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[nt][j];
+        }
+    const float cnt = (float)(cpg * p.T);
+    const float mean = group_sum(s, g, sh, p.groups) / cnt;
+    float q = 0.0f;
+    for (int i = 0; i < nt; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+    const float var = group_sum(q, g, sh, p.groups) / cnt;
+    const float rstd = rsqrtf(var + p.eps);
+    if (!active) return;
+    if (tlane == 0 && (c0 % cpg) == 0) {
+        p.mean_rstd[((int64_t)b * p.groups + g) * 2] = mean;
+        p.mean_rstd[((int64_t)b * p.groups + g) * 2 + 1] = rstd;
+    }
+    float ga[8], be[8], fs[8], fb[8];
+    load8(p.gamma + c0, ga);
+    load8(p.beta + c0, be);
+    if (p.film) {
+        load8(p.film + (int64_t)b * p.ld_film + c0, fs);
+        load8(p.film + (int64_t)b * p.ld_film + p.C + c0, fb);
+    }
+    int i = 0;
+    for (int t = tlane; t < p.T; t += tl, ++i) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float x = mish_f((v[i][j] - mean) * rstd * ga[j] + be[j]);
+            if (p.film) x = fs[j] * x + fb[j];
+            o[j] = x;
+        }
+        const int64_t row = (int64_t)b * p.T + t;
+        if (p.addend) {
+            float a[8];
+            load8(p.addend + row * p.ld_add + c0, a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += a[j];
+        }
+        if (p.out_f32) store8(p.out_f32 + row * p.ld_out + c0, o);
+        if (p.out_hi) {
+            uint4 h, l;
+            split8(o, h, l);
+            *reinterpret_cast<uint4*>(p.out_hi + row * p.ld_hl + c0) = h;
+            *reinterpret_cast<uint4*>(p.out_lo + row * p.ld_hl + c0) = l;
+        }
+    }
+}
+
+// backward of  out = film_s * mish(gamma * (y - mean) * rstd + beta) + film_b  (+ addend)
+__global__ void __launch_bounds__(kPolThreads) gn_act_bwd_kernel(const GnActParams p) {
+    __shared__ float sh[64];
+    const int b = blockIdx.x;
+    int octs, tl, oc, tlane;
+    thread_map(p.C, octs, tl, oc, tlane);
+    const bool active = tlane < tl && oc < octs;
+    const int c0 = oc * 8;
+    const int cpg = p.C / p.groups;
+    const int g = active ? c0 / cpg : 0;
+    const float mean = p.mean_rstd[((int64_t)b * p.groups + g) * 2];
+    const float rstd = p.mean_rstd[((int64_t)b * p.groups + g) * 2 + 1];
+    float ga[8], be[8], fs[8];
+    if (active) {
+        load8(p.gamma + c0, ga);
+        load8(p.beta + c0, be);
+        if (p.film) load8(p.film + (int64_t)b * p.ld_film + c0, fs);
+    }
+    float n[kMaxOct][8], dn[kMaxOct][8];  // normalised input, grad wrt normalised input
+    float dsc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dsh[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // FiLM grads
+    float dga[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dbe[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // gamma / beta grads
+    float s1 = 0.0f, s2 = 0.0f;
+    int nt = 0;
+    if (active)
+        for (int t = tlane; t < p.T; t += tl, ++nt) {
+            const int64_t row = (int64_t)b * p.T + t;
+            float y[8], d[8];
+            load8(p.y + row * p.C + c0, y);
+            load8(p.dout + row * p.ld_dout + c0, d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float nn = (y[j] - mean) * rstd;
+                const float gg = nn * ga[j] + be[j];
+                float dm = d[j];
+                if (p.film) {
+                    dsc[j] += d[j] * mish_f(gg);
+                    dsh[j] += d[j];
+                    dm = d[j] * fs[j];
+                }
+                const float dg = dm * mish_grad_f(gg);
+                dga[j] += dg * nn;
+                dbe[j] += dg;
+                const float dnn = dg * ga[j];
+                n[nt][j] = nn;
+                dn[nt][j] = dnn;
+                s1 += dnn;
+                s2 += dnn * nn;
+            }
+        }
+    const float cnt = (float)(cpg * p.T);
+    const float m1 = group_sum(s1, g, sh, p.groups) / cnt;
+    const float m2 = group_sum(s2, g, sh, p.groups) / cnt;
+    if (!active) return;
+    float dbi[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int i = 0;
+    const int64_t BT = (int64_t)p.B * p.T;
+    for (int t = tlane; t < p.T; t += tl, ++i) {
+        const int64_t row = (int64_t)b * p.T + t;
+        float dy[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            dy[j] = rstd * (dn[i][j] - m1 - n[i][j] * m2);
+            dbi[j] += dy[j];
+        }
+        if (p.dy_f32) store8(p.dy_f32 + row * p.C + c0, dy);
+        uint4 h, l;
+        split8(dy, h, l);
+        if (p.dy_hi) {
+            *reinterpret_cast<uint4*>(p.dy_hi + row * p.C + c0) = h;
+            *reinterpret_cast<uint4*>(p.dy_lo + row * p.C + c0) = l;
+        }
+        if (p.dyT_hi) {
+            const __nv_bfloat16* hh = reinterpret_cast<const __nv_bfloat16*>(&h);
+            const __nv_bfloat16* ll = reinterpret_cast<const __nv_bfloat16*>(&l);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                p.dyT_hi[(int64_t)(c0 + j) * BT + row] = hh[j];
+                p.dyT_lo[(int64_t)(c0 + j) * BT + row] = ll[j];
+            }
+        }
+    }
+    // per-channel reductions over this thread's rows -> global accumulators
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (p.dbias) atomicAdd(&p.dbias[c0 + j], dbi[j]);
+        atomicAdd(&p.dgamma[c0 + j], dga[j]);
+        atomicAdd(&p.dbeta[c0 + j], dbe[j]);
+        if (p.film) {
+            atomicAdd(&p.dfilm[(int64_t)b * p.ld_dfilm + c0 + j], dsc[j]);
+            atomicAdd(&p.dfilm[(int64_t)b * p.ld_dfilm + p.C + c0 + j], dsh[j]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// transposed im2col of a bf16 hi/lo activation: x [B][Tin][C] -> [C*ntaps][B*Tout],
+// row (c*ntaps + k), column (b*Tout + o) = x[b][stride*o + off[k]][c] (zero outside)
+// ---------------------------------------------------------------------------
+struct Im2colTParams {
+    const __nv_bfloat16* x_hi; const __nv_bfloat16* x_lo;
+    int ld_x, c_off;      // source row pitch and first channel (slice of a wider tensor)
+    __nv_bfloat16* o_hi; __nv_bfloat16* o_lo;
+    int B, Tin, Tout, C, ntaps, stride;
+    int off[8];
+};
+__global__ void __launch_bounds__(256) im2col_t_kernel(const Im2colTParams p) {
+    // one thread per (row = c*ntaps + k, b); writes Tout contiguous columns
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t rows = (int64_t)p.C * p.ntaps;
+    if (gid >= rows * p.B) return;
+    const int b = (int)(gid % p.B);
+    const int64_t r = gid / p.B;
+    const int k = (int)(r % p.ntaps);
+    const int c = (int)(r / p.ntaps);
+    const int64_t BT = (int64_t)p.B * p.Tout;
+    for (int o = 0; o < p.Tout; ++o) {
+        const int t = p.stride * o + p.off[k];
+        __nv_bfloat16 h = __float2bfloat16_rn(0.0f), l = h;
+        if (t >= 0 && t < p.Tin) {
+            const int64_t src = ((int64_t)b * p.Tin + t) * p.ld_x + p.c_off + c;
+            h = p.x_hi[src];
+            l = p.x_lo[src];
+        }
+        p.o_hi[r * BT + (int64_t)b * p.Tout + o] = h;
+        p.o_lo[r * BT + (int64_t)b * p.Tout + o] = l;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// gradient prep for convs whose output gradient arrives as plain fp32:
+// dy [rows][ld] (C used) -> dy_hl [rows][C], dy^T_hl [C][rows], colsum[C] += sum_rows
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grad_prep_kernel(const float* __restrict__ dy, int64_t rows, int C,
+                                                        int ld, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                                                        int ld_hl, __nv_bfloat16* t_hi, __nv_bfloat16* t_lo,
+                                                        float* colsum) {
+    __shared__ float tile[32][33];
+    const int c_base = blockIdx.x * 32, r_base = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int64_t r = r_base + i;
+        const int c = c_base + tx;
+        float v = 0.0f;
+        if (r < rows && c < C) v = dy[r * ld + c];
+        tile[i][tx] = v;
+        if (hi && r < rows && c < ld_hl) {
+            __nv_bfloat16 h, l;
+            split_bf16(c < C ? v : 0.0f, h, l);
+            hi[r * ld_hl + c] = h;
+            lo[r * ld_hl + c] = l;
+        }
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c_base + i;
+        const int64_t r = r_base + tx;
+        if (c < C && r < rows && t_hi) {
+            __nv_bfloat16 h, l;
+            split_bf16(tile[tx][i], h, l);
+            t_hi[(int64_t)c * rows + r] = h;
+            t_lo[(int64_t)c * rows + r] = l;
+        }
+    }
+    if (colsum && ty == 0) {
+        float s = 0.0f;
+        for (int i = 0; i < 32; ++i) s += tile[i][tx];
+        if (c_base + tx < C) atomicAdd(&colsum[c_base + tx], s);
+    }
+}
+
+// dx = dy * act'(x)  (act: 1 SiLU, 2 Mish), optional hi/lo split of the result
+__global__ void act_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* dx,
+                               __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, int act) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float xv = x[i];
+    float g;
+    if (act == 2) {
+        g = mish_grad_f(xv);
+    } else {
+        const float sg = 1.0f / (1.0f + expf(-xv));
+        g = sg * (1.0f + xv * (1.0f - sg));
+    }
+    const float r = dy[i] * g;
+    if (dx) dx[i] = r;
+    if (hi) {
+        __nv_bfloat16 h, l;
+        split_bf16(r, h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+// fused clip-by-global-norm + AdamW + EMA over one flat parameter slab
+// (trainer: clip_grad_norm_(1.0); AdamW(lr, betas, eps, wd).step; EMA.update —
+//  diffuser/libero/lb_online_trainer_v7.py:608-624)
+__global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, double* out) {
+    float s = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        s += g[i] * g[i];
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    __shared__ float w[32];
+    if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += (double)w[i];
+        atomicAdd(out, t);
+    }
+}
+__global__ void adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, float* __restrict__ ema, int64_t n,
+                                 const double* __restrict__ sumsq, float max_norm, float lr, float beta1,
+                                 float beta2, float eps, float wd, float bc1, float bc2, float ema_decay) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float clip = 1.0f;
+    if (max_norm > 0.0f) {
+        const float total = (float)sqrt(*sumsq);
+        const float c = max_norm / (total + 1e-6f);   // torch clip_grad_norm_
+        clip = c < 1.0f ? c : 1.0f;
+    }
+    const float gi = g[i] * clip;
+    float pi = p[i];
+    pi *= (1.0f - lr * wd);                            // decoupled weight decay
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi;
+    if (ema) ema[i] = ema[i] - (1.0f - ema_decay) * (ema[i] - pi);  // ema.lerp_(p, 1 - decay)
+}
+
+}  // namespace v2a
+
+using namespace v2a;
+
+#define POL_LAUNCH_OK()                  \
+    do {                                 \
+        V2A_CUDA_OK(cudaGetLastError()); \
+        g_launches.fetch_add(1);         \
+    } while (0)
+
+static int check_gn(const v2a_policy_gn_desc* d) {
+    V2A_REQUIRE(d->C % 8 == 0 && d->C / 8 <= kPolThreads, "policy_gn: C %d must be a multiple of 8, <= 2048", d->C);
+    V2A_REQUIRE(d->groups >= 1 && d->groups <= 64 && d->C % d->groups == 0 && (d->C / d->groups) % 8 == 0,
+                "policy_gn: channels per group must be a multiple of 8");
+    const int octs = d->C / 8;
+    const int tl = kPolThreads / octs > 0 ? kPolThreads / octs : 1;
+    V2A_REQUIRE((d->T + tl - 1) / tl <= kMaxOct, "policy_gn: T*C = %d*%d too large for one CTA", d->T, d->C);
+    return 0;
+}
+
+static GnActParams to_params(const v2a_policy_gn_desc* d) {
+    GnActParams p;
+    p.y = d->y; p.T = d->T; p.C = d->C; p.groups = d->groups; p.eps = d->eps;
+    p.gamma = d->gamma; p.beta = d->beta;
+    p.film = d->film; p.ld_film = d->ld_film;
+    p.addend = d->addend; p.ld_add = d->ld_add;
+    p.out_f32 = d->out_f32; p.ld_out = d->ld_out;
+    p.out_hi = (__nv_bfloat16*)d->out_hi; p.out_lo = (__nv_bfloat16*)d->out_lo; p.ld_hl = d->ld_hl;
+    p.mean_rstd = d->mean_rstd;
+    p.dout = d->dout; p.ld_dout = d->ld_dout;
+    p.dy_hi = (__nv_bfloat16*)d->dy_hi; p.dy_lo = (__nv_bfloat16*)d->dy_lo;
+    p.dyT_hi = (__nv_bfloat16*)d->dyT_hi; p.dyT_lo = (__nv_bfloat16*)d->dyT_lo;
+    p.dy_f32 = d->dy_f32;
+    p.dbias = d->dbias; p.dgamma = d->dgamma; p.dbeta = d->dbeta;
+    p.dfilm = d->dfilm; p.ld_dfilm = d->ld_dfilm;
+    p.B = d->B;
+    return p;
+}
+
+extern "C" {
+
+int v2a_policy_gn_act_fwd(const v2a_policy_gn_desc* d, void* stream) {
+    if (int rc = check_gn(d)) return rc;
+    V2A_REQUIRE(d->y && d->gamma && d->beta && d->mean_rstd, "policy_gn_fwd: missing pointers");
+    gn_act_fwd_kernel<<<d->B, kPolThreads, 0, (cudaStream_t)stream>>>(to_params(d));
+    POL_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_policy_gn_act_bwd(const v2a_policy_gn_desc* d, void* stream) {
+    if (int rc = check_gn(d)) return rc;
+    V2A_REQUIRE(d->y && d->dout && d->mean_rstd && d->dgamma && d->dbeta, "policy_gn_bwd: missing pointers");
+    V2A_REQUIRE(!d->film || d->dfilm, "policy_gn_bwd: FiLM needs dfilm");
+    gn_act_bwd_kernel<<<d->B, kPolThreads, 0, (cudaStream_t)stream>>>(to_params(d));
+    POL_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_policy_im2col_t(const void* x_hi, const void* x_lo, int ld_x, int c_off, int B, int Tin, int Tout,
+                        int C, int ntaps, int stride, const int* offsets, void* out_hi, void* out_lo,
+                        void* stream) {
+    V2A_REQUIRE(ntaps >= 1 && ntaps <= 8, "im2col_t: ntaps out of range");
+    Im2colTParams p;
+    p.x_hi = (const __nv_bfloat16*)x_hi; p.x_lo = (const __nv_bfloat16*)x_lo;
+    p.ld_x = ld_x; p.c_off = c_off;
+    p.o_hi = (__nv_bfloat16*)out_hi; p.o_lo = (__nv_bfloat16*)out_lo;
+    p.B = B; p.Tin = Tin; p.Tout = Tout; p.C = C; p.ntaps = ntaps; p.stride = stride;
+    for (int i = 0; i < ntaps; ++i) p.off[i] = offsets[i];
+    const int64_t total = (int64_t)C * ntaps * B;
+    im2col_t_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
+    POL_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_grad_prep(const float* dy, int64_t rows, int C, int ld, void* hi, void* lo, int ld_hl, void* t_hi,
+                  void* t_lo, float* colsum, void* stream) {
+    const int cw = ld_hl > C ? ld_hl : C;
+    dim3 grid((unsigned)((cw + 31) / 32), (unsigned)((rows + 31) / 32));
+    grad_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, rows, C, ld, (__nv_bfloat16*)hi,
+                                                             (__nv_bfloat16*)lo, ld_hl, (__nv_bfloat16*)t_hi,
+                                                             (__nv_bfloat16*)t_lo, colsum);
+    POL_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_act_bwd(const float* x, const float* dy, float* dx, void* hi, void* lo, int64_t n, int act,
+                void* stream) {
+    act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x, dy, dx, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n, act);
+    POL_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_grad_sumsq(const float* g, int64_t n, double* out, void* stream) {
+    int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, n, out);
+    POL_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n,
+                       const double* grad_sumsq, float max_norm, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int step, float ema_decay, void* stream) {
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2 = 1.0f - powf(beta2, (float)step);
+    adamw_ema_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        p, g, m, v, ema, n, grad_sumsq, max_norm, lr, beta1, beta2, eps, weight_decay, bc1, bc2, ema_decay);
+    POL_LAUNCH_OK();
+    return 0;
+}
+
+}  // extern "C"
