@@ -81,6 +81,8 @@ typedef struct v2a_igemm_desc {
     double* stats;          /* per (instance, channel) {sum, sumsq} of the written fp32 value, or NULL */
     int stats_mul[4];       /* instance = sum coord[d] * stats_mul[d] */
     int stats_ld;           /* channels per instance in the stats buffer */
+    int stats_replicas;     /* >= 1: CTAs spread their atomics over this many copies of the buffer */
+    int64_t stats_rep_stride;   /* doubles between consecutive copies */
 } v2a_igemm_desc;
 
 int v2a_igemm_plan_create(const v2a_igemm_desc* desc, void** plan_out);
@@ -126,6 +128,8 @@ typedef struct v2a_prep_desc {
     float* out_f32;         /* optional fp32 copy of the result (policy autograd) */
     void* raw_hi;           /* optional: hi/lo split of the un-normalised concat (1x1 skip operand) */
     void* raw_lo;
+    int stats_rep0, stats_rep1;                    /* replica counts of stats0 / stats1 (0 = 1) */
+    int64_t stats_rep_stride0, stats_rep_stride1;  /* doubles between replicas */
 } v2a_prep_desc;
 int v2a_prep(const v2a_prep_desc* d, void* stream);
 

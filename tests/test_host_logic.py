@@ -101,3 +101,79 @@ def test_bf16_split_error_bound():
     hl = ops.split_hl_torch(x)
     err = (hl.float() - x).abs() / x.abs().clamp_min(1e-30)
     assert err.max() < 2.0 ** -16
+
+
+def _im2col_t(x, offsets, stride, Tout):
+    """CPU twin of v2a_policy_im2col_t: x [B, Tin, C] -> [C*ntaps, B*Tout]."""
+    B, Tin, C = x.shape
+    out = torch.zeros(C, len(offsets), B, Tout, dtype=x.dtype)
+    for k, off in enumerate(offsets):
+        for o in range(Tout):
+            t = stride * o + off
+            if 0 <= t < Tin:
+                out[:, k, :, o] = x[:, t, :].t()
+    return out.reshape(C * len(offsets), B * Tout)
+
+
+def test_downsample1d_forward_dgrad_wgrad_programs():
+    B, T, C = 3, 8, 16
+    x = torch.randn(B, C, T, dtype=D, requires_grad=True)
+    w = torch.randn(C, C, 3, dtype=D, requires_grad=True)
+    y = F.conv1d(x, w, stride=2, padding=1)
+    dy = torch.randn_like(y)
+    dx, dw = torch.autograd.grad(y, (x, w), dy)
+    xl = x.detach().permute(0, 2, 1).contiguous()                 # [B, T, C]
+    prog = convs.down1d(C, B, T)
+    out = emulate(prog, [xl.reshape(1, B, T // 2, 2, C)], convs.conv1d_weight(w.detach()), C)
+    torch.testing.assert_close(out, y.detach().permute(0, 2, 1).reshape(-1, C), rtol=1e-12, atol=1e-12)
+    dyl = dy.permute(0, 2, 1).contiguous()                        # [B, T/2, C]
+    progb = convs.down1d_dgrad(C, B, T)
+    outb = emulate(progb, [dyl.reshape(1, 1, B, T // 2, C)], convs.down1d_dgrad_weight(w.detach()), 2 * C)
+    torch.testing.assert_close(outb.reshape(B, T, C), dx.permute(0, 2, 1), rtol=1e-12, atol=1e-12)
+    # wgrad: dW[co, ci, k] = dy^T [C, B*T/2] @ im2col^T(x)[C*3, B*T/2]^T
+    dyT = dyl.reshape(-1, C).t()
+    cols = _im2col_t(xl, [-1, 0, 1], 2, T // 2)
+    torch.testing.assert_close((dyT @ cols.t()).reshape(C, C, 3), dw, rtol=1e-12, atol=1e-12)
+
+
+def test_upsample1d_forward_dgrad_wgrad_programs():
+    B, T, C = 2, 4, 16
+    x = torch.randn(B, C, T, dtype=D, requires_grad=True)
+    wt = torch.randn(C, C, 4, dtype=D, requires_grad=True)       # ConvTranspose1d weight [Cin, Cout, k]
+    b = torch.randn(C, dtype=D)
+    y = F.conv_transpose1d(x, wt, b, stride=2, padding=1)          # [B, C, 2T]
+    dy = torch.randn_like(y)
+    dx, dw = torch.autograd.grad(y, (x, wt), dy)
+    xl = x.detach().permute(0, 2, 1).contiguous()
+    prog = convs.up1d(C, B, T)
+    out = emulate(prog, [xl.reshape(1, 1, B, T, C)], convs.up1d_weight(wt.detach()), 2 * C) + torch.cat([b, b])
+    torch.testing.assert_close(out.reshape(B, 2 * T, C), y.detach().permute(0, 2, 1), rtol=1e-12, atol=1e-12)
+    dyl = dy.permute(0, 2, 1).contiguous()                        # [B, 2T, C]
+    progb = convs.up1d_dgrad(C, B, T)
+    outb = emulate(progb, [dyl.reshape(1, B, T, 2, C)], convs.up1d_dgrad_weight(wt.detach()), C)
+    torch.testing.assert_close(outb.reshape(B, T, C), dx.permute(0, 2, 1), rtol=1e-12, atol=1e-12)
+    # wgrad: dWt[ci, co, k] = x^T [C, B*T] @ im2col^T(dy, stride 2, offsets k-1)[C*4, B*T]^T
+    xT = xl.reshape(-1, C).t()
+    cols = _im2col_t(dyl, [-1, 0, 1, 2], 2, T)
+    torch.testing.assert_close((xT @ cols.t()).reshape(C, C, 4), dw, rtol=1e-12, atol=1e-12)
+
+
+def test_conv1d_wgrad_via_transposed_im2col_and_concat_slices():
+    B, T, C0, C1, Co = 2, 8, 8, 16, 24
+    x = torch.randn(B, C0 + C1, T, dtype=D)
+    w = torch.randn(Co, C0 + C1, 5, dtype=D, requires_grad=True)
+    y = F.conv1d(x, w, padding=2)
+    dy = torch.randn_like(y)
+    (dw,) = torch.autograd.grad(y, w, dy)
+    dyT = dy.permute(0, 2, 1).reshape(-1, Co).t()
+    xl = x.permute(0, 2, 1).contiguous()
+    got = torch.zeros(Co, (C0 + C1) * 5, dtype=D)
+    for off, cpart in ((0, C0), (C0, C1)):  # concat parts land in column slices of [Co, Cin*k]
+        cols = _im2col_t(xl[:, :, off:off + cpart].contiguous(), [-2, -1, 0, 1, 2], 1, T)
+        got[:, off * 5:(off + cpart) * 5] = dyT @ cols.t()
+    torch.testing.assert_close(got.reshape(Co, C0 + C1, 5), dw, rtol=1e-12, atol=1e-12)
+    # forward over a 2-source concat: taps of source 0 then source 1, weights sliced the same way
+    prog = convs.conv1d_cat([C0, C1], B, T, 5, 2)
+    wpk = convs.conv1d_cat_weight(w.detach(), [C0, C1])
+    out = emulate(prog, [xl[:, :, :C0].reshape(1, 1, B, T, C0), xl[:, :, C0:].reshape(1, 1, B, T, C1)], wpk, Co)
+    torch.testing.assert_close(out, y.permute(0, 2, 1).reshape(-1, Co), rtol=1e-12, atol=1e-12)

@@ -50,6 +50,8 @@ class IgemmDesc(C.Structure):
         ("stats", C.c_void_p),
         ("stats_mul", C.c_int * 4),
         ("stats_ld", C.c_int),
+        ("stats_replicas", C.c_int),
+        ("stats_rep_stride", C.c_int64),
     ]
 
 
@@ -80,6 +82,10 @@ class PrepDesc(C.Structure):
         ("out_f32", C.c_void_p),
         ("raw_hi", C.c_void_p),
         ("raw_lo", C.c_void_p),
+        ("stats_rep0", C.c_int),
+        ("stats_rep1", C.c_int),
+        ("stats_rep_stride0", C.c_int64),
+        ("stats_rep_stride1", C.c_int64),
     ]
 
 

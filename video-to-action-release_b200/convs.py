@@ -115,3 +115,70 @@ def conv1d_dgrad_weight(w: torch.Tensor) -> torch.Tensor:
     """
     k = w.shape[2]
     return pack_weight_taps([w[:, :, j].t() for j in reversed(range(k))])
+
+
+# ---- policy: stride-2 Downsample1d = Conv1d(C, C, 3, 2, 1) on the phase view [B][T/2][2][C] ----
+def down1d(c: int, B: int, T: int) -> ConvProgram:
+    """input t = 2*o + k - 1:  k=0 -> (phase 1, o-1); k=1 -> (0, o); k=2 -> (1, o).  No copy:
+    [B][T][C] memory IS [B][T/2][2][C]."""
+    taps = [(0, (1, -1, 0, 0), nchunks(c)), (0, (0, 0, 0, 0), nchunks(c)), (0, (1, 0, 0, 0), nchunks(c))]
+    return ConvProgram([c], [(2, T // 2, B, 1)], taps, (1, T // 2, B, 1))
+
+
+def down1d_dgrad(c: int, B: int, T: int) -> ConvProgram:
+    """dx[2j] = W1^T dy[j]; dx[2j+1] = W2^T dy[j] + W0^T dy[j+1]: one GEMM with N = 2C whose
+    output row (b, j) holds [phase 0 | phase 1] = the [B][T][C] layout of dx.  T = INPUT length."""
+    taps = [(0, (0, 0, 0, 0), nchunks(c)), (0, (1, 0, 0, 0), nchunks(c))]
+    return ConvProgram([c], [(T // 2, B, 1, 1)], taps, (T // 2, B, 1, 1))
+
+
+def down1d_dgrad_weight(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3] -> [2*Cin, 2*pad64(Cout)]: rows p=0: [W1^T | 0]; rows p=1: [W2^T | W0^T]."""
+    z = torch.zeros_like(w[:, :, 0].t())
+    return torch.cat([pack_weight_taps([w[:, :, 1].t(), z]), pack_weight_taps([w[:, :, 2].t(), w[:, :, 0].t()])], 0)
+
+
+# ---- policy: Upsample1d = ConvTranspose1d(C, C, 4, 2, 1), weight [Cin, Cout, 4] ----
+def up1d(c: int, B: int, T: int) -> ConvProgram:
+    """out[2j] = Wt1^T x[j] + Wt3^T x[j-1]; out[2j+1] = Wt2^T x[j] + Wt0^T x[j+1] (+bias): one
+    GEMM with N = 2C over taps x[j-1], x[j], x[j+1]; output row (b, j) = [phase 0 | phase 1]."""
+    taps = [(0, (d, 0, 0, 0), nchunks(c)) for d in (-1, 0, 1)]
+    return ConvProgram([c], [(T, B, 1, 1)], taps, (T, B, 1, 1))
+
+
+def up1d_weight(wt: torch.Tensor) -> torch.Tensor:
+    """[Cin, Cout, 4] -> [2*Cout, 3*pad64(Cin)]."""
+    z = torch.zeros_like(wt[:, :, 0].t())
+    p0 = pack_weight_taps([wt[:, :, 3].t(), wt[:, :, 1].t(), z])
+    p1 = pack_weight_taps([z, wt[:, :, 2].t(), wt[:, :, 0].t()])
+    return torch.cat([p0, p1], 0)
+
+
+def up1d_dgrad(c: int, B: int, T: int) -> ConvProgram:
+    """dx[i] = sum_k Wt[:, :, k] dy[2i - 1 + k] on the phase view of dy [B][T][2][C] (T = INPUT length):
+    k=0 -> (1, i-1); k=1 -> (0, i); k=2 -> (1, i); k=3 -> (0, i+1)."""
+    taps = [(0, (1, -1, 0, 0), nchunks(c)), (0, (0, 0, 0, 0), nchunks(c)), (0, (1, 0, 0, 0), nchunks(c)),
+            (0, (0, 1, 0, 0), nchunks(c))]
+    return ConvProgram([c], [(2, T, B, 1)], taps, (1, T, B, 1))
+
+
+def up1d_dgrad_weight(wt: torch.Tensor) -> torch.Tensor:
+    """[Cin, Cout, 4] -> [Cin, 4*pad64(Cout)]."""
+    return pack_weight_taps([wt[:, :, k] for k in range(4)])
+
+
+def conv1d_cat(cins, B: int, T: int, k: int, pad: int) -> ConvProgram:
+    """Conv1d over a channel concat of up to two sources without materialising the concat."""
+    taps, dims = [], []
+    for s, c in enumerate(cins):
+        taps += [(s, (j - pad, 0, 0, 0), nchunks(c)) for j in range(k)]
+        dims.append((T, B, 1, 1))
+    return ConvProgram(list(cins), dims, taps, (T, B, 1, 1))
+
+
+def conv1d_cat_weight(w: torch.Tensor, cins) -> torch.Tensor:
+    parts, off = [], 0
+    for c in cins:
+        parts += [w[:, off:off + c, j] for j in range(w.shape[2])]
+        off += c
+    return pack_weight_taps(parts)

@@ -56,7 +56,8 @@ __global__ void channel_stats_kernel(const float* __restrict__ x, int64_t ppi, i
 // one warp per (sample, group): lanes stride over the (instance, channel) sums
 __global__ void gn_finalize_kernel(const double* __restrict__ st0, const double* __restrict__ st1,
                                    int C0, int C1, int groups, int inst_per_group, double count,
-                                   float eps, float2* __restrict__ mr, int samples) {
+                                   float eps, float2* __restrict__ mr, int samples, int rep0, long long rs0,
+                                   int rep1, long long rs1) {
     const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (idx >= samples * groups) return;
@@ -66,10 +67,15 @@ __global__ void gn_finalize_kernel(const double* __restrict__ st0, const double*
     for (int e = lane; e < inst_per_group * cpg; e += 32) {
         const int64_t inst = (int64_t)smp * inst_per_group + e / cpg;
         const int c = g * cpg + e % cpg;
-        const double2 v = c < C0 ? *reinterpret_cast<const double2*>(st0 + (inst * C0 + c) * 2)
-                                 : *reinterpret_cast<const double2*>(st1 + (inst * C1 + (c - C0)) * 2);
-        s += v.x;
-        ss += v.y;
+        const bool first = c < C0;
+        const double* base = first ? st0 + (inst * C0 + c) * 2 : st1 + (inst * C1 + (c - C0)) * 2;
+        const int reps = first ? rep0 : rep1;
+        const long long rs = first ? rs0 : rs1;
+        for (int r = 0; r < reps; ++r) {
+            const double2 v = *reinterpret_cast<const double2*>(base + r * rs);
+            s += v.x;
+            ss += v.y;
+        }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -425,7 +431,9 @@ int v2a_prep(const v2a_prep_desc* d, void* stream) {
         const double count = (double)p.pixels_per_sample * (double)(C / d->groups);
         const int n = samples * d->groups;
         gn_finalize_kernel<<<ceil_div(n * 32, 128), 128, 0, (cudaStream_t)stream>>>(
-            d->stats0, d->stats1, d->C0, d->C1, d->groups, d->inst_per_group, count, d->eps, mr, samples);
+            d->stats0, d->stats1, d->C0, d->C1, d->groups, d->inst_per_group, count, d->eps, mr, samples,
+            d->stats_rep0 > 0 ? d->stats_rep0 : 1, d->stats_rep_stride0, d->stats_rep1 > 0 ? d->stats_rep1 : 1,
+            d->stats_rep_stride1);
         V2A_LAUNCH_OK();
         p.mr = mr;
     }

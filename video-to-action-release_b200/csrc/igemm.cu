@@ -87,6 +87,8 @@ struct alignas(64) IgemmParams {
     double* stats;
     int stats_mul[4];
     int stats_ld;
+    int stats_replicas;
+    long long stats_rep_stride;
 };
 
 __device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int& n_idx, int o[4]) {
@@ -224,6 +226,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         const int quad = warp & 3;            // TMEM lane quarter this warp may read
         const int row = quad * 32 + lane;     // row of the 128-row tile
         float* addv = warp_add + quad * 256;  // this warp's private bias(+rowvec) staging
+        // same-address atomic contention is spread over `stats_replicas` copies of the sums
+        double* const stats = p.stats ? p.stats + (long long)(blockIdx.x % p.stats_replicas) * p.stats_rep_stride : nullptr;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             const bool rv_uniform = p.rowvec == nullptr || __all_sync(0xffffffffu, !valid || rv == rv0);
             const int inst0 = __shfl_sync(0xffffffffu, valid ? inst : -1, 0);
             const bool inst_uniform =
-                p.stats != nullptr && __all_sync(0xffffffffu, !valid || inst == inst0) && inst0 >= 0;
+                stats != nullptr && __all_sync(0xffffffffu, !valid || inst == inst0) && inst0 >= 0;
             // stage bias (+ the shared rowvec row) for this N tile: overlaps the tile's MMAs
             __syncwarp();
             for (int c = lane; c < p.block_n; c += 32) {
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                         lp[0] = l0; lp[1] = l1;
                     }
                 }
-                if (p.stats) {
+                if (stats) {
                     if (inst_uniform) {
                         // 32 quantities (16 column sums, 16 sums of squares) over 32 rows:
                         // recursive halving, 31 shuffles; lane L ends with the total of quantity L
@@ -341,13 +345,13 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                         }
                         const int col = n + (lane & 15);
                         if (col < p.cout)
-                            atomicAdd(&p.stats[((int64_t)inst0 * p.stats_ld + col) * 2 + (lane >> 4)],
+                            atomicAdd(&stats[((int64_t)inst0 * p.stats_ld + col) * 2 + (lane >> 4)],
                                       (double)w[0]);
                     } else if (valid) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             if (n + j < p.cout) {
-                                double* sp = &p.stats[((int64_t)inst * p.stats_ld + n + j) * 2];
+                                double* sp = &stats[((int64_t)inst * p.stats_ld + n + j) * 2];
                                 atomicAdd(sp, (double)v[j]);
                                 atomicAdd(sp + 1, (double)v[j] * (double)v[j]);
                             }
@@ -527,6 +531,8 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
     p.ld_res = d->ld_res;
     p.stats = d->stats;
     p.stats_ld = d->stats_ld;
+    p.stats_replicas = d->stats_replicas > 0 ? d->stats_replicas : 1;
+    p.stats_rep_stride = d->stats_rep_stride;
 
     // tensor maps: A boxes follow the output tile box; every source shares it
     int rc = 0;

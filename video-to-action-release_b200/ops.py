@@ -191,6 +191,9 @@ class Igemm:
             assert stats.dtype == torch.float64
             d.stats = stats.data_ptr()
             d.stats_ld = stats.shape[-2]
+            # optional leading replica dim: [R, instances, C, 2]
+            d.stats_replicas = stats.shape[0] if stats.dim() == 4 else 1
+            d.stats_rep_stride = stats.stride(0) if stats.dim() == 4 else 0
         self.desc = d
         self.flops = 2.0 * rows * cout * sum(nch * CHUNK_K for _, _, nch in taps)
         plan = C.c_void_p()
@@ -233,6 +236,10 @@ class Prep:
         C1 = 0 if x1 is None else x1.shape[1]
         d.x0, d.x1, d.C0, d.C1 = x0.data_ptr(), _ptr(x1), C0, C1
         d.stats0, d.stats1 = _ptr(stats0), _ptr(stats1)
+        for i, st in enumerate((stats0, stats1)):
+            if st is not None and st.dim() == 4:  # [R, instances, C, 2] replicated sums
+                setattr(d, f"stats_rep{i}", st.shape[0])
+                setattr(d, f"stats_rep_stride{i}", st.stride(0))
         d.pixels_per_inst, d.inst_per_group, d.groups, d.eps = pixels_per_inst, inst_per_group, groups, eps
         self.scratch = None
         if stats0 is not None:

@@ -299,7 +299,9 @@ class _Act:
         self.rows = N * H * W
         self._raw_store = eng.pool.get(self.rows * C * 4)
         self.raw = self._raw_store.view(torch.float32).view(self.rows, C)
-        self.stats = eng.take_stats(N, C)
+        # spread same-address atomics of the producer epilogue when many tiles share an instance
+        reps = max(1, min(8, (H * W) // 512))
+        self.stats = eng.take_stats(N, C, reps)
         self.refs = 1
 
 
@@ -339,12 +341,13 @@ class _UNetEngine:
         self._finalize_plans()
 
     # ---- buffers -----------------------------------------------------------
-    def take_stats(self, N, C):
-        """Reserve [N, C, 2] float64 in the stats arena (bound after the plan is known)."""
+    def take_stats(self, N, C, reps=1):
+        """Reserve [reps, N, C, 2] float64 in the stats arena (bound after the plan is known)."""
         holder: List[torch.Tensor] = []
-        self._stats_chunks.append((self._stats_total, N * C * 2, (N, C, 2)))
+        n = reps * N * C * 2
+        self._stats_chunks.append((self._stats_total, n, (reps, N, C, 2)))
         self._stats_views.append(holder)
-        self._stats_total += N * C * 2
+        self._stats_total += n
         return holder
 
     def hl(self, rows, cols) -> Tuple[HL, List[torch.Tensor]]:
