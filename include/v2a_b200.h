@@ -242,6 +242,9 @@ int v2a_grad_prep(const float* dy, int64_t rows, int C, int ld, void* hi, void* 
 /* dx = dy * act'(x), act 1 SiLU / 2 Mish; optional fp32 and hi/lo outputs */
 int v2a_act_bwd(const float* x, const float* dy, float* dx, void* hi, void* lo, int64_t n, int act,
                 void* stream);
+/* dst[r*ld_dst + c] (+)= src[r*ld_src + c], c < C (gradient fan-in of skip connections) */
+int v2a_add_strided(float* dst, int ld_dst, const float* src, int ld_src, int64_t rows, int C, int accumulate,
+                    void* stream);
 /* optimiser tail of the train step (lb_online_trainer_v7.py:608-624): global grad-norm clip,
  * AdamW, EMA; out[0] += sum g^2 */
 int v2a_grad_sumsq(const float* g, int64_t n, double* out, void* stream);

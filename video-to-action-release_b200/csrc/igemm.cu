@@ -51,7 +51,8 @@ std::atomic<int64_t> g_launches{0};
 // ---------------------------------------------------------------------------
 // kernel parameters
 // ---------------------------------------------------------------------------
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;                               // 4 control warps + 8 epilogue warps
+constexpr int kEpilogueThreads = 256;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                                 // bf16 elements per K step (128 B rows)
 constexpr int kATileBytes = kTileM * kChunkK * 2;           // 16 KB
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     uint64_t* tfull_bar = bars + 2 * S;    // [2]
     uint64_t* tempty_bar = bars + 2 * S + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
-    float* warp_add = reinterpret_cast<float*>(bars) + 64;  // 4 epilogue warps x 256 floats, after the 256 B barrier block
+    float* warp_add = reinterpret_cast<float*>(bars) + 64;  // 8 epilogue warps x 256 floats, after the 256 B barrier block
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 128);
+            mbar_init(&tempty_bar[s], kEpilogueThreads);
         }
         fence_mbar_init();
     } else if (warp == 1 && lane == 0) {
@@ -225,7 +226,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         // ===================== epilogue =====================
         const int quad = warp & 3;            // TMEM lane quarter this warp may read
         const int row = quad * 32 + lane;     // row of the 128-row tile
-        float* addv = warp_add + quad * 256;  // this warp's private bias(+rowvec) staging
+        const int half = (warp - 4) >> 2;     // two warps share a lane quarter and split the columns
+        float* addv = warp_add + (warp - 4) * 256;  // this warp's private bias(+rowvec) staging
+        const int nch = p.block_n >> 4;
+        const int c_begin = half == 0 ? 0 : ((nch + 1) >> 1) << 4;
+        const int c_end = half == 0 ? ((nch + 1) >> 1) << 4 : p.block_n;
         // same-address atomic contention is spread over `stats_replicas` copies of the sums
         double* const stats = p.stats ? p.stats + (long long)(blockIdx.x % p.stats_replicas) * p.stats_rep_stride : nullptr;
         int it = 0;
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 stats != nullptr && __all_sync(0xffffffffu, !valid || inst == inst0) && inst0 >= 0;
             // stage bias (+ the shared rowvec row) for this N tile: overlaps the tile's MMAs
             __syncwarp();
-            for (int c = lane; c < p.block_n; c += 32) {
+            for (int c = c_begin + lane; c < c_end; c += 32) {
                 float a = 0.0f;
                 if (n0 + c < p.cout) {
                     if (p.bias) a = __ldg(&p.bias[n0 + c]);
@@ -272,9 +277,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             __syncwarp();
             const float* res_row = p.residual ? p.residual + pix * p.ld_res + n0 : nullptr;
             float4 res_next[4];
-            if (res_row && valid) {
+            if (res_row && valid && c_begin < c_end) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) res_next[q] = __ldg(reinterpret_cast<const float4*>(res_row) + q);
+                for (int q = 0; q < 4; ++q) res_next[q] = *(reinterpret_cast<const float4*>(res_row + c_begin) + q);
             }
 
             mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
@@ -300,10 +305,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                             v[4 * q + 0] += res_next[q].x; v[4 * q + 1] += res_next[q].y;
                             v[4 * q + 2] += res_next[q].z; v[4 * q + 3] += res_next[q].w;
                         }
-                        if (c + 16 < p.block_n && n + 16 < p.cout) {  // prefetch the next chunk's residual
+                        if (c + 16 < c_end && n + 16 < p.cout) {  // prefetch the next chunk's residual
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
-                                res_next[q] = __ldg(reinterpret_cast<const float4*>(res_row + c + 16) + q);
+                                res_next[q] = *(reinterpret_cast<const float4*>(res_row + c + 16) + q);
                         }
                     }
                     if (p.out_f32) {
@@ -361,14 +366,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 
             // TMEM loads are software pipelined: chunk c+16 is in flight while chunk c is processed
             uint32_t ra[16], rb[16];
-            tmem_ld16(t_row, ra);
-            for (int c = 0; c < p.block_n; c += 32) {
+            if (c_begin < c_end) tmem_ld16(t_row + c_begin, ra);
+            for (int c = c_begin; c < c_end; c += 32) {
                 tmem_ld_wait16(ra);
-                if (c + 16 < p.block_n) tmem_ld16(t_row + c + 16, rb);
+                if (c + 16 < c_end) tmem_ld16(t_row + c + 16, rb);
                 process(ra, c);
-                if (c + 16 < p.block_n) {
+                if (c + 16 < c_end) {
                     tmem_ld_wait16(rb);
-                    if (c + 32 < p.block_n) tmem_ld16(t_row + c + 32, ra);
+                    if (c + 32 < c_end) tmem_ld16(t_row + c + 32, ra);
                     process(rb, c + 16);
                 }
             }
@@ -510,7 +515,7 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
     p.b_tile_bytes = (uint32_t)d->block_n * kChunkK * 2;
     p.stage_bytes = (uint32_t)d->passes == 3 ? 2 * (kATileBytes + p.b_tile_bytes)
                                              : (kATileBytes + p.b_tile_bytes);
-    const size_t overhead = 1024 /*align*/ + 256 /*barriers*/ + 4096 /*epilogue bias staging*/;
+    const size_t overhead = 1024 /*align*/ + 256 /*barriers*/ + 8192 /*epilogue bias staging*/;
     int stages = (int)((g_max_smem - overhead) / p.stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) {

@@ -324,6 +324,18 @@ __global__ void act_bwd_kernel(const float* __restrict__ x, const float* __restr
     }
 }
 
+// dst[r][c] (+)= src[r][c] over a column window of two row-pitched fp32 matrices
+__global__ void add_strided_kernel(float* dst, int ld_dst, const float* __restrict__ src, int ld_src,
+                                   int64_t rows, int C, int accumulate) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * C) return;
+    const int64_t r = i / C;
+    const int c = (int)(i % C);
+    const float v = src[r * ld_src + c];
+    float* d = dst + r * ld_dst + c;
+    *d = accumulate ? *d + v : v;
+}
+
 // fused clip-by-global-norm + AdamW + EMA over one flat parameter slab
 // (trainer: clip_grad_norm_(1.0); AdamW(lr, betas, eps, wd).step; EMA.update —
 //  diffuser/libero/lb_online_trainer_v7.py:608-624)
@@ -455,6 +467,15 @@ int v2a_act_bwd(const float* x, const float* dy, float* dx, void* hi, void* lo, 
                 void* stream) {
     act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         x, dy, dx, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n, act);
+    POL_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_add_strided(float* dst, int ld_dst, const float* src, int ld_src, int64_t rows, int C, int accumulate,
+                    void* stream) {
+    const int64_t n = rows * C;
+    add_strided_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dst, ld_dst, src, ld_src, rows,
+                                                                                      C, accumulate);
     POL_LAUNCH_OK();
     return 0;
 }
