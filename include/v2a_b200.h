@@ -226,6 +226,7 @@ typedef struct v2a_policy_gn_desc {
     float* dbeta;
     float* dfilm;            /* [B][ld_dfilm] += (d scale | d bias) */
     int ld_dfilm;
+    int64_t ld_T;            /* row pitch of dyT (>= B*T; the pad stays zero); 0 = B*T */
 } v2a_policy_gn_desc;
 int v2a_policy_gn_act_fwd(const v2a_policy_gn_desc* d, void* stream);
 int v2a_policy_gn_act_bwd(const v2a_policy_gn_desc* d, void* stream);
@@ -235,10 +236,10 @@ int v2a_policy_gn_act_bwd(const v2a_policy_gn_desc* d, void* stream);
  * operand of the weight-gradient GEMM dW[co][ci][k] = sum dy[b,o,co] x[b, s*o+off_k, ci] */
 int v2a_policy_im2col_t(const void* x_hi, const void* x_lo, int ld_x, int c_off, int B, int Tin, int Tout,
                         int C, int ntaps, int stride, const int* offsets, void* out_hi, void* out_lo,
-                        void* stream);
+                        int64_t ld_out, void* stream);
 /* dy fp32 [rows][ld] (C used) -> hl [rows][ld_hl] (zero padded), hl^T [C][rows], colsum[C] += */
 int v2a_grad_prep(const float* dy, int64_t rows, int C, int ld, void* hi, void* lo, int ld_hl, void* t_hi,
-                  void* t_lo, float* colsum, void* stream);
+                  void* t_lo, int64_t ld_T, float* colsum, void* stream);
 /* dx = dy * act'(x), act 1 SiLU / 2 Mish; optional fp32 and hi/lo outputs */
 int v2a_act_bwd(const float* x, const float* dy, float* dx, void* hi, void* lo, int64_t n, int act,
                 void* stream);

@@ -1,0 +1,137 @@
+"""GPU parity of the policy hot path (ConditionalUnet1D forward + backward through
+torch.autograd) against golden vectors from the unmodified reference and the CPU oracle.
+Tolerance (north_star): 1e-3 relative on the loss and on every parameter gradient."""
+import json
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+TOL = 1e-3
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _meta():
+    with open(os.path.join(HERE, "golden", "policy_golden_meta.json")) as f:
+        return json.load(f)
+
+
+def _run_ours(name, cfg):
+    from oracle import policy_oracle as PO
+    from tests.golden.configs import policy_inputs
+    from v2a_b200.policy_unet1d import ConditionalUnet1D
+    m = _meta()[name]
+    net = ConditionalUnet1D(**cfg)
+    sd = PO.seeded_policy_state_dict({k: tuple(v) for k, v in m["layout"].items()}, m["seed"])
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda()
+    traj, noise, t, gc = policy_inputs(m["B"], cfg, m["seed"])
+    acp = PO.ddpm_alphas_cumprod(100)
+    noisy = PO.add_noise(acp, traj, noise, t).cuda().requires_grad_(True)
+    gcd = gc.cuda().requires_grad_(True)
+    pred = net(noisy, t.cuda(), global_cond=gcd)
+    loss = F.mse_loss(pred, noise.cuda(), reduction="none").reshape(m["B"], -1).mean(1).mean()
+    loss.backward()
+    return net, sd, pred, loss, gcd, noisy, (traj, noise, t, gc, acp)
+
+
+@pytest.mark.parametrize("name", ["tiny", "libero"])
+def test_unet1d_forward_backward_matches_reference_golden(name):
+    from tests.golden.configs import POLICY_LIBERO, POLICY_TINY, grad_fingerprint
+    cfg = POLICY_TINY if name == "tiny" else POLICY_LIBERO
+    gold = torch.load(os.path.join(HERE, "golden", "policy_golden.pt"))
+    net, sd, pred, loss, gcd, noisy, _ = _run_ours(name, cfg)
+    assert rel_l2(pred, gold[f"{name}.pred"]) < TOL
+    assert abs(loss.item() - gold[f"{name}.loss"].item()) < TOL * abs(gold[f"{name}.loss"].item())
+    assert rel_l2(gcd.grad, gold[f"{name}.d_global_cond"]) < TOL
+    assert rel_l2(noisy.grad, gold[f"{name}.d_sample"]) < TOL
+    fps = _meta()[name]["grad_fingerprints"]
+    worst = 0.0
+    for k, p in net.named_parameters():
+        assert p.grad is not None, k
+        norm, proj = fps[k]
+        n2, p2 = grad_fingerprint(k, p.grad)
+        assert abs(n2 - norm) <= TOL * max(norm, 1e-8), (k, n2, norm)
+        # projection on a random direction: error bounded by TOL * |g| * sqrt(numel) (|r| ~ sqrt(numel))
+        assert abs(p2 - proj) <= TOL * max(norm, 1e-8) * (p.numel() ** 0.5), (k, p2, proj)
+        worst = max(worst, abs(n2 - norm) / max(norm, 1e-8))
+    print(f"{name}: worst gradient-norm deviation {worst:.2e}")
+
+
+def test_unet1d_every_gradient_matches_cpu_oracle_autograd():
+    from oracle import policy_oracle as PO
+    from tests.golden.configs import POLICY_TINY
+    net, sd, pred, loss, gcd, noisy, (traj, noise, t, gc, acp) = _run_ours("tiny", POLICY_TINY)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    gcr = gc.clone().requires_grad_(True)
+    nr = PO.add_noise(acp, traj, noise, t).requires_grad_(True)
+    pr = PO.unet1d_forward(sdr, nr, t, gcr)
+    lr = F.mse_loss(pr, noise, reduction="none").reshape(pr.shape[0], -1).mean(1).mean()
+    lr.backward()
+    assert rel_l2(pred, pr) < TOL
+    for k, p in net.named_parameters():
+        assert rel_l2(p.grad, sdr[k].grad) < TOL, k
+    assert rel_l2(gcd.grad, gcr.grad) < TOL and rel_l2(noisy.grad, nr.grad) < TOL
+    # second forward/backward on the same engine (static buffers, zeroed accumulators) gives the same grads
+    g0 = {k: p.grad.clone() for k, p in net.named_parameters()}
+    net.zero_grad()
+    pred2 = net(noisy.detach().requires_grad_(True), t.cuda(), global_cond=gcd.detach().requires_grad_(True))
+    F.mse_loss(pred2, noise.cuda(), reduction="none").reshape(pr.shape[0], -1).mean(1).mean().backward()
+    for k, p in net.named_parameters():
+        assert rel_l2(p.grad, g0[k]) < 1e-5, k
+    # int timestep + no-grad inference call (predict_action style)
+    with torch.no_grad():
+        o = net(noisy.detach(), 7, global_cond=gcd.detach())
+        r = PO.unet1d_forward(sd, noisy.detach().cpu(), torch.tensor(7), gc)
+    assert rel_l2(o, r) < TOL
+
+
+def test_policy_gn_kernels_match_autograd():
+    import ctypes as C
+    from v2a_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(0)
+    B, T, Cc, G = 5, 8, 64, 8
+    y = torch.randn(B, T, Cc, device="cuda", dtype=torch.float64, requires_grad=True)
+    gamma = torch.randn(Cc, device="cuda", dtype=torch.float64, requires_grad=True)
+    beta = torch.randn(Cc, device="cuda", dtype=torch.float64, requires_grad=True)
+    film = torch.randn(B, 2 * Cc, device="cuda", dtype=torch.float64, requires_grad=True)
+    ref = F.mish(F.group_norm(y.permute(0, 2, 1), G, gamma, beta, 1e-5))
+    ref = (film[:, :Cc, None] * ref + film[:, Cc:, None]).permute(0, 2, 1)
+    dout = torch.randn(B, T, Cc, device="cuda", dtype=torch.float64)
+    ref.backward(dout)
+    f32 = lambda t: t.detach().float().contiguous()
+    y32, g32, b32, f32_, d32 = f32(y), f32(gamma), f32(beta), f32(film), f32(dout)
+    out = torch.empty(B, T, Cc, device="cuda")
+    mr = torch.empty(B, G, 2, device="cuda")
+    d = _lib.PolicyGnDesc()
+    for k, v in dict(B=B, T=T, C=Cc, groups=G, eps=1e-5, y=y32, gamma=g32, beta=b32, film=f32_, ld_film=2 * Cc,
+                     out_f32=out, ld_out=Cc, mean_rstd=mr).items():
+        setattr(d, k, v.data_ptr() if torch.is_tensor(v) else v)
+    _lib.check(lib.v2a_policy_gn_act_fwd(C.byref(d), None))
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < 1e-5
+    kp = 64
+    dy = torch.empty(B, T, Cc, device="cuda")
+    dyh, dyl = torch.empty(B * T, Cc, device="cuda", dtype=torch.bfloat16), torch.empty(B * T, Cc, device="cuda", dtype=torch.bfloat16)
+    th, tl = torch.zeros(Cc, kp, device="cuda", dtype=torch.bfloat16), torch.zeros(Cc, kp, device="cuda", dtype=torch.bfloat16)
+    dbias, dga, dbe = (torch.zeros(Cc, device="cuda") for _ in range(3))
+    dfilm = torch.zeros(B, 2 * Cc, device="cuda")
+    for k, v in dict(dout=d32, ld_dout=Cc, dy_f32=dy, dy_hi=dyh, dy_lo=dyl, dyT_hi=th, dyT_lo=tl, ld_T=kp, dbias=dbias,
+                     dgamma=dga, dbeta=dbe, dfilm=dfilm, ld_dfilm=2 * Cc).items():
+        setattr(d, k, v.data_ptr() if torch.is_tensor(v) else v)
+    _lib.check(lib.v2a_policy_gn_act_bwd(C.byref(d), None))
+    torch.cuda.synchronize()
+    assert rel_l2(dy, y.grad) < 1e-4
+    assert rel_l2(dga, gamma.grad) < 1e-4 and rel_l2(dbe, beta.grad) < 1e-4 and rel_l2(dfilm, film.grad) < 1e-4
+    assert rel_l2(dbias, y.grad.sum((0, 1))) < 1e-4
+    assert rel_l2((dyh.float() + dyl.float()).reshape(B, T, Cc), y.grad) < 1e-4
+    assert rel_l2((th.float() + tl.float())[:, :B * T], y.grad.reshape(B * T, Cc).t()) < 1e-4
+    assert (th[:, B * T:] == 0).all()

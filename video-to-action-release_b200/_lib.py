@@ -105,6 +105,7 @@ class PolicyGnDesc(C.Structure):
         ("dy_f32", C.c_void_p),
         ("dbias", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
         ("dfilm", C.c_void_p), ("ld_dfilm", C.c_int),
+        ("ld_T", C.c_int64),
     ]
 
 
@@ -130,8 +131,8 @@ SIGNATURES = {
     "v2a_split_hl": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp]),
     "v2a_policy_gn_act_fwd": (_i, [C.POINTER(PolicyGnDesc), _vp]),
     "v2a_policy_gn_act_bwd": (_i, [C.POINTER(PolicyGnDesc), _vp]),
-    "v2a_policy_im2col_t": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _vp, _vp, _vp]),
-    "v2a_grad_prep": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "v2a_policy_im2col_t": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _vp, _vp, _i64, _vp]),
+    "v2a_grad_prep": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _i64, _vp, _vp]),
     "v2a_act_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "v2a_add_strided": (_i, [_vp, _i, _vp, _i, _i64, _i, _i, _vp]),
     "v2a_grad_sumsq": (_i, [_vp, _i64, _vp, _vp]),

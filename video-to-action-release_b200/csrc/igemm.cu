@@ -90,6 +90,7 @@ struct alignas(64) IgemmParams {
     int stats_ld;
     int stats_replicas;
     long long stats_rep_stride;
+    int debug;  // V2A_IGEMM_DEBUG bits: 1 skip stats, 2 skip stores, 4 skip residual (timing experiments only)
 };
 
 __device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int& n_idx, int o[4]) {
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         const int c_begin = half == 0 ? 0 : ((nch + 1) >> 1) << 4;
         const int c_end = half == 0 ? ((nch + 1) >> 1) << 4 : p.block_n;
         // same-address atomic contention is spread over `stats_replicas` copies of the sums
-        double* const stats = p.stats ? p.stats + (long long)(blockIdx.x % p.stats_replicas) * p.stats_rep_stride : nullptr;
+        double* const stats = (p.stats && !(p.debug & 1)) ? p.stats + (long long)(blockIdx.x % p.stats_replicas) * p.stats_rep_stride : nullptr;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 addv[c] = a;
             }
             __syncwarp();
-            const float* res_row = p.residual ? p.residual + pix * p.ld_res + n0 : nullptr;
+            const float* res_row = (p.residual && !(p.debug & 4)) ? p.residual + pix * p.ld_res + n0 : nullptr;
             float4 res_next[4];
             if (res_row && valid && c_begin < c_end) {
 #pragma unroll
@@ -311,13 +312,13 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                                 res_next[q] = *(reinterpret_cast<const float4*>(res_row + c + 16) + q);
                         }
                     }
-                    if (p.out_f32) {
+                    if (p.out_f32 && !(p.debug & 2)) {
                         float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * p.ldc + n);
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
                             op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                     }
-                    if (p.out_hi) {
+                    if (p.out_hi && !(p.debug & 2)) {
                         uint4 h0, l0, h1, l1;
                         split8(v, h0, l0);
                         split8(v + 8, h1, l1);
@@ -466,8 +467,9 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
     V2A_REQUIRE(d->passes == 1 || d->passes == 3, "igemm: passes must be 1 or 3");
     V2A_REQUIRE(d->block_n >= 16 && d->block_n <= 256 && d->block_n % 16 == 0,
                 "igemm: block_n %d must be a multiple of 16 in [16,256]", d->block_n);
-    V2A_REQUIRE(d->ldc % 16 == 0 && d->ldc >= d->cout, "igemm: ldc %d must be a multiple of 16 >= cout %d",
-                d->ldc, d->cout);
+    // 16-column chunks are stored whole: a partial last chunk needs the row padded to 16 columns
+    V2A_REQUIRE(d->ldc % (d->out_hi ? 8 : 4) == 0 && d->ldc >= ((d->cout + 15) / 16) * 16,
+                "igemm: ldc %d must be 16-byte aligned and >= cout %d rounded up to 16", d->ldc, d->cout);
     V2A_REQUIRE(d->out_f32 || d->out_hi, "igemm: no output tensor");
     V2A_REQUIRE(!d->out_hi || d->out_lo, "igemm: out_hi without out_lo");
     V2A_REQUIRE(!d->residual || d->ld_res % 4 == 0, "igemm: ld_res must be a multiple of 4");
@@ -538,6 +540,10 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
     p.stats_ld = d->stats_ld;
     p.stats_replicas = d->stats_replicas > 0 ? d->stats_replicas : 1;
     p.stats_rep_stride = d->stats_rep_stride;
+    {
+        const char* dbg = getenv("V2A_IGEMM_DEBUG");
+        p.debug = dbg ? atoi(dbg) : 0;
+    }
 
     // tensor maps: A boxes follow the output tile box; every source shares it
     int rc = 0;

@@ -31,7 +31,8 @@ struct GnActParams {
     // backward only
     const float* dout; int ld_dout;       // [B][T][ld_dout]
     __nv_bfloat16* dy_hi; __nv_bfloat16* dy_lo;     // [B][T][C]
-    __nv_bfloat16* dyT_hi; __nv_bfloat16* dyT_lo;   // [C][B*T]
+    __nv_bfloat16* dyT_hi; __nv_bfloat16* dyT_lo;   // [C][ld_T] (ld_T >= B*T, zero padded)
+    long long ld_T;
     float* dy_f32;                        // optional [B][T][C]
     float* dbias; float* dgamma; float* dbeta;      // [C] accumulated with atomics over samples
     float* dfilm; int ld_dfilm;           // [B][2C] written
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(kPolThreads) gn_act_bwd_kernel(const GnActPara
     if (!active) return;
     float dbi[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int i = 0;
-    const int64_t BT = (int64_t)p.B * p.T;
+    const int64_t BT = p.ld_T;
     for (int t = tlane; t < p.T; t += tl, ++i) {
         const int64_t row = (int64_t)b * p.T + t;
         float dy[8];
@@ -233,6 +234,7 @@ struct Im2colTParams {
     const __nv_bfloat16* x_hi; const __nv_bfloat16* x_lo;
     int ld_x, c_off;      // source row pitch and first channel (slice of a wider tensor)
     __nv_bfloat16* o_hi; __nv_bfloat16* o_lo;
+    long long ld_out;
     int B, Tin, Tout, C, ntaps, stride;
     int off[8];
 };
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(256) im2col_t_kernel(const Im2colTParams p) {
     const int64_t r = gid / p.B;
     const int k = (int)(r % p.ntaps);
     const int c = (int)(r / p.ntaps);
-    const int64_t BT = (int64_t)p.B * p.Tout;
+    const int64_t BT = p.ld_out;
     for (int o = 0; o < p.Tout; ++o) {
         const int t = p.stride * o + p.off[k];
         __nv_bfloat16 h = __float2bfloat16_rn(0.0f), l = h;
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(256) im2col_t_kernel(const Im2colTParams p) {
 __global__ void __launch_bounds__(256) grad_prep_kernel(const float* __restrict__ dy, int64_t rows, int C,
                                                         int ld, __nv_bfloat16* hi, __nv_bfloat16* lo,
                                                         int ld_hl, __nv_bfloat16* t_hi, __nv_bfloat16* t_lo,
-                                                        float* colsum) {
+                                                        long long ld_T, float* colsum) {
     __shared__ float tile[32][33];
     const int c_base = blockIdx.x * 32, r_base = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -290,8 +292,8 @@ __global__ void __launch_bounds__(256) grad_prep_kernel(const float* __restrict_
         if (c < C && r < rows && t_hi) {
             __nv_bfloat16 h, l;
             split_bf16(tile[tx][i], h, l);
-            t_hi[(int64_t)c * rows + r] = h;
-            t_lo[(int64_t)c * rows + r] = l;
+            t_hi[(int64_t)c * ld_T + r] = h;
+            t_lo[(int64_t)c * ld_T + r] = l;
         }
     }
     if (colsum && ty == 0) {
@@ -410,6 +412,7 @@ static GnActParams to_params(const v2a_policy_gn_desc* d) {
     p.dout = d->dout; p.ld_dout = d->ld_dout;
     p.dy_hi = (__nv_bfloat16*)d->dy_hi; p.dy_lo = (__nv_bfloat16*)d->dy_lo;
     p.dyT_hi = (__nv_bfloat16*)d->dyT_hi; p.dyT_lo = (__nv_bfloat16*)d->dyT_lo;
+    p.ld_T = d->ld_T > 0 ? d->ld_T : (long long)d->B * d->T;
     p.dy_f32 = d->dy_f32;
     p.dbias = d->dbias; p.dgamma = d->dgamma; p.dbeta = d->dbeta;
     p.dfilm = d->dfilm; p.ld_dfilm = d->ld_dfilm;
@@ -438,13 +441,14 @@ int v2a_policy_gn_act_bwd(const v2a_policy_gn_desc* d, void* stream) {
 
 int v2a_policy_im2col_t(const void* x_hi, const void* x_lo, int ld_x, int c_off, int B, int Tin, int Tout,
                         int C, int ntaps, int stride, const int* offsets, void* out_hi, void* out_lo,
-                        void* stream) {
+                        int64_t ld_out, void* stream) {
     V2A_REQUIRE(ntaps >= 1 && ntaps <= 8, "im2col_t: ntaps out of range");
     Im2colTParams p;
     p.x_hi = (const __nv_bfloat16*)x_hi; p.x_lo = (const __nv_bfloat16*)x_lo;
     p.ld_x = ld_x; p.c_off = c_off;
     p.o_hi = (__nv_bfloat16*)out_hi; p.o_lo = (__nv_bfloat16*)out_lo;
     p.B = B; p.Tin = Tin; p.Tout = Tout; p.C = C; p.ntaps = ntaps; p.stride = stride;
+    p.ld_out = ld_out > 0 ? ld_out : (long long)B * Tout;
     for (int i = 0; i < ntaps; ++i) p.off[i] = offsets[i];
     const int64_t total = (int64_t)C * ntaps * B;
     im2col_t_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
@@ -453,12 +457,12 @@ int v2a_policy_im2col_t(const void* x_hi, const void* x_lo, int ld_x, int c_off,
 }
 
 int v2a_grad_prep(const float* dy, int64_t rows, int C, int ld, void* hi, void* lo, int ld_hl, void* t_hi,
-                  void* t_lo, float* colsum, void* stream) {
+                  void* t_lo, int64_t ld_T, float* colsum, void* stream) {
     const int cw = ld_hl > C ? ld_hl : C;
     dim3 grid((unsigned)((cw + 31) / 32), (unsigned)((rows + 31) / 32));
     grad_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, rows, C, ld, (__nv_bfloat16*)hi,
                                                              (__nv_bfloat16*)lo, ld_hl, (__nv_bfloat16*)t_hi,
-                                                             (__nv_bfloat16*)t_lo, colsum);
+                                                             (__nv_bfloat16*)t_lo, ld_T > 0 ? ld_T : rows, colsum);
     POL_LAUNCH_OK();
     return 0;
 }

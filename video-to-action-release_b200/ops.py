@@ -166,15 +166,29 @@ class Igemm:
         d.block_n = block_n or choose_block_n(cout)
         d.passes = passes
         d.cout = cout
-        ldc = ldc or -(-cout // 16) * 16
-        d.ldc = ldc
         rows = out_dims[0] * out_dims[1] * out_dims[2] * out_dims[3]
+        # outputs may be column windows of wider row-pitched matrices: the pitch is the view's stride(0)
+        if ldc is None:
+            if out_f32 is not None and out_f32.dim() == 2:
+                ldc = out_f32.stride(0)
+            elif out_hl is not None and out_hl.hi.dim() == 2:
+                ldc = out_hl.hi.stride(0)
+            else:
+                ldc = -(-cout // 16) * 16
+        d.ldc = ldc
         self.rows, self.cout, self.ldc, self.ktot = rows, cout, ldc, ktot
         if out_f32 is not None:
-            assert out_f32.dtype == torch.float32 and out_f32.numel() == rows * ldc
+            assert out_f32.dtype == torch.float32
+            if out_f32.dim() == 2:
+                assert out_f32.shape[0] == rows and out_f32.stride(1) == 1 and out_f32.stride(0) == ldc
+            else:
+                assert out_f32.numel() == rows * ldc
             d.out_f32 = out_f32.data_ptr()
         if out_hl is not None:
-            assert out_hl.hi.numel() == rows * ldc
+            if out_hl.hi.dim() == 2:
+                assert out_hl.hi.shape[0] == rows and out_hl.hi.stride(0) == ldc == out_hl.lo.stride(0)
+            else:
+                assert out_hl.hi.numel() == rows * ldc
             d.out_hi, d.out_lo = out_hl.hi.data_ptr(), out_hl.lo.data_ptr()
         if bias is not None:
             assert bias.dtype == torch.float32 and bias.numel() >= cout
@@ -186,7 +200,7 @@ class Igemm:
         if residual is not None:
             assert residual.dtype == torch.float32
             d.residual = residual.data_ptr()
-            d.ld_res = residual.shape[-1]
+            d.ld_res = residual.stride(0) if residual.dim() == 2 else residual.shape[-1]
         if stats is not None:
             assert stats.dtype == torch.float64
             d.stats = stats.data_ptr()

@@ -10,10 +10,11 @@ is wrapped in a ``torch.autograd.Function`` whose backward runs a second planned
       -> GroupNorm+Mish+FiLM (one CTA per sample)           -> conv k5 -> GroupNorm+Mish
       -> + residual (identity: fused add; 1x1 conv: GEMM with the block result as residual)
   backward
-      GroupNorm/Mish/FiLM backward (one CTA per sample) emits dy (hi/lo), dy^T, bias/gamma/beta/FiLM grads
-      data gradient  = implicit GEMM over dy with flipped weights (accumulating in its epilogue)
+      GroupNorm/Mish/FiLM backward (one CTA per sample) emits dy (hi/lo), dy^T and the
+      bias / gamma / beta / FiLM gradients in one pass
+      data gradient   = implicit GEMM over dy with flipped weights (fan-in accumulates in its epilogue)
       weight gradient = GEMM dy^T x im2col^T(x), written straight into the parameter-gradient slab
-  all 12 FiLM linears run as ONE concatenated GEMM (forward, dgrad and wgrad).
+  all FiLM linears run as ONE concatenated GEMM (forward, dgrad and wgrad).
 
 Activations are channels-last [B, T, C] — exactly the layout ``sample`` arrives in, so the
 reference's two rearranges (conditional_unet1d.py:189,245) disappear.
@@ -23,10 +24,11 @@ from __future__ import annotations
 import ctypes as C
 import os
 import weakref
-from typing import Dict, List, Optional, Tuple, Union
+from typing import Callable, Dict, List, Optional, Union
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _lib, convs, ops
 from .ops import HL
@@ -135,8 +137,7 @@ class ConditionalUnet1D(nn.Module):
         t = t.expand(B).to(torch.int64)
         gc = global_cond if global_cond is not None else sample.new_zeros(B, 0)
         eng = _policy_engine(self, B, T, sample.device)
-        params = list(self.parameters())
-        return _UNet1DFunction.apply(self, eng, sample, t, gc, *params)
+        return _UNet1DFunction.apply(self, eng, sample, t, gc, *list(self.parameters()))
 
 
 def _policy_engine(model, B, T, device) -> "_PolicyEngine":
@@ -158,10 +159,9 @@ class _UNet1DFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, eng, sample, t, gc, *params):
         with torch.autocast("cuda", enabled=False):
-            out = eng.forward(model, sample.detach().float(), t, gc.detach().float())
+            out = eng.forward(sample.detach().float(), t, gc.detach().float())
         ctx.eng = eng
         ctx.token = eng.fwd_token
-        ctx.nparams = len(params)
         ctx.in_dtypes = (sample.dtype, gc.dtype)
         return out
 
@@ -170,7 +170,7 @@ class _UNet1DFunction(torch.autograd.Function):
         eng: _PolicyEngine = ctx.eng
         if ctx.token != eng.fwd_token:
             raise RuntimeError("v2a_b200.ConditionalUnet1D: backward() after another forward() on the same "
-                               "module/shape — activations are kept in static buffers (one forward per backward)")
+                               "module/shape — activations live in static buffers (one forward per backward)")
         with torch.autocast("cuda", enabled=False):
             d_sample, d_gc, pgrads = eng.backward(grad_out.float())
         return (None, None, d_sample.to(ctx.in_dtypes[0]), None, d_gc.to(ctx.in_dtypes[1]), *pgrads)
@@ -179,15 +179,23 @@ class _UNet1DFunction(torch.autograd.Function):
 # ---------------------------------------------------------------------------
 # engine
 # ---------------------------------------------------------------------------
-class _Ref:
-    """A column window of a row-pitched fp32 matrix (gradient buffers are shared through these)."""
+def _c16(n):
+    return -(-n // 16) * 16
 
-    def __init__(self, t: torch.Tensor, off: int, C: int):
-        self.t, self.off, self.C = t, off, C
-        self.ld = t.shape[1]
+
+def _c64(n):
+    return -(-n // 64) * 64
+
+
+class _Ref:
+    """Column window [off, off+C) of a row-pitched fp32 matrix t [rows, ld]."""
+
+    def __init__(self, t: torch.Tensor, off: int, Cc: int):
+        self.t, self.off, self.C = t, off, Cc
+        self.ld = t.stride(0)
 
     @property
-    def view(self):
+    def win(self):
         return self.t[:, self.off:self.off + self.C]
 
     @property
@@ -196,22 +204,13 @@ class _Ref:
 
 
 class _Node:
-    """An activation [B*T, C]: fp32 and/or hi/lo planes, plus its gradient window (set during backward planning)."""
+    """Activation [B*T, C] stored with row pitch ld (zero padded) as fp32 and/or hi/lo planes."""
 
-    def __init__(self, B, T, Cc, f32=None, hl=None, ld=None):
+    def __init__(self, B, T, Cc, ld=None, f32=None, hl=None):
         self.B, self.T, self.C = B, T, Cc
+        self.ld = ld or Cc
         self.f32, self.hl = f32, hl
-        self.ld = ld or Cc           # row pitch of hl / f32 (>= C when zero padded)
         self.grad: Optional[_Ref] = None
-
-
-def _gn_desc(**kw) -> _lib.PolicyGnDesc:
-    d = _lib.PolicyGnDesc()
-    for k, v in kw.items():
-        if isinstance(v, torch.Tensor):
-            v = v.data_ptr()
-        setattr(d, k, v)
-    return d
 
 
 class _PolicyEngine:
@@ -220,36 +219,31 @@ class _PolicyEngine:
         self.B, self.T, self.device = B, T, device
         self.passes = int(os.environ.get("V2A_PASSES", "3"))
         self.lib = _lib.load()
-        self.fwd: List = []
-        self.bwd: List = []
-        self.packers: List = []
-        self.vec_packers: List = []
-        self.keep: List = []
+        self.fwd: List[Callable] = []
+        self.bwd: List[Callable] = []
+        self.packers, self.vec_packers, self.keep = [], [], []
         self.fwd_token = 0
         self._wkey = None
         self.igemms: List[ops.Igemm] = []
-        f32 = dict(dtype=torch.float32, device=device)
-        params = list(model.parameters())
-        self.params = params
-        # flat parameter-gradient slab with per-parameter views
-        tot = sum(p.numel() for p in params)
-        self.gslab = torch.zeros(tot, **f32)
+        self.params = list(model.parameters())
+        tot = sum(p.numel() for p in self.params)
+        self.gslab = torch.zeros(tot, dtype=torch.float32, device=device)
         self.pgrad: Dict[int, torch.Tensor] = {}
         off = 0
-        for p in params:
+        for p in self.params:
             self.pgrad[id(p)] = self.gslab[off:off + p.numel()].view(p.shape)
             off += p.numel()
+        self._dcat: Dict[tuple, torch.Tensor] = {}
+        self._zero_each_bwd: List[torch.Tensor] = [self.gslab]
         self._build(model)
 
-    # ---- small helpers ------------------------------------------------------
-    def f32(self, rows, cols):
+    # ---- buffers / weights ---------------------------------------------------
+    def zeros(self, rows, cols):
         return torch.zeros(rows, cols, dtype=torch.float32, device=self.device)
 
-    def hlbuf(self, rows, cols) -> HL:
-        h = HL.empty(rows, cols, self.device)
-        h.hi.zero_()
-        h.lo.zero_()
-        return h
+    def hlz(self, rows, cols) -> HL:
+        return HL(torch.zeros(rows, cols, dtype=torch.bfloat16, device=self.device),
+                  torch.zeros(rows, cols, dtype=torch.bfloat16, device=self.device))
 
     def weight(self, fn, rows, cols) -> HL:
         hl = HL.empty(rows, cols, self.device)
@@ -275,111 +269,125 @@ class _PolicyEngine:
                 v.copy_(fn().detach().to(self.device, torch.float32).reshape(-1))
         self._wkey = key
 
-    def igemm(self, steps, **kw) -> ops.Igemm:
+    # ---- launch wrappers -------------------------------------------------------
+    def igemm(self, steps, **kw):
         g = ops.Igemm(passes=self.passes, **kw)
         self.igemms.append(g)
         steps.append(g.run)
-        return g
 
-    def call(self, steps, fn, *args):
-        steps.append(lambda: _lib.check(fn(*args, ops._stream()), fn.__name__ if hasattr(fn, "__name__") else "call"))
+    def gn(self, steps, backward: bool, **kw):
+        d = _lib.PolicyGnDesc()
+        for k, v in kw.items():
+            setattr(d, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+        self.keep.append((d, kw))
+        fn = self.lib.v2a_policy_gn_act_bwd if backward else self.lib.v2a_policy_gn_act_fwd
+        steps.append(lambda: _lib.check(fn(C.byref(d), ops._stream()), "policy_gn_act"))
 
-    def gn_fwd(self, desc):
-        self.keep.append(desc)
-        self.fwd.append(lambda: _lib.check(self.lib.v2a_policy_gn_act_fwd(C.byref(desc), ops._stream()), "gn_act_fwd"))
-
-    def gn_bwd(self, steps, desc):
-        self.keep.append(desc)
-        steps.append(lambda: _lib.check(self.lib.v2a_policy_gn_act_bwd(C.byref(desc), ops._stream()), "gn_act_bwd"))
-
-    def im2col_t(self, steps, src: HL, ld, c_off, B, Tin, Tout, Cc, offsets, stride, out: HL):
+    def im2col_t(self, steps, src: HL, ld, Bn, Tin, Tout, Cc, offsets, stride) -> HL:
+        """-> planes [Cc*len(offsets), pad64(Bn*Tout)] (zero padded K), the B operand of a weight-gradient GEMM."""
+        kpad = _c64(Bn * Tout)
+        out = self.hlz(Cc * len(offsets), kpad)
         arr = (C.c_int * len(offsets))(*offsets)
         self.keep.append(arr)
         steps.append(lambda: _lib.check(self.lib.v2a_policy_im2col_t(
-            src.hi.data_ptr(), src.lo.data_ptr(), ld, c_off, B, Tin, Tout, Cc, len(offsets), stride, arr,
-            out.hi.data_ptr(), out.lo.data_ptr(), ops._stream()), "im2col_t"))
+            src.hi.data_ptr(), src.lo.data_ptr(), ld, 0, Bn, Tin, Tout, Cc, len(offsets), stride, arr,
+            out.hi.data_ptr(), out.lo.data_ptr(), kpad, ops._stream()), "im2col_t"))
+        return out
 
-    def grad_prep(self, steps, ref: _Ref, rows, hl: Optional[HL], ld_hl, tr: Optional[HL], colsum):
+    def grad_prep(self, steps, ref: _Ref, rows, *, want_hl=True, colsum=None):
+        """fp32 gradient window -> (planes [rows, c16(C)], transposed planes [C, pad64(rows)]) (+ column sums)."""
+        ldh = _c16(ref.C)
+        hl = self.hlz(rows, ldh) if want_hl else None
+        kpad = _c64(rows)
+        tr = self.hlz(ref.C, kpad)
         steps.append(lambda: _lib.check(self.lib.v2a_grad_prep(
             ref.ptr, rows, ref.C, ref.ld, None if hl is None else hl.hi.data_ptr(),
-            None if hl is None else hl.lo.data_ptr(), ld_hl, None if tr is None else tr.hi.data_ptr(),
-            None if tr is None else tr.lo.data_ptr(), None if colsum is None else colsum.data_ptr(),
-            ops._stream()), "grad_prep"))
+            None if hl is None else hl.lo.data_ptr(), ldh, tr.hi.data_ptr(), tr.lo.data_ptr(), kpad,
+            None if colsum is None else colsum.data_ptr(), ops._stream()), "grad_prep"))
+        return hl, ldh, tr
 
     def add_into(self, steps, dst: _Ref, src: _Ref, rows, accumulate=True):
         steps.append(lambda: _lib.check(self.lib.v2a_add_strided(dst.ptr, dst.ld, src.ptr, src.ld, rows, dst.C,
                                                                 1 if accumulate else 0, ops._stream()), "add"))
 
-    # ---- gradient fan-in ----------------------------------------------------
-    def grad_target(self, node: _Node) -> Tuple[_Ref, bool]:
-        """Where a producer of d(node) must write, and whether it must accumulate."""
-        if node.grad is None:
-            node.grad = _Ref(self.f32(node.B * node.T, node.C), 0, node.C)
-            return node.grad, False
-        return node.grad, True
+    def act_bwd(self, steps, x, dy, dx, n, act):
+        steps.append(lambda: _lib.check(self.lib.v2a_act_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), None, None,
+                                                            n, act, ops._stream()), "act_bwd"))
 
-    # ---- generic conv (stride-1 Conv1d over [B, T, C], optionally over a 2-source concat) -----------------
-    def conv_fwd(self, conv: nn.Conv1d, ins: List[_Node], out_f32=None, out_hl=None, residual=None, ldc=None):
-        B, T = ins[0].B, ins[0].T
-        k, pad = conv.kernel_size[0], conv.padding[0]
-        cins = [n.C for n in ins]
-        cout = conv.out_channels
-        prog = convs.conv1d_cat([n.ld for n in ins], B, T, k, pad)
-        # weights sliced per source; sources narrower than their pitch (zero-padded input) read zeros
-        def wfn(conv=conv, ins=ins):
+    # ---- generic stride-1 conv over [B, T, C] (k taps; inputs may be a 2-way channel concat) -------------
+    def conv_fwd(self, wfn, bfn, cout, k, pad, ins: List[_Node], *, out_f32=None, out_hl=None, residual=None):
+        Bn, T = ins[0].B, ins[0].T
+        prog = convs.conv1d_cat([n.ld for n in ins], Bn, T, k, pad)
+
+        def packed(wfn=wfn, ins=ins):
+            w = wfn()
             parts, off = [], 0
             for n in ins:
                 for j in range(k):
-                    w = conv.weight[:, off:off + n.C, j]
-                    parts.append(torch.nn.functional.pad(w, (0, n.ld - n.C)) if n.ld != n.C else w)
+                    wj = w[:, off:off + n.C, j]
+                    parts.append(F.pad(wj, (0, n.ld - n.C)) if n.ld != n.C else wj)
                 off += n.C
             return ops.pack_weight_taps(parts)
-        w = self.weight(wfn, cout, prog.ktot)
-        b = self.vec(lambda conv=conv: conv.bias, cout)
+        w = self.weight(packed, cout, prog.ktot)
+        b = self.vec(bfn, cout) if bfn is not None else None
         self.igemm(self.fwd, srcs=[(n.hl, n.ld, d) for n, d in zip(ins, prog.src_dims)], taps=prog.taps, w=w,
-                   out_dims=prog.out_dims, cout=cout, ldc=ldc, out_f32=out_f32, out_hl=out_hl, bias=b,
-                   residual=residual)
+                   out_dims=prog.out_dims, cout=cout, out_f32=out_f32, out_hl=out_hl, bias=b, residual=residual)
 
-    def conv_bwd(self, steps, conv: nn.Conv1d, ins: List[_Node], dy_hl: HL, dyT_hl: HL, ld_dy: int,
-                 extra_residual: Optional[_Ref] = None):
-        """dW (into the gradient slab) and dX (fan-in aware) of a stride-1 Conv1d given dy planes."""
-        B, T = ins[0].B, ins[0].T
-        rows = B * T
-        k, pad = conv.kernel_size[0], conv.padding[0]
-        cout = conv.out_channels
+    def wgrad(self, steps, dyT: HL, m_rows, col: HL, ncols, target: torch.Tensor, col_off):
+        """target[:, col_off:col_off+ncols] = dyT [m_rows, K] x col [ncols, K]^T (fp32, straight into the slab)."""
+        kpad = dyT.hi.shape[1]
+        assert col.hi.shape[1] == kpad
+        prog = convs.pointwise(kpad, (m_rows,))
+        ntot = target.shape[1]
+        if ncols % 16 == 0 and col_off % 4 == 0 and ntot % 4 == 0:
+            self.igemm(steps, srcs=[(dyT, kpad, prog.src_dims[0])], taps=prog.taps, w=col, out_dims=prog.out_dims,
+                       cout=ncols, out_f32=target[:, col_off:col_off + ncols])
+        else:  # narrow / unaligned parameter (7-channel input or output): padded scratch, then a strided copy
+            tmp = self.zeros(m_rows, _c16(ncols))
+            self.igemm(steps, srcs=[(dyT, kpad, prog.src_dims[0])], taps=prog.taps, w=col, out_dims=prog.out_dims,
+                       cout=ncols, out_f32=tmp)
+            steps.append(lambda: target[:, col_off:col_off + ncols].copy_(tmp[:, :ncols]))
+
+    def conv_bwd(self, steps, wfn, wgrad_target, k, pad, ins: List[_Node], dy: HL, ld_dy, dyT: HL, cout,
+                 dx_residual: Optional[_Ref] = None):
+        """Weight gradient into `wgrad_target` [cout, cin_tot*k] and input gradient (fan-in aware)."""
+        Bn, T = ins[0].B, ins[0].T
+        rows = Bn * T
         cin_tot = sum(n.C for n in ins)
-        dW = self.pgrad[id(conv.weight)].view(cout, cin_tot * k)
         off = 0
-        for n in ins:  # weight gradient per concat part: dy^T [cout, rows] x im2col^T(x) [C*k, rows]
-            col = self.scratch_hl("col", n.C * k, rows)
-            self.im2col_t(steps, n.hl, n.ld, 0, B, T, T, n.C, [j - pad for j in range(k)], 1, col)
-            progw = convs.pointwise(rows, (cout,))
-            self.igemm(steps, srcs=[(dyT_hl, rows, progw.src_dims[0])], taps=progw.taps, w=col,
-                       out_dims=progw.out_dims, cout=n.C * k, ldc=cin_tot * k,
-                       out_f32=_window(dW, off * k, n.C * k))
+        for n in ins:
+            col = self.im2col_t(steps, n.hl, n.ld, Bn, T, T, n.C, [j - pad for j in range(k)], 1)
+            self.wgrad(steps, dyT, cout, col, n.C * k, wgrad_target, off * k)
             off += n.C
-        # data gradient over the whole (concatenated) input, then fan out to the parts
-        need = [n for n in ins if n.f32 is not None or n.grad is not None or getattr(n, "needs_grad", True)]
-        if not need:
-            return
-        progd = convs.conv1d(ld_dy, B, T, k, pad)
-        wd = self.weight(lambda conv=conv: torch.nn.functional.pad(
-            convs.conv1d_dgrad_weight(conv.weight), (0, 0)), cin_tot, None)
-        # (cols fixed below: K = k * pad64(ld_dy); conv1d_dgrad_weight pads Cout to 64 per tap already)
+        progd = convs.conv1d(ld_dy, Bn, T, k, pad)
+
+        def packed_d(wfn=wfn):
+            w = wfn()  # [cout, cin_tot, k]; dgrad taps ascend in offset: j = k-1 .. 0
+            parts = [F.pad(w[:, :, j].t(), (0, ld_dy - cout)) if ld_dy != cout else w[:, :, j].t()
+                     for j in reversed(range(k))]
+            return ops.pack_weight_taps(parts)
+        wd = self.weight(packed_d, cin_tot, progd.ktot)
+        src = [(dy, ld_dy, progd.src_dims[0])]
         if len(ins) == 1:
-            tgt, acc = self.grad_target(ins[0])
-            res = tgt if acc else extra_residual
-            if acc and extra_residual is not None:
-                self.add_into(steps, tgt, extra_residual, rows)
-            self.igemm(steps, srcs=[(dy_hl, ld_dy, progd.src_dims[0])], taps=progd.taps, w=wd,
-                       out_dims=progd.out_dims, cout=cin_tot, ldc=tgt.ld, out_f32=_window(tgt.t, tgt.off, tgt.C),
-                       residual=None if res is None else _window(res.t, res.off, res.C))
-        else:
-            dcat = self.f32(rows, cin_tot)
-            self.igemm(steps, srcs=[(dy_hl, ld_dy, progd.src_dims[0])], taps=progd.taps, w=wd,
-                       out_dims=progd.out_dims, cout=cin_tot, out_f32=dcat,
-                       residual=None if extra_residual is None else _window(extra_residual.t, extra_residual.off,
-                                                                           extra_residual.C))
+            n = ins[0]
+            if n.grad is None:
+                n.grad = _Ref(self.zeros(rows, _c16(n.C)), 0, n.C)
+                res = dx_residual
+            else:
+                if dx_residual is not None:
+                    self.add_into(steps, n.grad, dx_residual, rows)
+                res = n.grad
+            self.igemm(steps, srcs=src, taps=progd.taps, w=wd, out_dims=progd.out_dims, cout=cin_tot,
+                       out_f32=n.grad.t[:, n.grad.off:n.grad.off + _c16(n.C)] if n.grad.C % 16 else n.grad.win,
+                       residual=None if res is None else (res.t[:, res.off:res.off + _c16(res.C)] if res.C % 16 else res.win))
+            return
+        assert dx_residual is None
+        key = tuple(id(n) for n in ins)
+        dcat = self._dcat.get(key)
+        if dcat is None:  # first gradient into this concat: parts become windows of one buffer
+            dcat = self.zeros(rows, cin_tot)
+            self._dcat[key] = dcat
+            self.igemm(steps, srcs=src, taps=progd.taps, w=wd, out_dims=progd.out_dims, cout=cin_tot, out_f32=dcat)
             off = 0
             for n in ins:
                 part = _Ref(dcat, off, n.C)
@@ -388,21 +396,277 @@ class _PolicyEngine:
                 else:
                     self.add_into(steps, n.grad, part, rows)
                 off += n.C
+        else:         # further gradients accumulate in place in the GEMM epilogue
+            assert all(n.grad is not None and n.grad.t is dcat for n in ins)
+            self.igemm(steps, srcs=src, taps=progd.taps, w=wd, out_dims=progd.out_dims, cout=cin_tot, out_f32=dcat,
+                       residual=dcat)
 
-    def scratch_hl(self, tag, rows, cols) -> HL:
-        """Reusable scratch planes (backward runs sequentially on one stream)."""
-        key = (tag, rows * cols)
-        pool = self.__dict__.setdefault("_scratch", {})
-        if key not in pool:
-            pool[key] = HL.empty(rows * cols, 1, self.device)
-        h = pool[key]
-        return HL(h.hi.view(rows, cols), h.lo.view(rows, cols))
-
-    # ---- plan -----------------------------------------------------------------
+    # ---- network plan ------------------------------------------------------------
     def _build(self, model: ConditionalUnet1D):
-        raise NotImplementedError  # replaced below (kept separate for readability)
+        Bn, T, dev = self.B, self.T, self.device
+        dsed, gcd = model.dsed, model.global_cond_dim
+        cd = dsed + gcd
+        G = model.n_groups
+        g = lambda p: self.pgrad[id(p)]
+        self.tape: List[Callable] = []       # backward planners, run in reverse
+        # ---------------- conditioning path ----------------
+        self.t_buf = torch.zeros(Bn, dtype=torch.int64, device=dev)
+        temb = self.zeros(Bn, dsed)
+        temb_hl = self.hlz(Bn, dsed)
+        self.fwd.append(lambda: ops.timestep_embedding(self.t_buf, dsed, 1, temb))
+        self.fwd.append(lambda: _lib.check(self.lib.v2a_split_hl(temb.data_ptr(), Bn, dsed, dsed, temb_hl.hi.data_ptr(),
+                                                                temb_hl.lo.data_ptr(), ops._stream()), "split"))
+        lin1, lin3 = model.diffusion_step_encoder[1], model.diffusion_step_encoder[3]
+        n_temb = _Node(Bn, 1, dsed, hl=temb_hl)
+        a1 = self.zeros(Bn, 4 * dsed)
+        self.conv_fwd(lambda: lin1.weight.unsqueeze(-1), lambda: lin1.bias, 4 * dsed, 1, 0, [n_temb], out_f32=a1)
+        m1_hl = self.hlz(Bn, 4 * dsed)
+        p1 = ops.Prep(x0=a1, act=ops.ACT_MISH, out_hl=m1_hl)
+        self.fwd.append(p1.run)
+        n_m1 = _Node(Bn, 1, 4 * dsed, hl=m1_hl)
+        self.gf = self.zeros(Bn, cd)
+        self.conv_fwd(lambda: lin3.weight.unsqueeze(-1), lambda: lin3.bias, dsed, 1, 0, [n_m1],
+                      out_f32=self.gf[:, :dsed])
+        self.gc_in = self.gf[:, dsed:]
+        mgf_hl = self.hlz(Bn, cd)
+        p2 = ops.Prep(x0=self.gf, act=ops.ACT_MISH, out_hl=mgf_hl)
+        self.fwd.append(p2.run)
+        n_mgf = _Node(Bn, 1, cd, hl=mgf_hl)
+        blocks = [m for m in model.modules() if isinstance(m, ConditionalResidualBlock1D)]
+        ftot = sum(2 * m.out_channels for m in blocks)
+        self.film = self.zeros(Bn, ftot)
+        self.dfilm = self.zeros(Bn, ftot)
+        self._zero_each_bwd.append(self.dfilm)
+        film_off, o = {}, 0
+        for m in blocks:
+            film_off[id(m)] = o
+            o += 2 * m.out_channels
+        wfilm = lambda: torch.cat([m.cond_encoder[1].weight for m in blocks], 0).unsqueeze(-1)
+        self.conv_fwd(wfilm, lambda: torch.cat([m.cond_encoder[1].bias for m in blocks], 0), ftot, 1, 0, [n_mgf],
+                      out_f32=self.film)
 
+        # ---------------- residual blocks ----------------
+        def res_block(m: ConditionalResidualBlock1D, ins: List[_Node]) -> _Node:
+            Tn, rows, Co = ins[0].T, Bn * ins[0].T, m.out_channels
+            k, pad = m.blocks[0].block[0].kernel_size[0], m.blocks[0].block[0].padding[0]
+            c1, gn1 = m.blocks[0].block[0], m.blocks[0].block[1]
+            c2, gn2 = m.blocks[1].block[0], m.blocks[1].block[1]
+            fo = film_off[id(m)]
+            y1, y2 = self.zeros(rows, Co), self.zeros(rows, Co)
+            mr1, mr2 = self.zeros(Bn, 2 * G), self.zeros(Bn, 2 * G)
+            hf = _Node(Bn, Tn, Co, hl=self.hlz(rows, Co))
+            out = _Node(Bn, Tn, Co, f32=self.zeros(rows, Co), hl=self.hlz(rows, Co))
+            ga1, be1 = self.vec(lambda: gn1.weight, Co), self.vec(lambda: gn1.bias, Co)
+            ga2, be2 = self.vec(lambda: gn2.weight, Co), self.vec(lambda: gn2.bias, Co)
+            film_ptr = self.film.data_ptr() + 4 * fo
+            self.conv_fwd(lambda: c1.weight, lambda: c1.bias, Co, k, pad, ins, out_f32=y1)
+            self.gn(self.fwd, False, B=Bn, T=Tn, C=Co, groups=G, eps=gn1.eps, y=y1, gamma=ga1, beta=be1,
+                    film=film_ptr, ld_film=ftot, out_hi=hf.hl.hi, out_lo=hf.hl.lo, ld_hl=Co, mean_rstd=mr1)
+            self.conv_fwd(lambda: c2.weight, lambda: c2.bias, Co, k, pad, [hf], out_f32=y2)
+            has_res = not isinstance(m.residual_conv, nn.Identity)
+            if has_res:
+                h2 = self.zeros(rows, Co)
+                self.gn(self.fwd, False, B=Bn, T=Tn, C=Co, groups=G, eps=gn2.eps, y=y2, gamma=ga2, beta=be2,
+                        out_f32=h2, ld_out=Co, mean_rstd=mr2)
+                rc = m.residual_conv
+                self.conv_fwd(lambda: rc.weight, lambda: rc.bias, Co, 1, 0, ins, out_f32=out.f32, out_hl=out.hl,
+                              residual=h2)
+            else:
+                x = ins[0]
+                self.gn(self.fwd, False, B=Bn, T=Tn, C=Co, groups=G, eps=gn2.eps, y=y2, gamma=ga2, beta=be2,
+                        addend=x.f32, ld_add=x.f32.stride(0), out_f32=out.f32, ld_out=Co, out_hi=out.hl.hi,
+                        out_lo=out.hl.lo, ld_hl=Co, mean_rstd=mr2)
 
-def _window(t: torch.Tensor, off: int, C_: int) -> torch.Tensor:
-    """Column window view whose data_ptr / row pitch the kernels use (rows stay pitched by t.shape[1])."""
-    return t[:, off:off + C_]
+            def plan_bwd():
+                st = self.bwd
+                dO = out.grad
+                assert dO is not None
+                kp = _c64(rows)
+                dy2, dy2T = self.hlz(rows, Co), self.hlz(Co, kp)
+                self.gn(st, True, B=Bn, T=Tn, C=Co, groups=G, eps=gn2.eps, y=y2, gamma=ga2, beta=be2, mean_rstd=mr2,
+                        dout=dO.ptr, ld_dout=dO.ld, dy_hi=dy2.hi, dy_lo=dy2.lo, dyT_hi=dy2T.hi, dyT_lo=dy2T.lo,
+                        ld_T=kp, dbias=g(c2.bias), dgamma=g(gn2.weight), dbeta=g(gn2.bias))
+                self.conv_bwd(st, lambda: c2.weight, g(c2.weight).view(Co, -1), k, pad, [hf], dy2, Co, dy2T, Co)
+                dy1, dy1T = self.hlz(rows, Co), self.hlz(Co, kp)
+                self.gn(st, True, B=Bn, T=Tn, C=Co, groups=G, eps=gn1.eps, y=y1, gamma=ga1, beta=be1, mean_rstd=mr1,
+                        film=film_ptr, ld_film=ftot, dout=hf.grad.ptr, ld_dout=hf.grad.ld, dy_hi=dy1.hi, dy_lo=dy1.lo,
+                        dyT_hi=dy1T.hi, dyT_lo=dy1T.lo, ld_T=kp, dbias=g(c1.bias), dgamma=g(gn1.weight),
+                        dbeta=g(gn1.bias), dfilm=self.dfilm.data_ptr() + 4 * fo, ld_dfilm=ftot)
+                if has_res:
+                    rc = m.residual_conv
+                    dOh, ldh, dOT = self.grad_prep(st, dO, rows, colsum=g(rc.bias))
+                    self.conv_bwd(st, lambda: rc.weight, g(rc.weight).view(Co, -1), 1, 0, ins, dOh, ldh, dOT, Co)
+                    self.conv_bwd(st, lambda: c1.weight, g(c1.weight).view(Co, -1), k, pad, ins, dy1, Co, dy1T, Co)
+                else:
+                    self.conv_bwd(st, lambda: c1.weight, g(c1.weight).view(Co, -1), k, pad, ins, dy1, Co, dy1T, Co,
+                                  dx_residual=dO)
+            self.tape.append(plan_bwd)
+            return out
+
+        def down(mod: Downsample1d, x: _Node) -> _Node:
+            Cc, Tn = x.C, x.T
+            conv = mod.conv
+            out = _Node(Bn, Tn // 2, Cc, f32=self.zeros(Bn * Tn // 2, Cc), hl=self.hlz(Bn * Tn // 2, Cc))
+            prog = convs.down1d(Cc, Bn, Tn)
+            w = self.weight(lambda: convs.conv1d_weight(conv.weight), Cc, prog.ktot)
+            b = self.vec(lambda: conv.bias, Cc)
+            self.igemm(self.fwd, srcs=[(x.hl, Cc, prog.src_dims[0])], taps=prog.taps, w=w, out_dims=prog.out_dims,
+                       cout=Cc, out_f32=out.f32, out_hl=out.hl, bias=b)
+
+            def plan_bwd():
+                st, rows_o = self.bwd, Bn * Tn // 2
+                dOh, ldh, dOT = self.grad_prep(st, out.grad, rows_o, colsum=g(conv.bias))
+                col = self.im2col_t(st, x.hl, x.ld, Bn, Tn, Tn // 2, Cc, [-1, 0, 1], 2)
+                self.wgrad(st, dOT, Cc, col, Cc * 3, g(conv.weight).view(Cc, -1), 0)
+                progd = convs.down1d_dgrad(ldh, Bn, Tn)
+                wd = self.weight(lambda: convs.down1d_dgrad_weight(conv.weight), 2 * Cc, progd.ktot)
+                tmp = self.zeros(rows_o, 2 * Cc)  # == [B*T, C] memory
+                self.igemm(st, srcs=[(dOh, ldh, progd.src_dims[0])], taps=progd.taps, w=wd, out_dims=progd.out_dims,
+                           cout=2 * Cc, out_f32=tmp)
+                part = _Ref(tmp.view(Bn * Tn, Cc), 0, Cc)
+                if x.grad is None:
+                    x.grad = part
+                else:
+                    self.add_into(st, x.grad, part, Bn * Tn)
+            self.tape.append(plan_bwd)
+            return out
+
+        def up(mod: Upsample1d, x: _Node) -> _Node:
+            Cc, Tn = x.C, x.T
+            conv = mod.conv
+            rows = Bn * Tn
+            o32, ohl = self.zeros(rows, 2 * Cc), self.hlz(rows, 2 * Cc)
+            out = _Node(Bn, 2 * Tn, Cc, f32=o32.view(2 * rows, Cc),
+                        hl=HL(ohl.hi.view(2 * rows, Cc), ohl.lo.view(2 * rows, Cc)))
+            prog = convs.up1d(Cc, Bn, Tn)
+            w = self.weight(lambda: convs.up1d_weight(conv.weight), 2 * Cc, prog.ktot)
+            b = self.vec(lambda: torch.cat([conv.bias, conv.bias]), 2 * Cc)
+            self.igemm(self.fwd, srcs=[(x.hl, Cc, prog.src_dims[0])], taps=prog.taps, w=w, out_dims=prog.out_dims,
+                       cout=2 * Cc, out_f32=o32, out_hl=ohl, bias=b)
+
+            def plan_bwd():
+                st = self.bwd
+                dOh, ldh, _ = self.grad_prep(st, out.grad, 2 * rows, colsum=g(conv.bias))
+                # dWt[ci, co, k] = x^T [C, B*T] x im2col^T(dy, stride 2, offsets k-1) [C*4, B*T]
+                xT = self.im2col_t(st, x.hl, x.ld, Bn, Tn, Tn, Cc, [0], 1)
+                col = self.im2col_t(st, dOh, ldh, Bn, 2 * Tn, Tn, Cc, [-1, 0, 1, 2], 2)
+                self.wgrad(st, xT, Cc, col, Cc * 4, g(conv.weight).view(Cc, -1), 0)
+                progd = convs.up1d_dgrad(ldh, Bn, Tn)
+                wd = self.weight(lambda: convs.up1d_dgrad_weight(conv.weight), Cc, progd.ktot)
+                if x.grad is None:
+                    x.grad = _Ref(self.zeros(rows, Cc), 0, Cc)
+                    res = None
+                else:
+                    res = x.grad.win
+                self.igemm(st, srcs=[(dOh, ldh, progd.src_dims[0])], taps=progd.taps, w=wd, out_dims=progd.out_dims,
+                           cout=Cc, out_f32=x.grad.win, residual=res)
+            self.tape.append(plan_bwd)
+            return out
+
+        # ---------------- UNet ----------------
+        din = model.input_dim
+        self.x_in_base = self.zeros(Bn * T, 16)               # input rows zero padded to 16 channels
+        self.x_in = self.x_in_base[:, :din]
+        x0 = _Node(Bn, T, din, ld=16, f32=None, hl=self.hlz(Bn * T, 16))
+        self.x0 = x0
+        self.fwd.append(lambda: _lib.check(self.lib.v2a_split_hl(self.x_in_base.data_ptr(), Bn * T, 16, 16,
+                                                                x0.hl.hi.data_ptr(), x0.hl.lo.data_ptr(),
+                                                                ops._stream()), "split"))
+        x, hs = x0, []
+        for (r1, r2, dn) in model.down_modules:
+            x = res_block(r1, [x])
+            x = res_block(r2, [x])
+            hs.append(x)
+            if not isinstance(dn, nn.Identity):
+                x = down(dn, x)
+        for m in model.mid_modules:
+            x = res_block(m, [x])
+        for (r1, r2, upm) in model.up_modules:
+            x = res_block(r1, [x, hs.pop()])
+            x = res_block(r2, [x])
+            if not isinstance(upm, nn.Identity):
+                x = up(upm, x)
+        # final: Conv1dBlock (default 8 groups) + 1x1 conv to input_dim (row padded to 16)
+        fb, fc = model.final_conv[0].block, model.final_conv[1]
+        Cs, rows = x.C, Bn * T
+        assert x.T == T
+        yf, mrf = self.zeros(rows, Cs), self.zeros(Bn, 2 * fb[1].num_groups)
+        hfin = _Node(Bn, T, Cs, hl=self.hlz(rows, Cs))
+        gaf, bef = self.vec(lambda: fb[1].weight, Cs), self.vec(lambda: fb[1].bias, Cs)
+        kf, pf = fb[0].kernel_size[0], fb[0].padding[0]
+        self.conv_fwd(lambda: fb[0].weight, lambda: fb[0].bias, Cs, kf, pf, [x], out_f32=yf)
+        self.gn(self.fwd, False, B=Bn, T=T, C=Cs, groups=fb[1].num_groups, eps=fb[1].eps, y=yf, gamma=gaf, beta=bef,
+                out_hi=hfin.hl.hi, out_lo=hfin.hl.lo, ld_hl=Cs, mean_rstd=mrf)
+        self.out16 = self.zeros(rows, 16)
+        self.conv_fwd(lambda: fc.weight, lambda: fc.bias, din, 1, 0, [hfin], out_f32=self.out16)
+        self.dout16 = self.zeros(rows, 16)
+        x_last = x
+
+        def plan_final_bwd():
+            st = self.bwd
+            dO = _Ref(self.dout16, 0, din)
+            dOh, ldh, dOT = self.grad_prep(st, dO, rows, colsum=g(fc.bias))
+            self.conv_bwd(st, lambda: fc.weight, g(fc.weight).view(din, -1), 1, 0, [hfin], dOh, ldh, dOT, din)
+            kp = _c64(rows)
+            dyf, dyfT = self.hlz(rows, Cs), self.hlz(Cs, kp)
+            self.gn(st, True, B=Bn, T=T, C=Cs, groups=fb[1].num_groups, eps=fb[1].eps, y=yf, gamma=gaf, beta=bef,
+                    mean_rstd=mrf, dout=hfin.grad.ptr, ld_dout=hfin.grad.ld, dy_hi=dyf.hi, dy_lo=dyf.lo,
+                    dyT_hi=dyfT.hi, dyT_lo=dyfT.lo, ld_T=kp, dbias=g(fb[0].bias), dgamma=g(fb[1].weight),
+                    dbeta=g(fb[1].bias))
+            self.conv_bwd(st, lambda: fb[0].weight, g(fb[0].weight).view(Cs, -1), kf, pf, [x_last], dyf, Cs, dyfT, Cs)
+        self.tape.append(plan_final_bwd)
+
+        # ---------------- backward plan: tape in reverse, then the conditioning path ----------------
+        for planner in reversed(self.tape):
+            planner()
+        st = self.bwd
+        dF = _Ref(self.dfilm, 0, ftot)
+        self.dbfilm = torch.zeros(ftot, dtype=torch.float32, device=dev)
+        self.dwfilm = self.zeros(ftot, cd)
+        self._zero_each_bwd.append(self.dbfilm)
+        dFh, ldF, dFT = self.grad_prep(st, dF, Bn, colsum=self.dbfilm)
+        self.conv_bwd(st, wfilm, self.dwfilm, 1, 0, [n_mgf], dFh, ldF, dFT, ftot)
+        dgf = self.zeros(Bn, cd)
+        self.act_bwd(st, self.gf, n_mgf.grad.t, dgf, Bn * cd, 2)
+        self.dgf = dgf
+
+        def scatter_film():
+            o = 0
+            for m in blocks:
+                n2 = 2 * m.out_channels
+                g(m.cond_encoder[1].weight).copy_(self.dwfilm[o:o + n2])
+                g(m.cond_encoder[1].bias).copy_(self.dbfilm[o:o + n2])
+                o += n2
+        st.append(scatter_film)
+        ddse = _Ref(dgf, 0, dsed)
+        d3h, ld3, d3T = self.grad_prep(st, ddse, Bn, colsum=g(lin3.bias))
+        self.conv_bwd(st, lambda: lin3.weight.unsqueeze(-1), g(lin3.weight), 1, 0, [n_m1], d3h, ld3, d3T, dsed)
+        da1 = self.zeros(Bn, 4 * dsed)
+        self.act_bwd(st, a1, n_m1.grad.t, da1, Bn * 4 * dsed, 2)
+        d1h, ld1, d1T = self.grad_prep(st, _Ref(da1, 0, 4 * dsed), Bn, colsum=g(lin1.bias))
+        self.conv_bwd(st, lambda: lin1.weight.unsqueeze(-1), g(lin1.weight), 1, 0, [n_temb], d1h, ld1, d1T, 4 * dsed)
+
+    # ---- execution -----------------------------------------------------------------
+    def forward(self, sample, t, gc):
+        self.refresh_weights()
+        Bn, T = self.B, self.T
+        self.t_buf.copy_(t)
+        self.x_in.copy_(sample.reshape(Bn * T, -1))
+        if self.gc_in.shape[1]:
+            self.gc_in.copy_(gc)
+        for s in self.fwd:
+            s()
+        self.fwd_token += 1
+        return self.out16[:, :self.x0.C].reshape(Bn, T, -1).clone()
+
+    def backward(self, grad_out):
+        Bn, T = self.B, self.T
+        for z in self._zero_each_bwd:
+            z.zero_()
+        self.dout16[:, :self.x0.C].copy_(grad_out.reshape(Bn * T, -1))
+        for s in self.bwd:
+            s()
+        d_sample = self.x0.grad.win.reshape(Bn, T, -1).clone()
+        d_gc = self.dgf[:, self.dgf.shape[1] - self.gc_in.shape[1]:].clone()
+        pgrads = [self.pgrad[id(p)].clone() for p in self.params]
+        return d_sample, d_gc, pgrads
