@@ -21,6 +21,7 @@ dp/ = diffuser/diffusion_policy/model/ in the reference checkout.
 from __future__ import annotations
 
 import math
+import re
 from typing import Dict, List, Optional
 
 import torch
@@ -139,4 +140,36 @@ def seeded_policy_state_dict(shapes: Dict[str, tuple], seed: int) -> SD:
             # ConvTranspose1d weights are [Cin, Cout, k]; fan-in is still prod(shape[1:]) up to k/stride
             v = torch.randn(shp, generator=g) / math.sqrt(max(1, math.prod(shp[1:])))
         sd[name] = v
+    return sd
+
+
+def seeded_full_policy_state_dict(layout: Dict[str, list], seed: int) -> SD:
+    """Weights for the WHOLE DiffusionUnetImagePolicy state_dict (414 keys: UNet1D + two VisualCore
+    encoders, whose Sequential aliases 'nets.0...' / 'backbone...' must carry the SAME tensor)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: SD = {}
+    canon: Dict[str, Tensor] = {}
+    for name in layout:
+        shp = tuple(layout[name])
+        leaf = name.rsplit(".", 1)[-1]
+        # VisualCore registers backbone/pool both directly and inside .nets (Sequential): alias by canonical key
+        key = re.sub(r"^(.*key_model_map\.[^.]+)\.nets\.0\.", r"\1.backbone.", name)
+        key = re.sub(r"^(.*key_model_map\.[^.]+)\.nets\.1\.", r"\1.pool.", key)
+        if key in canon:
+            sd[name] = canon[key]
+            continue
+        if leaf in ("pos_x", "pos_y", "temperature"):
+            v = None                                  # buffers keep their constructed values (merge with
+                                                      # the module's own state_dict before loading)
+        elif len(shp) == 0 or math.prod(shp) == 0:
+            v = torch.zeros(shp)
+        elif leaf == "weight" and len(shp) == 1:
+            v = 1.0 + 0.2 * torch.randn(shp, generator=g)
+        elif leaf == "bias":
+            v = 0.1 * torch.randn(shp, generator=g)
+        else:
+            v = torch.randn(shp, generator=g) / math.sqrt(max(1, math.prod(shp[1:])))
+        if v is not None:
+            canon[key] = v
+            sd[name] = v
     return sd

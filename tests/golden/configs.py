@@ -51,3 +51,11 @@ def grad_fingerprint(name, grad):
     r = torch.randn(grad.shape, generator=g, dtype=torch.float64)
     gd = grad.detach().double().cpu()
     return [gd.norm().item(), (gd * r).sum().item()]
+
+
+def policy_loss_batch(B, seed):
+    """compute_loss batch in the trainer's format (lb_online_trainer_v7.py:1296-1310)."""
+    g = torch.Generator().manual_seed(seed)
+    return {"obs": {"img_obs_1": torch.rand(B, 1, 3, 128, 128, generator=g),
+                    "img_goal_1": torch.rand(B, 1, 3, 128, 128, generator=g)},
+            "action": torch.rand(B, 16, 7, generator=g) * 2 - 1}

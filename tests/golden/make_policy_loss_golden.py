@@ -1,0 +1,66 @@
+"""Golden vectors for DiffusionUnetImagePolicy.compute_loss from the UNMODIFIED reference policy class,
+observation encoder and normaliser (run in the build container only:
+python tests/golden/make_policy_loss_golden.py).  The diffusers schedulers are absent offline; the
+reference class receives the restated scheduler objects of v2a_b200.diffusion_policy (third-party
+boundary: parity unpinned by reference tests, see oracle/policy_oracle.py)."""
+import importlib
+import json
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import ref_import as R  # noqa: E402
+from oracle import policy_oracle as PO  # noqa: E402
+from tests.golden.configs import grad_fingerprint, policy_loss_batch  # noqa: E402
+
+
+def build_reference_policy():
+    R.install_shims()
+    from v2a_b200 import diffusion_policy as DP
+    pol = importlib.import_module("diffuser.diffusion_policy.diffusion_unet_image_policy")
+    moe = importlib.import_module("diffuser.diffusion_policy.model.multi_image_obs_encoder")
+    vn = importlib.import_module("diffuser.diffusion_policy.common.vision_nets")
+    meta = DP.libero_shape_meta()
+    core = vn.VisualCore(input_shape=[3, 128, 128], backbone_class="ResNet18Conv",
+                         backbone_kwargs=dict(pretrained=None, input_coord_conv=False), pool_class="SpatialSoftmax",
+                         pool_kwargs=dict(num_kp=32, learnable_temperature=False, temperature=1.0, noise_std=0.0,
+                                          output_variance=False), flatten=True, feature_dimension=64)
+    enc = moe.MultiImageObsEncoder(meta, core, use_group_norm=True)
+    sched = dict(num_train_timesteps=100, beta_start=0.0001, beta_end=0.02, beta_schedule="squaredcos_cap_v2",
+                 clip_sample=True, prediction_type="epsilon")
+    return pol.DiffusionUnetImagePolicy(meta, DP.DDPMScheduler(**sched), DP.DDIMScheduler(**sched), enc, horizon=16,
+                                        n_action_steps=8, n_obs_steps=1, num_inference_steps=100,
+                                        diffusion_step_embed_dim=128, down_dims=[256, 512, 1024], kernel_size=5,
+                                        n_groups=8, cond_predict_scale=True)
+
+
+def main():
+    B, seed = 2, 21
+    policy = build_reference_policy()
+    layout = {k: list(v.shape) for k, v in policy.state_dict().items()}
+    sd = policy.state_dict()
+    sd.update(PO.seeded_full_policy_state_dict(layout, seed))
+    policy.load_state_dict(sd, strict=True)
+    policy.train()
+    batch = policy_loss_batch(B, seed)
+    torch.manual_seed(seed)                       # the RNG stream compute_loss consumes
+    loss = policy.compute_loss(batch)
+    loss.backward()
+    fps = {n: grad_fingerprint(n, p.grad) for n, p in policy.named_parameters() if p.grad is not None}
+    # inference entry: 8-step DDIM from a seeded stream, eval mode
+    policy.eval()
+    torch.manual_seed(seed + 1)
+    with torch.no_grad():
+        act = policy.predict_action(batch["obs"], use_ddim=True)
+    out = {"loss": loss.detach(), "action": act["action"], "action_pred": act["action_pred"]}
+    torch.save(out, os.path.join(HERE, "policy_loss_golden.pt"))
+    with open(os.path.join(HERE, "policy_loss_golden_meta.json"), "w") as f:
+        json.dump({"layout": layout, "grad_fingerprints": fps, "B": B, "seed": seed}, f)
+    print("loss", loss.item(), "params with grad", len(fps), "action", tuple(act["action"].shape))
+
+
+if __name__ == "__main__":
+    main()

@@ -135,3 +135,129 @@ def test_policy_gn_kernels_match_autograd():
     assert rel_l2((dyh.float() + dyl.float()).reshape(B, T, Cc), y.grad) < 1e-4
     assert rel_l2((th.float() + tl.float())[:, :B * T], y.grad.reshape(B * T, Cc).t()) < 1e-4
     assert (th[:, B * T:] == 0).all()
+
+
+def test_fused_train_step_matches_torch_adamw_clip_ema():
+    """PolicyTrainStep (slab gradients -> v2a_grad_sumsq -> v2a_adamw_ema_step) against the trainer's
+    torch sequence clip_grad_norm_(1.0) / AdamW.step / EMA.update on the SAME CUDA forward+backward."""
+    import copy
+    from oracle import policy_oracle as PO
+    from tests.golden.configs import POLICY_TINY, policy_inputs
+    from v2a_b200.policy_unet1d import ConditionalUnet1D
+    from v2a_b200.train_step import PolicyTrainStep, ema_decay
+
+    class Wrapped(torch.nn.Module):
+        """UNet1D plus a small torch 'encoder' producing global_cond (the autograd-accumulated segment)."""
+
+        def __init__(self, net, gcd):
+            super().__init__()
+            self.enc = torch.nn.Linear(gcd, gcd)
+            self.model = net
+
+        def loss(self, noisy, t, raw, noise):
+            pred = self.model(noisy, t, global_cond=self.enc(raw))
+            return F.mse_loss(pred, noise, reduction="none").reshape(noise.shape[0], -1).mean(1).mean()
+
+    m = _meta()["tiny"]
+    net = ConditionalUnet1D(**POLICY_TINY)
+    net.load_state_dict(PO.seeded_policy_state_dict({k: tuple(v) for k, v in m["layout"].items()}, m["seed"]))
+    torch.manual_seed(5)
+    a = Wrapped(net, POLICY_TINY["global_cond_dim"]).cuda()
+    b = copy.deepcopy(a)
+    hp = dict(lr=1e-2, betas=(0.95, 0.999), eps=1e-8, weight_decay=1e-2)   # large lr / wd so every term shows
+    opt = torch.optim.AdamW(b.parameters(), **hp)
+    ema_b = copy.deepcopy(b)
+    step = PolicyTrainStep(a, max_norm=1.0, **hp)
+    acp = PO.ddpm_alphas_cumprod(100)
+    for it in range(4):
+        traj, noise, t, gc = policy_inputs(m["B"], POLICY_TINY, seed=100 + it)
+        noisy = (PO.add_noise(acp, traj, noise, t) * (30.0 if it == 1 else 1.0)).cuda()  # it 1: clip engages
+        t, gc, noise = t.cuda(), gc.cuda(), noise.cuda()
+        # ONE backward (ours, slab mode); the torch optimiser gets the very same gradients, so the
+        # comparison isolates the fused tail (Adam amplifies the run-to-run atomics noise of two backwards)
+        la = a.loss(noisy, t, gc, noise)
+        la.backward()
+        from v2a_b200 import policy_unet1d as PU
+        gslab = PU.last_engine(a.model).gslab
+        off = 0
+        for p_a, p_b in zip(a.model.parameters(), b.model.parameters()):
+            p_b.grad = gslab[off:off + p_a.numel()].view(p_a.shape).clone()
+            off += p_a.numel()
+        for p_a, p_b in zip(a.enc.parameters(), b.enc.parameters()):
+            p_b.grad = p_a.grad.clone()
+        step.optimizer_tail()
+        with torch.no_grad():
+            lb = b.loss(noisy, t, gc, noise) if it == 0 else la   # same weights at it 0: same loss
+        total = torch.nn.utils.clip_grad_norm_(b.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad()
+        d = ema_decay(it)
+        with torch.no_grad():
+            for pe, pb in zip(ema_b.parameters(), b.parameters()):
+                pe.copy_(pb) if d == 0.0 else pe.lerp_(pb, 1.0 - d)
+        assert abs(la.item() - lb.item()) <= 1e-4 * abs(lb.item()), it
+        assert abs(step.grad_norm().item() - total.item()) <= 1e-4 * total.item(), it
+        if it == 1:
+            assert total.item() > 1.0
+        for (k, pa), pb in zip(a.named_parameters(), b.parameters()):
+            assert rel_l2(pa, pb) < 1e-5, (it, k)
+    ema_a = copy.deepcopy(b)
+    step.copy_ema_to(ema_a)
+    for (k, pa), pb in zip(ema_a.named_parameters(), ema_b.parameters()):
+        assert rel_l2(pa, pb) < 1e-5, k
+    # the module still exposes the reference's state_dict layout after its parameters moved into slabs
+    assert list(a.model.state_dict().keys()) == list(m["layout"].keys())
+
+
+def _cpu_stream_noise(monkeypatch):
+    """The golden was produced on CPU: replay that generator stream (draw on CPU, move to the GPU)."""
+    from v2a_b200 import diffusion_policy as DP
+    monkeypatch.setattr(DP, "_randn", lambda shape, device, dtype=torch.float32, generator=None:
+                        torch.randn(tuple(shape), dtype=dtype).to(device))
+    monkeypatch.setattr(DP, "_randint", lambda high, shape, device: torch.randint(0, high, shape).long().to(device))
+
+
+def test_compute_loss_and_predict_action_match_reference_policy_golden(monkeypatch):
+    """DiffusionUnetImagePolicy.compute_loss (fwd + every parameter gradient, encoders included) and the
+    8-step DDIM predict_action against the UNMODIFIED reference policy (tests/golden/make_policy_loss_golden.py)."""
+    from oracle import policy_oracle as PO
+    from tests.golden.configs import grad_fingerprint, policy_loss_batch
+    from v2a_b200 import diffusion_policy as DP
+    with open(os.path.join(HERE, "golden", "policy_loss_golden_meta.json")) as f:
+        meta = json.load(f)
+    gold = torch.load(os.path.join(HERE, "golden", "policy_loss_golden.pt"))
+    _cpu_stream_noise(monkeypatch)
+    pol = DP.build_libero_policy()
+    sd = pol.state_dict()
+    sd.update(PO.seeded_full_policy_state_dict(meta["layout"], meta["seed"]))
+    pol.load_state_dict(sd, strict=True)
+    pol = pol.to("cuda")
+    pol.train()
+    # fp32 truth setting for the cuDNN encoder (SURVEY.md §8g.13): TF32 off
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    batch = policy_loss_batch(meta["B"], meta["seed"])
+    dev = {"obs": {k: v.cuda() for k, v in batch["obs"].items()}, "action": batch["action"].cuda()}
+    torch.manual_seed(meta["seed"])
+    loss = pol.compute_loss(dev)
+    loss.backward()
+    assert abs(loss.item() - gold["loss"].item()) < TOL * abs(gold["loss"].item())
+    worst, n = 0.0, 0
+    for k, p in pol.named_parameters():
+        if k not in meta["grad_fingerprints"]:
+            continue
+        norm, proj = meta["grad_fingerprints"][k]
+        n2, p2 = grad_fingerprint(k, p.grad)
+        assert abs(n2 - norm) <= TOL * max(norm, 1e-8), (k, n2, norm)
+        assert abs(p2 - proj) <= TOL * max(norm, 1e-8) * (p.numel() ** 0.5), (k, p2, proj)
+        worst = max(worst, abs(n2 - norm) / max(norm, 1e-8))
+        n += 1
+    assert n == len(meta["grad_fingerprints"]) == 276
+    pol.eval()
+    torch.manual_seed(meta["seed"] + 1)
+    with torch.no_grad():
+        act = pol.predict_action(dev["obs"], use_ddim=True)
+    assert act["action"].shape == (meta["B"], 8, 7) and act["action_pred"].shape == (meta["B"], 16, 7)
+    assert rel_l2(act["action_pred"], gold["action_pred"]) < TOL
+    assert rel_l2(act["action"], gold["action"]) < TOL
+    print(f"compute_loss {loss.item():.7f} (gold {gold['loss'].item():.7f}); worst gradient-norm deviation {worst:.2e}")

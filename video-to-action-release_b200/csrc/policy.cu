@@ -343,7 +343,13 @@ __global__ void add_strided_kernel(float* dst, int ld_dst, const float* __restri
 //  diffuser/libero/lb_online_trainer_v7.py:608-624)
 __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, double* out) {
     float s = 0.0f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = ((reinterpret_cast<uintptr_t>(g) & 15) == 0) ? (n >> 2) : 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 q = reinterpret_cast<const float4*>(g)[i];
+        s += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+    }
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         s += g[i] * g[i];
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     __shared__ float w[32];
@@ -355,29 +361,49 @@ __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, double* out
         atomicAdd(out, t);
     }
 }
+__device__ __forceinline__ void adamw_ema_one(float& pi, const float gi_raw, float& mi, float& vi, float* ei,
+                                              float clip, float lr, float beta1, float beta2, float eps, float wd,
+                                              float bc1, float rsqrt_bc2, float ema_decay) {
+    const float gi = gi_raw * clip;
+    pi *= (1.0f - lr * wd);                            // decoupled weight decay
+    mi = beta1 * mi + (1.0f - beta1) * gi;
+    vi = beta2 * vi + (1.0f - beta2) * gi * gi;
+    const float denom = sqrtf(vi) * rsqrt_bc2 + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    if (ei) *ei = *ei - (1.0f - ema_decay) * (*ei - pi);  // ema.lerp_(p, 1 - decay)
+}
+// 16-byte accesses over the slab (7 HBM streams: read p g m v ema, write p m v ema); scalar tail
 __global__ void adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, float* __restrict__ ema, int64_t n,
                                  const double* __restrict__ sumsq, float max_norm, float lr, float beta1,
                                  float beta2, float eps, float wd, float bc1, float bc2, float ema_decay) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     float clip = 1.0f;
     if (max_norm > 0.0f) {
         const float total = (float)sqrt(*sumsq);
         const float c = max_norm / (total + 1e-6f);   // torch clip_grad_norm_
         clip = c < 1.0f ? c : 1.0f;
     }
-    const float gi = g[i] * clip;
-    float pi = p[i];
-    pi *= (1.0f - lr * wd);                            // decoupled weight decay
-    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
-    pi -= (lr / bc1) * (mi / denom);
-    p[i] = pi;
-    if (ema) ema[i] = ema[i] - (1.0f - ema_decay) * (ema[i] - pi);  // ema.lerp_(p, 1 - decay)
+    const float rs2 = 1.0f / sqrtf(bc2);
+    const int64_t n4 = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 pp = reinterpret_cast<float4*>(p)[i];
+        const float4 gg = reinterpret_cast<const float4*>(g)[i];
+        float4 mm = reinterpret_cast<float4*>(m)[i];
+        float4 vv = reinterpret_cast<float4*>(v)[i];
+        float4 ee = ema ? reinterpret_cast<float4*>(ema)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        adamw_ema_one(pp.x, gg.x, mm.x, vv.x, ema ? &ee.x : nullptr, clip, lr, beta1, beta2, eps, wd, bc1, rs2, ema_decay);
+        adamw_ema_one(pp.y, gg.y, mm.y, vv.y, ema ? &ee.y : nullptr, clip, lr, beta1, beta2, eps, wd, bc1, rs2, ema_decay);
+        adamw_ema_one(pp.z, gg.z, mm.z, vv.z, ema ? &ee.z : nullptr, clip, lr, beta1, beta2, eps, wd, bc1, rs2, ema_decay);
+        adamw_ema_one(pp.w, gg.w, mm.w, vv.w, ema ? &ee.w : nullptr, clip, lr, beta1, beta2, eps, wd, bc1, rs2, ema_decay);
+        reinterpret_cast<float4*>(p)[i] = pp;
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+        if (ema) reinterpret_cast<float4*>(ema)[i] = ee;
+    }
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        adamw_ema_one(p[i], g[i], m[i], v[i], ema ? &ema[i] : nullptr, clip, lr, beta1, beta2, eps, wd, bc1, rs2,
+                      ema_decay);
 }
 
 }  // namespace v2a
@@ -498,7 +524,12 @@ int v2a_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema,
                        float weight_decay, int step, float ema_decay, void* stream) {
     const float bc1 = 1.0f - powf(beta1, (float)step);
     const float bc2 = 1.0f - powf(beta2, (float)step);
-    adamw_ema_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    V2A_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)ema) % 16 == 0,
+                "adamw_ema_step: slabs must be 16-byte aligned");
+    int64_t blocks = ((n >> 2) + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;   // grid-stride: a multiple of the SM count
+    if (blocks < 1) blocks = 1;
+    adamw_ema_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         p, g, m, v, ema, n, grad_sumsq, max_norm, lr, beta1, beta2, eps, weight_decay, bc1, bc2, ema_decay);
     POL_LAUNCH_OK();
     return 0;

@@ -1,0 +1,478 @@
+"""Goal-conditioned diffusion policy behind the reference's call surface.
+
+Mirrors ``DiffusionUnetImagePolicy`` (diffuser/diffusion_policy/diffusion_unet_image_policy.py:15-283):
+same constructor arguments (the observation encoder and the two noise schedulers are injected, as
+``Init_Diffusion_Policy`` does at diffuser/diffusion_policy/get_dp.py:27-89), ``compute_loss(batch)``,
+``predict_action(obs_dict, use_ddim)``, ``conditional_sample`` and ``.to()`` moving the normaliser.
+
+What runs where:
+  * P2-P5  ``self.model`` = v2a_b200 ``ConditionalUnet1D``: planned CUDA forward + backward (the hot path);
+  * P7     ``add_noise`` and the scheduler steps: restated here — ``diffusers`` is a third-party
+           dependency the reference leaves unpinned (requirements.txt:4) and is absent offline;
+  * P6     the observation encoder (2x ResNet18-GroupNorm + SpatialSoftmax, 80 % of compute_loss FLOPs,
+           not named by north_star) stays on torch/cuDNN this round (row N1 is next): the modules below
+           only restate its structure with the reference's ``state_dict`` names.
+
+RNG order of ``compute_loss`` follows the reference: SpatialSoftmax draws (goal, then
+obs encoder, training mode only), ``randn(trajectory.shape)``, ``randint(0, T, (B,))``.
+"""
+from __future__ import annotations
+
+import copy
+import math
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .policy_unet1d import ConditionalUnet1D
+
+
+# ---------------------------------------------------------------------------
+# noise draws (module-level so tests can replay a CPU stream)
+# ---------------------------------------------------------------------------
+def _randn(shape, device, dtype=torch.float32, generator=None):
+    return torch.randn(shape, device=device, dtype=dtype, generator=generator)
+
+
+def _randint(high, shape, device):
+    return torch.randint(0, high, shape, device=device).long()
+
+
+# ---------------------------------------------------------------------------
+# schedulers (diffusers DDPMScheduler / DDIMScheduler restated for the yaml's settings:
+# squaredcos_cap_v2, epsilon | sample prediction, clip_sample, fixed_small variance, eta = 0)
+# config/diff_policy/lb_train_diffusion_unet_image_orn10.yaml:45-53,101-113
+# ---------------------------------------------------------------------------
+def squaredcos_cap_v2_betas(num_train_timesteps: int, max_beta: float = 0.999) -> torch.Tensor:
+    """betas_for_alpha_bar with alpha_bar(s) = cos^2((s + .008) / 1.008 * pi / 2); in-repo twin of the
+    formula: flowdiffusion/.../guided_diffusion/gaussian_diffusion.py:45-62."""
+    bar = lambda s: math.cos((s + 0.008) / 1.008 * math.pi / 2) ** 2
+    T = num_train_timesteps
+    return torch.tensor([min(1 - bar((i + 1) / T) / bar(i / T), max_beta) for i in range(T)], dtype=torch.float32)
+
+
+class _SchedulerBase:
+    def __init__(self, num_train_timesteps=100, beta_start=0.0001, beta_end=0.02,
+                 beta_schedule="squaredcos_cap_v2", clip_sample=True, prediction_type="epsilon", **extra):
+        if beta_schedule != "squaredcos_cap_v2":
+            raise NotImplementedError("only the squaredcos_cap_v2 schedule of the Libero policy yaml is restated")
+        self.config = SimpleNamespace(num_train_timesteps=num_train_timesteps, beta_start=beta_start,
+                                      beta_end=beta_end, beta_schedule=beta_schedule, clip_sample=clip_sample,
+                                      prediction_type=prediction_type, **extra)
+        self.betas = squaredcos_cap_v2_betas(num_train_timesteps)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.one = torch.tensor(1.0)
+        self.num_inference_steps = None
+        self.timesteps = torch.arange(num_train_timesteps - 1, -1, -1)
+
+    def add_noise(self, original_samples, noise, timesteps):
+        """sqrt(acp_t) x0 + sqrt(1 - acp_t) eps, coefficients broadcast over trailing dims."""
+        acp = self.alphas_cumprod.to(device=original_samples.device, dtype=original_samples.dtype)
+        t = timesteps.to(original_samples.device)
+        a, b = acp[t] ** 0.5, (1 - acp[t]) ** 0.5
+        while a.dim() < original_samples.dim():
+            a, b = a.unsqueeze(-1), b.unsqueeze(-1)
+        return a * original_samples + b * noise
+
+    def _x0(self, model_output, sample, a_t):
+        pt = self.config.prediction_type
+        if pt == "epsilon":
+            x0 = (sample - (1 - a_t) ** 0.5 * model_output) / a_t ** 0.5
+        elif pt == "sample":
+            x0 = model_output
+        else:
+            raise ValueError(f"Unsupported prediction type {pt}")
+        return x0.clamp(-1.0, 1.0) if self.config.clip_sample else x0
+
+
+class DDPMScheduler(_SchedulerBase):
+    def __init__(self, variance_type="fixed_small", **kw):
+        super().__init__(variance_type=variance_type, **kw)
+
+    def set_timesteps(self, num_inference_steps: int):
+        T = self.config.num_train_timesteps
+        self.num_inference_steps = num_inference_steps
+        ratio = T // num_inference_steps
+        self.timesteps = torch.from_numpy((np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64))
+
+    def step(self, model_output, timestep, sample, generator=None, **kw):
+        t = int(timestep)
+        n = self.num_inference_steps or self.config.num_train_timesteps
+        prev = t - self.config.num_train_timesteps // n
+        acp = self.alphas_cumprod
+        a_t = acp[t]
+        a_prev = acp[prev] if prev >= 0 else self.one
+        b_t, b_prev = 1 - a_t, 1 - a_prev
+        cur_a = a_t / a_prev
+        cur_b = 1 - cur_a
+        x0 = self._x0(model_output, sample, a_t)
+        mean = (a_prev ** 0.5 * cur_b / b_t) * x0 + (cur_a ** 0.5 * b_prev / b_t) * sample
+        if t > 0:
+            var = (b_prev / b_t * cur_b).clamp(min=1e-20)   # fixed_small
+            mean = mean + var ** 0.5 * _randn(model_output.shape, model_output.device, model_output.dtype, generator)
+        return SimpleNamespace(prev_sample=mean, pred_original_sample=x0)
+
+
+class DDIMScheduler(_SchedulerBase):
+    def __init__(self, set_alpha_to_one=True, steps_offset=0, **kw):
+        super().__init__(set_alpha_to_one=set_alpha_to_one, steps_offset=steps_offset, **kw)
+        self.final_alpha_cumprod = self.one if set_alpha_to_one else self.alphas_cumprod[0]
+
+    def set_timesteps(self, num_inference_steps: int):
+        T = self.config.num_train_timesteps
+        self.num_inference_steps = num_inference_steps
+        ratio = T // num_inference_steps            # "leading" spacing: [84, 72, ..., 0] for 8 of 100
+        ts = (np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64)
+        self.timesteps = torch.from_numpy(ts + self.config.steps_offset)
+
+    def step(self, model_output, timestep, sample, eta: float = 0.0, generator=None, **kw):
+        t = int(timestep)
+        prev = t - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev] if prev >= 0 else self.final_alpha_cumprod
+        x0 = self._x0(model_output, sample, a_t)
+        eps = model_output if self.config.prediction_type == "epsilon" else \
+            (sample - a_t ** 0.5 * x0) / (1 - a_t) ** 0.5
+        var = (1 - a_prev) / (1 - a_t) * (1 - a_t / a_prev)
+        std = eta * var ** 0.5
+        out = a_prev ** 0.5 * x0 + (1 - a_prev - std ** 2) ** 0.5 * eps
+        if eta > 0:
+            out = out + std * _randn(model_output.shape, model_output.device, model_output.dtype, generator)
+        return SimpleNamespace(prev_sample=out, pred_original_sample=x0)
+
+
+# ---------------------------------------------------------------------------
+# constant [min, max] -> [-1, 1] normalisers (diffuser/diffusion_policy/normalizer.py:11-147)
+# ---------------------------------------------------------------------------
+class LimitsConstNormalizer:
+    def __init__(self, min_max, in_shape):
+        self.mins = torch.as_tensor(np.asarray(min_max[0], dtype=np.float32)).reshape(*in_shape)
+        self.maxs = torch.as_tensor(np.asarray(min_max[1], dtype=np.float32)).reshape(*in_shape)
+
+    def __call__(self, x):
+        return self.normalize(x)
+
+    def normalize(self, x):
+        return 2 * ((x - self.mins) / (self.maxs - self.mins)) - 1
+
+    def unnormalize(self, x, eps=0):
+        if x.max() > 1 + eps or x.min() < -1 - eps:
+            x = torch.clamp(x, -1, 1)
+        return (x + 1) / 2.0 * (self.maxs - self.mins) + self.mins
+
+
+class ConstNormalizerGroup:
+    """One normaliser per obs key plus 'action'; shape_meta[...]['minmax_shape'] = (min, max, shape)."""
+
+    def __init__(self, normalizer, shape_meta, n_obs_steps):
+        if isinstance(normalizer, str):
+            normalizer = eval(normalizer)
+        self.normalizers = {}
+        entries = dict(shape_meta["obs"])
+        entries["action"] = shape_meta["action"]
+        for key, attr in entries.items():
+            mn, mx, shp = attr["minmax_shape"]
+            shp = list(shp)
+            steps = 1  # horizon axis broadcasts for the action; n_obs_steps == 1 on this path
+            self.normalizers[key] = normalizer((mn, mx), (shp[0], steps, *shp[1:]))
+
+    def __call__(self, x, key):
+        return self.normalize(x, key)
+
+    def __getitem__(self, key):
+        return self.normalizers[key]
+
+    def normalize(self, x, key):
+        return self.normalizers[key].normalize(x)
+
+    def unnormalize(self, x, key):
+        return self.normalizers[key].unnormalize(x)
+
+    def normalize_d(self, obs_dict):
+        return {k: self.normalize(v, k) for k, v in obs_dict.items()}
+
+    def to_device(self, *args, **kwargs):
+        for n in self.normalizers.values():
+            n.mins, n.maxs = n.mins.to(*args, **kwargs), n.maxs.to(*args, **kwargs)
+
+    @property
+    def device(self):
+        return next(iter(self.normalizers.values())).mins.device
+
+
+# ---------------------------------------------------------------------------
+# observation encoder (row P6 — torch/cuDNN this round; structure + state_dict names of the reference)
+# ---------------------------------------------------------------------------
+class _AttrMixin(nn.Module):
+    """common/module_attr_mixin.py:3-15 — an empty parameter pins .device/.dtype (and is in state_dict)."""
+
+    def __init__(self):
+        super().__init__()
+        self._dummy_variable = nn.Parameter()
+
+    @property
+    def device(self):
+        return next(iter(self.parameters())).device
+
+    @property
+    def dtype(self):
+        return next(iter(self.parameters())).dtype
+
+
+class ResNet18Conv(nn.Module):
+    """torchvision ResNet18 trunk without avgpool/fc (common/vision_nets.py:9-39)."""
+
+    def __init__(self, input_channel=3, pretrained=False, input_coord_conv=False):
+        super().__init__()
+        from torchvision import models as vision_models
+        if input_coord_conv:
+            raise NotImplementedError("CoordConv2d input layer is not used by the Libero policy yaml")
+        net = vision_models.resnet18(weights=None)
+        if input_channel != 3:
+            net.conv1 = nn.Conv2d(input_channel, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.nets = nn.Sequential(*(list(net.children())[:-2]))
+
+    def output_shape(self, input_shape):
+        return [512, int(math.ceil(input_shape[1] / 32.0)), int(math.ceil(input_shape[2] / 32.0))]
+
+    def forward(self, x):
+        return self.nets(x)
+
+
+class SpatialSoftmax(nn.Module):
+    """1x1 conv to K keypoint maps, softmax over pixels, expected (x, y) (common/base_nets.py:153-285)."""
+
+    def __init__(self, input_shape, num_kp=None, temperature=1.0, learnable_temperature=False,
+                 output_variance=False, noise_std=0.0):
+        super().__init__()
+        if output_variance or learnable_temperature:
+            raise NotImplementedError("the Libero yaml uses a constant temperature and no variance output")
+        self._in_c, self._in_h, self._in_w = input_shape
+        self.nets = nn.Conv2d(self._in_c, num_kp, kernel_size=1) if num_kp is not None else None
+        self._num_kp = num_kp if num_kp is not None else self._in_c
+        self.noise_std = noise_std
+        self.register_buffer("temperature", torch.ones(1) * temperature)
+        px, py = np.meshgrid(np.linspace(-1.0, 1.0, self._in_w), np.linspace(-1.0, 1.0, self._in_h))
+        self.register_buffer("pos_x", torch.from_numpy(px.reshape(1, -1)).float())
+        self.register_buffer("pos_y", torch.from_numpy(py.reshape(1, -1)).float())
+
+    def output_shape(self, input_shape):
+        return [self._num_kp, 2]
+
+    def forward(self, feature):
+        if self.nets is not None:
+            feature = self.nets(feature)
+        att = F.softmax(feature.reshape(-1, self._in_h * self._in_w) / self.temperature, dim=-1)
+        ex = torch.sum(self.pos_x * att, dim=1, keepdim=True)
+        ey = torch.sum(self.pos_y * att, dim=1, keepdim=True)
+        kp = torch.cat([ex, ey], 1).view(-1, self._num_kp, 2)
+        if self.training:  # drawn even when noise_std == 0 (keeps the RNG stream of the reference)
+            kp = kp + _randn(kp.shape, kp.device, kp.dtype) * self.noise_std
+        return kp
+
+
+class VisualCore(nn.Module):
+    """backbone -> pool -> flatten -> Linear (common/vision_nets.py:65-177)."""
+
+    def __init__(self, input_shape, backbone_class="ResNet18Conv", backbone_kwargs=None, pool_class="SpatialSoftmax",
+                 pool_kwargs=None, flatten=True, feature_dimension=None, **kwargs):
+        super().__init__()
+        if backbone_class != "ResNet18Conv" or pool_class != "SpatialSoftmax" or not flatten:
+            raise NotImplementedError("VisualCore restates the ResNet18Conv + SpatialSoftmax configuration")
+        self.input_shape = tuple(input_shape)
+        bk = {k: v for k, v in dict(backbone_kwargs or {}).items() if k in ("pretrained", "input_coord_conv")}
+        self.backbone = ResNet18Conv(input_channel=input_shape[0], pretrained=bool(bk.get("pretrained")),
+                                     input_coord_conv=bool(bk.get("input_coord_conv", False)))
+        feat = self.backbone.output_shape(input_shape)
+        pk = {k: v for k, v in dict(pool_kwargs or {}).items()
+              if k in ("num_kp", "temperature", "learnable_temperature", "output_variance", "noise_std")}
+        self.pool = SpatialSoftmax(feat, **pk)
+        feat = self.pool.output_shape(feat)
+        layers = [self.backbone, self.pool, nn.Flatten(start_dim=1, end_dim=-1)]
+        self.feature_dimension = feature_dimension
+        if feature_dimension is not None:
+            layers.append(nn.Linear(int(np.prod(feat)), feature_dimension))
+        self.nets = nn.Sequential(*layers)
+        self._out = [feature_dimension] if feature_dimension is not None else [int(np.prod(feat))]
+
+    def output_shape(self, input_shape=None):
+        return list(self._out)
+
+    def forward(self, x):
+        assert tuple(x.shape[-3:]) == self.input_shape
+        return self.nets(x)
+
+
+def _bn_to_gn(root: nn.Module) -> nn.Module:
+    """BatchNorm2d(C) -> GroupNorm(C // 16, C) everywhere (model/multi_image_obs_encoder.py:67-74)."""
+    for name, child in list(root.named_children()):
+        if isinstance(child, nn.BatchNorm2d):
+            setattr(root, name, nn.GroupNorm(child.num_features // 16, child.num_features))
+        else:
+            _bn_to_gn(child)
+    return root
+
+
+class MultiImageObsEncoder(_AttrMixin):
+    """One independent VisualCore per rgb key, features concatenated in SORTED key order
+    (model/multi_image_obs_encoder.py:11-196)."""
+
+    def __init__(self, shape_meta: dict, rgb_model, resize_shape=None, crop_shape=None, random_crop=True,
+                 use_group_norm=False, share_rgb_model=False, imagenet_norm=False, _target_=None):
+        super().__init__()
+        if resize_shape is not None or crop_shape is not None or share_rgb_model or imagenet_norm or not use_group_norm:
+            raise NotImplementedError("MultiImageObsEncoder restates the Libero yaml setting: per-key models, "
+                                      "GroupNorm, no resize / crop / imagenet normalisation")
+        self.key_model_map = nn.ModuleDict()
+        self.key_transform_map = nn.ModuleDict()
+        self.key_shape_map, rgb_keys, low_dim_keys = {}, [], []
+        for key, attr in shape_meta["obs"].items():
+            self.key_shape_map[key] = tuple(attr["shape"])
+            kind = attr.get("type", "low_dim")
+            if kind == "rgb":
+                rgb_keys.append(key)
+                model = rgb_model[key] if isinstance(rgb_model, dict) else copy.deepcopy(rgb_model)
+                self.key_model_map[key] = _bn_to_gn(model)
+                self.key_transform_map[key] = nn.Sequential(nn.Identity(), nn.Identity(), nn.Identity())
+            elif kind == "low_dim":
+                low_dim_keys.append(key)
+            else:
+                raise RuntimeError(f"Unsupported obs type: {kind}")
+        self.shape_meta = shape_meta
+        self.share_rgb_model = False
+        self.rgb_keys, self.low_dim_keys = sorted(rgb_keys), sorted(low_dim_keys)
+
+    def forward(self, obs_dict):
+        feats, bs = [], None
+        for key in self.rgb_keys + self.low_dim_keys:
+            x = obs_dict[key]
+            bs = x.shape[0] if bs is None else bs
+            assert x.shape[0] == bs and tuple(x.shape[1:]) == self.key_shape_map[key]
+            feats.append(self.key_model_map[key](x) if key in self.key_model_map else x)
+        return torch.cat(feats, dim=-1)
+
+    @torch.no_grad()
+    def output_shape(self):
+        ex = {k: torch.zeros((1,) + tuple(a["shape"]), dtype=self.dtype, device=self.device)
+              for k, a in self.shape_meta["obs"].items()}
+        return self.forward(ex).shape[1:]
+
+
+# ---------------------------------------------------------------------------
+# the policy
+# ---------------------------------------------------------------------------
+class DiffusionUnetImagePolicy(_AttrMixin):
+    def __init__(self, shape_meta: dict, noise_scheduler, noise_scheduler_ddim, obs_encoder, horizon,
+                 n_action_steps, n_obs_steps, num_inference_steps=None, num_inference_steps_ddim=8,
+                 obs_as_global_cond=True, diffusion_step_embed_dim=256, down_dims=(256, 512, 1024), kernel_size=5,
+                 n_groups=8, cond_predict_scale=True, _target_=None, cond_unet1d_config={}, **kwargs):
+        super().__init__()
+        if not obs_as_global_cond:
+            raise NotImplementedError("the reference asserts obs_as_global_cond on this path")
+        action_shape = shape_meta["action"]["shape"]
+        assert len(action_shape) == 1
+        action_dim = action_shape[0]
+        obs_feature_dim = obs_encoder.output_shape()[0]
+        self.obs_encoder = obs_encoder
+        self.model = ConditionalUnet1D(input_dim=action_dim, local_cond_dim=None,
+                                       global_cond_dim=obs_feature_dim * n_obs_steps,
+                                       diffusion_step_embed_dim=diffusion_step_embed_dim, down_dims=list(down_dims),
+                                       kernel_size=kernel_size, n_groups=n_groups,
+                                       cond_predict_scale=cond_predict_scale, cond_unet1d_config=cond_unet1d_config)
+        self.noise_scheduler, self.noise_scheduler_ddim = noise_scheduler, noise_scheduler_ddim
+        self.ddpm_var_temp = 1.0
+        self.cond_unet1d_config = cond_unet1d_config
+        self.normalizer = ConstNormalizerGroup(LimitsConstNormalizer, shape_meta, n_obs_steps)
+        self.horizon, self.obs_feature_dim, self.action_dim = horizon, obs_feature_dim, action_dim
+        self.n_action_steps, self.n_obs_steps, self.obs_as_global_cond = n_action_steps, n_obs_steps, True
+        self.kwargs = kwargs
+        if num_inference_steps is None:
+            num_inference_steps = noise_scheduler.config.num_train_timesteps
+        self.num_inference_steps, self.num_inference_steps_ddim = num_inference_steps, num_inference_steps_ddim
+
+    # ---- shared: normalise + encode -> global_cond [B, Do * To] (:215-239, :148-170) ----
+    def _global_cond(self, obs: Dict[str, torch.Tensor]):
+        nobs = self.normalizer.normalize_d(obs)
+        B = next(iter(nobs.values())).shape[0]
+        To = self.n_obs_steps
+        this = {k: v[:, :To, ...].reshape(-1, *v.shape[2:]) for k, v in nobs.items()}
+        return self.obs_encoder(this).reshape(B, -1), B
+
+    def conditional_sample(self, condition_data, condition_mask, local_cond=None, global_cond=None, generator=None,
+                           use_ddim=False, **kwargs):
+        assert (condition_mask == False).all(), "no given condition"  # noqa: E712
+        trajectory = _randn(condition_data.shape, condition_data.device, condition_data.dtype, generator)
+        scheduler = self.noise_scheduler_ddim if use_ddim else self.noise_scheduler
+        scheduler.set_timesteps(self.num_inference_steps_ddim if use_ddim else self.num_inference_steps)
+        for t in scheduler.timesteps:
+            out = self.model(trajectory, t, local_cond=local_cond, global_cond=global_cond)
+            trajectory = scheduler.step(out, t, trajectory, generator=generator, **kwargs).prev_sample
+        return trajectory
+
+    def predict_action(self, obs_dict: Dict[str, torch.Tensor], use_ddim=False) -> Dict[str, torch.Tensor]:
+        assert "past_action" not in obs_dict
+        global_cond, B = self._global_cond(obs_dict)
+        cond = torch.zeros((B, self.horizon, self.action_dim), device=self.device, dtype=self.dtype)
+        nsample = self.conditional_sample(cond, torch.zeros_like(cond, dtype=torch.bool), global_cond=global_cond,
+                                          use_ddim=use_ddim, **self.kwargs)
+        action_pred = self.normalizer["action"].unnormalize(nsample[..., :self.action_dim]).detach()
+        start = self.n_obs_steps - 1
+        return {"action": action_pred[:, start:start + self.n_action_steps], "action_pred": action_pred}
+
+    def compute_loss(self, batch: dict) -> torch.Tensor:
+        assert "valid_mask" not in batch
+        assert self.n_obs_steps == 1, "temporally"
+        assert batch["action"].shape[-1] == self.action_dim
+        global_cond, B = self._global_cond(batch["obs"])
+        trajectory = self.normalizer["action"].normalize(batch["action"])
+        noise = _randn(trajectory.shape, trajectory.device)
+        timesteps = _randint(self.noise_scheduler.config.num_train_timesteps, (B,), trajectory.device)
+        noisy = self.noise_scheduler.add_noise(trajectory, noise, timesteps)
+        pred = self.model(noisy, timesteps, local_cond=None, global_cond=global_cond)
+        pt = self.noise_scheduler.config.prediction_type
+        if pt == "epsilon":
+            target = noise
+        elif pt == "sample":
+            target = trajectory
+        else:
+            raise ValueError(f"Unsupported prediction type {pt}")
+        loss = F.mse_loss(pred, target, reduction="none")
+        return loss.reshape(loss.shape[0], -1).mean(dim=1).mean()
+
+    def to(self, *args, **kwargs):
+        super().to(*args, **kwargs)
+        self.normalizer.to_device(*args, **kwargs)
+        return self
+
+
+# ---------------------------------------------------------------------------
+# the shipped Libero policy (config/diff_policy/lb_train_diffusion_unet_image_orn10.yaml) without OmegaConf
+# ---------------------------------------------------------------------------
+def libero_shape_meta() -> dict:
+    img = (np.zeros(3, np.float32), np.ones(3, np.float32), [1, 3, 1, 1])           # image_minmax_01
+    act = (-np.ones(7, np.float32), np.ones(7, np.float32), [1, 7])                 # lb_action_minmax (+-1)
+    return {"obs": {"img_obs_1": {"shape": [3, 128, 128], "minmax_shape": img, "type": "rgb"},
+                    "img_goal_1": {"shape": [3, 128, 128], "minmax_shape": img, "type": "rgb"}},
+            "action": {"shape": [7], "minmax_shape": act}}
+
+
+def build_libero_policy() -> DiffusionUnetImagePolicy:
+    meta = libero_shape_meta()
+    core = VisualCore(input_shape=[3, 128, 128], backbone_class="ResNet18Conv",
+                      backbone_kwargs=dict(pretrained=None, input_coord_conv=False), pool_class="SpatialSoftmax",
+                      pool_kwargs=dict(num_kp=32, learnable_temperature=False, temperature=1.0, noise_std=0.0,
+                                       output_variance=False), flatten=True, feature_dimension=64)
+    enc = MultiImageObsEncoder(meta, core, use_group_norm=True)
+    sched = dict(num_train_timesteps=100, beta_start=0.0001, beta_end=0.02, beta_schedule="squaredcos_cap_v2",
+                 clip_sample=True, prediction_type="epsilon")
+    return DiffusionUnetImagePolicy(meta, DDPMScheduler(variance_type="fixed_small", **sched),
+                                    DDIMScheduler(set_alpha_to_one=True, steps_offset=0, **sched), enc, horizon=16,
+                                    n_action_steps=8, n_obs_steps=1, num_inference_steps=100,
+                                    num_inference_steps_ddim=8, obs_as_global_cond=True,
+                                    diffusion_step_embed_dim=128, down_dims=[256, 512, 1024], kernel_size=5,
+                                    n_groups=8, cond_predict_scale=True)

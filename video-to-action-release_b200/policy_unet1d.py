@@ -79,6 +79,26 @@ class ConditionalResidualBlock1D(nn.Module):
 
 
 _ENGINES: "weakref.WeakKeyDictionary[nn.Module, Dict[tuple, _PolicyEngine]]" = weakref.WeakKeyDictionary()
+# modules whose parameter gradients stay in the engine's flat slab (train_step.PolicyTrainStep) instead of
+# being handed to autograd as per-parameter tensors
+_SLAB_GRADS: "weakref.WeakKeyDictionary[nn.Module, bool]" = weakref.WeakKeyDictionary()
+_LAST_ENGINE: "weakref.WeakKeyDictionary[nn.Module, _PolicyEngine]" = weakref.WeakKeyDictionary()
+
+
+def set_slab_grads(model: nn.Module, on: bool = True) -> None:
+    """Leave parameter gradients in ``engine.gslab`` (flat, parameters() order) and return None to autograd."""
+    _SLAB_GRADS[model] = bool(on)
+
+
+def last_engine(model: nn.Module) -> "Optional[_PolicyEngine]":
+    """The engine the most recent forward() of ``model`` ran on (holds that step's gradient slab)."""
+    return _LAST_ENGINE.get(model)
+
+
+def invalidate_weights(model: nn.Module) -> None:
+    """Parameters were updated in place through raw pointers (fused optimiser): repack on next forward."""
+    for eng in _ENGINES.get(model, {}).values():
+        eng._wkey = None
 
 
 class ConditionalUnet1D(nn.Module):
@@ -137,6 +157,7 @@ class ConditionalUnet1D(nn.Module):
         t = t.expand(B).to(torch.int64)
         gc = global_cond if global_cond is not None else sample.new_zeros(B, 0)
         eng = _policy_engine(self, B, T, sample.device)
+        _LAST_ENGINE[self] = eng
         return _UNet1DFunction.apply(self, eng, sample, t, gc, *list(self.parameters()))
 
 
@@ -161,6 +182,7 @@ class _UNet1DFunction(torch.autograd.Function):
         with torch.autocast("cuda", enabled=False):
             out = eng.forward(sample.detach().float(), t, gc.detach().float())
         ctx.eng = eng
+        ctx.slab = _SLAB_GRADS.get(model, False)
         ctx.token = eng.fwd_token
         ctx.in_dtypes = (sample.dtype, gc.dtype)
         return out
@@ -172,7 +194,7 @@ class _UNet1DFunction(torch.autograd.Function):
             raise RuntimeError("v2a_b200.ConditionalUnet1D: backward() after another forward() on the same "
                                "module/shape — activations live in static buffers (one forward per backward)")
         with torch.autocast("cuda", enabled=False):
-            d_sample, d_gc, pgrads = eng.backward(grad_out.float())
+            d_sample, d_gc, pgrads = eng.backward(grad_out.float(), clone_param_grads=not ctx.slab)
         return (None, None, d_sample.to(ctx.in_dtypes[0]), None, d_gc.to(ctx.in_dtypes[1]), *pgrads)
 
 
@@ -659,7 +681,7 @@ class _PolicyEngine:
         self.fwd_token += 1
         return self.out16[:, :self.x0.C].reshape(Bn, T, -1).clone()
 
-    def backward(self, grad_out):
+    def backward(self, grad_out, clone_param_grads=True):
         Bn, T = self.B, self.T
         for z in self._zero_each_bwd:
             z.zero_()
@@ -668,5 +690,8 @@ class _PolicyEngine:
             s()
         d_sample = self.x0.grad.win.reshape(Bn, T, -1).clone()
         d_gc = self.dgf[:, self.dgf.shape[1] - self.gc_in.shape[1]:].clone()
-        pgrads = [self.pgrad[id(p)].clone() for p in self.params]
+        if clone_param_grads:
+            pgrads = [self.pgrad[id(p)].clone() for p in self.params]
+        else:  # slab mode: the gradients stay in self.gslab for the fused optimiser
+            pgrads = [None] * len(self.params)
         return d_sample, d_gc, pgrads

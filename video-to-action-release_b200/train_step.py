@@ -1,0 +1,163 @@
+"""Fused optimisation step of the policy training loop.
+
+Replaces, for a module whose hot part is ``ConditionalUnet1D``, what the reference trainer does
+each iteration (diffuser/libero/lb_online_trainer_v7.py:593-624; hyper-parameters from
+config/libero/lb_tk8_65to72.py:138-153):
+
+    loss = compute_loss(batch); loss.backward()          -> planned CUDA forward / backward
+    [DDP gradient all-reduce under multi-process]        -> distributed.allreduce_mean_ (NCCL)
+    clip_grad_norm_(params, 1.0)                         -> v2a_grad_sumsq
+    AdamW.step(); zero_grad()                            -> v2a_adamw_ema_step (ONE pass over flat
+    EMA.update()                                            slabs: p, g, m, v, ema)
+
+Parameters are re-pointed into one flat fp32 slab per segment (their ``state_dict`` names and
+shapes are unchanged); the UNet1D's gradients never leave the engine's gradient slab, other
+parameters (the cuDNN observation encoder) accumulate through autograd into slab views.
+
+EMA follows ``ema_pytorch`` 0.2.3 as the trainer configures it (``EMA(model, beta=0.9999,
+update_after_step=0, inv_gamma=1, power=0.75, min_value=0, update_every=1)``; third-party, not
+vendored in the reference — restated from its published algorithm, parity unpinned by reference
+tests): the first two ``update()`` calls copy the online parameters, call c >= 2 uses
+decay = clamp(1 - (1 + c)^-0.75, 0, beta).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Iterable, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, distributed, ops, policy_unet1d
+
+
+def ema_decay(call_index: int, *, beta: float = 0.9999, inv_gamma: float = 1.0, power: float = 0.75,
+              min_value: float = 0.0, update_after_step: int = 0) -> float:
+    """Decay used by the ``call_index``-th (0-based) ``EMA.update()`` call; 0.0 means 'copy online params'."""
+    if call_index <= update_after_step + 1:
+        return 0.0
+    epoch = call_index - update_after_step
+    value = 1.0 - (1.0 + epoch / inv_gamma) ** (-power)
+    return float(min(max(value, min_value), beta))
+
+
+class _Segment:
+    """A group of parameters living in one flat slab, with optimiser state beside it."""
+
+    def __init__(self, params: List[nn.Parameter], device, own_grad: bool, ema: bool):
+        self.params = params
+        self.numel = sum(p.numel() for p in params)
+        f32 = dict(dtype=torch.float32, device=device)
+        self.p = torch.empty(self.numel, **f32)
+        self.m = torch.zeros(self.numel, **f32)
+        self.v = torch.zeros(self.numel, **f32)
+        self.g: Optional[torch.Tensor] = torch.zeros(self.numel, **f32) if own_grad else None
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                n = p.numel()
+                view = self.p[off:off + n].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                if own_grad:
+                    p.grad = self.g[off:off + n].view(p.shape)
+                off += n
+        self.ema = self.p.clone() if ema else None
+
+    def ema_views(self):
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            yield p, self.ema[off:off + n].view(p.shape)
+            off += n
+
+
+class PolicyTrainStep:
+    """``step(loss_fn)`` = forward + backward + (all-reduce) + clip + AdamW + EMA on CUDA."""
+
+    def __init__(self, module: nn.Module, *, unet1d: Optional[nn.Module] = None, lr: float = 1e-4,
+                 betas=(0.95, 0.999), eps: float = 1e-8, weight_decay: float = 1e-6, max_norm: float = 1.0,
+                 ema: bool = True, ema_beta: float = 0.9999, ema_power: float = 0.75, ema_inv_gamma: float = 1.0,
+                 group=None, bucket_bytes: int = 64 << 20):
+        if unet1d is None:
+            unet1d = module if isinstance(module, policy_unet1d.ConditionalUnet1D) else getattr(module, "model", None)
+        if not isinstance(unet1d, policy_unet1d.ConditionalUnet1D):
+            raise TypeError("PolicyTrainStep needs a v2a_b200 ConditionalUnet1D (module itself or module.model)")
+        dev = next(unet1d.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("PolicyTrainStep runs on CUDA only (no CPU fallback): move the module first")
+        self.module, self.unet = module, unet1d
+        self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, tuple(betas), eps, weight_decay, max_norm
+        self.ema_cfg = dict(beta=ema_beta, power=ema_power, inv_gamma=ema_inv_gamma)
+        self.group, self.bucket_bytes = group, bucket_bytes
+        unet_params = list(unet1d.parameters())
+        ids = {id(p) for p in unet_params}
+        other = [p for p in module.parameters() if id(p) not in ids and p.requires_grad and p.numel() > 0]
+        self.seg_unet = _Segment(unet_params, dev, own_grad=False, ema=ema)
+        self.seg_other = _Segment(other, dev, own_grad=True, ema=ema) if other else None
+        policy_unet1d.set_slab_grads(unet1d, True)
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.steps_done = 0
+        self.collectives = 0
+        self._lib = _lib.load()
+
+    # ---- pieces (also used one by one in tests) ------------------------------------------------
+    def _unet_grad_slab(self) -> torch.Tensor:
+        eng = policy_unet1d.last_engine(self.unet)
+        if eng is None:
+            raise RuntimeError("PolicyTrainStep.step: the loss closure did not run the ConditionalUnet1D")
+        return eng.gslab
+
+    def _segments(self):
+        yield self.seg_unet, self._unet_grad_slab()
+        if self.seg_other is not None:
+            yield self.seg_other, self.seg_other.g
+
+    def optimizer_tail(self) -> None:
+        """all-reduce (mean) -> global grad-norm -> clip + AdamW + EMA, all asynchronous on the stream."""
+        st = ops._stream()
+        segs = list(self._segments())
+        self.collectives += distributed.allreduce_mean_([g for _, g in segs], self.group, self.bucket_bytes)
+        self.sumsq.zero_()
+        for _, g in segs:
+            _lib.check(self._lib.v2a_grad_sumsq(g.data_ptr(), g.numel(), self.sumsq.data_ptr(), st), "grad_sumsq")
+        decay = ema_decay(self.steps_done, **self.ema_cfg)
+        self.steps_done += 1
+        for seg, g in segs:
+            _lib.check(self._lib.v2a_adamw_ema_step(
+                seg.p.data_ptr(), g.data_ptr(), seg.m.data_ptr(), seg.v.data_ptr(),
+                None if seg.ema is None else seg.ema.data_ptr(), seg.numel, self.sumsq.data_ptr(),
+                self.max_norm, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.steps_done,
+                decay, st), "adamw_ema_step")
+        policy_unet1d.invalidate_weights(self.unet)
+        if self.seg_other is not None:
+            self.seg_other.g.zero_()          # zero_grad() for the autograd-accumulated segment
+
+    def step(self, loss_fn: Callable[[], torch.Tensor]) -> torch.Tensor:
+        """Run ``loss_fn`` (it must call the module), backward, and the optimiser tail.  Returns the loss
+        tensor (device resident; reading it synchronises)."""
+        loss = loss_fn()
+        loss.backward()
+        self.optimizer_tail()
+        return loss.detach()
+
+    def grad_norm(self) -> torch.Tensor:
+        """Global gradient L2 norm of the last step (before clipping), as a device tensor."""
+        return self.sumsq.sqrt()
+
+    # ---- EMA export --------------------------------------------------------------------------
+    @torch.no_grad()
+    def copy_ema_to(self, target: nn.Module) -> None:
+        """Write the EMA weights into ``target`` (same architecture), e.g. the trainer's ``ema.ema_model``."""
+        if self.seg_unet.ema is None:
+            raise RuntimeError("PolicyTrainStep was built with ema=False")
+        src = {}
+        names = {id(p): n for n, p in self.module.named_parameters()}
+        for seg in (self.seg_unet, self.seg_other):
+            if seg is None:
+                continue
+            for p, e in seg.ema_views():
+                src[names[id(p)]] = e
+        for n, p in target.named_parameters():
+            if n in src:
+                p.data.copy_(src[n])
