@@ -179,6 +179,128 @@ def measure_kernel_roofline(diff, batch, peaks):
             "tensor_pipe_frac": achieved * eng.passes / peak, "kernel_ms_per_denoise_step": tot_ms}
 
 
+
+# ---------------------------------------------------------------------------------------------
+# policy arm: BASELINE.json configs[2] — ConditionalUnet1D training, 7-DoF actions, horizon 16, B=256/GPU
+# ---------------------------------------------------------------------------------------------
+POLICY_B, POLICY_T, POLICY_DA = 256, 16, 7
+POLICY_METRIC = "policy samples/s (ConditionalUnet1D train step: fwd + bwd + grad all-reduce + clip + AdamW + EMA)"
+
+
+def synthetic_policy_state_dict(layout):
+    from oracle.policy_oracle import seeded_policy_state_dict  # weight recipe shared with the tests
+    return seeded_policy_state_dict({k: tuple(v) for k, v in layout.items()}, 12)
+
+
+def policy_cpu_reference_step(threads: int, B: int):
+    """One fwd+bwd of the reference algorithm (CPU oracle port of ConditionalUnet1D + epsilon loss)."""
+    from oracle import policy_oracle as PO
+    with open(os.path.join(ROOT, "tests", "golden", "policy_golden_meta.json")) as f:
+        layout = json.load(f)["libero"]["layout"]
+    torch.set_num_threads(threads)
+    sd = {k: v.requires_grad_(True) for k, v in synthetic_policy_state_dict(layout).items()}
+    g = torch.Generator().manual_seed(0)
+    traj = torch.rand(B, POLICY_T, POLICY_DA, generator=g) * 2 - 1
+    noise = torch.randn(B, POLICY_T, POLICY_DA, generator=g)
+    t = torch.randint(0, 100, (B,), generator=g)
+    gc = torch.randn(B, 128, generator=g)
+    acp = PO.ddpm_alphas_cumprod(100)
+    PO.epsilon_loss(sd, traj, gc, noise, t, acp).backward()       # warm-up
+    t0 = time.perf_counter()
+    PO.epsilon_loss(sd, traj, gc, noise, t, acp).backward()
+    return time.perf_counter() - t0
+
+
+def run_policy(args, world, rank, local, barrier, max_over_ranks, peaks):
+    """Policy samples/s at B=256 per GPU (weak scaling; one gradient all-reduce per step for N>1)."""
+    import torch.nn.functional as F
+    from v2a_b200 import ops
+    from v2a_b200 import policy_unet1d as PU
+    from v2a_b200.diffusion_policy import build_libero_policy
+    from v2a_b200.train_step import PolicyTrainStep
+
+    B, T, Da = POLICY_B, POLICY_T, POLICY_DA
+    steps, warm = args.policy_steps, max(3, args.warmup)
+    torch.manual_seed(77)                                   # same initial weights on every rank (DDP semantics)
+    policy = build_libero_policy().to("cuda")
+    policy.train()
+    torch.backends.cudnn.allow_tf32 = False                 # fp32 truth setting for the cuDNN encoders
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(2000 + rank)
+    host = {"img_obs_1": torch.rand(B, 1, 3, 128, 128, generator=g).pin_memory(),
+            "img_goal_1": torch.rand(B, 1, 3, 128, 128, generator=g).pin_memory(),
+            "action": (torch.rand(B, T, Da, generator=g) * 2 - 1).pin_memory()}
+    loss_host = torch.zeros(1).pin_memory()
+    dev = {k: v.cuda() for k, v in host.items()}
+
+    def timed(fn, n):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        l0 = ops.launch_count()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / n, (ops.launch_count() - l0) // n
+
+    # (a) the path north_star names: ConditionalUnet1D fwd + bwd (+ all-reduce) + fused optimiser tail
+    net = policy.model
+    step_u = PolicyTrainStep(net)
+    noisy = torch.randn(B, T, Da, device="cuda")
+    noise = torch.randn(B, T, Da, device="cuda")
+    tt = torch.randint(0, 100, (B,), device="cuda")
+    gc = torch.randn(B, 128, device="cuda")
+    loss_u = lambda: F.mse_loss(net(noisy, tt, global_cond=gc), noise)
+    ms_u, launches_u = timed(lambda: step_u.step(loss_u), steps)
+    eng = PU.last_engine(net)
+    flops = sum(gm.flops for gm in eng.igemms)              # forward + dgrad + wgrad GEMMs of one step
+
+    # (b) e2e through the public API: host batch -> compute_loss -> backward -> optimiser -> loss to host
+    PU.set_slab_grads(net, False)
+    del step_u
+    step_p = PolicyTrainStep(policy)
+
+    def e2e_step():
+        b = {"obs": {"img_obs_1": host["img_obs_1"].to("cuda", non_blocking=True),
+                     "img_goal_1": host["img_goal_1"].to("cuda", non_blocking=True)},
+             "action": host["action"].to("cuda", non_blocking=True)}
+        loss = step_p.step(lambda: policy.compute_loss(b))
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+    ms_e2e, launches_p = timed(e2e_step, steps)
+    # (c) the same step with the batch already resident
+    batch_dev = {"obs": {"img_obs_1": dev["img_obs_1"], "img_goal_1": dev["img_goal_1"]}, "action": dev["action"]}
+    ms_p, _ = timed(lambda: step_p.step(lambda: policy.compute_loss(batch_dev)), steps)
+    peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    out = {"metric": POLICY_METRIC, "unit": "samples/s", "value": B * world / (ms_u * 1e-3),
+           "ms_per_step": ms_u, "steps": steps, "warmup": warm, "batch_per_gpu": B, "horizon": T, "action_dim": Da,
+           "params_unet1d": sum(p.numel() for p in net.parameters()), "gpu_launches_per_step": int(launches_u),
+           "collectives_per_step": 0 if world == 1 else "see DESIGN.md §5 (64 MiB buckets over the gradient slab)",
+           "roofline": {"bound": "tensor", "kernel": "igemm_kernel (fwd + dgrad + wgrad GEMMs of one step)",
+                        "achieved": flops / (ms_u * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": flops / (ms_u * 1e-3) / 1e12 / peak, "flop_per_step": flops, "traffic": None,
+                        "note": "whole-step time (launch/latency-bound at M = B*T = 1024..4096 rows)"},
+           "compute_loss_step": {"what": "DiffusionUnetImagePolicy.compute_loss + backward + optimiser; the two "
+                                         "ResNet18-GN observation encoders (80% of FLOPs) run on cuDNN fp32, TF32 off "
+                                         "(SURVEY.md §8a row P6 / §8f N1)",
+                                 "value": B * world / (ms_p * 1e-3), "ms_per_step": ms_p,
+                                 "params": sum(p.numel() for p in policy.parameters()),
+                                 "gpu_launches_per_step_ours": int(launches_p)},
+           "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": sum(v.numel() * 4 for v in host.values()), "d2h_bytes_per_step": 4}}
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sec = policy_cpu_reference_step(threads, 64)
+        out["cpu_baseline"] = {"value": 64 / sec, "unit": "samples/s", "cores": threads, "kind": "port",
+                               "sample": "1 timed ConditionalUnet1D fwd+bwd (oracle port, torch autograd) at B=64 after "
+                                         "1 warm-up; no encoders, no optimiser"}
+    del step_p, policy
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from v2a_b200 import ops
@@ -257,6 +379,9 @@ def run_ours(args):
 
     eng = net.unet.engine(B, FRAMES, H, W, "cuda")
     launches_per_denoise = len(eng.steps) + 3  # + emb-path extra launches + sampler update
+    policy_line = None
+    if not args.no_policy:
+        policy_line = run_policy(args, world, rank, local, barrier, max_over_ranks, peaks)
     if rank == 0:
         roof = measure_kernel_roofline(diff, B, peaks)
         roof["peak_source"] = peak_src
@@ -279,7 +404,7 @@ def run_ours(args):
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
                 "videos_per_s": value / FRAMES, "frames_per_s_counting_cond_frame": value * 8 / 7,
                 "algorithmic_tflops_whole_step": args.steps * B * world * DENOISE_STEPS * FLOP_PER_VIDEO_STEP / (ms * 1e-3) / 1e12,
-                "out_checksum": float(res.double().mean().item())}
+                "out_checksum": float(res.double().mean().item()), "policy": policy_line}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -302,6 +427,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="videos per GPU (configs[1]: 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-policy", action="store_true", help="skip the policy-samples/s object")
+    ap.add_argument("--policy-steps", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -191,6 +191,12 @@ int v2a_unnormalize_clamp(const float* x, float* out, int64_t n, void* stream);
 int v2a_split_hl(const float* x, int64_t rows, int cols, int ld_out, void* out_hi, void* out_lo,
                  void* stream);
 
+/* table-driven weight repack after an optimiser step: out[i] = map[i] ? src[map[i]-1] : 0 as bf16 hi/lo
+ * planes and/or fp32.  Replaces the per-layer re-layout PyTorch does implicitly when cuDNN consumes
+ * nn.Conv1d / nn.Linear weights (conditional_unet1d.py:36-44, conv1d_components.py:7-40). */
+int v2a_gather_split(const float* src, const int32_t* map, int64_t n, void* out_hi, void* out_lo,
+                     float* out_f32, void* stream);
+
 /* ------------------------------------------------------------------------
  * Policy path (ConditionalUnet1D forward / backward).  One CTA per batch sample.
  * replaces Conv1dBlock's GroupNorm -> Mish (conv1d_components.py:23-40), the FiLM

@@ -243,14 +243,17 @@ def test_compute_loss_and_predict_action_match_reference_policy_golden(monkeypat
     loss.backward()
     assert abs(loss.item() - gold["loss"].item()) < TOL * abs(gold["loss"].item())
     worst, n = 0.0, 0
+    # gradients that are structurally zero (SpatialSoftmax is shift invariant: d/d pool.nets.bias == 0 up to
+    # rounding, ~1e-9) are compared on the scale of the largest gradient, not on their own noise
+    floor = 1e-6 * max(v[0] for v in meta["grad_fingerprints"].values())
     for k, p in pol.named_parameters():
         if k not in meta["grad_fingerprints"]:
             continue
         norm, proj = meta["grad_fingerprints"][k]
         n2, p2 = grad_fingerprint(k, p.grad)
-        assert abs(n2 - norm) <= TOL * max(norm, 1e-8), (k, n2, norm)
-        assert abs(p2 - proj) <= TOL * max(norm, 1e-8) * (p.numel() ** 0.5), (k, p2, proj)
-        worst = max(worst, abs(n2 - norm) / max(norm, 1e-8))
+        assert abs(n2 - norm) <= TOL * max(norm, floor), (k, n2, norm)
+        assert abs(p2 - proj) <= TOL * max(norm, floor) * (p.numel() ** 0.5), (k, p2, proj)
+        worst = max(worst, abs(n2 - norm) / max(norm, floor))
         n += 1
     assert n == len(meta["grad_fingerprints"]) == 276
     pol.eval()

@@ -71,14 +71,16 @@ def main():
         for name, steps in (("fwd", eng.fwd), ("bwd", eng.bwd)):
             rows = []
             for i, s in enumerate(steps):
-                rows.append((timed(s, n=5, warm=1), i, getattr(s, "__self__", None)))
+                rows.append((timed(s, n=5, warm=1), i, steps.tags[i]))
             tot = sum(r[0] for r in rows)
             print(f"{name}: sum of per-launch times {tot:.3f} ms over {len(rows)} launches")
-            for m, i, o in sorted(rows, key=lambda r: -r[0])[:25]:
-                d = ""
-                if o is not None and hasattr(o, "ktot"):
-                    d = f"igemm rows {o.rows} cout {o.cout} K {o.ktot} {o.flops / m / 1e9:.1f} TFLOP/s"
-                print(f"  #{i:3d} {m:7.4f} ms {d}")
+            by = {}
+            for m, i, tag in rows:
+                k = tag.split()[0]
+                by[k] = (by.get(k, (0, 0))[0] + m, by.get(k, (0, 0))[1] + 1)
+            print("  by kind: " + ", ".join(f"{k} {v[0]:.3f} ms/{v[1]}" for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])))
+            for m, i, tag in sorted(rows, key=lambda r: -r[0])[:30]:
+                print(f"  #{i:3d} {m:7.4f} ms {tag}")
 
 
 if __name__ == "__main__":

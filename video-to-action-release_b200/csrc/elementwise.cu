@@ -383,6 +383,44 @@ __global__ void split_hl_kernel(const float* __restrict__ x, int64_t rows, int c
 
 using namespace v2a;
 
+// ---------------------------------------------------------------------------
+// table-driven weight repack: out[i] = map[i] ? src[map[i] - 1] : 0, written as bf16 hi/lo planes
+// (tensor-core operand layout) or fp32 (bias / gain vectors).  The map is traced once per engine from
+// the host-side packers (pure gathers), so re-packing after an optimiser step is ONE launch per arena.
+// ---------------------------------------------------------------------------
+__global__ void gather_split_kernel(const float* __restrict__ src, const int32_t* __restrict__ map, int64_t n,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                    float* __restrict__ out_f32) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
+    for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i0 < n; i0 += stride) {
+        float v[8];
+        if (i0 + 8 <= n) {
+            const int4 m0 = *reinterpret_cast<const int4*>(map + i0);
+            const int4 m1 = *reinterpret_cast<const int4*>(map + i0 + 4);
+            const int32_t m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = m[j] ? __ldg(src + (m[j] - 1)) : 0.0f;
+            if (hi) {
+                uint4 h, l;
+                split8(v, h, l);
+                *reinterpret_cast<uint4*>(hi + i0) = h;
+                *reinterpret_cast<uint4*>(lo + i0) = l;
+            }
+            if (out_f32) {
+                *reinterpret_cast<float4*>(out_f32 + i0) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(out_f32 + i0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        } else {
+            for (int64_t i = i0; i < n; ++i) {
+                const int32_t m = map[i];
+                const float x = m ? src[m - 1] : 0.0f;
+                if (hi) split_bf16(x, hi[i], lo[i]);
+                if (out_f32) out_f32[i] = x;
+            }
+        }
+    }
+}
+
 extern "C" {
 
 int v2a_channel_stats(const float* x, int64_t instances, int64_t ppi, int C, double* stats,
@@ -508,6 +546,22 @@ int v2a_ddim_step(float* x, const float* v, const float* noise, const float* coe
 
 int v2a_unnormalize_clamp(const float* x, float* out, int64_t n, void* stream) {
     unnormalize_clamp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, n);
+    V2A_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_gather_split(const float* src, const int32_t* map, int64_t n, void* out_hi, void* out_lo,
+                     float* out_f32, void* stream) {
+    V2A_REQUIRE(src && map && n >= 0, "gather_split: missing pointers");
+    V2A_REQUIRE((out_hi != nullptr) == (out_lo != nullptr) && (out_hi || out_f32), "gather_split: no output");
+    V2A_REQUIRE(((uintptr_t)map | (uintptr_t)out_hi | (uintptr_t)out_lo | (uintptr_t)out_f32) % 16 == 0,
+                "gather_split: map / outputs must be 16-byte aligned");
+    if (n == 0) return 0;
+    int64_t blocks = (n / 8 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    gather_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        src, map, n, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32);
     V2A_LAUNCH_OK();
     return 0;
 }

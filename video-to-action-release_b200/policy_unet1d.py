@@ -235,15 +235,31 @@ class _Node:
         self.grad: Optional[_Ref] = None
 
 
+class _Steps(list):
+    """Launch list that remembers what each entry is (developer timing probes read .tags)."""
+
+    def __init__(self):
+        super().__init__()
+        self.tags: List[str] = []
+
+    def add(self, tag: str, fn: Callable) -> None:
+        self.tags.append(tag)
+        list.append(self, fn)
+
+    def append(self, fn: Callable) -> None:
+        self.add(getattr(fn, "__name__", "step"), fn)
+
+
 class _PolicyEngine:
     def __init__(self, model: ConditionalUnet1D, B, T, device):
         self.model_ref = weakref.ref(model)
         self.B, self.T, self.device = B, T, device
         self.passes = int(os.environ.get("V2A_PASSES", "3"))
         self.lib = _lib.load()
-        self.fwd: List[Callable] = []
-        self.bwd: List[Callable] = []
+        self.fwd: _Steps = _Steps()
+        self.bwd: _Steps = _Steps()
         self.packers, self.vec_packers, self.keep = [], [], []
+        self._wchunks, self._vchunks = [], []
         self.fwd_token = 0
         self._wkey = None
         self.igemms: List[ops.Igemm] = []
@@ -258,6 +274,7 @@ class _PolicyEngine:
         self._dcat: Dict[tuple, torch.Tensor] = {}
         self._zero_each_bwd: List[torch.Tensor] = [self.gslab]
         self._build(model)
+        self._trace_packers()
 
     # ---- buffers / weights ---------------------------------------------------
     def zeros(self, rows, cols):
@@ -267,35 +284,116 @@ class _PolicyEngine:
         return HL(torch.zeros(rows, cols, dtype=torch.bfloat16, device=self.device),
                   torch.zeros(rows, cols, dtype=torch.bfloat16, device=self.device))
 
+    def _carve(self, kind: str, n: int):
+        """n elements (multiple of 128) from the growing weight ('w': bf16 hi/lo planes) or vector ('v': fp32)
+        arena; every arena chunk is re-packed by ONE v2a_gather_split launch."""
+        n_al = -(-n // 128) * 128
+        chunks = self._wchunks if kind == "w" else self._vchunks
+        if not chunks or chunks[-1]["used"] + n_al > chunks[-1]["cap"]:
+            cap = max(n_al, (16 << 20) if kind == "w" else (1 << 20))
+            c = dict(cap=cap, used=0, map=torch.zeros(cap, dtype=torch.int32, device=self.device))
+            if kind == "w":
+                c["hi"] = torch.zeros(cap, dtype=torch.bfloat16, device=self.device)
+                c["lo"] = torch.zeros(cap, dtype=torch.bfloat16, device=self.device)
+            else:
+                c["f32"] = torch.zeros(cap, dtype=torch.float32, device=self.device)
+            chunks.append(c)
+        c = chunks[-1]
+        lo, hi = c["used"], c["used"] + n
+        c["used"] += n_al
+        return c, lo, hi
+
     def weight(self, fn, rows, cols) -> HL:
-        hl = HL.empty(rows, cols, self.device)
-        self.packers.append((fn, hl))
+        c, lo, hi = self._carve("w", rows * cols)
+        hl = HL(c["hi"][lo:hi].view(rows, cols), c["lo"][lo:hi].view(rows, cols))
+        self.packers.append((fn, hl, c["map"][lo:hi].view(rows, cols)))
         return hl
 
     def vec(self, fn, n) -> torch.Tensor:
-        v = torch.empty(n, dtype=torch.float32, device=self.device)
-        self.vec_packers.append((fn, v))
+        c, lo, hi = self._carve("v", n)
+        v = c["f32"][lo:hi]
+        self.vec_packers.append((fn, v, c["map"][lo:hi]))
         return v
+
+    def _trace_packers(self):
+        """Every packer is a pure gather of parameter elements (slices, transposes, zero padding, cat):
+        run each ONCE on index-valued stand-ins of the parameters to record out[i] <- flat parameter index
+        (+1; 0 = structural zero).  Re-packing after an optimiser step is then table driven."""
+        saved = [p.data for p in self.params]
+        try:
+            off = 0
+            for p in self.params:
+                n = p.numel()
+                p.data = torch.arange(off + 1, off + n + 1, dtype=torch.float64, device=self.device).view(p.shape)
+                off += n
+            assert off < 2 ** 31 - 1
+            with torch.no_grad():
+                for fn, hl, mp in self.packers:
+                    mp.copy_(fn().to(self.device).reshape(mp.shape).to(torch.int32))
+                for fn, v, mp in self.vec_packers:
+                    mp.copy_(fn().to(self.device).reshape(-1).to(torch.int32))
+        finally:
+            for p, d in zip(self.params, saved):
+                p.data = d
+        self._stage = None
+        self._trace_checked = False
+
+    def _param_slab(self) -> torch.Tensor:
+        """The parameters as ONE flat fp32 tensor in parameters() order: the live slab when they already are
+        consecutive views of one (train_step.PolicyTrainStep), else a staging copy (one cat launch)."""
+        ps = [p for p in self.params if p.numel()]
+        ptr, ok = ps[0].data_ptr(), True
+        for p in ps:
+            if p.data_ptr() != ptr or not p.is_contiguous() or p.dtype != torch.float32 or p.device != self.device:
+                ok = False
+                break
+            ptr += 4 * p.numel()
+        tot = sum(p.numel() for p in ps)
+        if ok:
+            st = ps[0].untyped_storage()
+            first = (ps[0].data_ptr() - st.data_ptr()) // 4
+            return torch.empty(0, dtype=torch.float32, device=self.device).set_(st, first, (tot,))
+        if self._stage is None:
+            self._stage = torch.empty(tot, dtype=torch.float32, device=self.device)
+        with torch.no_grad():
+            torch.cat([p.detach().to(self.device, torch.float32).reshape(-1) for p in ps], out=self._stage)
+        return self._stage
+
+    def _repack_reference(self):
+        """The packers evaluated with torch ops on the real parameters (one-off check of the traced tables)."""
+        with torch.no_grad():
+            for fn, hl, _ in self.packers:
+                w = fn().detach().to(self.device, torch.float32).reshape(hl.hi.shape)
+                hi = w.to(torch.bfloat16)
+                yield hl.hi, hi
+                yield hl.lo, (w - hi.float()).to(torch.bfloat16)
+            for fn, v, _ in self.vec_packers:
+                yield v, fn().detach().to(self.device, torch.float32).reshape(-1)
 
     def refresh_weights(self):
         key = tuple((p.data_ptr(), p._version) for p in self.params)
         if key == self._wkey:
             return
-        with torch.no_grad():
-            for fn, hl in self.packers:
-                w = fn().detach().to(self.device, torch.float32)
-                hi = w.to(torch.bfloat16)
-                hl.hi.copy_(hi)
-                hl.lo.copy_((w - hi.float()).to(torch.bfloat16))
-            for fn, v in self.vec_packers:
-                v.copy_(fn().detach().to(self.device, torch.float32).reshape(-1))
+        src = self._param_slab()
+        st = ops._stream()
+        for c in self._wchunks:
+            _lib.check(self.lib.v2a_gather_split(src.data_ptr(), c["map"].data_ptr(), c["used"], c["hi"].data_ptr(),
+                                                 c["lo"].data_ptr(), None, st), "gather_split")
+        for c in self._vchunks:
+            _lib.check(self.lib.v2a_gather_split(src.data_ptr(), c["map"].data_ptr(), c["used"], None, None,
+                                                 c["f32"].data_ptr(), st), "gather_split")
+        if not self._trace_checked:   # first pack: the traced gather must reproduce the torch packers bit for bit
+            for got, want in self._repack_reference():
+                if not torch.equal(got, want):
+                    raise RuntimeError("v2a_b200 policy engine: traced weight table disagrees with its packer")
+            self._trace_checked = True
         self._wkey = key
 
     # ---- launch wrappers -------------------------------------------------------
     def igemm(self, steps, **kw):
         g = ops.Igemm(passes=self.passes, **kw)
         self.igemms.append(g)
-        steps.append(g.run)
+        steps.add(f"igemm M{g.rows} N{g.cout} K{g.ktot}", g.run)
 
     def gn(self, steps, backward: bool, **kw):
         d = _lib.PolicyGnDesc()
@@ -303,7 +401,7 @@ class _PolicyEngine:
             setattr(d, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
         self.keep.append((d, kw))
         fn = self.lib.v2a_policy_gn_act_bwd if backward else self.lib.v2a_policy_gn_act_fwd
-        steps.append(lambda: _lib.check(fn(C.byref(d), ops._stream()), "policy_gn_act"))
+        steps.add("gn_bwd" if backward else "gn_fwd", lambda: _lib.check(fn(C.byref(d), ops._stream()), "policy_gn_act"))
 
     def im2col_t(self, steps, src: HL, ld, Bn, Tin, Tout, Cc, offsets, stride) -> HL:
         """-> planes [Cc*len(offsets), pad64(Bn*Tout)] (zero padded K), the B operand of a weight-gradient GEMM."""
@@ -311,7 +409,7 @@ class _PolicyEngine:
         out = self.hlz(Cc * len(offsets), kpad)
         arr = (C.c_int * len(offsets))(*offsets)
         self.keep.append(arr)
-        steps.append(lambda: _lib.check(self.lib.v2a_policy_im2col_t(
+        steps.add(f"im2col_t C{Cc} taps{len(offsets)} K{kpad}", lambda: _lib.check(self.lib.v2a_policy_im2col_t(
             src.hi.data_ptr(), src.lo.data_ptr(), ld, 0, Bn, Tin, Tout, Cc, len(offsets), stride, arr,
             out.hi.data_ptr(), out.lo.data_ptr(), kpad, ops._stream()), "im2col_t"))
         return out
@@ -322,18 +420,18 @@ class _PolicyEngine:
         hl = self.hlz(rows, ldh) if want_hl else None
         kpad = _c64(rows)
         tr = self.hlz(ref.C, kpad)
-        steps.append(lambda: _lib.check(self.lib.v2a_grad_prep(
+        steps.add(f"grad_prep rows{rows} C{ref.C}", lambda: _lib.check(self.lib.v2a_grad_prep(
             ref.ptr, rows, ref.C, ref.ld, None if hl is None else hl.hi.data_ptr(),
             None if hl is None else hl.lo.data_ptr(), ldh, tr.hi.data_ptr(), tr.lo.data_ptr(), kpad,
             None if colsum is None else colsum.data_ptr(), ops._stream()), "grad_prep"))
         return hl, ldh, tr
 
     def add_into(self, steps, dst: _Ref, src: _Ref, rows, accumulate=True):
-        steps.append(lambda: _lib.check(self.lib.v2a_add_strided(dst.ptr, dst.ld, src.ptr, src.ld, rows, dst.C,
+        steps.add("add_strided", lambda: _lib.check(self.lib.v2a_add_strided(dst.ptr, dst.ld, src.ptr, src.ld, rows, dst.C,
                                                                 1 if accumulate else 0, ops._stream()), "add"))
 
     def act_bwd(self, steps, x, dy, dx, n, act):
-        steps.append(lambda: _lib.check(self.lib.v2a_act_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), None, None,
+        steps.add("act_bwd", lambda: _lib.check(self.lib.v2a_act_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), None, None,
                                                             n, act, ops._stream()), "act_bwd"))
 
     # ---- generic stride-1 conv over [B, T, C] (k taps; inputs may be a 2-way channel concat) -------------
@@ -368,7 +466,7 @@ class _PolicyEngine:
             tmp = self.zeros(m_rows, _c16(ncols))
             self.igemm(steps, srcs=[(dyT, kpad, prog.src_dims[0])], taps=prog.taps, w=col, out_dims=prog.out_dims,
                        cout=ncols, out_f32=tmp)
-            steps.append(lambda: target[:, col_off:col_off + ncols].copy_(tmp[:, :ncols]))
+            steps.add("copy_narrow", lambda: target[:, col_off:col_off + ncols].copy_(tmp[:, :ncols]))
 
     def conv_bwd(self, steps, wfn, wgrad_target, k, pad, ins: List[_Node], dy: HL, ld_dy, dyT: HL, cout,
                  dx_residual: Optional[_Ref] = None):
@@ -435,8 +533,8 @@ class _PolicyEngine:
         self.t_buf = torch.zeros(Bn, dtype=torch.int64, device=dev)
         temb = self.zeros(Bn, dsed)
         temb_hl = self.hlz(Bn, dsed)
-        self.fwd.append(lambda: ops.timestep_embedding(self.t_buf, dsed, 1, temb))
-        self.fwd.append(lambda: _lib.check(self.lib.v2a_split_hl(temb.data_ptr(), Bn, dsed, dsed, temb_hl.hi.data_ptr(),
+        self.fwd.add("timestep_embedding", lambda: ops.timestep_embedding(self.t_buf, dsed, 1, temb))
+        self.fwd.add("split_hl", lambda: _lib.check(self.lib.v2a_split_hl(temb.data_ptr(), Bn, dsed, dsed, temb_hl.hi.data_ptr(),
                                                                 temb_hl.lo.data_ptr(), ops._stream()), "split"))
         lin1, lin3 = model.diffusion_step_encoder[1], model.diffusion_step_encoder[3]
         n_temb = _Node(Bn, 1, dsed, hl=temb_hl)
@@ -444,7 +542,7 @@ class _PolicyEngine:
         self.conv_fwd(lambda: lin1.weight.unsqueeze(-1), lambda: lin1.bias, 4 * dsed, 1, 0, [n_temb], out_f32=a1)
         m1_hl = self.hlz(Bn, 4 * dsed)
         p1 = ops.Prep(x0=a1, act=ops.ACT_MISH, out_hl=m1_hl)
-        self.fwd.append(p1.run)
+        self.fwd.add("prep_mish", p1.run)
         n_m1 = _Node(Bn, 1, 4 * dsed, hl=m1_hl)
         self.gf = self.zeros(Bn, cd)
         self.conv_fwd(lambda: lin3.weight.unsqueeze(-1), lambda: lin3.bias, dsed, 1, 0, [n_m1],
@@ -452,7 +550,7 @@ class _PolicyEngine:
         self.gc_in = self.gf[:, dsed:]
         mgf_hl = self.hlz(Bn, cd)
         p2 = ops.Prep(x0=self.gf, act=ops.ACT_MISH, out_hl=mgf_hl)
-        self.fwd.append(p2.run)
+        self.fwd.add("prep_mish", p2.run)
         n_mgf = _Node(Bn, 1, cd, hl=mgf_hl)
         blocks = [m for m in model.modules() if isinstance(m, ConditionalResidualBlock1D)]
         ftot = sum(2 * m.out_channels for m in blocks)
@@ -591,7 +689,7 @@ class _PolicyEngine:
         self.x_in = self.x_in_base[:, :din]
         x0 = _Node(Bn, T, din, ld=16, f32=None, hl=self.hlz(Bn * T, 16))
         self.x0 = x0
-        self.fwd.append(lambda: _lib.check(self.lib.v2a_split_hl(self.x_in_base.data_ptr(), Bn * T, 16, 16,
+        self.fwd.add("split_hl", lambda: _lib.check(self.lib.v2a_split_hl(self.x_in_base.data_ptr(), Bn * T, 16, 16,
                                                                 x0.hl.hi.data_ptr(), x0.hl.lo.data_ptr(),
                                                                 ops._stream()), "split"))
         x, hs = x0, []
@@ -659,7 +757,7 @@ class _PolicyEngine:
                 g(m.cond_encoder[1].weight).copy_(self.dwfilm[o:o + n2])
                 g(m.cond_encoder[1].bias).copy_(self.dbfilm[o:o + n2])
                 o += n2
-        st.append(scatter_film)
+        st.add("scatter_film", scatter_film)
         ddse = _Ref(dgf, 0, dsed)
         d3h, ld3, d3T = self.grad_prep(st, ddse, Bn, colsum=g(lin3.bias))
         self.conv_bwd(st, lambda: lin3.weight.unsqueeze(-1), g(lin3.weight), 1, 0, [n_m1], d3h, ld3, d3T, dsed)
