@@ -88,6 +88,8 @@ typedef struct v2a_igemm_desc {
 int v2a_igemm_plan_create(const v2a_igemm_desc* desc, void** plan_out);
 int v2a_igemm_plan_run(void* plan, void* stream);
 void v2a_igemm_plan_destroy(void* plan);
+/* how many CTAs share one output tile's K loop (1 = no split-K); introspection for tests / probes */
+int v2a_igemm_plan_k_splits(void* plan);
 /* kernel launches performed by v2a_* calls since process start */
 int64_t v2a_launch_count(void);
 
@@ -249,6 +251,11 @@ int v2a_grad_prep(const float* dy, int64_t rows, int C, int ld, void* hi, void* 
 /* dx = dy * act'(x), act 1 SiLU / 2 Mish; optional fp32 and hi/lo outputs */
 int v2a_act_bwd(const float* x, const float* dy, float* dx, void* hi, void* lo, int64_t n, int act,
                 void* stream);
+/* dst[dst_off[r] + c] = src[r*ld + c], c < cols: rows of a concatenated gradient matrix back into the
+ * per-module parameter-gradient windows (the FiLM cond_encoder linears run as ONE GEMM,
+ * conditional_unet1d.py:36-40) */
+int v2a_scatter_rows(const float* src, int ld, int64_t rows, int cols, const int64_t* dst_off, float* dst,
+                     void* stream);
 /* dst[r*ld_dst + c] (+)= src[r*ld_src + c], c < C (gradient fan-in of skip connections) */
 int v2a_add_strided(float* dst, int ld_dst, const float* src, int ld_src, int64_t rows, int C, int accumulate,
                     void* stream);

@@ -58,9 +58,18 @@ def main():
         print(f"sum of igemm launches {tot:.2f} ms ({len(eng.igemms)} launches)")
         for m, i, r, c, k, bn, tf in sorted(rows, reverse=True)[:40]:
             print(f"  #{i:3d} rows {r:8d} cout {c:5d} K {k:6d} bn {bn:3d}  {m:7.3f} ms  {tf:7.1f} TFLOP/s")
-        # non-igemm remainder
-        other = [s for s in eng.steps]
         print(f"non-igemm share ~ {ms - tot:.2f} ms")
+        # every planned step, eagerly, by kind (static I/O bound by the forward above)
+        eng.stats_arena.zero_()
+        by, rows2 = {}, []
+        for i, (st, tag) in enumerate(zip(eng.steps, eng.tags)):
+            m = timed(st, n=2, warm=1)
+            by[tag.split()[0]] = (by.get(tag.split()[0], (0, 0))[0] + m, by.get(tag.split()[0], (0, 0))[1] + 1)
+            if not tag.startswith("igemm"):
+                rows2.append((m, i, tag))
+        print("by kind: " + ", ".join(f"{k} {v[0]:.2f} ms/{v[1]}" for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])))
+        for m, i, tag in sorted(rows2, reverse=True)[:25]:
+            print(f"  step {i:3d} {m:7.3f} ms {tag}")
 
 
 if __name__ == "__main__":

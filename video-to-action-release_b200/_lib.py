@@ -118,6 +118,7 @@ SIGNATURES = {
     "v2a_igemm_plan_create": (_i, [C.POINTER(IgemmDesc), C.POINTER(_vp)]),
     "v2a_igemm_plan_run": (_i, [_vp, _vp]),
     "v2a_igemm_plan_destroy": (None, [_vp]),
+    "v2a_igemm_plan_k_splits": (_i, [_vp]),
     "v2a_channel_stats": (_i, [_vp, _i64, _i64, _i, _vp, _vp]),
     "v2a_prep": (_i, [C.POINTER(PrepDesc), _vp]),
     "v2a_attention": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
@@ -135,6 +136,7 @@ SIGNATURES = {
     "v2a_policy_im2col_t": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _vp, _vp, _i64, _vp]),
     "v2a_grad_prep": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _i64, _vp, _vp]),
     "v2a_act_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    "v2a_scatter_rows": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp]),
     "v2a_add_strided": (_i, [_vp, _i, _vp, _i, _i64, _i, _i, _vp]),
     "v2a_grad_sumsq": (_i, [_vp, _i64, _vp, _vp]),
     "v2a_adamw_ema_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _f, _i, _f, _vp]),

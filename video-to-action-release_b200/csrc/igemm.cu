@@ -90,10 +90,14 @@ struct alignas(64) IgemmParams {
     int stats_ld;
     int stats_replicas;
     long long stats_rep_stride;
+    int k_splits;         // >1: the K loop of one output tile is shared by k_splits CTAs (fp32 atomics)
+    int kps;              // K iterations per split
     int debug;  // V2A_IGEMM_DEBUG bits: 1 skip stats, 2 skip stores, 4 skip residual (timing experiments only)
 };
 
-__device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int& n_idx, int o[4]) {
+__device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int& n_idx, int o[4], int& split) {
+    split = tile % p.k_splits;     // splits of one output tile are adjacent: they run concurrently
+    tile /= p.k_splits;
     n_idx = tile % p.num_n_tiles;
     int m = tile / p.num_n_tiles;
 #pragma unroll
@@ -102,6 +106,27 @@ __device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int&
         m /= p.ntile[d];
         o[d] = j << p.tile_log2[d];
     }
+}
+
+// Tiles of one CTA.  Plain plans walk a CONTIGUOUS range (consecutive tiles share the GroupNorm instance,
+// so the epilogue keeps partial sums on chip and issues ~2 rounds of global atomics per launch instead of
+// one per tile); split-K plans interleave CTAs so the splits of one output tile run concurrently.
+struct TileRange {
+    int first, step, count;
+};
+__device__ __forceinline__ TileRange cta_tiles(const IgemmParams& p, int total) {
+    TileRange r;
+    if (p.k_splits > 1) {
+        r.first = blockIdx.x;
+        r.step = gridDim.x;
+        r.count = total > r.first ? (total - r.first + r.step - 1) / r.step : 0;
+    } else {
+        const int per = (total + gridDim.x - 1) / gridDim.x;
+        r.first = blockIdx.x * per;
+        r.step = 1;
+        r.count = total > r.first ? min(per, total - r.first) : 0;
+    }
+    return r;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
@@ -120,6 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     uint64_t* tempty_bar = bars + 2 * S + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
     float* warp_add = reinterpret_cast<float*>(bars) + 64;  // 8 epilogue warps x 256 floats, after the 256 B barrier block
+    double* stat_acc = reinterpret_cast<double*>(warp_add + 8 * 256);  // 8 warps x [8 chunks][32 lanes] partial sums
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -146,22 +172,28 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int total_tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
+    const TileRange tr = cta_tiles(p, total_tiles);
 
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            int n_idx, o[4];
-            decode_tile(p, tile, n_idx, o);
+        for (int ti = 0; ti < tr.count; ++ti) {
+            const int tile = tr.first + ti * tr.step;
+            int n_idx, o[4], split;
+            decode_tile(p, tile, n_idx, o, split);
             const int n0 = n_idx * p.block_n;
+            const int kb = split * p.kps;
+            const int ke = min(kb + p.kps, p.k_iters);
             int kit = 0;
             for (int e = 0; e < p.ntaps; ++e) {
                 const int src = p.tap_src[e];
                 const int c1 = o[0] + p.tap_d[e][0], c2 = o[1] + p.tap_d[e][1];
                 const int c3 = o[2] + p.tap_d[e][2], c4 = o[3] + p.tap_d[e][3];
+                if (kit + p.tap_chunks[e] <= kb || kit >= ke) { kit += p.tap_chunks[e]; continue; }
                 for (int ch = 0; ch < p.tap_chunks[e]; ++ch, ++kit) {
+                    if (kit < kb || kit >= ke) continue;
                     mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
                     uint8_t* st = smem + (size_t)stage * p.stage_bytes;
                     mbar_arrive_expect_tx(&full_bar[stage], p.stage_bytes);
@@ -185,14 +217,16 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         const uint32_t idesc = umma_idesc_bf16(kTileM, p.block_n);
         int stage = 0;
         uint32_t phase = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int it = 0; it < tr.count; ++it) {
+            const int tile = tr.first + it * tr.step;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * kAccStride;
-            for (int kit = 0; kit < p.k_iters; ++kit) {
+            const int kb = (tile % p.k_splits) * p.kps;
+            const int n_it = min(kb + p.kps, p.k_iters) - kb;
+            for (int kit = 0; kit < n_it; ++kit) {
                 mbar_wait(&full_bar[stage], phase, 300 + stage);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
@@ -219,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                         umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kit | k) != 0);
                 }
                 umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-                if (kit == p.k_iters - 1) umma_commit(&tfull_bar[acc]);
+                if (kit == n_it - 1) umma_commit(&tfull_bar[acc]);
                 if (++stage == S) { stage = 0; phase ^= 1; }
             }
         }
@@ -234,13 +268,30 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         const int c_end = half == 0 ? ((nch + 1) >> 1) << 4 : p.block_n;
         // same-address atomic contention is spread over `stats_replicas` copies of the sums
         double* const stats = (p.stats && !(p.debug & 1)) ? p.stats + (long long)(blockIdx.x % p.stats_replicas) * p.stats_rep_stride : nullptr;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        // on-chip GroupNorm partial sums of the tiles this CTA walks (flushed when the instance changes)
+        double* sacc = stat_acc + (warp - 4) * 256;
+        for (int i = lane; i < 256; i += 32) sacc[i] = 0.0;
+        int held_inst = -1, held_n0 = 0;
+        auto flush_stats = [&]() {
+            if (held_inst >= 0) {
+                for (int c = c_begin; c < c_end; c += 16) {
+                    const int col = held_n0 + c + (lane & 15);
+                    const int slot = ((c - c_begin) >> 4) * 32 + lane;
+                    if (col < p.cout)
+                        atomicAdd(&stats[((int64_t)held_inst * p.stats_ld + col) * 2 + (lane >> 4)], sacc[slot]);
+                    sacc[slot] = 0.0;
+                }
+            }
+            held_inst = -1;
+        };
+        for (int it = 0; it < tr.count; ++it) {
+            const int tile = tr.first + it * tr.step;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            int n_idx, o[4];
-            decode_tile(p, tile, n_idx, o);
+            int n_idx, o[4], split;
+            decode_tile(p, tile, n_idx, o, split);
             const int n0 = n_idx * p.block_n;
+            const bool lead = split == 0;   // bias / rowvec / residual enter the sum exactly once
             // row -> output pixel
             int r = row, coord[4];
             bool valid = true;
@@ -261,22 +312,27 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             }
             // warp-uniform row group / stats instance?  (true for every large layer)
             const int rv0 = __shfl_sync(0xffffffffu, rv, 0);
-            const bool rv_uniform = p.rowvec == nullptr || __all_sync(0xffffffffu, !valid || rv == rv0);
+            const bool rv_uniform = p.rowvec == nullptr || !lead || __all_sync(0xffffffffu, !valid || rv == rv0);
             const int inst0 = __shfl_sync(0xffffffffu, valid ? inst : -1, 0);
             const bool inst_uniform =
                 stats != nullptr && __all_sync(0xffffffffu, !valid || inst == inst0) && inst0 >= 0;
+            if (inst_uniform && (inst0 != held_inst || n0 != held_n0)) {
+                flush_stats();
+                held_inst = inst0;
+                held_n0 = n0;
+            }
             // stage bias (+ the shared rowvec row) for this N tile: overlaps the tile's MMAs
             __syncwarp();
             for (int c = c_begin + lane; c < c_end; c += 32) {
                 float a = 0.0f;
-                if (n0 + c < p.cout) {
+                if (lead && n0 + c < p.cout) {
                     if (p.bias) a = __ldg(&p.bias[n0 + c]);
                     if (p.rowvec && rv_uniform) a += __ldg(&p.rowvec[(int64_t)rv0 * p.ld_rowvec + n0 + c]);
                 }
                 addv[c] = a;
             }
             __syncwarp();
-            const float* res_row = (p.residual && !(p.debug & 4)) ? p.residual + pix * p.ld_res + n0 : nullptr;
+            const float* res_row = (p.residual && lead && !(p.debug & 4)) ? p.residual + pix * p.ld_res + n0 : nullptr;
             float4 res_next[4];
             if (res_row && valid && c_begin < c_end) {
 #pragma unroll
@@ -294,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) + addv[c + j];
                 if (valid) {
-                    if (p.rowvec && !rv_uniform) {
+                    if (p.rowvec && !rv_uniform && lead) {
                         const float* rp = p.rowvec + (int64_t)rv * p.ld_rowvec + n;
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
@@ -314,9 +370,15 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                     }
                     if (p.out_f32 && !(p.debug & 2)) {
                         float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * p.ldc + n);
+                        if (p.k_splits > 1) {   // partial sum of this K range (output zeroed / pre-loaded by the host)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                            for (int q = 0; q < 4; ++q)
+                                atomicAdd(op + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        }
                     }
                     if (p.out_hi && !(p.debug & 2)) {
                         uint4 h0, l0, h1, l1;
@@ -349,10 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                                 w[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                             }
                         }
-                        const int col = n + (lane & 15);
-                        if (col < p.cout)
-                            atomicAdd(&stats[((int64_t)inst0 * p.stats_ld + col) * 2 + (lane >> 4)],
-                                      (double)w[0]);
+                        sacc[((c - c_begin) >> 4) * 32 + lane] += (double)w[0];   // warp-private slot
                     } else if (valid) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
@@ -381,6 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
         }
+        if (stats) flush_stats();
     }
 
     tc_fence_before();
@@ -446,6 +506,9 @@ struct IgemmPlan {
     IgemmParams p;
     int grid;
     size_t smem;
+    bool zero_out;        // split-K: clear the output window before the launch
+    size_t zero_width;    // bytes per row to clear
+    int64_t zero_rows;
 };
 
 static int g_num_sms = 0;
@@ -517,7 +580,8 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
     p.b_tile_bytes = (uint32_t)d->block_n * kChunkK * 2;
     p.stage_bytes = (uint32_t)d->passes == 3 ? 2 * (kATileBytes + p.b_tile_bytes)
                                              : (kATileBytes + p.b_tile_bytes);
-    const size_t overhead = 1024 /*align*/ + 256 /*barriers*/ + 8192 /*epilogue bias staging*/;
+    const size_t overhead = 1024 /*align*/ + 256 /*barriers*/ + 8192 /*epilogue bias staging*/ +
+                            16384 /*epilogue GroupNorm partial sums*/;
     int stages = (int)((g_max_smem - overhead) / p.stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) {
@@ -575,7 +639,36 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
         delete pl;
         return rc;
     }
-    const int total = p.num_m_tiles * p.num_n_tiles;
+    // split-K: a GEMM with few output tiles (policy layers: M = B*T = 1024 rows) leaves most SMs idle; share
+    // each tile's K loop between CTAs that add fp32 partial sums with vector atomics.  Needs a plain fp32
+    // output (no hi/lo planes, no GroupNorm sums, which want the finished value).
+    p.k_splits = 1;
+    p.kps = p.k_iters;
+    pl->zero_out = false;
+    {
+        const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+        const char* env = getenv("V2A_SPLIT_K");
+        const bool allowed = d->out_f32 && !d->out_hi && !d->stats && !(env && atoi(env) == 0);
+        if (allowed && tiles_mn * 2 <= g_num_sms && p.k_iters >= 8) {
+            int want = g_num_sms / tiles_mn;
+            if (want > 16) want = 16;
+            if (want > p.k_iters / 4) want = p.k_iters / 4;
+            if (env && atoi(env) > 1) want = atoi(env);
+            if (want > 1) {
+                p.kps = ceil_div(p.k_iters, want);
+                p.k_splits = ceil_div(p.k_iters, p.kps);
+            }
+        }
+        if (p.k_splits > 1) {
+            // accumulate-in-place (residual aliases the output): the atomics add onto what is there
+            const bool in_place = d->residual == d->out_f32 && d->ld_res == d->ldc;
+            if (in_place) p.residual = nullptr;
+            pl->zero_out = !in_place;
+            pl->zero_width = (size_t)(((d->cout + 15) / 16) * 16) * sizeof(float);
+            pl->zero_rows = (int64_t)d->out_dims[0] * d->out_dims[1] * d->out_dims[2] * d->out_dims[3];
+        }
+    }
+    const int total = p.num_m_tiles * p.num_n_tiles * p.k_splits;
     pl->grid = total < g_num_sms ? total : g_num_sms;
     static bool attr_set = false;
     if (!attr_set) {
@@ -609,11 +702,16 @@ int v2a_igemm_plan_create(const v2a_igemm_desc* desc, void** plan_out) {
 
 int v2a_igemm_plan_run(void* plan, void* stream) {
     v2a::IgemmPlan* pl = reinterpret_cast<v2a::IgemmPlan*>(plan);
+    if (pl->zero_out)
+        V2A_CUDA_OK(cudaMemset2DAsync(pl->p.out_f32, (size_t)pl->p.ldc * sizeof(float), 0, pl->zero_width,
+                                      (size_t)pl->zero_rows, (cudaStream_t)stream));
     v2a::igemm_kernel<<<pl->grid, v2a::kThreads, pl->smem, (cudaStream_t)stream>>>(pl->p);
     V2A_CUDA_OK(cudaGetLastError());
     v2a::g_launches.fetch_add(1);
     return 0;
 }
+
+int v2a_igemm_plan_k_splits(void* plan) { return reinterpret_cast<v2a::IgemmPlan*>(plan)->p.k_splits; }
 
 void v2a_igemm_plan_destroy(void* plan) { delete reinterpret_cast<v2a::IgemmPlan*>(plan); }
 

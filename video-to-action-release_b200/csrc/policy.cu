@@ -37,6 +37,7 @@ struct GnActParams {
     float* dbias; float* dgamma; float* dbeta;      // [C] accumulated with atomics over samples
     float* dfilm; int ld_dfilm;           // [B][2C] written
     int B;
+    int stage_words;                      // bwd: T*C when dy^T is staged through shared memory, else 0
 };
 
 // thread -> (octet of 8 channels, lane over t); values of a thread share one group
@@ -184,35 +185,59 @@ __global__ void __launch_bounds__(kPolThreads) gn_act_bwd_kernel(const GnActPara
     const float cnt = (float)(cpg * p.T);
     const float m1 = group_sum(s1, g, sh, p.groups) / cnt;
     const float m2 = group_sum(s2, g, sh, p.groups) / cnt;
-    if (!active) return;
+    // dy^T staging: (hi, lo) pairs of the whole sample, [T][C] 32-bit words, when it fits (policy sizes: 16 KB)
+    extern __shared__ uint32_t stage[];
+    const bool staged = p.dyT_hi != nullptr && p.stage_words > 0;
     float dbi[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int i = 0;
     const int64_t BT = p.ld_T;
-    for (int t = tlane; t < p.T; t += tl, ++i) {
-        const int64_t row = (int64_t)b * p.T + t;
-        float dy[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            dy[j] = rstd * (dn[i][j] - m1 - n[i][j] * m2);
-            dbi[j] += dy[j];
-        }
-        if (p.dy_f32) store8(p.dy_f32 + row * p.C + c0, dy);
-        uint4 h, l;
-        split8(dy, h, l);
-        if (p.dy_hi) {
-            *reinterpret_cast<uint4*>(p.dy_hi + row * p.C + c0) = h;
-            *reinterpret_cast<uint4*>(p.dy_lo + row * p.C + c0) = l;
-        }
-        if (p.dyT_hi) {
-            const __nv_bfloat16* hh = reinterpret_cast<const __nv_bfloat16*>(&h);
-            const __nv_bfloat16* ll = reinterpret_cast<const __nv_bfloat16*>(&l);
+    if (active)
+        for (int t = tlane; t < p.T; t += tl, ++i) {
+            const int64_t row = (int64_t)b * p.T + t;
+            float dy[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                p.dyT_hi[(int64_t)(c0 + j) * BT + row] = hh[j];
-                p.dyT_lo[(int64_t)(c0 + j) * BT + row] = ll[j];
+                dy[j] = rstd * (dn[i][j] - m1 - n[i][j] * m2);
+                dbi[j] += dy[j];
+            }
+            if (p.dy_f32) store8(p.dy_f32 + row * p.C + c0, dy);
+            uint4 h, l;
+            split8(dy, h, l);
+            if (p.dy_hi) {
+                *reinterpret_cast<uint4*>(p.dy_hi + row * p.C + c0) = h;
+                *reinterpret_cast<uint4*>(p.dy_lo + row * p.C + c0) = l;
+            }
+            if (p.dyT_hi) {
+                const uint16_t* hh = reinterpret_cast<const uint16_t*>(&h);
+                const uint16_t* ll = reinterpret_cast<const uint16_t*>(&l);
+                if (staged) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        stage[t * p.C + c0 + j] = (uint32_t)hh[j] | ((uint32_t)ll[j] << 16);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        reinterpret_cast<uint16_t*>(p.dyT_hi)[(int64_t)(c0 + j) * BT + row] = hh[j];
+                        reinterpret_cast<uint16_t*>(p.dyT_lo)[(int64_t)(c0 + j) * BT + row] = ll[j];
+                    }
+                }
+            }
+        }
+    if (staged) {
+        __syncthreads();
+        // one channel per thread: its T values are one contiguous run of dy^T (4 bf16 = 8 B per store)
+        for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+            uint16_t* dh = reinterpret_cast<uint16_t*>(p.dyT_hi) + (int64_t)c * BT + (int64_t)b * p.T;
+            uint16_t* dl = reinterpret_cast<uint16_t*>(p.dyT_lo) + (int64_t)c * BT + (int64_t)b * p.T;
+            for (int t = 0; t < p.T; t += 4) {
+                const uint32_t w0 = stage[t * p.C + c], w1 = stage[(t + 1) * p.C + c];
+                const uint32_t w2 = stage[(t + 2) * p.C + c], w3 = stage[(t + 3) * p.C + c];
+                *reinterpret_cast<uint2*>(dh + t) = make_uint2((w0 & 0xffffu) | (w1 << 16), (w2 & 0xffffu) | (w3 << 16));
+                *reinterpret_cast<uint2*>(dl + t) = make_uint2((w0 >> 16) | (w1 & 0xffff0000u), (w2 >> 16) | (w3 & 0xffff0000u));
             }
         }
     }
+    if (!active) return;
     // per-channel reductions over this thread's rows -> global accumulators
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -239,26 +264,56 @@ struct Im2colTParams {
     int off[8];
 };
 __global__ void __launch_bounds__(256) im2col_t_kernel(const Im2colTParams p) {
-    // one thread per (row = c*ntaps + k, b); writes Tout contiguous columns
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t rows = (int64_t)p.C * p.ntaps;
-    if (gid >= rows * p.B) return;
-    const int b = (int)(gid % p.B);
-    const int64_t r = gid / p.B;
-    const int k = (int)(r % p.ntaps);
-    const int c = (int)(r / p.ntaps);
+    // tile = 64 channels x 64 output columns (b, o); per tap: coalesced 128-byte channel rows in,
+    // transposed through shared memory, 128-byte column runs out.  grid (C/64, cols/64).
+    __shared__ uint32_t tile[64][65];   // (hi, lo) pairs
+    const int c_base = blockIdx.x * 64;
+    const int64_t col_base = (int64_t)blockIdx.y * 64;
+    const int64_t ncols = (int64_t)p.B * p.Tout;
     const int64_t BT = p.ld_out;
-    for (int o = 0; o < p.Tout; ++o) {
-        const int t = p.stride * o + p.off[k];
-        __nv_bfloat16 h = __float2bfloat16_rn(0.0f), l = h;
-        if (t >= 0 && t < p.Tin) {
-            const int64_t src = ((int64_t)b * p.Tin + t) * p.ld_x + p.c_off + c;
-            h = p.x_hi[src];
-            l = p.x_lo[src];
+    const uint16_t* xh = reinterpret_cast<const uint16_t*>(p.x_hi);
+    const uint16_t* xl = reinterpret_cast<const uint16_t*>(p.x_lo);
+    uint16_t* oh = reinterpret_cast<uint16_t*>(p.o_hi);
+    uint16_t* ol = reinterpret_cast<uint16_t*>(p.o_lo);
+    for (int k = 0; k < p.ntaps; ++k) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
+            const int col = idx >> 6, ch = idx & 63;
+            const int64_t gc = col_base + col;
+            uint32_t w = 0;
+            if (gc < ncols && c_base + ch < p.C) {
+                const int bb = (int)(gc / p.Tout), o = (int)(gc % p.Tout);
+                const int t = p.stride * o + p.off[k];
+                if (t >= 0 && t < p.Tin) {
+                    const int64_t src = ((int64_t)bb * p.Tin + t) * p.ld_x + p.c_off + c_base + ch;
+                    w = (uint32_t)xh[src] | ((uint32_t)xl[src] << 16);
+                }
+            }
+            tile[col][ch] = w;
         }
-        p.o_hi[r * BT + (int64_t)b * p.Tout + o] = h;
-        p.o_lo[r * BT + (int64_t)b * p.Tout + o] = l;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
+            const int ch = idx >> 6, col = idx & 63;
+            const int64_t gc = col_base + col;
+            if (gc < ncols && c_base + ch < p.C) {
+                const uint32_t w = tile[col][ch];
+                const int64_t r = (int64_t)(c_base + ch) * p.ntaps + k;
+                oh[r * BT + gc] = (uint16_t)(w & 0xffffu);
+                ol[r * BT + gc] = (uint16_t)(w >> 16);
+            }
+        }
     }
+}
+
+// dst[dst_off[r] + c] = src[r * ld + c]: the concatenated FiLM weight / bias gradients back into the
+// per-block parameter-gradient windows (one launch instead of one copy per block)
+__global__ void scatter_rows_kernel(const float* __restrict__ src, int ld, int64_t rows, int cols,
+                                    const int64_t* __restrict__ dst_off, float* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int64_t r = i / cols;
+    const int c = (int)(i % cols);
+    dst[dst_off[r] + c] = src[r * ld + c];
 }
 
 // ---------------------------------------------------------------------------
@@ -443,6 +498,7 @@ static GnActParams to_params(const v2a_policy_gn_desc* d) {
     p.dbias = d->dbias; p.dgamma = d->dgamma; p.dbeta = d->dbeta;
     p.dfilm = d->dfilm; p.ld_dfilm = d->ld_dfilm;
     p.B = d->B;
+    p.stage_words = 0;
     return p;
 }
 
@@ -460,7 +516,11 @@ int v2a_policy_gn_act_bwd(const v2a_policy_gn_desc* d, void* stream) {
     if (int rc = check_gn(d)) return rc;
     V2A_REQUIRE(d->y && d->dout && d->mean_rstd && d->dgamma && d->dbeta, "policy_gn_bwd: missing pointers");
     V2A_REQUIRE(!d->film || d->dfilm, "policy_gn_bwd: FiLM needs dfilm");
-    gn_act_bwd_kernel<<<d->B, kPolThreads, 0, (cudaStream_t)stream>>>(to_params(d));
+    GnActParams p = to_params(d);
+    // dy^T goes through shared memory (vector stores of T-long runs) when the sample fits 48 KB
+    if (d->dyT_hi && d->T % 4 == 0 && (size_t)d->T * d->C * 4 <= 48 * 1024 && p.ld_T % 4 == 0)
+        p.stage_words = d->T * d->C;
+    gn_act_bwd_kernel<<<d->B, kPolThreads, (size_t)p.stage_words * 4, (cudaStream_t)stream>>>(p);
     POL_LAUNCH_OK();
     return 0;
 }
@@ -476,8 +536,19 @@ int v2a_policy_im2col_t(const void* x_hi, const void* x_lo, int ld_x, int c_off,
     p.B = B; p.Tin = Tin; p.Tout = Tout; p.C = C; p.ntaps = ntaps; p.stride = stride;
     p.ld_out = ld_out > 0 ? ld_out : (long long)B * Tout;
     for (int i = 0; i < ntaps; ++i) p.off[i] = offsets[i];
-    const int64_t total = (int64_t)C * ntaps * B;
-    im2col_t_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
+    dim3 grid((unsigned)((C + 63) / 64), (unsigned)(((int64_t)B * Tout + 63) / 64));
+    im2col_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    POL_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_scatter_rows(const float* src, int ld, int64_t rows, int cols, const int64_t* dst_off, float* dst,
+                     void* stream) {
+    V2A_REQUIRE(src && dst_off && dst && cols >= 1 && ld >= cols, "scatter_rows: bad arguments");
+    const int64_t total = rows * cols;
+    if (total == 0) return 0;
+    scatter_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, ld, rows, cols,
+                                                                                        dst_off, dst);
     POL_LAUNCH_OK();
     return 0;
 }

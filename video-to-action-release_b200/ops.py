@@ -214,6 +214,7 @@ class Igemm:
         _lib.check(lib.v2a_igemm_plan_create(C.byref(d), C.byref(plan)), "igemm_plan_create")
         self._plan = plan
         self._lib = lib
+        self.k_splits = int(lib.v2a_igemm_plan_k_splits(plan))
 
     def run(self) -> None:
         _lib.check(self._lib.v2a_igemm_plan_run(self._plan, _stream()), "igemm_plan_run")

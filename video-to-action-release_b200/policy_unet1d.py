@@ -260,6 +260,7 @@ class _PolicyEngine:
         self.bwd: _Steps = _Steps()
         self.packers, self.vec_packers, self.keep = [], [], []
         self._wchunks, self._vchunks = [], []
+        self._graphs: Dict[str, object] = {}
         self.fwd_token = 0
         self._wkey = None
         self.igemms: List[ops.Igemm] = []
@@ -750,14 +751,22 @@ class _PolicyEngine:
         self.act_bwd(st, self.gf, n_mgf.grad.t, dgf, Bn * cd, 2)
         self.dgf = dgf
 
-        def scatter_film():
-            o = 0
-            for m in blocks:
-                n2 = 2 * m.out_channels
-                g(m.cond_encoder[1].weight).copy_(self.dwfilm[o:o + n2])
-                g(m.cond_encoder[1].bias).copy_(self.dbfilm[o:o + n2])
-                o += n2
-        st.add("scatter_film", scatter_film)
+        # rows of the concatenated FiLM gradient -> the per-block windows of the gradient slab (2 launches)
+        base = self.gslab.data_ptr()
+        w_off, b_off, o = [], [], 0
+        for m in blocks:
+            n2 = 2 * m.out_channels
+            gw, gb = g(m.cond_encoder[1].weight), g(m.cond_encoder[1].bias)
+            w_off += [(gw.data_ptr() - base) // 4 + r * cd for r in range(n2)]
+            b_off += [(gb.data_ptr() - base) // 4 + r for r in range(n2)]
+            o += n2
+        w_off_t = torch.tensor(w_off, dtype=torch.int64, device=dev)
+        b_off_t = torch.tensor(b_off, dtype=torch.int64, device=dev)
+        self.keep.append((w_off_t, b_off_t))
+        st.add("scatter_film_w", lambda: _lib.check(self.lib.v2a_scatter_rows(
+            self.dwfilm.data_ptr(), cd, ftot, cd, w_off_t.data_ptr(), base, ops._stream()), "scatter_rows"))
+        st.add("scatter_film_b", lambda: _lib.check(self.lib.v2a_scatter_rows(
+            self.dbfilm.data_ptr(), 1, ftot, 1, b_off_t.data_ptr(), base, ops._stream()), "scatter_rows"))
         ddse = _Ref(dgf, 0, dsed)
         d3h, ld3, d3T = self.grad_prep(st, ddse, Bn, colsum=g(lin3.bias))
         self.conv_bwd(st, lambda: lin3.weight.unsqueeze(-1), g(lin3.weight), 1, 0, [n_m1], d3h, ld3, d3T, dsed)
@@ -767,6 +776,32 @@ class _PolicyEngine:
         self.conv_bwd(st, lambda: lin1.weight.unsqueeze(-1), g(lin1.weight), 1, 0, [n_temb], d1h, ld1, d1T, 4 * dsed)
 
     # ---- execution -----------------------------------------------------------------
+    def _run(self, name: str, steps, pre=()):
+        """Launch a planned list.  Every buffer is static, so after one eager (warm-up) run the list is
+        captured into a CUDA graph and replayed (one launch instead of 68 / 169; V2A_NO_GRAPH=1 disables)."""
+        def eager():
+            for z in pre:
+                z.zero_()
+            for s in steps:
+                s()
+        if os.environ.get("V2A_NO_GRAPH", "0") == "1":
+            return eager()
+        seen = self._graphs.get(name)
+        if seen is None:            # first call: eager (lazy CUDA module loads must not happen under capture)
+            self._graphs[name] = False
+            return eager()
+        if seen is False:
+            g = torch.cuda.CUDAGraph()
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    eager()
+            cur.wait_stream(side)
+            self._graphs[name] = seen = g
+        seen.replay()
+
     def forward(self, sample, t, gc):
         self.refresh_weights()
         Bn, T = self.B, self.T
@@ -774,18 +809,14 @@ class _PolicyEngine:
         self.x_in.copy_(sample.reshape(Bn * T, -1))
         if self.gc_in.shape[1]:
             self.gc_in.copy_(gc)
-        for s in self.fwd:
-            s()
+        self._run("fwd", self.fwd)
         self.fwd_token += 1
         return self.out16[:, :self.x0.C].reshape(Bn, T, -1).clone()
 
     def backward(self, grad_out, clone_param_grads=True):
         Bn, T = self.B, self.T
-        for z in self._zero_each_bwd:
-            z.zero_()
         self.dout16[:, :self.x0.C].copy_(grad_out.reshape(Bn * T, -1))
-        for s in self.bwd:
-            s()
+        self._run("bwd", self.bwd, pre=self._zero_each_bwd)
         d_sample = self.x0.grad.win.reshape(Bn, T, -1).clone()
         d_gc = self.dgf[:, self.dgf.shape[1] - self.gc_in.shape[1]:].clone()
         if clone_param_grads:

@@ -315,6 +315,7 @@ class _UNetEngine:
         self.passes = int(os.environ.get("V2A_PASSES", "3"))
         self.pool = _Pool(device)
         self.steps: List = []          # callables, in launch order
+        self.tags: List[str] = []      # what each step is (developer timing probes)
         self.igemms: List[ops.Igemm] = []
         self.packers: List = []        # (fn(model) -> fp32 tensor, HL destination)
         self.bias_packers: List = []
@@ -390,18 +391,22 @@ class _UNetEngine:
         self._task_key = None
 
     # ---- deferred plan creation (stats views exist only after _build) -------
+    def _step(self, fn, tag: str) -> None:
+        self.steps.append(fn)
+        self.tags.append(tag)
+
     def add_igemm(self, **kw):
         self._pending = getattr(self, "_pending", [])
         slot = [None]
         self._pending.append((slot, kw))
-        self.steps.append(lambda s=slot: s[0].run())
+        self._step(lambda s=slot: s[0].run(), "igemm")
         return slot
 
     def add_prep(self, **kw):
         self._pending = getattr(self, "_pending", [])
         slot = [None]
         self._pending.append((slot, ("prep", kw)))
-        self.steps.append(lambda s=slot: s[0].run())
+        self._step(lambda s=slot: s[0].run(), "prep" + ("_gn" if kw.get("stats0") is not None else f"_mode{kw.get('mode', 0)}"))
         return slot
 
     def _finalize_plans(self):
@@ -502,7 +507,7 @@ class _UNetEngine:
                        cout=3 * C, out_f32=qkv, bias=b_qkv)
         h_hl, h_st = self.hl(x.rows, C)
         heads = m.num_heads
-        self.steps.append(lambda: ops.attention(qkv, N, L, heads, h_hl))
+        self._step(lambda: ops.attention(qkv, N, L, heads, h_hl), f"attention L{L}")
         out = _Act(self, N, H, W, C)
         prog2 = convs.pointwise(C, (L, N))
         w_p = self.weight(lambda: convs.pointwise_weight(m.proj_out.weight), C, prog2.ktot)
@@ -568,14 +573,14 @@ class _UNetEngine:
             ops.linear(self.temb, self.w_te0, self.b_te0, self.temb_h, act_out=ops.ACT_SILU)
             ops.linear(self.temb_h, self.w_te2, self.b_te2, self.emb, add=self.task_emb)
             ops.linear(self.emb, self.w_emb, self.b_emb, self.emb_all, act_in=ops.ACT_SILU)
-        self.steps.append(emb_path)
+        self._step(emb_path, "emb_path")
 
         # input conv: im2col'd 6-channel 3x3 (K = 54 -> one 64-wide chunk)
         conv0: Conv3d = model.input_blocks[0][0]
         c0 = conv0.spatial_conv.out_channels
         self.in_hl, _ = self.hl(N * H * W, 64)
-        self.steps.append(lambda: ops.unet_input_pack(self.io["x"], self.io["xs"], self.io["c"], self.io["cs"],
-                                                      B, Fr, H, W, self.in_hl))
+        self._step(lambda: ops.unet_input_pack(self.io["x"], self.io["xs"], self.io["c"], self.io["cs"],
+                                               B, Fr, H, W, self.in_hl), "input_pack")
         prog = convs.pointwise(64, (N * H * W,))
         w0 = self.weight(lambda: convs.input_conv_weight(conv0.spatial_conv.weight), c0, 64)
         b0 = self.vec(lambda: conv0.spatial_conv.bias, c0)
@@ -610,8 +615,8 @@ class _UNetEngine:
                        ldc=16, out_f32=self.y_out, bias=bo)
         self.wt_out = self.vec(lambda: convo.temporal_conv.weight, 27)
         self.bt_out = self.vec(lambda: convo.temporal_conv.bias, 3)
-        self.steps.append(lambda: ops.unet_output_head(self.y_out, 16, self.wt_out, self.bt_out, B, Fr, H, W,
-                                                       self.io["o"], self.io["os"]))
+        self._step(lambda: ops.unet_output_head(self.y_out, 16, self.wt_out, self.bt_out, B, Fr, H, W,
+                                                self.io["o"], self.io["os"]), "output_head")
         self.release(a_st)
         self.free_act(h)
 
