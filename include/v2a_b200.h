@@ -235,6 +235,9 @@ typedef struct v2a_policy_gn_desc {
     float* dfilm;            /* [B][ld_dfilm] += (d scale | d bias) */
     int ld_dfilm;
     int64_t ld_T;            /* row pitch of dyT (>= B*T; the pad stays zero); 0 = B*T */
+    float* partials;         /* bwd scratch [B][3][C] or NULL: per-sample bias/gamma/beta sums reduced by a second
+                                launch instead of global atomics from every CTA (dfilm then needs no zeroing race:
+                                one CTA owns each row) */
 } v2a_policy_gn_desc;
 int v2a_policy_gn_act_fwd(const v2a_policy_gn_desc* d, void* stream);
 int v2a_policy_gn_act_bwd(const v2a_policy_gn_desc* d, void* stream);

@@ -240,8 +240,26 @@ def _ex(a: Tensor, t: Tensor) -> Tensor:
     return a.gather(-1, t).reshape(-1, 1, 1, 1)
 
 
+def _pred_v_to_x0_eps(buf, model, img, x_cond, task_embed, t, guidance_weight: float):
+    """model_predictions for objective pred_v (:499-559).  guidance_weight > 0: the batch is doubled
+    (second half with zeroed task tokens), noise is mixed as (1+w) eps_c - w eps_u and x0 re-derived from it."""
+    sa, s1 = _ex(buf["sqrt_alphas_cumprod"], t), _ex(buf["sqrt_one_minus_alphas_cumprod"], t)
+    ra, rm1 = _ex(buf["sqrt_recip_alphas_cumprod"], t), _ex(buf["sqrt_recipm1_alphas_cumprod"], t)
+    x_in = torch.cat([img, x_cond], dim=1)
+    if guidance_weight > 0.0:
+        n = img.shape[0]
+        te2 = torch.cat([task_embed, torch.zeros_like(task_embed)], dim=0)
+        out = model(x_in.repeat(2, 1, 1, 1), t.repeat(2), te2)
+        x0_c = sa * img - s1 * out[:n]
+        x0_u = sa * img - s1 * out[n:]
+        eps = (1 + guidance_weight) * ((ra * img - x0_c) / rm1) - guidance_weight * ((ra * img - x0_u) / rm1)
+        return ra * img - rm1 * eps, eps
+    x0 = sa * img - s1 * model(x_in, t, task_embed)
+    return x0, (ra * img - x0) / rm1
+
+
 def ddpm_sample(sd: SD, buf: Dict[str, Tensor], x_cond: Tensor, task_embed: Tensor, shape,
-                var_temp: float = 1.0, model=None) -> Tensor:
+                var_temp: float = 1.0, model=None, guidance_weight: float = 0.0) -> Tensor:
     """sample() -> p_sample_loop -> p_sample (:561-599,643-650): ancestral sampling with
     x0 clamped to [-1, 1]; RNG order = one randn(shape), then randn_like per step t>0."""
     model = model or (lambda xx, tt, te: unet_libero_forward(sd, xx, tt, te))
@@ -249,9 +267,8 @@ def ddpm_sample(sd: SD, buf: Dict[str, Tensor], x_cond: Tensor, task_embed: Tens
     img = torch.randn(shape)
     for step in reversed(range(T)):
         t = torch.full((shape[0],), step, dtype=torch.long)
-        v = model(torch.cat([img, x_cond], dim=1), t, task_embed)
-        x0 = _ex(buf["sqrt_alphas_cumprod"], t) * img - _ex(buf["sqrt_one_minus_alphas_cumprod"], t) * v
-        x0.clamp_(-1.0, 1.0)
+        x0, _ = _pred_v_to_x0_eps(buf, model, img, x_cond, task_embed, t, guidance_weight)
+        x0 = x0.clamp(-1.0, 1.0)
         mean = _ex(buf["posterior_mean_coef1"], t) * x0 + _ex(buf["posterior_mean_coef2"], t) * img
         logvar = _ex(buf["posterior_log_variance_clipped"], t)
         noise = torch.randn_like(img) if step > 0 else 0.0
@@ -260,7 +277,7 @@ def ddpm_sample(sd: SD, buf: Dict[str, Tensor], x_cond: Tensor, task_embed: Tens
 
 
 def ddim_sample(sd: SD, buf: Dict[str, Tensor], x_cond: Tensor, task_embed: Tensor, shape,
-                sampling_timesteps: int, eta: float = 0.0, model=None) -> Tensor:
+                sampling_timesteps: int, eta: float = 0.0, model=None, guidance_weight: float = 0.0) -> Tensor:
     """ddim_sample (:601-641): eta-DDIM, x0 NOT clipped, randn_like drawn every non-final step."""
     model = model or (lambda xx, tt, te: unet_libero_forward(sd, xx, tt, te))
     T = buf["betas"].shape[0]
@@ -268,9 +285,7 @@ def ddim_sample(sd: SD, buf: Dict[str, Tensor], x_cond: Tensor, task_embed: Tens
     img = torch.randn(shape)
     for time, time_next in zip(times[:-1], times[1:]):
         t = torch.full((shape[0],), time, dtype=torch.long)
-        v = model(torch.cat([img, x_cond], dim=1), t, task_embed)
-        x0 = _ex(buf["sqrt_alphas_cumprod"], t) * img - _ex(buf["sqrt_one_minus_alphas_cumprod"], t) * v
-        eps = (_ex(buf["sqrt_recip_alphas_cumprod"], t) * img - x0) / _ex(buf["sqrt_recipm1_alphas_cumprod"], t)
+        x0, eps = _pred_v_to_x0_eps(buf, model, img, x_cond, task_embed, t, guidance_weight)
         if time_next < 0:
             img = x0
             continue

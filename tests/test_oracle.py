@@ -48,6 +48,22 @@ def test_tiny_forward_and_samplers_match_reference_golden():
         assert rel_l2(s, GOLD["tiny_ddim3of10"]) < 1e-5
 
 
+def test_classifier_free_guidance_samplers_match_reference_golden():
+    """guidance_weight > 0: doubled batch, zeroed task tokens, noise-space mixing."""
+    gold = torch.load(os.path.join(HERE, "golden", "video_cfg_golden.pt"))
+    sd = VO.seeded_state_dict(tiny_shapes(), 1)
+    _, _, x_cond, te = tiny_inputs()
+    with torch.no_grad():
+        torch.manual_seed(81)
+        s = VO.ddpm_sample(sd, VO.cosine_schedule_buffers(4), x_cond, te, (2, 9, 16, 16), guidance_weight=1.5)
+        assert rel_l2(s, gold["tiny_ddpm4_cfg"]) < 1e-5
+        torch.manual_seed(82)
+        s = VO.ddim_sample(sd, VO.cosine_schedule_buffers(10), x_cond, te, (2, 9, 16, 16), 3, guidance_weight=1.5)
+        assert rel_l2(s, gold["tiny_ddim3of10_cfg"]) < 1e-5
+        # guidance really changes the result (the fixture is not vacuous)
+        assert rel_l2(s, GOLD["tiny_ddim3of10"]) > 1e-2
+
+
 def test_config1_forward_matches_reference_golden():
     shapes = {k[len("model."):]: tuple(v) for k, v in LAYOUT.items() if k.startswith("model.")}
     sd = VO.seeded_state_dict(shapes, 2)

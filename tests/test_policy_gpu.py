@@ -135,6 +135,16 @@ def test_policy_gn_kernels_match_autograd():
     assert rel_l2((dyh.float() + dyl.float()).reshape(B, T, Cc), y.grad) < 1e-4
     assert rel_l2((th.float() + tl.float())[:, :B * T], y.grad.reshape(B * T, Cc).t()) < 1e-4
     assert (th[:, B * T:] == 0).all()
+    # same backward through the partial-sum path (no global atomics): per-sample sums + column-sum launch
+    part = torch.zeros(B, 3, Cc, device="cuda")
+    for tns in (dbias, dga, dbe, dfilm):
+        tns.zero_()
+    d.partials = part.data_ptr()
+    _lib.check(lib.v2a_policy_gn_act_bwd(C.byref(d), None))
+    torch.cuda.synchronize()
+    assert rel_l2(dga, gamma.grad) < 1e-4 and rel_l2(dbe, beta.grad) < 1e-4 and rel_l2(dfilm, film.grad) < 1e-4
+    assert rel_l2(dbias, y.grad.sum((0, 1))) < 1e-4
+    assert rel_l2((th.float() + tl.float())[:, :B * T], y.grad.reshape(B * T, Cc).t()) < 1e-4
 
 
 def test_fused_train_step_matches_torch_adamw_clip_ema():

@@ -107,6 +107,29 @@ def test_tiny_samplers_match_reference_golden(cpu_rng_stream):
     assert rel_l2(s, gold["tiny_ddim3of10"]) < TOL
 
 
+def test_classifier_free_guidance_matches_reference_golden(cpu_rng_stream):
+    """guidance_weight poked from outside (diffuser/models/train_utils.py:23-30): the general sampling loop
+    around the CUDA UNet (one 2B-sample forward per step) against the unmodified reference."""
+    from tests.golden.configs import tiny_inputs
+    net, _ = _tiny_model(1)
+    _, _, x_cond, te = tiny_inputs()
+    gold = torch.load(os.path.join(HERE, "golden", "video_cfg_golden.pt"))
+    d = _diffusion(net, 9, (16, 16), 4, 4)
+    d.guidance_weight = 1.5
+    torch.manual_seed(81)
+    s = d.sample(x_cond.cuda(), te.cuda(), batch_size=2)
+    assert s.shape == (2, 9, 16, 16) and s.min() >= 0 and s.max() <= 1
+    assert rel_l2(s, gold["tiny_ddpm4_cfg"]) < TOL
+    d10 = _diffusion(net, 9, (16, 16), 10, 3)
+    d10.guidance_weight = 1.5
+    torch.manual_seed(82)
+    assert rel_l2(d10.sample(x_cond.cuda(), te.cuda(), batch_size=2), gold["tiny_ddim3of10_cfg"]) < TOL
+    # back to the fused path when guidance is switched off again
+    d.guidance_weight = 0
+    torch.manual_seed(77)
+    assert rel_l2(d.sample(x_cond.cuda(), te.cuda(), batch_size=2), _gold()["tiny_ddpm4"]) < TOL
+
+
 def test_graph_replay_equals_eager_launches(cpu_rng_stream, monkeypatch):
     from tests.golden.configs import tiny_inputs
     net, _ = _tiny_model(3)

@@ -106,6 +106,7 @@ class PolicyGnDesc(C.Structure):
         ("dbias", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
         ("dfilm", C.c_void_p), ("ld_dfilm", C.c_int),
         ("ld_T", C.c_int64),
+        ("partials", C.c_void_p),
     ]
 
 

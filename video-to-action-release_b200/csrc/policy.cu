@@ -38,6 +38,7 @@ struct GnActParams {
     float* dfilm; int ld_dfilm;           // [B][2C] written
     int B;
     int stage_words;                      // bwd: T*C when dy^T is staged through shared memory, else 0
+    float* partials;                      // bwd: [B][3][C] per-sample bias/gamma/beta sums (no global atomics) or null
 };
 
 // thread -> (octet of 8 channels, lane over t); values of a thread share one group
@@ -237,8 +238,36 @@ __global__ void __launch_bounds__(kPolThreads) gn_act_bwd_kernel(const GnActPara
             }
         }
     }
+    // per-channel reductions.  Global atomics from every CTA onto the same 3C addresses were the whole cost of
+    // this kernel (L2 serialises them: ~5*C*B atomics per launch); instead the CTA reduces its T lanes in shared
+    // memory, stores FiLM gradients plainly (one owner per (sample, channel)) and writes its bias / gamma / beta
+    // partial sums to partials[b][3][C] for colsum_partials_kernel.
+    if (p.partials) {
+        float* red = reinterpret_cast<float*>(stage);   // [5][C], after the dy^T staging is consumed
+        __syncthreads();
+        for (int i = threadIdx.x; i < 5 * p.C; i += blockDim.x) red[i] = 0.0f;
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                atomicAdd(&red[c0 + j], dbi[j]);
+                atomicAdd(&red[p.C + c0 + j], dga[j]);
+                atomicAdd(&red[2 * p.C + c0 + j], dbe[j]);
+                if (p.film) {
+                    atomicAdd(&red[3 * p.C + c0 + j], dsc[j]);
+                    atomicAdd(&red[4 * p.C + c0 + j], dsh[j]);
+                }
+            }
+        }
+        __syncthreads();
+        float* part = p.partials + (int64_t)b * 3 * p.C;
+        for (int i = threadIdx.x; i < 3 * p.C; i += blockDim.x) part[i] = red[i];
+        if (p.film)
+            for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x)
+                p.dfilm[(int64_t)b * p.ld_dfilm + i] += red[3 * p.C + i];
+        return;
+    }
     if (!active) return;
-    // per-channel reductions over this thread's rows -> global accumulators
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         if (p.dbias) atomicAdd(&p.dbias[c0 + j], dbi[j]);
@@ -248,6 +277,27 @@ __global__ void __launch_bounds__(kPolThreads) gn_act_bwd_kernel(const GnActPara
             atomicAdd(&p.dfilm[(int64_t)b * p.ld_dfilm + c0 + j], dsc[j]);
             atomicAdd(&p.dfilm[(int64_t)b * p.ld_dfilm + p.C + c0 + j], dsh[j]);
         }
+    }
+}
+
+// out_k[c] += sum_b partials[b][k][c], k = bias | gamma | beta.  grid = ceil(3C / 32), block 32 x 8
+__global__ void __launch_bounds__(256) colsum_partials_kernel(const float* __restrict__ partials, int B, int C,
+                                                              float* dbias, float* dgamma, float* dbeta) {
+    __shared__ float sh[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + tx;
+    float s = 0.0f;
+    if (col < 3 * C)
+        for (int b = ty; b < B; b += 8) s += __ldg(&partials[(int64_t)b * 3 * C + col]);
+    sh[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && col < 3 * C) {
+        float t = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sh[i][tx];
+        const int k = col / C, c = col - k * C;
+        float* dst = k == 0 ? dbias : (k == 1 ? dgamma : dbeta);
+        if (dst) dst[c] += t;
     }
 }
 
@@ -499,6 +549,7 @@ static GnActParams to_params(const v2a_policy_gn_desc* d) {
     p.dfilm = d->dfilm; p.ld_dfilm = d->ld_dfilm;
     p.B = d->B;
     p.stage_words = 0;
+    p.partials = d->partials;
     return p;
 }
 
@@ -520,7 +571,15 @@ int v2a_policy_gn_act_bwd(const v2a_policy_gn_desc* d, void* stream) {
     // dy^T goes through shared memory (vector stores of T-long runs) when the sample fits 48 KB
     if (d->dyT_hi && d->T % 4 == 0 && (size_t)d->T * d->C * 4 <= 48 * 1024 && p.ld_T % 4 == 0)
         p.stage_words = d->T * d->C;
-    gn_act_bwd_kernel<<<d->B, kPolThreads, (size_t)p.stage_words * 4, (cudaStream_t)stream>>>(p);
+    size_t smem_words = (size_t)p.stage_words;
+    if (p.partials && (size_t)5 * d->C > smem_words) smem_words = (size_t)5 * d->C;
+    V2A_REQUIRE(smem_words * 4 <= 48 * 1024, "policy_gn_bwd: C %d too large for the shared-memory reductions", d->C);
+    gn_act_bwd_kernel<<<d->B, kPolThreads, smem_words * 4, (cudaStream_t)stream>>>(p);
+    if (p.partials) {
+        POL_LAUNCH_OK();
+        colsum_partials_kernel<<<(unsigned)((3 * d->C + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+            p.partials, d->B, d->C, d->dbias, d->dgamma, d->dbeta);
+    }
     POL_LAUNCH_OK();
     return 0;
 }

@@ -148,17 +148,20 @@ class GoalGaussianDiffusion(nn.Module):
             _extract(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise
 
     @torch.no_grad()
-    def model_predictions(self, x, t, x_cond, task_embed, clip_x_start=False, rederive_pred_noise=False):
-        """goal_diffusion.py:499-559 — one UNet call (two stacked under CFG)."""
+    def model_predictions(self, x, t, x_cond, task_embed, clip_x_start=False, rederive_pred_noise=False,
+                          _te2=None):
+        """goal_diffusion.py:499-559 — one UNet call; under classifier-free guidance the batch is doubled
+        (conditional | unconditional = zeroed task tokens) and run as ONE UNet call of 2B samples."""
         gw = self.guidance_weight
+        cfg = gw > 0.0
         clip = (lambda z: z.clamp(-1.0, 1.0)) if clip_x_start else (lambda z: z)
-        if gw > 0.0:
+        if cfg:
+            n = len(t)
             x_in = torch.cat([x, x_cond], dim=1)
-            x2 = torch.cat([x_in, x_in], dim=0)
-            t2 = torch.cat([t, t], dim=0)
-            te2 = torch.cat([task_embed, torch.zeros_like(task_embed)], dim=0)
-            out = self.model(x2, t2, te2)
-            e_c, e_u = out[: len(t)], out[len(t):]
+            if _te2 is None:
+                _te2 = torch.cat([task_embed, torch.zeros_like(task_embed)], dim=0)
+            out = self.model(x_in.repeat(2, 1, 1, 1), t.repeat(2), _te2)
+            e_c, e_u = out[:n], out[n:]
             model_output = (1 + gw) * e_c - gw * e_u
         else:
             model_output = self.model(torch.cat([x, x_cond], dim=1), t, task_embed)
@@ -170,7 +173,7 @@ class GoalGaussianDiffusion(nn.Module):
         elif self.objective == "pred_x0":
             x_start = clip(model_output)
             pred_noise = self.predict_noise_from_start(x, t, x_start)
-        elif gw > 0.0:  # pred_v under classifier-free guidance (:536-548)
+        elif cfg:  # pred_v under guidance: mix in NOISE space, then back to x0 (:536-548)
             x_start = clip(self.predict_start_from_v(x, t, e_c))
             u_start = self.predict_start_from_v(x, t, e_u)
             pred_noise = (1 + gw) * self.predict_noise_from_start(x, t, x_start) - \
@@ -180,6 +183,64 @@ class GoalGaussianDiffusion(nn.Module):
             x_start = clip(self.predict_start_from_v(x, t, model_output))
             pred_noise = self.predict_noise_from_start(x, t, x_start)
         return ModelPrediction(pred_noise, x_start)
+
+    def q_posterior(self, x_start, x_t, t):
+        """goal_diffusion.py:490-497."""
+        mean = _extract(self.posterior_mean_coef1, t, x_t.shape) * x_start + \
+            _extract(self.posterior_mean_coef2, t, x_t.shape) * x_t
+        return mean, _extract(self.posterior_variance, t, x_t.shape), \
+            _extract(self.posterior_log_variance_clipped, t, x_t.shape)
+
+    @torch.no_grad()
+    def _sample_general(self, x_cond, task_embed, batch_size, ddim: bool, return_all_timesteps=False):
+        """Every setting the fused sampler does not cover (classifier-free guidance, pred_noise / pred_x0
+        objectives, auto_normalize off): the UNet forwards still run on the CUDA engine (2B samples per call
+        under guidance); the per-step update is a handful of elementwise torch ops on [B, 3F, H, W]
+        (SURVEY.md §8f N5).  Same RNG order as the reference loops (:582-641)."""
+        dev = self.betas.device
+        if dev.type != "cuda":
+            raise RuntimeError("v2a_b200 GoalGaussianDiffusion.sample needs the module on a CUDA device "
+                               "(there is no CPU fallback)")
+        H, W = self.image_size
+        shape = (batch_size, self.channels, H, W)
+        with torch.autocast("cuda", enabled=False):
+            x_cond = x_cond.to(dev, torch.float32).contiguous()
+            task_embed = task_embed.to(dev, torch.float32)
+            te2 = torch.cat([task_embed, torch.zeros_like(task_embed)], 0) if self.guidance_weight > 0.0 else None
+            img = _initial_noise(shape, dev)
+            imgs = [img]
+            noise = torch.empty_like(img)
+            if ddim:
+                T, S, eta = self.num_timesteps, self.sampling_timesteps, self.ddim_sampling_eta
+                times = list(reversed(torch.linspace(-1, T - 1, steps=S + 1).int().tolist()))
+                for time, nxt in zip(times[:-1], times[1:]):
+                    tc = torch.full((batch_size,), time, device=dev, dtype=torch.long)
+                    pred_noise, x_start = self.model_predictions(img, tc, x_cond, task_embed, clip_x_start=False,
+                                                                 rederive_pred_noise=True, _te2=te2)
+                    if nxt < 0:
+                        img = x_start
+                        imgs.append(img)
+                        continue
+                    a, an = self.alphas_cumprod[time], self.alphas_cumprod[nxt]
+                    sigma = eta * ((1 - a / an) * (1 - an) / (1 - a)).sqrt()
+                    c = (1 - an - sigma ** 2).sqrt()
+                    _step_noise_(noise)
+                    img = x_start * an.sqrt() + c * pred_noise + sigma * noise
+                    imgs.append(img)
+            else:
+                for t in reversed(range(self.num_timesteps)):
+                    tc = torch.full((batch_size,), t, device=dev, dtype=torch.long)
+                    x_start = self.model_predictions(img, tc, x_cond, task_embed, _te2=te2).pred_x_start
+                    x_start = x_start.clamp(-1.0, 1.0)
+                    mean, _, logvar = self.q_posterior(x_start, img, tc)
+                    if t > 0:
+                        _step_noise_(noise)
+                        img = mean + (0.5 * logvar).exp() * (noise * self.var_temp)
+                    else:
+                        img = mean
+                    imgs.append(img)
+            ret = img if not return_all_timesteps else torch.stack(imgs, dim=1)
+            return self.unnormalize(ret).clamp(min=0, max=1)
 
     # ---- the hot path ---------------------------------------------------------------------
     def _fast_path_ok(self) -> bool:
@@ -273,20 +334,23 @@ class GoalGaussianDiffusion(nn.Module):
     @torch.no_grad()
     def p_sample_loop(self, shape, x_cond, task_embed, return_all_timesteps=False):
         assert tuple(shape[1:]) == (self.channels, *self.image_size)
-        return self._sample_fast(x_cond, task_embed, shape[0], False, return_all_timesteps)
+        fn = self._sample_fast if self._fast_path_ok() else self._sample_general
+        return fn(x_cond, task_embed, shape[0], False, return_all_timesteps)
 
     @torch.no_grad()
     def ddim_sample(self, shape, x_cond, task_embed, return_all_timesteps=False):
         assert tuple(shape[1:]) == (self.channels, *self.image_size)
-        return self._sample_fast(x_cond, task_embed, shape[0], True, return_all_timesteps)
+        fn = self._sample_fast if self._fast_path_ok() else self._sample_general
+        return fn(x_cond, task_embed, shape[0], True, return_all_timesteps)
 
     @torch.no_grad()
     def sample(self, x_cond, task_embed, batch_size=16, return_all_timesteps=False):
         """goal_diffusion.py:643-650.  Returns [B, channels, H, W] in [0, 1]."""
-        if not self._fast_path_ok():
-            raise NotImplementedError(
-                "v2a_b200 sample(): the CUDA path covers the shipped Libero setting (Unet_Libero, pred_v, "
-                "guidance_weight == 0); classifier-free guidance is SURVEY.md §8(f) N5")
+        if not isinstance(self.model, Unet_Libero):
+            raise NotImplementedError("v2a_b200 sample(): the CUDA path is built for Unet_Libero")
+        if not self._fast_path_ok():   # classifier-free guidance etc.: general loop around the CUDA UNet
+            return self._sample_general(x_cond, task_embed, batch_size, bool(self.is_ddim_sampling),
+                                        return_all_timesteps)
         return self._sample_fast(x_cond, task_embed, batch_size, bool(self.is_ddim_sampling), return_all_timesteps)
 
     def forward(self, img, img_cond, task_embed):

@@ -241,9 +241,12 @@ class _Steps(list):
     def __init__(self):
         super().__init__()
         self.tags: List[str] = []
+        self.lanes: List[int] = []
+        self.lane = 0            # lane given to steps added while it is set (1 = side stream)
 
-    def add(self, tag: str, fn: Callable) -> None:
+    def add(self, tag: str, fn: Callable, lane: Optional[int] = None) -> None:
         self.tags.append(tag)
+        self.lanes.append(self.lane if lane is None else lane)
         list.append(self, fn)
 
     def append(self, fn: Callable) -> None:
@@ -261,6 +264,8 @@ class _PolicyEngine:
         self.packers, self.vec_packers, self.keep = [], [], []
         self._wchunks, self._vchunks = [], []
         self._graphs: Dict[str, object] = {}
+        self._gn_partials = None
+        self._side = None if os.environ.get("V2A_NO_SIDE_STREAM", "0") == "1" else torch.cuda.Stream(device=device)
         self.fwd_token = 0
         self._wkey = None
         self.igemms: List[ops.Igemm] = []
@@ -398,6 +403,12 @@ class _PolicyEngine:
 
     def gn(self, steps, backward: bool, **kw):
         d = _lib.PolicyGnDesc()
+        if backward:   # shared scratch for the per-sample bias / gamma / beta sums (launches are stream ordered)
+            need = kw["B"] * 3 * kw["C"]
+            if self._gn_partials is None or self._gn_partials.numel() < need:
+                assert not self.bwd, "gn partial-sum scratch must be sized before the first backward launch is planned"
+                self._gn_partials = torch.zeros(self.B * 3 * 2048, dtype=torch.float32, device=self.device)
+            kw["partials"] = self._gn_partials
         for k, v in kw.items():
             setattr(d, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
         self.keep.append((d, kw))
@@ -476,10 +487,12 @@ class _PolicyEngine:
         rows = Bn * T
         cin_tot = sum(n.C for n in ins)
         off = 0
+        steps.lane = 1
         for n in ins:
             col = self.im2col_t(steps, n.hl, n.ld, Bn, T, T, n.C, [j - pad for j in range(k)], 1)
             self.wgrad(steps, dyT, cout, col, n.C * k, wgrad_target, off * k)
             off += n.C
+        steps.lane = 0
         progd = convs.conv1d(ld_dy, Bn, T, k, pad)
 
         def packed_d(wfn=wfn):
@@ -637,8 +650,10 @@ class _PolicyEngine:
             def plan_bwd():
                 st, rows_o = self.bwd, Bn * Tn // 2
                 dOh, ldh, dOT = self.grad_prep(st, out.grad, rows_o, colsum=g(conv.bias))
+                st.lane = 1
                 col = self.im2col_t(st, x.hl, x.ld, Bn, Tn, Tn // 2, Cc, [-1, 0, 1], 2)
                 self.wgrad(st, dOT, Cc, col, Cc * 3, g(conv.weight).view(Cc, -1), 0)
+                st.lane = 0
                 progd = convs.down1d_dgrad(ldh, Bn, Tn)
                 wd = self.weight(lambda: convs.down1d_dgrad_weight(conv.weight), 2 * Cc, progd.ktot)
                 tmp = self.zeros(rows_o, 2 * Cc)  # == [B*T, C] memory
@@ -669,9 +684,11 @@ class _PolicyEngine:
                 st = self.bwd
                 dOh, ldh, _ = self.grad_prep(st, out.grad, 2 * rows, colsum=g(conv.bias))
                 # dWt[ci, co, k] = x^T [C, B*T] x im2col^T(dy, stride 2, offsets k-1) [C*4, B*T]
+                st.lane = 1
                 xT = self.im2col_t(st, x.hl, x.ld, Bn, Tn, Tn, Cc, [0], 1)
                 col = self.im2col_t(st, dOh, ldh, Bn, 2 * Tn, Tn, Cc, [-1, 0, 1, 2], 2)
                 self.wgrad(st, xT, Cc, col, Cc * 4, g(conv.weight).view(Cc, -1), 0)
+                st.lane = 0
                 progd = convs.up1d_dgrad(ldh, Bn, Tn)
                 wd = self.weight(lambda: convs.up1d_dgrad_weight(conv.weight), Cc, progd.ktot)
                 if x.grad is None:
@@ -764,7 +781,7 @@ class _PolicyEngine:
         b_off_t = torch.tensor(b_off, dtype=torch.int64, device=dev)
         self.keep.append((w_off_t, b_off_t))
         st.add("scatter_film_w", lambda: _lib.check(self.lib.v2a_scatter_rows(
-            self.dwfilm.data_ptr(), cd, ftot, cd, w_off_t.data_ptr(), base, ops._stream()), "scatter_rows"))
+            self.dwfilm.data_ptr(), cd, ftot, cd, w_off_t.data_ptr(), base, ops._stream()), "scatter_rows"), lane=1)
         st.add("scatter_film_b", lambda: _lib.check(self.lib.v2a_scatter_rows(
             self.dbfilm.data_ptr(), 1, ftot, 1, b_off_t.data_ptr(), base, ops._stream()), "scatter_rows"))
         ddse = _Ref(dgf, 0, dsed)
@@ -780,10 +797,24 @@ class _PolicyEngine:
         """Launch a planned list.  Every buffer is static, so after one eager (warm-up) run the list is
         captured into a CUDA graph and replayed (one launch instead of 68 / 169; V2A_NO_GRAPH=1 disables)."""
         def eager():
+            # lane 1 = weight-gradient chains (im2col^T -> wgrad GEMM): nothing on the main lane reads their
+            # results, so they run on a side stream beside the data-gradient chain and join at the end
+            main = torch.cuda.current_stream()
             for z in pre:
                 z.zero_()
-            for s in steps:
-                s()
+            used_side = False
+            for fn, lane in zip(steps, steps.lanes):
+                if lane == 1 and self._side is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    self._side.wait_event(ev)
+                    with torch.cuda.stream(self._side):
+                        fn()
+                    used_side = True
+                else:
+                    fn()
+            if used_side:
+                main.wait_stream(self._side)
         if os.environ.get("V2A_NO_GRAPH", "0") == "1":
             return eager()
         seen = self._graphs.get(name)
