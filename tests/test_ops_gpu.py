@@ -318,3 +318,26 @@ def test_igemm_split_k_matches_unsplit(rows, K, cout, T):
     torch.cuda.synchronize()
     want = res[:, :cout].double() + 2 * ref2
     assert _rel(acc[:, :cout], want) < 5e-5
+
+
+@pytest.mark.parametrize("N,H,W,ci,co", [(7, 16, 16, 64, 128), (3, 32, 32, 128, 256), (5, 16, 8, 64, 64)])
+def test_igemm_cta_pair_multicast_matches_single_cta(N, H, W, ci, co, monkeypatch):
+    """Cout <= 256 (one N tile): CTA pairs share every weight tile through TMA multicast; odd tile counts
+    end in ghost tiles.  Same numbers as the one-CTA plan (V2A_CLUSTER=0) and as the float64 reference."""
+    ops, convs = _ops()
+    torch.manual_seed(N * H + ci + co)
+    x = torch.randn(N, H, W, ci, device=DEV)
+    w = torch.randn(co, ci, 3, 3, device=DEV) / math.sqrt(9 * ci)
+    b = torch.randn(co, device=DEV)
+    prog = convs.spatial3x3(ci, N, H, W)
+    stats_mul = (0, 0, 1, 0)
+    got, st, ref = _run_igemm(prog, [x], convs.spatial3x3_weight(w), co, bias=b, stats_mul=stats_mul)
+    ref = ref + b.double()
+    assert _rel(got, ref) < 5e-5
+    want_s = ref.reshape(N, H * W, co).sum(1)
+    want_ss = (ref.reshape(N, H * W, co) ** 2).sum(1)
+    assert _rel(st[..., 0], want_s) < 1e-5 and _rel(st[..., 1], want_ss) < 1e-5
+    monkeypatch.setenv("V2A_CLUSTER", "0")
+    got1, st1, _ = _run_igemm(prog, [x], convs.spatial3x3_weight(w), co, bias=b, stats_mul=stats_mul)
+    assert torch.equal(got, got1)            # same MMA order per tile: bit identical outputs
+    assert _rel(st, st1) < 1e-12

@@ -56,8 +56,19 @@ def main():
             d = g.desc
             rows.append((m, i, g.rows, g.cout, g.ktot, d.block_n, g.flops / m / 1e9))
         print(f"sum of igemm launches {tot:.2f} ms ({len(eng.igemms)} launches)")
-        for m, i, r, c, k, bn, tf in sorted(rows, reverse=True)[:40]:
-            print(f"  #{i:3d} rows {r:8d} cout {c:5d} K {k:6d} bn {bn:3d}  {m:7.3f} ms  {tf:7.1f} TFLOP/s")
+        ideal_tf = 1390.7 / eng.passes   # measured sustained bf16 peak / MMA passes
+        lost = lambda m, tf: m * (1.0 - min(tf / ideal_tf, 1.0))
+        print(f"  time above the tensor roofline ({ideal_tf:.0f} TFLOP/s algorithmic): "
+              f"{sum(lost(m, tf) for m, _, _, _, _, _, tf in rows):.2f} ms; by (cout, kind):")
+        cls = {}
+        for m, i, r, c, k, bn, tf in rows:
+            key = (c, "temporal/1x1" if k <= 6 * 64 * max(1, c // 64) and k < 9 * c else "spatial")
+            a = cls.setdefault(key, [0.0, 0.0, 0])
+            a[0] += m; a[1] += lost(m, tf); a[2] += 1
+        for key, a in sorted(cls.items(), key=lambda kv: -kv[1][1]):
+            print(f"    cout {key[0]:5d} {key[1]:12s} n={a[2]:3d}  {a[0]:7.2f} ms  lost {a[1]:6.2f} ms")
+        for m, i, r, c, k, bn, tf in sorted(rows, reverse=True):
+            print(f"  #{i:3d} rows {r:8d} cout {c:5d} K {k:6d} bn {bn:3d}  {m:7.3f} ms  {tf:7.1f} TFLOP/s  ks {eng.igemms[i].k_splits}")
         print(f"non-igemm share ~ {ms - tot:.2f} ms")
         # every planned step, eagerly, by kind (static I/O bound by the forward above)
         eng.stats_arena.zero_()

@@ -111,29 +111,34 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepParams p, int64_t t
     const int oct = C >> 3;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total_out_pix * oct) return;
-    const int o8 = (int)(gid % oct);
-    const int64_t op = gid / oct;
+    // index arithmetic in 32 bits (the host guarantees pixel counts and chunk counts < 2^31): the 64-bit
+    // divisions this replaces cost more instructions than the whole GroupNorm + SiLU + split of the thread
+    const uint32_t g32 = (uint32_t)gid;
+    const uint32_t op = g32 / (uint32_t)oct;
+    const int o8 = (int)(g32 - op * (uint32_t)oct);
     const int c = o8 * 8;
     // output pixel -> input pixel
-    int64_t ip = op;
-    int64_t out_index = op;
+    uint32_t ip = op;
+    uint32_t out_index = op;
     if (p.mode == 1) {
-        const int W2 = p.W * 2, H2 = p.H * 2;
-        const int w = (int)(op % W2);
-        const int h = (int)((op / W2) % H2);
-        const int64_t img = op / ((int64_t)W2 * H2);
+        const uint32_t W2 = p.W * 2, H2 = p.H * 2;
+        const uint32_t row = op / W2;
+        const uint32_t w = op - row * W2;
+        const uint32_t img = row / H2;
+        const uint32_t h = row - img * H2;
         ip = (img * p.H + (h >> 1)) * p.W + (w >> 1);
     } else if (p.mode == 2) {
         // iterate input pixels, scatter to [img][ph*2+pw][H/2][W/2]
-        const int w = (int)(op % p.W);
-        const int h = (int)((op / p.W) % p.H);
-        const int64_t img = op / ((int64_t)p.W * p.H);
-        const int Hh = p.H >> 1, Wh = p.W >> 1;
+        const uint32_t row = op / (uint32_t)p.W;
+        const uint32_t w = op - row * p.W;
+        const uint32_t img = row / (uint32_t)p.H;
+        const uint32_t h = row - img * p.H;
+        const uint32_t Hh = p.H >> 1, Wh = p.W >> 1;
         out_index = ((img * 4 + (h & 1) * 2 + (w & 1)) * Hh + (h >> 1)) * Wh + (w >> 1);
     }
     float v[8];
     {
-        const float* src = c < p.C0 ? p.x0 + ip * p.C0 + c : p.x1 + ip * p.C1 + (c - p.C0);
+        const float* src = c < p.C0 ? p.x0 + (int64_t)ip * p.C0 + c : p.x1 + (int64_t)ip * p.C1 + (c - p.C0);
         const float4 a = __ldg(reinterpret_cast<const float4*>(src));
         const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
@@ -142,14 +147,14 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepParams p, int64_t t
     if (p.raw_hi) {
         uint4 h, l;
         split8(v, h, l);
-        *reinterpret_cast<uint4*>(p.raw_hi + out_index * C + c) = h;
-        *reinterpret_cast<uint4*>(p.raw_lo + out_index * C + c) = l;
+        *reinterpret_cast<uint4*>(p.raw_hi + (int64_t)out_index * C + c) = h;
+        *reinterpret_cast<uint4*>(p.raw_lo + (int64_t)out_index * C + c) = l;
     }
     if (p.mr) {
-        const int64_t smp = ip / p.pixels_per_sample;
+        const uint32_t smp = ip / (uint32_t)p.pixels_per_sample;
         const int cpg = C / p.groups;
         int g = c / cpg, rem = c - g * cpg;   // walk the (at most 8) groups without divisions
-        const float2* mrp = p.mr + smp * p.groups;
+        const float2* mrp = p.mr + (int64_t)smp * p.groups;
         float2 m = __ldg(&mrp[g]);
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
         const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + c) + 1);
@@ -176,18 +181,18 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepParams p, int64_t t
         for (int j = 0; j < 8; ++j) v[j] = mish_f(v[j]);
     }
     if (p.film) {
-        const float* f = p.film + (ip / p.pixels_per_film) * (2 * C);
+        const float* f = p.film + (int64_t)(ip / (uint32_t)p.pixels_per_film) * (2 * C);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = __ldg(&f[c + j]) * v[j] + __ldg(&f[C + c + j]);
     }
     if (p.out_hi) {
         uint4 h, l;
         split8(v, h, l);
-        *reinterpret_cast<uint4*>(p.out_hi + out_index * C + c) = h;
-        *reinterpret_cast<uint4*>(p.out_lo + out_index * C + c) = l;
+        *reinterpret_cast<uint4*>(p.out_hi + (int64_t)out_index * C + c) = h;
+        *reinterpret_cast<uint4*>(p.out_lo + (int64_t)out_index * C + c) = l;
     }
     if (p.out_f32) {
-        float4* o = reinterpret_cast<float4*>(p.out_f32 + out_index * C + c);
+        float4* o = reinterpret_cast<float4*>(p.out_f32 + (int64_t)out_index * C + c);
         o[0] = make_float4(v[0], v[1], v[2], v[3]);
         o[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
@@ -482,6 +487,9 @@ int v2a_prep(const v2a_prep_desc* d, void* stream) {
                         (d->mode == 1 || (d->H % 2 == 0 && d->W % 2 == 0)),
                     "prep: bad H/W for resampling mode");
     const int64_t total = out_pix * (C / 8);
+    V2A_REQUIRE(total < (int64_t)1 << 31 && p.pixels_per_sample < (int64_t)1 << 31 &&
+                    (!d->film || d->pixels_per_film < (int64_t)1 << 31),
+                "prep: %lld 8-channel chunks exceed the 32-bit index range of the kernel", (long long)total);
     prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, out_pix);
     V2A_LAUNCH_OK();
     return 0;

@@ -64,6 +64,8 @@ struct alignas(64) IgemmParams {
     CUtensorMap a_lo[V2A_MAX_SRC];
     CUtensorMap b_hi;
     CUtensorMap b_lo;
+    CUtensorMap bh_hi;    // cluster mode: box of block_n/2 rows (each CTA of the pair loads one half, multicast)
+    CUtensorMap bh_lo;
     int tap_src[V2A_MAX_TAPS];
     int tap_d[V2A_MAX_TAPS][4];
     int tap_chunks[V2A_MAX_TAPS];
@@ -90,12 +92,23 @@ struct alignas(64) IgemmParams {
     int stats_ld;
     int stats_replicas;
     long long stats_rep_stride;
+    int cluster;          // 2: CTA pairs share every B (weight) tile through TMA multicast
+    int iters_per_cta;    // cluster mode: tile iterations of every CTA (ghost tiles pad the last ones)
     int k_splits;         // >1: the K loop of one output tile is shared by k_splits CTAs (fp32 atomics)
     int kps;              // K iterations per split
     int debug;  // V2A_IGEMM_DEBUG bits: 1 skip stats, 2 skip stores, 4 skip residual (timing experiments only)
 };
 
 __device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int& n_idx, int o[4], int& split) {
+    if (tile >= p.num_m_tiles * p.num_n_tiles * p.k_splits) {
+        // ghost tile (cluster mode pads every CTA to the same iteration count): a box wholly outside the
+        // tensor -> TMA zero fill, no row is valid in the epilogue
+        n_idx = 0;
+        split = 0;
+        o[0] = o[1] = o[2] = 0;
+        o[3] = p.ntile[3] << p.tile_log2[3];
+        return;
+    }
     split = tile % p.k_splits;     // splits of one output tile are adjacent: they run concurrently
     tile /= p.k_splits;
     n_idx = tile % p.num_n_tiles;
@@ -116,7 +129,13 @@ struct TileRange {
 };
 __device__ __forceinline__ TileRange cta_tiles(const IgemmParams& p, int total) {
     TileRange r;
-    if (p.k_splits > 1) {
+    if (p.cluster > 1) {
+        // the two CTAs of a pair walk interleaved tiles of one contiguous range, in lockstep
+        const int pair = blockIdx.x >> 1;
+        r.first = pair * 2 * p.iters_per_cta + (blockIdx.x & 1);
+        r.step = 2;
+        r.count = p.iters_per_cta;
+    } else if (p.k_splits > 1) {
         r.first = blockIdx.x;
         r.step = gridDim.x;
         r.count = total > r.first ? (total - r.first + r.step - 1) / r.step : 0;
@@ -150,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], p.cluster > 1 ? 2 : 1);   // pair mode: both CTAs must release a stage
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
@@ -169,11 +188,13 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();   // the peer's barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int total_tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
     const TileRange tr = cta_tiles(p, total_tiles);
+    const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0;
 
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
@@ -197,7 +218,17 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                     mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
                     uint8_t* st = smem + (size_t)stage * p.stage_bytes;
                     mbar_arrive_expect_tx(&full_bar[stage], p.stage_bytes);
-                    if (p.passes == 3) {
+                    if (p.passes == 3 && p.cluster > 1) {
+                        tma_load_5d(st, &p.a_hi[src], &full_bar[stage], ch * kChunkK, c1, c2, c3, c4);
+                        tma_load_5d(st + kATileBytes, &p.a_lo[src], &full_bar[stage], ch * kChunkK,
+                                    c1, c2, c3, c4);
+                        // this CTA fetches its half of the weight tile for BOTH CTAs of the pair
+                        const uint32_t half_rows = p.block_n >> 1, half_bytes = p.b_tile_bytes >> 1;
+                        uint8_t* sb = st + 2 * kATileBytes + crank * half_bytes;
+                        tma_load_2d_mc(sb, &p.bh_hi, &full_bar[stage], kit * kChunkK, n0 + crank * half_rows, 3);
+                        tma_load_2d_mc(sb + p.b_tile_bytes, &p.bh_lo, &full_bar[stage], kit * kChunkK,
+                                       n0 + crank * half_rows, 3);
+                    } else if (p.passes == 3) {
                         tma_load_5d(st, &p.a_hi[src], &full_bar[stage], ch * kChunkK, c1, c2, c3, c4);
                         tma_load_5d(st + kATileBytes, &p.a_lo[src], &full_bar[stage], ch * kChunkK,
                                     c1, c2, c3, c4);
@@ -252,7 +283,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                     for (int k = 0; k < 4; ++k)
                         umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kit | k) != 0);
                 }
-                umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                // smem slot reusable once these MMAs retire (pair mode: the peer multicasts into it too)
+                if (p.cluster > 1) umma_commit_mc(&empty_bar[stage], 3);
+                else umma_commit(&empty_bar[stage]);
                 if (kit == n_it - 1) umma_commit(&tfull_bar[acc]);
                 if (++stage == S) { stage = 0; phase ^= 1; }
             }
@@ -310,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 rv += coord[d] * p.rowvec_mul[d];
                 inst += coord[d] * p.stats_mul[d];
             }
+            const bool any_valid = __any_sync(0xffffffffu, valid);   // false for a whole ghost / padding warp
             // warp-uniform row group / stats instance?  (true for every large layer)
             const int rv0 = __shfl_sync(0xffffffffu, rv, 0);
             const bool rv_uniform = p.rowvec == nullptr || !lead || __all_sync(0xffffffffu, !valid || rv == rv0);
@@ -325,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             __syncwarp();
             for (int c = c_begin + lane; c < c_end; c += 32) {
                 float a = 0.0f;
-                if (lead && n0 + c < p.cout) {
+                if (lead && any_valid && n0 + c < p.cout) {
                     if (p.bias) a = __ldg(&p.bias[n0 + c]);
                     if (p.rowvec && rv_uniform) a += __ldg(&p.rowvec[(int64_t)rv0 * p.ld_rowvec + n0 + c]);
                 }
@@ -449,6 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
+    if (p.cluster > 1) cluster_sync_all();   // no CTA leaves while its peer can still signal its barriers
 }
 
 // ---------------------------------------------------------------------------
@@ -670,6 +705,32 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
     }
     const int total = p.num_m_tiles * p.num_n_tiles * p.k_splits;
     pl->grid = total < g_num_sms ? total : g_num_sms;
+    // CTA pairs (thread-block clusters of 2) share each weight tile through TMA multicast: halves the B part of
+    // the L2 -> shared-memory traffic, which bounds the Cout <= 256 layers.  One N tile only (every tile of
+    // the launch then uses the same B), 3-pass plans, no split-K.
+    p.cluster = 1;
+    p.iters_per_cta = 0;
+    {
+        const char* env = getenv("V2A_CLUSTER");
+        const bool want = !(env && atoi(env) == 0);
+        if (want && p.num_n_tiles == 1 && p.k_splits == 1 && d->passes == 3 && d->block_n % 16 == 0 &&
+            p.num_m_tiles >= 4 && g_num_sms >= 2) {
+            int grid = (g_num_sms / 2) * 2;
+            const int pairs_needed = ceil_div(p.num_m_tiles, 2);
+            if (grid > 2 * pairs_needed) grid = 2 * pairs_needed;
+            p.cluster = 2;
+            p.iters_per_cta = ceil_div(p.num_m_tiles, grid);
+            pl->grid = grid;
+            uint64_t dims[2] = {(uint64_t)d->ktot, (uint64_t)d->wrows};
+            uint32_t box[2] = {kChunkK, (uint32_t)d->block_n / 2};
+            rc = make_map(&p.bh_hi, d->w_hi, 2, dims, box);
+            if (!rc) rc = make_map(&p.bh_lo, d->w_lo, 2, dims, box);
+            if (rc) {
+                delete pl;
+                return rc;
+            }
+        }
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -705,7 +766,23 @@ int v2a_igemm_plan_run(void* plan, void* stream) {
     if (pl->zero_out)
         V2A_CUDA_OK(cudaMemset2DAsync(pl->p.out_f32, (size_t)pl->p.ldc * sizeof(float), 0, pl->zero_width,
                                       (size_t)pl->zero_rows, (cudaStream_t)stream));
-    v2a::igemm_kernel<<<pl->grid, v2a::kThreads, pl->smem, (cudaStream_t)stream>>>(pl->p);
+    if (pl->p.cluster > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)pl->grid);
+        cfg.blockDim = dim3(v2a::kThreads);
+        cfg.dynamicSmemBytes = pl->smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        V2A_CUDA_OK(cudaLaunchKernelEx(&cfg, v2a::igemm_kernel, pl->p));
+    } else {
+        v2a::igemm_kernel<<<pl->grid, v2a::kThreads, pl->smem, (cudaStream_t)stream>>>(pl->p);
+    }
     V2A_CUDA_OK(cudaGetLastError());
     v2a::g_launches.fetch_add(1);
     return 0;

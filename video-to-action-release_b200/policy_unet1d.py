@@ -404,10 +404,9 @@ class _PolicyEngine:
     def gn(self, steps, backward: bool, **kw):
         d = _lib.PolicyGnDesc()
         if backward:   # shared scratch for the per-sample bias / gamma / beta sums (launches are stream ordered)
-            need = kw["B"] * 3 * kw["C"]
-            if self._gn_partials is None or self._gn_partials.numel() < need:
-                assert not self.bwd, "gn partial-sum scratch must be sized before the first backward launch is planned"
+            if self._gn_partials is None:
                 self._gn_partials = torch.zeros(self.B * 3 * 2048, dtype=torch.float32, device=self.device)
+            assert kw["B"] * 3 * kw["C"] <= self._gn_partials.numel()
             kw["partials"] = self._gn_partials
         for k, v in kw.items():
             setattr(d, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
