@@ -50,15 +50,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+// two floats -> packed bf16x2 (a in the low half) with ONE cvt.rn.bf16x2.f32: the scalar conversion is an
+// XU-pipe instruction (quarter rate) and made the GroupNorm-apply kernel transcendental-bound
+__device__ __forceinline__ uint32_t pack2_bf16_rn(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// (hi, lo) planes of two floats: hi = rn(x), lo = rn(x - hi); a bf16 widens to fp32 by a 16-bit shift
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack2_bf16_rn(a, b);
+    const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+    lo = pack2_bf16_rn(a - ha, b - hb);
+}
 // split 8 floats -> one uint4 of hi and one uint4 of lo
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
-    __nv_bfloat16 h[8], l[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) split_bf16(v[i], h[i], l[i]);
-    hi = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]),
-                    pack_bf16x2(h[6], h[7]));
-    lo = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]),
-                    pack_bf16x2(l[6], l[7]));
+    split2(v[0], v[1], hi.x, lo.x);
+    split2(v[2], v[3], hi.y, lo.y);
+    split2(v[4], v[5], hi.z, lo.z);
+    split2(v[6], v[7], hi.w, lo.w);
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }

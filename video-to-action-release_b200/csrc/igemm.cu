@@ -58,6 +58,7 @@ constexpr int kChunkK = 64;                                 // bf16 elements per
 constexpr int kATileBytes = kTileM * kChunkK * 2;           // 16 KB
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;                             // TMEM columns per accumulator stage
+constexpr int kSlabStride = 20;                             // words per staged row: 16 + 4 (bank spread, 16 B aligned)
 
 struct alignas(64) IgemmParams {
     CUtensorMap a_hi[V2A_MAX_SRC];
@@ -121,30 +122,18 @@ __device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int&
     }
 }
 
-// Tiles of one CTA.  Plain plans walk a CONTIGUOUS range (consecutive tiles share the GroupNorm instance,
-// so the epilogue keeps partial sums on chip and issues ~2 rounds of global atomics per launch instead of
-// one per tile); split-K plans interleave CTAs so the splits of one output tile run concurrently.
+// Tiles of one CTA (tile = first + i * step).
 struct TileRange {
     int first, step, count;
 };
 __device__ __forceinline__ TileRange cta_tiles(const IgemmParams& p, int total) {
     TileRange r;
-    if (p.cluster > 1) {
-        // the two CTAs of a pair walk interleaved tiles of one contiguous range, in lockstep
-        const int pair = blockIdx.x >> 1;
-        r.first = pair * 2 * p.iters_per_cta + (blockIdx.x & 1);
-        r.step = 2;
-        r.count = p.iters_per_cta;
-    } else if (p.k_splits > 1) {
-        r.first = blockIdx.x;
-        r.step = gridDim.x;
-        r.count = total > r.first ? (total - r.first + r.step - 1) / r.step : 0;
-    } else {
-        const int per = (total + gridDim.x - 1) / gridDim.x;
-        r.first = blockIdx.x * per;
-        r.step = 1;
-        r.count = total > r.first ? min(per, total - r.first) : 0;
-    }
+    // round-robin: the CTAs of the grid work on neighbouring tiles at the same time, so conv halos and the
+    // three temporal taps of a pixel block are re-read from L2, not from HBM
+    r.first = blockIdx.x;
+    r.step = gridDim.x;
+    if (p.cluster > 1) r.count = p.iters_per_cta;   // CTA pairs stay in lockstep (ghost tiles pad the tail)
+    else r.count = total > r.first ? (total - r.first + r.step - 1) / r.step : 0;
     return r;
 }
 
@@ -164,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     uint64_t* tempty_bar = bars + 2 * S + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
     float* warp_add = reinterpret_cast<float*>(bars) + 64;  // 8 epilogue warps x 256 floats, after the 256 B barrier block
-    double* stat_acc = reinterpret_cast<double*>(warp_add + 8 * 256);  // 8 warps x [8 chunks][32 lanes] partial sums
+    float* stage_slab = warp_add + 8 * 256;   // 8 epilogue warps x [32 rows][kSlabStride] coalescing slabs
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -301,22 +290,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         const int c_end = half == 0 ? ((nch + 1) >> 1) << 4 : p.block_n;
         // same-address atomic contention is spread over `stats_replicas` copies of the sums
         double* const stats = (p.stats && !(p.debug & 1)) ? p.stats + (long long)(blockIdx.x % p.stats_replicas) * p.stats_rep_stride : nullptr;
-        // on-chip GroupNorm partial sums of the tiles this CTA walks (flushed when the instance changes)
-        double* sacc = stat_acc + (warp - 4) * 256;
-        for (int i = lane; i < 256; i += 32) sacc[i] = 0.0;
-        int held_inst = -1, held_n0 = 0;
-        auto flush_stats = [&]() {
-            if (held_inst >= 0) {
-                for (int c = c_begin; c < c_end; c += 16) {
-                    const int col = held_n0 + c + (lane & 15);
-                    const int slot = ((c - c_begin) >> 4) * 32 + lane;
-                    if (col < p.cout)
-                        atomicAdd(&stats[((int64_t)held_inst * p.stats_ld + col) * 2 + (lane >> 4)], sacc[slot]);
-                    sacc[slot] = 0.0;
-                }
-            }
-            held_inst = -1;
-        };
+        // Per-warp staging slab [32 rows][16 words + 4 pad].  TMEM hands each lane one ROW (16 consecutive
+        // columns); storing that directly makes every 16-byte store instruction touch 32 different 128-byte
+        // lines and bounded the whole kernel on the narrow layers.  Staged through the slab, 4 lanes write one
+        // row's 64 bytes (8 rows per instruction), the residual is read the same way, and the GroupNorm column
+        // sums are plain shared-memory column walks instead of a 31-shuffle tree.
+        float* slab = stage_slab + (warp - 4) * (32 * kSlabStride);
+        const int srow0 = lane >> 2;          // store phase: row (srow0 + 8 i), 16-byte piece (lane & 3)
+        const int piece = lane & 3;
         for (int it = 0; it < tr.count; ++it) {
             const int tile = tr.first + it * tr.step;
             const int acc = it & 1;
@@ -350,10 +331,13 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             const int inst0 = __shfl_sync(0xffffffffu, valid ? inst : -1, 0);
             const bool inst_uniform =
                 stats != nullptr && __all_sync(0xffffffffu, !valid || inst == inst0) && inst0 >= 0;
-            if (inst_uniform && (inst0 != held_inst || n0 != held_n0)) {
-                flush_stats();
-                held_inst = inst0;
-                held_n0 = n0;
+            // the 4 rows this lane stores: their pixel index / validity come from the lanes that own them
+            int64_t spix[4];
+            bool svalid[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                spix[i] = __shfl_sync(0xffffffffu, pix, srow0 + 8 * i);
+                svalid[i] = __shfl_sync(0xffffffffu, (int)valid, srow0 + 8 * i) != 0;
             }
             // stage bias (+ the shared rowvec row) for this N tile: overlaps the tile's MMAs
             __syncwarp();
@@ -366,12 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 addv[c] = a;
             }
             __syncwarp();
-            const float* res_row = (p.residual && lead && !(p.debug & 4)) ? p.residual + pix * p.ld_res + n0 : nullptr;
-            float4 res_next[4];
-            if (res_row && valid && c_begin < c_end) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) res_next[q] = *(reinterpret_cast<const float4*>(res_row + c_begin) + q);
-            }
+            const bool use_res = p.residual != nullptr && lead && !(p.debug & 4);
 
             mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
             tc_fence_after();
@@ -383,78 +362,97 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) + addv[c + j];
-                if (valid) {
-                    if (p.rowvec && !rv_uniform && lead) {
-                        const float* rp = p.rowvec + (int64_t)rv * p.ld_rowvec + n;
+                if (valid && p.rowvec && !rv_uniform && lead) {
+                    const float* rp = p.rowvec + (int64_t)rv * p.ld_rowvec + n;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (n + j < p.cout) v[j] += __ldg(&rp[j]);
-                    }
-                    if (res_row) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            v[4 * q + 0] += res_next[q].x; v[4 * q + 1] += res_next[q].y;
-                            v[4 * q + 2] += res_next[q].z; v[4 * q + 3] += res_next[q].w;
-                        }
-                        if (c + 16 < c_end && n + 16 < p.cout) {  // prefetch the next chunk's residual
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                res_next[q] = *(reinterpret_cast<const float4*>(res_row + c + 16) + q);
-                        }
-                    }
-                    if (p.out_f32 && !(p.debug & 2)) {
-                        float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * p.ldc + n);
-                        if (p.k_splits > 1) {   // partial sum of this K range (output zeroed / pre-loaded by the host)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                atomicAdd(op + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        }
-                    }
-                    if (p.out_hi && !(p.debug & 2)) {
-                        uint4 h0, l0, h1, l1;
-                        split8(v, h0, l0);
-                        split8(v + 8, h1, l1);
-                        uint4* hp = reinterpret_cast<uint4*>(p.out_hi + pix * p.ldc + n);
-                        uint4* lp = reinterpret_cast<uint4*>(p.out_lo + pix * p.ldc + n);
-                        hp[0] = h0; hp[1] = h1;
-                        lp[0] = l0; lp[1] = l1;
-                    }
+                    for (int j = 0; j < 16; ++j)
+                        if (n + j < p.cout) v[j] += __ldg(&rp[j]);
                 }
-                if (stats) {
-                    if (inst_uniform) {
-                        // 32 quantities (16 column sums, 16 sums of squares) over 32 rows:
-                        // recursive halving, 31 shuffles; lane L ends with the total of quantity L
-                        float w[32];
+                const bool need_f32_phase = (p.out_f32 != nullptr) || use_res || (stats != nullptr);
+                if (need_f32_phase) {
+                    // A: own row -> slab (rows / columns that do not exist are staged as 0 for the column sums)
+                    float4* srow = reinterpret_cast<float4*>(slab + lane * kSlabStride);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float x = (valid && n + j < p.cout) ? v[j] : 0.0f;
-                            w[j] = x;
-                            w[16 + j] = x * x;
-                        }
-#pragma unroll
-                        for (int off = 16; off > 0; off >>= 1) {
-                            const bool up = (lane & off) != 0;
-#pragma unroll
-                            for (int j = 0; j < off; ++j) {
-                                const float send = up ? w[j] : w[j + off];
-                                const float keep = up ? w[j + off] : w[j];
-                                w[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                            }
-                        }
-                        sacc[((c - c_begin) >> 4) * 32 + lane] += (double)w[0];   // warp-private slot
-                    } else if (valid) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (n + j < p.cout) {
-                                double* sp = &stats[((int64_t)inst * p.stats_ld + n + j) * 2];
-                                atomicAdd(sp, (double)v[j]);
-                                atomicAdd(sp + 1, (double)v[j] * (double)v[j]);
-                            }
+                    for (int q = 0; q < 4; ++q) {
+                        float4 x = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        if (!valid) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                        srow[q] = x;
                     }
+                    __syncwarp();
+                    // C: coalesced residual read + output store: 4 lanes per row, 8 rows per instruction
+                    if (p.out_f32 != nullptr || use_res) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (!svalid[i]) continue;
+                            float4* sp = reinterpret_cast<float4*>(slab + (srow0 + 8 * i) * kSlabStride) + piece;
+                            float4 x = *sp;
+                            if (use_res) {
+                                const float4 rr = *reinterpret_cast<const float4*>(
+                                    p.residual + spix[i] * p.ld_res + n + 4 * piece);
+                                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+                                *sp = x;
+                            }
+                            if (p.out_f32 && !(p.debug & 2)) {
+                                float4* op = reinterpret_cast<float4*>(p.out_f32 + spix[i] * p.ldc + n) + piece;
+                                if (p.k_splits > 1) atomicAdd(op, x);   // partial sum of this K range
+                                else *op = x;
+                            }
+                        }
+                        if (use_res) {
+                            __syncwarp();
+                            if (p.out_hi || (stats && !inst_uniform)) {   // own row again, residual included
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float4 x = srow[q];
+                                    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+                                }
+                            }
+                        }
+                    }
+                    // D: GroupNorm partial sums of the 32 x 16 block: lane = (column, sum | sum of squares)
+                    if (stats) {
+                        if (inst_uniform) {
+                            const int col = lane & 15;
+                            const bool sq = lane >= 16;
+                            float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll 8
+                            for (int rr2 = 0; rr2 < 32; rr2 += 2) {
+                                const float x0 = slab[rr2 * kSlabStride + col];
+                                const float x1 = slab[(rr2 + 1) * kSlabStride + col];
+                                s0 += sq ? x0 * x0 : x0;
+                                s1 += sq ? x1 * x1 : x1;
+                            }
+                            if (n + col < p.cout)
+                                atomicAdd(&stats[((int64_t)inst0 * p.stats_ld + n + col) * 2 + (sq ? 1 : 0)],
+                                          (double)(s0 + s1));
+                        } else if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (n + j < p.cout) {
+                                    double* sp = &stats[((int64_t)inst * p.stats_ld + n + j) * 2];
+                                    atomicAdd(sp, (double)v[j]);
+                                    atomicAdd(sp + 1, (double)v[j] * (double)v[j]);
+                                }
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (p.out_hi && !(p.debug & 2)) {
+                    // bf16 planes: one slab row = [16 hi | 16 lo] = 64 bytes; pieces 0,1 -> hi plane, 2,3 -> lo
+                    uint4 h0, l0, h1, l1;
+                    split8(v, h0, l0);
+                    split8(v + 8, h1, l1);
+                    uint4* srow = reinterpret_cast<uint4*>(slab + lane * kSlabStride);
+                    srow[0] = h0; srow[1] = h1; srow[2] = l0; srow[3] = l1;
+                    __syncwarp();
+                    __nv_bfloat16* plane = piece < 2 ? p.out_hi : p.out_lo;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (!svalid[i]) continue;
+                        const uint4 x = *(reinterpret_cast<const uint4*>(slab + (srow0 + 8 * i) * kSlabStride) + piece);
+                        *reinterpret_cast<uint4*>(plane + spix[i] * p.ldc + n + 8 * (piece & 1)) = x;
+                    }
+                    __syncwarp();
                 }
             };
 
@@ -474,7 +472,6 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
         }
-        if (stats) flush_stats();
     }
 
     tc_fence_before();
@@ -616,7 +613,7 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
     p.stage_bytes = (uint32_t)d->passes == 3 ? 2 * (kATileBytes + p.b_tile_bytes)
                                              : (kATileBytes + p.b_tile_bytes);
     const size_t overhead = 1024 /*align*/ + 256 /*barriers*/ + 8192 /*epilogue bias staging*/ +
-                            16384 /*epilogue GroupNorm partial sums*/;
+                            8 * 32 * kSlabStride * 4 /*epilogue coalescing slabs*/;
     int stages = (int)((g_max_smem - overhead) / p.stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) {
