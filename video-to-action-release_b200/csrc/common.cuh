@@ -86,6 +86,18 @@ __device__ __forceinline__ float mish_grad_f(float x) {
     return th + x * (1.0f - th * th) * sg;
 }
 
+// streaming 16-byte read-only load / L2 prefetch of global data that is read exactly once
+__device__ __forceinline__ float4 ld_nc_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // ----------------------------------------------------------------------------
 // shared-memory address + mbarrier
 // ----------------------------------------------------------------------------
