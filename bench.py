@@ -172,8 +172,19 @@ def measure_kernel_roofline(diff, batch, peaks):
     n = len(evs)
     achieved = flops / (tot_ms * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    # DRAM traffic per launch comes from a committed ncu capture of the same workload (not measurable live)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_igemm_traffic.json")) as f:
+            tj = json.load(f)
+        if batch == 16:
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    except (OSError, KeyError, ValueError):
+        pass
     return {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv)", "achieved": achieved,
-            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+            "traffic_source": traffic_src,
             "launches_per_denoise_step": n, "avg_launch_ms": tot_ms / n, "flop_per_launch": flops / n,
             "mma_passes": eng.passes, "tensor_pipe_tflops": achieved * eng.passes,
             "tensor_pipe_frac": achieved * eng.passes / peak, "kernel_ms_per_denoise_step": tot_ms}
