@@ -287,6 +287,24 @@ def run_policy(args, world, rank, local, barrier, max_over_ranks, peaks):
     # (c) the same step with the batch already resident
     batch_dev = {"obs": {"img_obs_1": dev["img_obs_1"], "img_goal_1": dev["img_goal_1"]}, "action": dev["action"]}
     ms_p, _ = timed(lambda: step_p.step(lambda: policy.compute_loss(batch_dev)), steps)
+    from v2a_b200 import obs_encoder as OE
+    enc_flops, enc_launches = 0.0, 0
+    for core in step_p.cores:
+        e = OE.last_engine(core)
+        enc_flops += sum(gm.flops for gm in e.igemms) + sum(gm.flops for gm in e.wgrads)
+        enc_launches += e.planned_launches()
+    # A/B: the same step with the stock torch / cuDNN encoders (fp32, TF32 off) -- what row P6 ran on before
+    ms_p_torch = None
+    if os.environ.get("V2A_ENCODER", "cuda") != "torch":
+        os.environ["V2A_ENCODER"] = "torch"
+        try:
+            del step_p
+            step_t = PolicyTrainStep(policy)
+            ms_p_torch, _ = timed(lambda: step_t.step(lambda: policy.compute_loss(batch_dev)), max(2, steps // 4))
+            del step_t
+        finally:
+            os.environ["V2A_ENCODER"] = "cuda"
+        step_p = None
     peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     out = {"metric": POLICY_METRIC, "unit": "samples/s", "value": B * world / (ms_u * 1e-3),
            "ms_per_step": ms_u, "steps": steps, "warmup": warm, "batch_per_gpu": B, "horizon": T, "action_dim": Da,
@@ -296,12 +314,17 @@ def run_policy(args, world, rank, local, barrier, max_over_ranks, peaks):
                         "achieved": flops / (ms_u * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                         "frac": flops / (ms_u * 1e-3) / 1e12 / peak, "flop_per_step": flops, "traffic": None,
                         "note": "whole-step time (launch/latency-bound at M = B*T = 1024..4096 rows)"},
-           "compute_loss_step": {"what": "DiffusionUnetImagePolicy.compute_loss + backward + optimiser; the two "
-                                         "ResNet18-GN observation encoders (80% of FLOPs) run on cuDNN fp32, TF32 off "
-                                         "(SURVEY.md §8a row P6 / §8f N1)",
+           "compute_loss_step": {"what": "DiffusionUnetImagePolicy.compute_loss + backward + optimiser, everything on "
+                                         "v2a_b200 kernels: the two ResNet18-GN observation encoders (80% of FLOPs; "
+                                         "SURVEY.md §8a row P6 / §8f N1) run the planned tcgen05 forward / dgrad / "
+                                         "MN-major wgrad engine (obs_encoder.py)",
                                  "value": B * world / (ms_p * 1e-3), "ms_per_step": ms_p,
                                  "params": sum(p.numel() for p in policy.parameters()),
-                                 "gpu_launches_per_step_ours": int(launches_u) + 2},
+                                 "gpu_launches_per_step_ours": int(launches_u) + 2 + int(enc_launches),
+                                 "tensor_flop_per_step": flops + enc_flops,
+                                 "achieved_tflops": (flops + enc_flops) / (ms_p * 1e-3) / 1e12,
+                                 "frac_of_bf16_peak": (flops + enc_flops) / (ms_p * 1e-3) / 1e12 / peak,
+                                 "ms_per_step_with_torch_cudnn_encoders_fp32": ms_p_torch},
            "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": sum(v.numel() * 4 for v in host.values()), "d2h_bytes_per_step": 4}}
     if rank == 0 and not args.no_cpu_baseline:
@@ -311,6 +334,7 @@ def run_policy(args, world, rank, local, barrier, max_over_ranks, peaks):
                                "sample": "1 timed ConditionalUnet1D fwd+bwd (oracle port, torch autograd) at B=64 after "
                                          "1 warm-up; no encoders, no optimiser"}
     del step_p, policy
+    OE._ENGINES.clear()
     torch.cuda.empty_cache()
     return out
 

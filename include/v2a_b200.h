@@ -83,6 +83,8 @@ typedef struct v2a_igemm_desc {
     int stats_ld;           /* channels per instance in the stats buffer */
     int stats_replicas;     /* >= 1: CTAs spread their atomics over this many copies of the buffer */
     int64_t stats_rep_stride;   /* doubles between consecutive copies */
+    int a_fp16;             /* source planes are fp16 (hi, lo) pairs instead of bf16 ones (22+ bit operands) */
+    int b_fp16;             /* same for the weight planes */
 } v2a_igemm_desc;
 
 int v2a_igemm_plan_create(const v2a_igemm_desc* desc, void** plan_out);
@@ -92,6 +94,44 @@ void v2a_igemm_plan_destroy(void* plan);
 int v2a_igemm_plan_k_splits(void* plan);
 /* kernel launches performed by v2a_* calls since process start */
 int64_t v2a_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Weight-gradient GEMM straight from channels-last operands (MN-major UMMA):
+ *
+ *   out[(unit, ci), co] += sum_pixels x_src(unit)[pixel + d(unit), 64*chunk(unit) + ci] * dy[pixel, co]
+ *
+ * replaces autograd's conv weight gradient for the observation encoder's
+ * ResNet18 / keypoint convs   diffusion_policy/common/vision_nets.py:29-39
+ *                             diffusion_policy/common/base_nets.py:183
+ * `out` is accumulated with fp32 REDs (the pixel reduction is split between
+ * CTAs): the caller zeroes it.  v2a_wgrad_scatter adds the [(tap, ci)][co]
+ * scratch into a parameter-gradient tensor laid out [co][ci][tap].
+ * ---------------------------------------------------------------------- */
+#define V2A_WGRAD_MAX_UNITS 80
+typedef struct v2a_wgrad_unit {
+    int src;     /* index into desc.src */
+    int d[4];    /* pixel offset of this tap in X0..X3 (zero padding outside) */
+    int chunk;   /* 64-channel chunk of the source */
+} v2a_wgrad_unit;
+
+typedef struct v2a_wgrad_desc {
+    v2a_igemm_src src[V2A_MAX_SRC];   /* x operands (bf16 hi/lo planes, channels-last) */
+    int nsrc;
+    v2a_wgrad_unit units[V2A_WGRAD_MAX_UNITS];   /* output rows = 64 * nunits, unit-major */
+    int nunits;
+    v2a_igemm_src dy;       /* output-gradient planes over the OUTPUT pixel grid dy.dims */
+    int box_log2[4];        /* log2 of the 64-pixel reduction box along D0..D3 (sums to 6) */
+    int cout;               /* multiple of 4 */
+    int passes;             /* 3 = hi*hi + hi*lo + lo*hi; 1 = bf16 only */
+    float* out;             /* fp32 [64*nunits][ld_out], accumulated */
+    int ld_out;
+    int x_fp16;             /* x AND dy planes are fp16 (hi, lo) pairs (one format per MMA) */
+} v2a_wgrad_desc;
+int v2a_wgrad_plan_create(const v2a_wgrad_desc* desc, void** plan_out);
+int v2a_wgrad_plan_run(void* plan, void* stream);
+int v2a_wgrad_plan_k_splits(void* plan);
+void v2a_wgrad_plan_destroy(void* plan);
+int v2a_wgrad_scatter(const float* wt, int ld, int cout, int cin, int ntaps, float* dw, void* stream);
 
 /* ------------------------------------------------------------------------
  * GroupNorm statistics + apply (HBM-bound elementwise).
@@ -268,6 +308,87 @@ int v2a_grad_sumsq(const float* g, int64_t n, double* out, void* stream);
 int v2a_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n,
                        const double* grad_sumsq, float max_norm, float lr, float beta1, float beta2, float eps,
                        float weight_decay, int step, float ema_decay, void* stream);
+
+/* out[i] = src[map[i] - 1] (0 where map[i] == 0), split into planes of format plane_fmt (0 bf16, 1 fp16) */
+int v2a_gather_split_fmt(const float* src, const int32_t* map, int64_t n, void* hi, void* lo, float* f32,
+                         int plane_fmt, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Observation encoder (2 x ResNet18-GroupNorm + SpatialSoftmax + Linear), forward and backward:
+ * the HBM-bound kernels around the igemm / wgrad tensor-core contractions.
+ * replaces  ResNet18Conv (BatchNorm -> GroupNorm(C/16))   diffusion_policy/common/vision_nets.py:9-39
+ *                                                         diffusion_policy/model/multi_image_obs_encoder.py:67-74
+ *           SpatialSoftmax.forward                        diffusion_policy/common/base_nets.py:234-285
+ *           VisualCore's Linear                           diffusion_policy/common/vision_nets.py:113-143
+ *           and their autograd backward.
+ * ---------------------------------------------------------------------- */
+/* (mean, rstd) per (instance, group) from the {sum, sumsq} a producing igemm accumulated */
+int v2a_gn_finalize(const double* stats, int replicas, int64_t rep_stride, int instances, int C, int groups,
+                    int64_t pixels_per_inst, float eps, float* mean_rstd, void* stream);
+/* im2col of the 7x7 stride-2 pad-3 stem conv over x [B,3,H,W] (scale*x+shift folded in):
+ * planes [B*(H/2)*(W/2)][192], k = c*49 + ky*7 + kx, zero padded */
+int v2a_enc_stem_pack(const float* x, float scale, float shift, int B, int H, int W, void* out_hi, void* out_lo,
+                      int plane_fmt, void* twin_hi, void* twin_lo, void* stream);
+/* GroupNorm -> ReLU -> MaxPool2d(3, 2, 1): raw [B,H,W,C] -> out fp32 + planes [B,H/2,W/2,C] */
+int v2a_enc_gn_relu_maxpool(const float* raw, const float* mean_rstd, int groups, const float* gamma,
+                            const float* beta, int B, int H, int W, int C, float* out, void* out_hi, void* out_lo,
+                            int plane_fmt, void* twin_hi, void* twin_lo, void* stream);
+/* its backward up to the GroupNorm: g [B,H,W,C] from dpooled */
+int v2a_enc_maxpool_relu_bwd(const float* raw, const float* mean_rstd, int groups, const float* gamma,
+                             const float* beta, const float* pooled, const float* dpooled, int B, int H, int W, int C,
+                             float* g, void* stream);
+
+typedef struct v2a_enc_prep_desc {
+    const float* xa;            /* fp32 [images*H*W][C] conv output */
+    const float* mean_rstd_a;   /* [images][groups][2] */
+    const float* gamma_a;
+    const float* beta_a;
+    const float* xb;            /* optional second normalised source (downsample path) */
+    const float* mean_rstd_b;
+    const float* gamma_b;
+    const float* beta_b;
+    const float* idn;           /* optional fp32 identity added after the GroupNorm (exclusive with xb) */
+    int groups, C, H, W, images;
+    int relu;
+    int phase_split;            /* planes written as [img][py*2+px][H/2][W/2][C] (operand of a stride-2 conv) */
+    int plane_fmt;              /* 0: bf16 (hi, lo) planes, 1: fp16 (hi, lo) planes */
+    float* out_f32;             /* optional */
+    void* out_hi;               /* optional */
+    void* out_lo;
+    void* out2_hi;              /* optional bf16 twin of the planes: the weight-gradient GEMM pairs x with the bf16 */
+    void* out2_lo;              /* gradient planes and one tcgen05 MMA takes a single operand format */
+} v2a_enc_prep_desc;
+int v2a_enc_prep(const v2a_enc_prep_desc* d, void* stream);
+
+typedef struct v2a_enc_gn_bwd_desc {
+    const float* dout;          /* gradient wrt the block's post-activation output, fp32 [images*HW][C] */
+    const float* outv;          /* mask_mode 1: saved post-ReLU output */
+    const float* raw;           /* the GroupNorm's input (conv output) */
+    const float* mean_rstd;
+    const float* gamma;
+    const float* beta;
+    int mask_mode;              /* 0 none, 1 outv > 0, 2 GroupNorm(raw) > 0 (recomputed) */
+    int groups, C, HW, images;
+    float* sums;                /* scratch [images][C][2], zero on entry, zero on exit */
+    float* coef;                /* scratch [images][groups][2] */
+    void* d_hi;                 /* out: gradient wrt raw, bf16 planes */
+    void* d_lo;
+    float* g_out;               /* optional out: masked dout (identity / downsample branch gradient) */
+    float* dgamma;              /* accumulated */
+    float* dbeta;
+} v2a_enc_gn_bwd_desc;
+int v2a_enc_gn_bwd(const v2a_enc_gn_bwd_desc* d, void* stream);
+
+/* phase-blocked data gradient of a stride-2 conv [img][H/2][W/2][4][C] (+ ds at phase 0) -> dx [img][H][W][C] */
+int v2a_enc_unblock_add(const float* blocked, const float* ds, int images, int H, int W, int C, float* dx,
+                        void* stream);
+int v2a_enc_spatial_softmax_fwd(const float* logits, int ld, int B, int P, int K, float temperature,
+                                const float* pos_x, const float* pos_y, float* att, float* kp, void* stream);
+int v2a_enc_spatial_softmax_bwd(const float* att, const float* kp, const float* dkp, int B, int P, int K,
+                                float temperature, const float* pos_x, const float* pos_y, void* d_hi, void* d_lo,
+                                float* dbias, void* stream);
+int v2a_enc_linear_bwd(const float* x, const float* dy, const float* W, int B, int IN, int OUT, float* dx, float* dW,
+                       float* db, void* stream);
 
 #ifdef __cplusplus
 }

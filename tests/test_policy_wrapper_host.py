@@ -87,7 +87,8 @@ def test_compute_loss_fails_loudly_without_cuda(policy):
 
 
 @pytest.mark.skipif(not R.available(), reason="reference checkout not mounted")
-def test_encoder_and_install_against_live_reference(policy):
+def test_encoder_and_install_against_live_reference(policy, monkeypatch):
+    monkeypatch.setenv("V2A_ENCODER", "torch")   # host-side check of the parameter-holding torch modules
     from tests.golden.make_policy_loss_golden import build_reference_policy
     from v2a_b200 import install
     ref = build_reference_policy()

@@ -52,6 +52,53 @@ class IgemmDesc(C.Structure):
         ("stats_ld", C.c_int),
         ("stats_replicas", C.c_int),
         ("stats_rep_stride", C.c_int64),
+        ("a_fp16", C.c_int),
+        ("b_fp16", C.c_int),
+    ]
+
+
+V2A_WGRAD_MAX_UNITS = 80
+
+
+class WgradUnit(C.Structure):
+    _fields_ = [("src", C.c_int), ("d", C.c_int * 4), ("chunk", C.c_int)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("src", IgemmSrc * V2A_MAX_SRC),
+        ("nsrc", C.c_int),
+        ("units", WgradUnit * V2A_WGRAD_MAX_UNITS),
+        ("nunits", C.c_int),
+        ("dy", IgemmSrc),
+        ("box_log2", C.c_int * 4),
+        ("cout", C.c_int),
+        ("passes", C.c_int),
+        ("out", C.c_void_p),
+        ("ld_out", C.c_int),
+        ("x_fp16", C.c_int),
+    ]
+
+
+class EncPrepDesc(C.Structure):
+    _fields_ = [
+        ("xa", C.c_void_p), ("mean_rstd_a", C.c_void_p), ("gamma_a", C.c_void_p), ("beta_a", C.c_void_p),
+        ("xb", C.c_void_p), ("mean_rstd_b", C.c_void_p), ("gamma_b", C.c_void_p), ("beta_b", C.c_void_p),
+        ("idn", C.c_void_p),
+        ("groups", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int), ("images", C.c_int),
+        ("relu", C.c_int), ("phase_split", C.c_int), ("plane_fmt", C.c_int),
+        ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
+        ("out2_hi", C.c_void_p), ("out2_lo", C.c_void_p),
+    ]
+
+
+class EncGnBwdDesc(C.Structure):
+    _fields_ = [
+        ("dout", C.c_void_p), ("outv", C.c_void_p), ("raw", C.c_void_p), ("mean_rstd", C.c_void_p),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("mask_mode", C.c_int), ("groups", C.c_int), ("C", C.c_int), ("HW", C.c_int), ("images", C.c_int),
+        ("sums", C.c_void_p), ("coef", C.c_void_p), ("d_hi", C.c_void_p), ("d_lo", C.c_void_p),
+        ("g_out", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
     ]
 
 
@@ -120,6 +167,22 @@ SIGNATURES = {
     "v2a_igemm_plan_run": (_i, [_vp, _vp]),
     "v2a_igemm_plan_destroy": (None, [_vp]),
     "v2a_igemm_plan_k_splits": (_i, [_vp]),
+    "v2a_wgrad_plan_create": (_i, [C.POINTER(WgradDesc), C.POINTER(_vp)]),
+    "v2a_wgrad_plan_run": (_i, [_vp, _vp]),
+    "v2a_wgrad_plan_k_splits": (_i, [_vp]),
+    "v2a_wgrad_plan_destroy": (None, [_vp]),
+    "v2a_wgrad_scatter": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "v2a_gn_finalize": (_i, [_vp, _i, _i64, _i, _i, _i, _i64, _f, _vp, _vp]),
+    "v2a_enc_stem_pack": (_i, [_vp, _f, _f, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "v2a_enc_gn_relu_maxpool": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "v2a_gather_split_fmt": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i, _vp]),
+    "v2a_enc_maxpool_relu_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "v2a_enc_prep": (_i, [C.POINTER(EncPrepDesc), _vp]),
+    "v2a_enc_gn_bwd": (_i, [C.POINTER(EncGnBwdDesc), _vp]),
+    "v2a_enc_unblock_add": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "v2a_enc_spatial_softmax_fwd": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "v2a_enc_spatial_softmax_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "v2a_enc_linear_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "v2a_channel_stats": (_i, [_vp, _i64, _i64, _i, _vp, _vp]),
     "v2a_prep": (_i, [C.POINTER(PrepDesc), _vp]),
     "v2a_attention": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),

@@ -11,7 +11,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libv2a_b200.so")
 STAMP = os.path.join(PKG_DIR, ".libv2a_b200.stamp")
 
-SOURCES = ["igemm.cu", "elementwise.cu", "attention.cu", "policy.cu"]
+SOURCES = ["igemm.cu", "wgrad.cu", "elementwise.cu", "attention.cu", "policy.cu", "encoder.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -69,6 +70,31 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     split2(v[2], v[3], hi.y, lo.y);
     split2(v[4], v[5], hi.z, lo.z);
     split2(v[6], v[7], hi.w, lo.w);
+}
+
+// fp16 (hi, lo) planes: hi = rn_f16(x), lo = rn_f16(x - hi).  22+ significant bits (|x - hi - lo| <= 2^-23 |x| while
+// lo stays a normal fp16, i.e. |x| >~ 0.25; absolute error <= 3e-8 below that): fp32-class operands for the
+// observation encoder's FORWARD convolutions, whose inputs (GroupNorm outputs, weights) sit well inside the fp16
+// range.  The bf16 split (8 + 8 bits, error 2^-17) leaves ~2e-5 of forward error, enough to flip ~1e-5 of the
+// ReLU masks against the reference and move parameter gradients by > 1e-3; gradients themselves keep bf16 planes
+// (range).  tcgen05 kind::f16 takes either format per operand (instruction-descriptor a_format / b_format).
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void split8_f16(const float* v, uint4& hi, uint4& lo) {
+    split2_f16(v[0], v[1], hi.x, lo.x);
+    split2_f16(v[2], v[3], hi.y, lo.y);
+    split2_f16(v[4], v[5], hi.z, lo.z);
+    split2_f16(v[6], v[7], hi.w, lo.w);
+}
+// format-selecting split (fmt: 0 bf16 planes, 1 fp16 planes)
+__device__ __forceinline__ void split8_fmt(const float* v, uint4& hi, uint4& lo, int fmt) {
+    if (fmt) split8_f16(v, hi, lo);
+    else split8(v, hi, lo);
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
@@ -274,6 +300,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N tile.
 __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(m >> 4) << 24);
+}
+// same with the operand formats chosen per operand (a_format [7,10), b_format [10,13): 0 = fp16, 1 = bf16)
+__host__ __device__ __forceinline__ uint32_t umma_idesc_16(int m, int n, int a_fp16, int b_fp16) {
+    return (1u << 4) | ((a_fp16 ? 0u : 1u) << 7) | ((b_fp16 ? 0u : 1u) << 10) | ((uint32_t)(n >> 3) << 17) |
            ((uint32_t)(m >> 4) << 24);
 }
 

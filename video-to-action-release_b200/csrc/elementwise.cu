@@ -418,7 +418,7 @@ using namespace v2a;
 // ---------------------------------------------------------------------------
 __global__ void gather_split_kernel(const float* __restrict__ src, const int32_t* __restrict__ map, int64_t n,
                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                    float* __restrict__ out_f32) {
+                                    float* __restrict__ out_f32, int fmt) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
     for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i0 < n; i0 += stride) {
         float v[8];
@@ -430,7 +430,7 @@ __global__ void gather_split_kernel(const float* __restrict__ src, const int32_t
             for (int j = 0; j < 8; ++j) v[j] = m[j] ? __ldg(src + (m[j] - 1)) : 0.0f;
             if (hi) {
                 uint4 h, l;
-                split8(v, h, l);
+                split8_fmt(v, h, l, fmt);
                 *reinterpret_cast<uint4*>(hi + i0) = h;
                 *reinterpret_cast<uint4*>(lo + i0) = l;
             }
@@ -442,7 +442,16 @@ __global__ void gather_split_kernel(const float* __restrict__ src, const int32_t
             for (int64_t i = i0; i < n; ++i) {
                 const int32_t m = map[i];
                 const float x = m ? src[m - 1] : 0.0f;
-                if (hi) split_bf16(x, hi[i], lo[i]);
+                if (hi) {
+                    if (fmt) {
+                        const __half h = __float2half_rn(x);
+                        const __half l = __float2half_rn(x - __half2float(h));
+                        hi[i] = *reinterpret_cast<const __nv_bfloat16*>(&h);
+                        lo[i] = *reinterpret_cast<const __nv_bfloat16*>(&l);
+                    } else {
+                        split_bf16(x, hi[i], lo[i]);
+                    }
+                }
                 if (out_f32) out_f32[i] = x;
             }
         }
@@ -466,6 +475,18 @@ int v2a_channel_stats(const float* x, int64_t instances, int64_t ppi, int C, dou
     dim3 grid((unsigned)chunks, (unsigned)instances);
     channel_stats_kernel<<<grid, threads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
         x, ppi, C, (int)pix_per_block, stats);
+    V2A_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_gn_finalize(const double* stats, int replicas, int64_t rep_stride, int instances, int C, int groups,
+                    int64_t pixels_per_inst, float eps, float* mean_rstd, void* stream) {
+    V2A_REQUIRE(C % groups == 0 && instances >= 1, "gn_finalize: bad shape");
+    const int n = instances * groups;
+    const double count = (double)pixels_per_inst * (double)(C / groups);
+    gn_finalize_kernel<<<ceil_div(n * 32, 128), 128, 0, (cudaStream_t)stream>>>(
+        stats, nullptr, C, 0, groups, 1, count, eps, reinterpret_cast<float2*>(mean_rstd), instances,
+        replicas > 0 ? replicas : 1, rep_stride, 1, 0);
     V2A_LAUNCH_OK();
     return 0;
 }
@@ -592,6 +613,11 @@ int v2a_unnormalize_clamp(const float* x, float* out, int64_t n, void* stream) {
 
 int v2a_gather_split(const float* src, const int32_t* map, int64_t n, void* out_hi, void* out_lo,
                      float* out_f32, void* stream) {
+    return v2a_gather_split_fmt(src, map, n, out_hi, out_lo, out_f32, 0, stream);
+}
+
+int v2a_gather_split_fmt(const float* src, const int32_t* map, int64_t n, void* out_hi, void* out_lo,
+                         float* out_f32, int plane_fmt, void* stream) {
     V2A_REQUIRE(src && map && n >= 0, "gather_split: missing pointers");
     V2A_REQUIRE((out_hi != nullptr) == (out_lo != nullptr) && (out_hi || out_f32), "gather_split: no output");
     V2A_REQUIRE(((uintptr_t)map | (uintptr_t)out_hi | (uintptr_t)out_lo | (uintptr_t)out_f32) % 16 == 0,
@@ -601,7 +627,7 @@ int v2a_gather_split(const float* src, const int32_t* map, int64_t n, void* out_
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
     gather_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        src, map, n, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32);
+        src, map, n, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32, plane_fmt);
     V2A_LAUNCH_OK();
     return 0;
 }

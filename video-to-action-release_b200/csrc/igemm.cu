@@ -97,6 +97,7 @@ struct alignas(64) IgemmParams {
     int iters_per_cta;    // cluster mode: tile iterations of every CTA (ghost tiles pad the last ones)
     int k_splits;         // >1: the K loop of one output tile is shared by k_splits CTAs (fp32 atomics)
     int kps;              // K iterations per split
+    int a_fp16, b_fp16;   // operand planes hold fp16 (hi, lo) pairs instead of bf16 ones
     int debug;  // V2A_IGEMM_DEBUG bits: 1 skip stats, 2 skip stores, 4 skip residual (timing experiments only)
 };
 
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         }
     } else if (warp == 1 && lane == 0) {
         // ===================== MMA issuer =====================
-        const uint32_t idesc = umma_idesc_bf16(kTileM, p.block_n);
+        const uint32_t idesc = umma_idesc_16(kTileM, p.block_n, p.a_fp16, p.b_fp16);
         int stage = 0;
         uint32_t phase = 0;
         for (int it = 0; it < tr.count; ++it) {
@@ -576,6 +577,11 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
     return 0;
 }
 
+// shared with wgrad.cu
+int make_tensor_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+    return make_map(m, base, rank, dims, box);
+}
+
 struct IgemmPlan {
     IgemmParams p;
     int grid;
@@ -678,6 +684,8 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
     p.stats_ld = d->stats_ld;
     p.stats_replicas = d->stats_replicas > 0 ? d->stats_replicas : 1;
     p.stats_rep_stride = d->stats_rep_stride;
+    p.a_fp16 = d->a_fp16;
+    p.b_fp16 = d->b_fp16;
     {
         const char* dbg = getenv("V2A_IGEMM_DEBUG");
         p.debug = dbg ? atoi(dbg) : 0;

@@ -28,6 +28,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import obs_encoder
 from .policy_unet1d import ConditionalUnet1D
 
 
@@ -304,8 +305,17 @@ class VisualCore(nn.Module):
         return list(self._out)
 
     def forward(self, x):
+        """Planned CUDA engine (obs_encoder.py: tcgen05 convs + GroupNorm/ReLU/MaxPool/SpatialSoftmax kernels,
+        forward and backward).  ``V2A_ENCODER=torch`` runs the stock torch modules instead (host-side
+        comparisons and A/B timing only)."""
         assert tuple(x.shape[-3:]) == self.input_shape
-        return self.nets(x)
+        if not obs_encoder.enabled():
+            return self.nets(x)
+        if self.pool.noise_std != 0.0:
+            raise NotImplementedError("the CUDA VisualCore covers noise_std == 0 (the Libero yaml)")
+        if self.training:   # the reference draws randn_like(keypoints) * noise_std even for noise_std == 0
+            _randn((x.shape[0], self.pool._num_kp, 2), x.device, torch.float32)
+        return obs_encoder.visual_core_forward(self, x)
 
 
 def _bn_to_gn(root: nn.Module) -> nn.Module:
@@ -358,9 +368,12 @@ class MultiImageObsEncoder(_AttrMixin):
 
     @torch.no_grad()
     def output_shape(self):
-        ex = {k: torch.zeros((1,) + tuple(a["shape"]), dtype=self.dtype, device=self.device)
-              for k, a in self.shape_meta["obs"].items()}
-        return self.forward(ex).shape[1:]
+        """Feature width of the concatenated output (the reference probes this with a zero forward pass,
+        model/multi_image_obs_encoder.py:198-212; here it is read off the modules)."""
+        n = 0
+        for key in self.rgb_keys + self.low_dim_keys:
+            n += self.key_model_map[key].output_shape()[0] if key in self.key_model_map else self.key_shape_map[key][0]
+        return torch.Size([n])
 
 
 # ---------------------------------------------------------------------------

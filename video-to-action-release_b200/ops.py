@@ -39,6 +39,7 @@ class HL:
 
     hi: torch.Tensor
     lo: torch.Tensor
+    fp16: bool = False   # planes hold fp16 (hi, lo) bit patterns (in bf16-typed storage) instead of bf16 ones
 
     @staticmethod
     def empty(rows: int, cols: int, device) -> "HL":
@@ -46,6 +47,8 @@ class HL:
                   torch.empty(rows, cols, dtype=torch.bfloat16, device=device))
 
     def float(self) -> torch.Tensor:
+        if self.fp16:
+            return self.hi.view(torch.float16).float() + self.lo.view(torch.float16).float()
         return self.hi.float() + self.lo.float()
 
 
@@ -71,14 +74,15 @@ def split_hl(x: torch.Tensor, ld: Optional[int] = None) -> HL:
 # ---------------------------------------------------------------------------
 # tile / block heuristics (host logic, unit-tested on CPU)
 # ---------------------------------------------------------------------------
-def choose_tile(out_dims: Sequence[int]) -> tuple[int, int, int, int]:
-    """log2 of the 128-row tile box along D0..D3 minimising padded rows.
+def choose_tile(out_dims: Sequence[int], total_log2: int = 7) -> tuple[int, int, int, int]:
+    """log2 of the 2^total_log2-row tile box along D0..D3 minimising padded rows (128-row output tiles of
+    the implicit GEMM; 64-pixel reduction boxes of the weight-gradient GEMM).
 
     Ties prefer boxes that are long in the fastest dims (contiguous TMA rows).
     """
     best = None
-    for l in itertools.product(range(8), repeat=4):
-        if sum(l) != 7:
+    for l in itertools.product(range(total_log2 + 1), repeat=4):
+        if sum(l) != total_log2:
             continue
         rows = 1
         over = 0
@@ -142,6 +146,9 @@ class Igemm:
             for k in range(4):
                 d.src[i].dims[k] = dims[k]
         d.nsrc = len(srcs)
+        fmts = {bool(hl.fp16) for hl, _, _ in srcs}
+        assert fmts == {bool(w.fp16)}, "sources and weights of one igemm share a plane format"
+        d.a_fp16 = d.b_fp16 = int(bool(w.fp16))
         assert 1 <= len(taps) <= _lib.V2A_MAX_TAPS
         ktot = 0
         for i, (src, off, nch) in enumerate(taps):
@@ -226,6 +233,71 @@ class Igemm:
                 self._plan = None
         except Exception:
             pass
+
+
+class Wgrad:
+    """One planned weight-gradient GEMM (MN-major tcgen05, operands straight from channels-last planes):
+    out[(unit, ci), co] += sum_pixels x[pixel + d(unit), 64 * chunk(unit) + ci] * dy[pixel, co]."""
+
+    def __init__(self, *, srcs, units, dy: HL, dy_channels: int, dy_dims, cout: int, out: torch.Tensor,
+                 passes: int = 3, box_log2=None):
+        lib = _lib.load()
+        d = _lib.WgradDesc()
+        self._keep = [srcs, dy, out]
+        assert 1 <= len(srcs) <= _lib.V2A_MAX_SRC and 1 <= len(units) <= _lib.V2A_WGRAD_MAX_UNITS
+        for i, (hl, channels, dims) in enumerate(srcs):
+            _require_cuda(hl.hi, hl.lo)
+            dims = list(dims) + [1] * (4 - len(dims))
+            assert hl.hi.numel() == channels * dims[0] * dims[1] * dims[2] * dims[3], f"src {i}: size mismatch"
+            d.src[i].hi, d.src[i].lo, d.src[i].channels = hl.hi.data_ptr(), hl.lo.data_ptr(), channels
+            for k in range(4):
+                d.src[i].dims[k] = dims[k]
+        d.nsrc = len(srcs)
+        fmts = {bool(hl.fp16) for hl, _, _ in srcs}
+        assert fmts == {bool(dy.fp16)}, "x and dy planes share one format (a tcgen05 MMA takes a single operand format)"
+        d.x_fp16 = int(fmts.pop())
+        for i, (src, off, chunk) in enumerate(units):
+            off = list(off) + [0] * (4 - len(off))
+            d.units[i].src, d.units[i].chunk = src, chunk
+            for k in range(4):
+                d.units[i].d[k] = off[k]
+        d.nunits = len(units)
+        dy_dims = list(dy_dims) + [1] * (4 - len(dy_dims))
+        assert dy.hi.numel() == dy_channels * dy_dims[0] * dy_dims[1] * dy_dims[2] * dy_dims[3]
+        d.dy.hi, d.dy.lo, d.dy.channels = dy.hi.data_ptr(), dy.lo.data_ptr(), dy_channels
+        box_log2 = box_log2 or choose_tile(dy_dims, 6)
+        for k in range(4):
+            d.dy.dims[k] = dy_dims[k]
+            d.box_log2[k] = box_log2[k]
+        assert out.dtype == torch.float32 and out.dim() == 2 and out.shape[0] == 64 * len(units) and out.stride(1) == 1
+        d.cout, d.passes, d.out, d.ld_out = cout, passes, out.data_ptr(), out.stride(0)
+        self.desc = d
+        self.rows, self.cout = 64 * len(units), cout
+        pixels = dy_dims[0] * dy_dims[1] * dy_dims[2] * dy_dims[3]
+        self.flops = 2.0 * pixels * cout * 64 * len(units)
+        plan = C.c_void_p()
+        _lib.check(lib.v2a_wgrad_plan_create(C.byref(d), C.byref(plan)), "wgrad_plan_create")
+        self._plan, self._lib = plan, lib
+        self.k_splits = int(lib.v2a_wgrad_plan_k_splits(plan))
+
+    def run(self) -> None:
+        _lib.check(self._lib.v2a_wgrad_plan_run(self._plan, _stream()), "wgrad_plan_run")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None):
+                self._lib.v2a_wgrad_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:
+            pass
+
+
+def wgrad_scatter(wt: torch.Tensor, cout: int, cin: int, ntaps: int, dw: torch.Tensor) -> None:
+    """dw [cout, cin, taps...] += wt[(tap * ceil(cin/64) + chunk) * 64 + ci % 64, co]."""
+    _require_cuda(wt, dw)
+    assert dw.is_contiguous() and dw.numel() == cout * cin * ntaps
+    _lib.check(_lib.load().v2a_wgrad_scatter(wt.data_ptr(), wt.stride(0), cout, cin, ntaps, dw.data_ptr(), _stream()),
+               "wgrad_scatter")
 
 
 # ---------------------------------------------------------------------------

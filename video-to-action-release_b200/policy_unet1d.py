@@ -32,6 +32,7 @@ import torch.nn.functional as F
 
 from . import _lib, convs, ops
 from .ops import HL
+from .packing import PackedParams
 
 # ---------------------------------------------------------------------------
 # parameter holders (reference-identical names)
@@ -253,7 +254,7 @@ class _Steps(list):
         self.add(getattr(fn, "__name__", "step"), fn)
 
 
-class _PolicyEngine:
+class _PolicyEngine(PackedParams):
     def __init__(self, model: ConditionalUnet1D, B, T, device):
         self.model_ref = weakref.ref(model)
         self.B, self.T, self.device = B, T, device
@@ -261,8 +262,8 @@ class _PolicyEngine:
         self.lib = _lib.load()
         self.fwd: _Steps = _Steps()
         self.bwd: _Steps = _Steps()
-        self.packers, self.vec_packers, self.keep = [], [], []
-        self._wchunks, self._vchunks = [], []
+        self._init_packing()
+        self.keep = []
         self._graphs: Dict[str, object] = {}
         self._gn_partials = None
         self._side = None if os.environ.get("V2A_NO_SIDE_STREAM", "0") == "1" else torch.cuda.Stream(device=device)
@@ -289,111 +290,6 @@ class _PolicyEngine:
     def hlz(self, rows, cols) -> HL:
         return HL(torch.zeros(rows, cols, dtype=torch.bfloat16, device=self.device),
                   torch.zeros(rows, cols, dtype=torch.bfloat16, device=self.device))
-
-    def _carve(self, kind: str, n: int):
-        """n elements (multiple of 128) from the growing weight ('w': bf16 hi/lo planes) or vector ('v': fp32)
-        arena; every arena chunk is re-packed by ONE v2a_gather_split launch."""
-        n_al = -(-n // 128) * 128
-        chunks = self._wchunks if kind == "w" else self._vchunks
-        if not chunks or chunks[-1]["used"] + n_al > chunks[-1]["cap"]:
-            cap = max(n_al, (16 << 20) if kind == "w" else (1 << 20))
-            c = dict(cap=cap, used=0, map=torch.zeros(cap, dtype=torch.int32, device=self.device))
-            if kind == "w":
-                c["hi"] = torch.zeros(cap, dtype=torch.bfloat16, device=self.device)
-                c["lo"] = torch.zeros(cap, dtype=torch.bfloat16, device=self.device)
-            else:
-                c["f32"] = torch.zeros(cap, dtype=torch.float32, device=self.device)
-            chunks.append(c)
-        c = chunks[-1]
-        lo, hi = c["used"], c["used"] + n
-        c["used"] += n_al
-        return c, lo, hi
-
-    def weight(self, fn, rows, cols) -> HL:
-        c, lo, hi = self._carve("w", rows * cols)
-        hl = HL(c["hi"][lo:hi].view(rows, cols), c["lo"][lo:hi].view(rows, cols))
-        self.packers.append((fn, hl, c["map"][lo:hi].view(rows, cols)))
-        return hl
-
-    def vec(self, fn, n) -> torch.Tensor:
-        c, lo, hi = self._carve("v", n)
-        v = c["f32"][lo:hi]
-        self.vec_packers.append((fn, v, c["map"][lo:hi]))
-        return v
-
-    def _trace_packers(self):
-        """Every packer is a pure gather of parameter elements (slices, transposes, zero padding, cat):
-        run each ONCE on index-valued stand-ins of the parameters to record out[i] <- flat parameter index
-        (+1; 0 = structural zero).  Re-packing after an optimiser step is then table driven."""
-        saved = [p.data for p in self.params]
-        try:
-            off = 0
-            for p in self.params:
-                n = p.numel()
-                p.data = torch.arange(off + 1, off + n + 1, dtype=torch.float64, device=self.device).view(p.shape)
-                off += n
-            assert off < 2 ** 31 - 1
-            with torch.no_grad():
-                for fn, hl, mp in self.packers:
-                    mp.copy_(fn().to(self.device).reshape(mp.shape).to(torch.int32))
-                for fn, v, mp in self.vec_packers:
-                    mp.copy_(fn().to(self.device).reshape(-1).to(torch.int32))
-        finally:
-            for p, d in zip(self.params, saved):
-                p.data = d
-        self._stage = None
-        self._trace_checked = False
-
-    def _param_slab(self) -> torch.Tensor:
-        """The parameters as ONE flat fp32 tensor in parameters() order: the live slab when they already are
-        consecutive views of one (train_step.PolicyTrainStep), else a staging copy (one cat launch)."""
-        ps = [p for p in self.params if p.numel()]
-        ptr, ok = ps[0].data_ptr(), True
-        for p in ps:
-            if p.data_ptr() != ptr or not p.is_contiguous() or p.dtype != torch.float32 or p.device != self.device:
-                ok = False
-                break
-            ptr += 4 * p.numel()
-        tot = sum(p.numel() for p in ps)
-        if ok:
-            st = ps[0].untyped_storage()
-            first = (ps[0].data_ptr() - st.data_ptr()) // 4
-            return torch.empty(0, dtype=torch.float32, device=self.device).set_(st, first, (tot,))
-        if self._stage is None:
-            self._stage = torch.empty(tot, dtype=torch.float32, device=self.device)
-        with torch.no_grad():
-            torch.cat([p.detach().to(self.device, torch.float32).reshape(-1) for p in ps], out=self._stage)
-        return self._stage
-
-    def _repack_reference(self):
-        """The packers evaluated with torch ops on the real parameters (one-off check of the traced tables)."""
-        with torch.no_grad():
-            for fn, hl, _ in self.packers:
-                w = fn().detach().to(self.device, torch.float32).reshape(hl.hi.shape)
-                hi = w.to(torch.bfloat16)
-                yield hl.hi, hi
-                yield hl.lo, (w - hi.float()).to(torch.bfloat16)
-            for fn, v, _ in self.vec_packers:
-                yield v, fn().detach().to(self.device, torch.float32).reshape(-1)
-
-    def refresh_weights(self):
-        key = tuple((p.data_ptr(), p._version) for p in self.params)
-        if key == self._wkey:
-            return
-        src = self._param_slab()
-        st = ops._stream()
-        for c in self._wchunks:
-            _lib.check(self.lib.v2a_gather_split(src.data_ptr(), c["map"].data_ptr(), c["used"], c["hi"].data_ptr(),
-                                                 c["lo"].data_ptr(), None, st), "gather_split")
-        for c in self._vchunks:
-            _lib.check(self.lib.v2a_gather_split(src.data_ptr(), c["map"].data_ptr(), c["used"], None, None,
-                                                 c["f32"].data_ptr(), st), "gather_split")
-        if not self._trace_checked:   # first pack: the traced gather must reproduce the torch packers bit for bit
-            for got, want in self._repack_reference():
-                if not torch.equal(got, want):
-                    raise RuntimeError("v2a_b200 policy engine: traced weight table disagrees with its packer")
-            self._trace_checked = True
-        self._wkey = key
 
     # ---- launch wrappers -------------------------------------------------------
     def igemm(self, steps, **kw):

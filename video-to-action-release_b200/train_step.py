@@ -28,7 +28,7 @@ from typing import Callable, Iterable, List, Optional
 import torch
 import torch.nn as nn
 
-from . import _lib, distributed, ops, policy_unet1d
+from . import _lib, distributed, obs_encoder, ops, policy_unet1d
 
 
 def ema_decay(call_index: int, *, beta: float = 0.9999, inv_gamma: float = 1.0, power: float = 0.75,
@@ -92,6 +92,17 @@ class PolicyTrainStep:
         self.group, self.bucket_bytes = group, bucket_bytes
         unet_params = list(unet1d.parameters())
         ids = {id(p) for p in unet_params}
+        # observation encoders that run on the planned CUDA engine keep their gradients in the engine's slab too
+        self.cores = []
+        if obs_encoder.enabled():
+            from .diffusion_policy import VisualCore
+            self.cores = [m for m in module.modules() if isinstance(m, VisualCore)]
+        self.seg_cores = []
+        for core in self.cores:
+            cp = [p for p in core.parameters()]
+            ids |= {id(p) for p in cp}
+            self.seg_cores.append(_Segment(cp, dev, own_grad=False, ema=ema))
+            obs_encoder.set_slab_grads(core, True)
         other = [p for p in module.parameters() if id(p) not in ids and p.requires_grad and p.numel() > 0]
         self.seg_unet = _Segment(unet_params, dev, own_grad=False, ema=ema)
         self.seg_other = _Segment(other, dev, own_grad=True, ema=ema) if other else None
@@ -110,6 +121,11 @@ class PolicyTrainStep:
 
     def _segments(self):
         yield self.seg_unet, self._unet_grad_slab()
+        for core, seg in zip(self.cores, self.seg_cores):
+            eng = obs_encoder.last_engine(core)
+            if eng is None:
+                raise RuntimeError("PolicyTrainStep.step: the loss closure did not run an observation encoder")
+            yield seg, eng.gslab
         if self.seg_other is not None:
             yield self.seg_other, self.seg_other.g
 
@@ -130,6 +146,8 @@ class PolicyTrainStep:
                 self.max_norm, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.steps_done,
                 decay, st), "adamw_ema_step")
         policy_unet1d.invalidate_weights(self.unet)
+        for core in self.cores:
+            obs_encoder.invalidate_weights(core)
         if self.seg_other is not None:
             self.seg_other.g.zero_()          # zero_grad() for the autograd-accumulated segment
 
@@ -153,7 +171,7 @@ class PolicyTrainStep:
             raise RuntimeError("PolicyTrainStep was built with ema=False")
         src = {}
         names = {id(p): n for n, p in self.module.named_parameters()}
-        for seg in (self.seg_unet, self.seg_other):
+        for seg in (self.seg_unet, *self.seg_cores, self.seg_other):
             if seg is None:
                 continue
             for p, e in seg.ema_views():
