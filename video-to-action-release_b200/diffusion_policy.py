@@ -359,11 +359,29 @@ class MultiImageObsEncoder(_AttrMixin):
 
     def forward(self, obs_dict):
         feats, bs = [], None
-        for key in self.rgb_keys + self.low_dim_keys:
+        keys = self.rgb_keys + self.low_dim_keys
+        cur = torch.cuda.current_stream() if torch.cuda.is_available() else None
+        joined = []
+        for i, key in enumerate(keys):
             x = obs_dict[key]
             bs = x.shape[0] if bs is None else bs
             assert x.shape[0] == bs and tuple(x.shape[1:]) == self.key_shape_map[key]
-            feats.append(self.key_model_map[key](x) if key in self.key_model_map else x)
+            if key not in self.key_model_map:
+                feats.append(x)
+            elif x.is_cuda and obs_encoder.enabled() and i + 1 < len(self.rgb_keys):
+                # independent encoders overlap: all but the last run on side streams (the RNG draws and the
+                # Python-side order stay the reference's; autograd replays the backward on the same streams)
+                s = obs_encoder.side_stream(x.device, i)
+                s.wait_stream(cur)
+                with torch.cuda.stream(s):
+                    f = self.key_model_map[key](x)
+                f.record_stream(cur)
+                joined.append(s)
+                feats.append(f)
+            else:
+                feats.append(self.key_model_map[key](x))
+        for s in joined:
+            cur.wait_stream(s)
         return torch.cat(feats, dim=-1)
 
     @torch.no_grad()

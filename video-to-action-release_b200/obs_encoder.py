@@ -172,6 +172,8 @@ class _EncoderEngine(PackedParams):
         self._stats_req: List = []       # (holder, reps, N, C)
         self._scratch_req: List = []     # (holder, rows, cols) weight-gradient scratch, zeroed every backward
         self._graphs: Dict[str, object] = {}
+        self._side = None if os.environ.get("V2A_NO_SIDE_STREAM", "0") == "1" else torch.cuda.Stream(device=device)
+        self.done = torch.cuda.Event()
         self._build(core)
         self._bind_arenas()
         self._trace_packers()
@@ -237,9 +239,9 @@ class _EncoderEngine(PackedParams):
             slot[0] = g
             self.wgrads.append(g)
         self._deferred.append(make)
-        steps.add(f"wgrad M{64 * len(units)} N{cout}", lambda: slot[0].run())
+        steps.add(f"wgrad M{64 * len(units)} N{cout}", lambda: slot[0].run(), lane=1)
         dst = self.pgrad[id(param)]
-        steps.add("wgrad_scatter", lambda: ops.wgrad_scatter(sc[0], cout, cin, ntaps, dst))
+        steps.add("wgrad_scatter", lambda: ops.wgrad_scatter(sc[0], cout, cin, ntaps, dst), lane=1)
 
     def gn_finalize(self, steps, st, N, Cc, groups, HW, eps, mr):
         steps.add("gn_finalize", lambda: _lib.check(self.lib.v2a_gn_finalize(
@@ -510,21 +512,72 @@ class _EncoderEngine(PackedParams):
         return n + len(self._wchunks) + len(self._vchunks)
 
     # ---- execution -----------------------------------------------------------------------------
+    def _run(self, name: str, steps, pre=()):
+        """Launch a planned list.  Every buffer is static, so after one eager (warm-up) run the list is captured
+        into a CUDA graph and replayed (V2A_NO_GRAPH=1 disables).  Lane 1 = weight-gradient GEMMs + their scatter:
+        nothing on the main chain reads their results, so they run on a side stream beside the data-gradient chain."""
+        def eager():
+            main = torch.cuda.current_stream()
+            for z in pre:
+                z.zero_()
+            used_side = False
+            for fn, lane in zip(steps, steps.lanes):
+                if lane == 1 and self._side is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    self._side.wait_event(ev)
+                    with torch.cuda.stream(self._side):
+                        fn()
+                    used_side = True
+                else:
+                    fn()
+            if used_side:
+                main.wait_stream(self._side)
+        if os.environ.get("V2A_NO_GRAPH", "0") == "1":
+            return eager()
+        seen = self._graphs.get(name)
+        if seen is None:            # first call: eager (lazy CUDA module loads must not happen under capture)
+            self._graphs[name] = False
+            return eager()
+        if seen is False:
+            g = torch.cuda.CUDAGraph()
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    eager()
+            cur.wait_stream(side)
+            self._graphs[name] = seen = g
+        seen.replay()
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         self.refresh_weights()
         self.x_in.copy_(x)
-        self.stats_arena.zero_()
-        for s in self.fwd:
-            s()
+        self._run("fwd", self.fwd, pre=(self.stats_arena,))
         self.fwd_token += 1
         return self.feat.clone()
 
     def backward(self, dfeat: torch.Tensor, clone_param_grads: bool = True):
         self.dfeat.copy_(dfeat)
-        self.gslab.zero_()
-        self.wg_arena.zero_()
-        for s in self.bwd:
-            s()
+        self._run("bwd", self.bwd, pre=(self.gslab, self.wg_arena))
+        self.done.record(torch.cuda.current_stream())   # consumers of gslab on other streams wait on this
         if clone_param_grads:
             return [self.pgrad[id(p)].clone() if p.requires_grad else None for p in self.params]
         return [None] * len(self.params)
+
+
+_SIDE_STREAMS: Dict[tuple, "torch.cuda.Stream"] = {}
+
+
+def side_stream(device, index: int) -> "torch.cuda.Stream":
+    """Per-device streams on which MultiImageObsEncoder runs all but its last encoder, so the independent
+    ResNets (many launches that do not fill 148 SMs at 8x8 / 4x4) overlap, forward and -- since autograd runs a
+    Function's backward on its forward stream -- backward."""
+    device = torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    key = (str(device), index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]

@@ -125,6 +125,7 @@ class PolicyTrainStep:
             eng = obs_encoder.last_engine(core)
             if eng is None:
                 raise RuntimeError("PolicyTrainStep.step: the loss closure did not run an observation encoder")
+            torch.cuda.current_stream().wait_event(eng.done)   # its backward may have run on a side stream
             yield seg, eng.gslab
         if self.seg_other is not None:
             yield self.seg_other, self.seg_other.g
