@@ -27,42 +27,49 @@ extern std::atomic<int64_t> g_launches;
 // `scale * x + shift` is the policy's image normaliser (2x - 1) folded in; padding is zero AFTER it.
 // one thread = 8 consecutive k of one output pixel
 // ---------------------------------------------------------------------------
+// one block = one output row of one image: the 7 input rows x 3 channels it needs are staged in shared memory
+// (coalesced, normalised, zero padded) and every thread assembles 8 consecutive k of one output pixel from there
+// (the first version gathered 8 scalars per thread from global memory: 0.50 ms at B = 256, LSU-bound)
 __global__ void __launch_bounds__(256) enc_stem_pack_kernel(const float* __restrict__ x, float scale, float shift,
                                                             int B, int H, int W, __nv_bfloat16* __restrict__ hi,
                                                             __nv_bfloat16* __restrict__ lo, int fmt,
                                                             __nv_bfloat16* __restrict__ hi2,
                                                             __nv_bfloat16* __restrict__ lo2) {
-    const int Ho = H >> 1, Wo = W >> 1;
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t total = (int64_t)B * Ho * Wo * 24;
-    if (gid >= total) return;
-    const int o8 = (int)(gid % 24);
-    const int64_t pix = gid / 24;
-    const int ox = (int)(pix % Wo);
-    const int oy = (int)((pix / Wo) % Ho);
-    const int b = (int)(pix / ((int64_t)Wo * Ho));
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int k = o8 * 8 + j;
-        float r = 0.0f;
-        if (k < 147) {
-            const int c = k / 49, t = k - c * 49;
-            const int ky = t / 7, kx = t - ky * 7;
-            const int iy = 2 * oy + ky - 3, ix = 2 * ox + kx - 3;
-            if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-                r = fmaf(__ldg(&x[(((int64_t)b * 3 + c) * H + iy) * W + ix]), scale, shift);
-        }
-        v[j] = r;
+    extern __shared__ float tile[];   // [3][7][W + 6]
+    const int Ho = H >> 1, Wo = W >> 1, Wp = W + 6;
+    const int b = blockIdx.x / Ho, oy = blockIdx.x - b * Ho;
+    for (int i = threadIdx.x; i < 21 * Wp; i += blockDim.x) {
+        const int xx = i % Wp, r = (i / Wp) % 7, c = i / (7 * Wp);
+        const int iy = 2 * oy + r - 3, ix = xx - 3;
+        float v = 0.0f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = fmaf(__ldg(&x[(((int64_t)b * 3 + c) * H + iy) * W + ix]), scale, shift);
+        tile[i] = v;
     }
-    uint4 h, l;
-    split8_fmt(v, h, l, fmt);
-    *reinterpret_cast<uint4*>(hi + pix * 192 + o8 * 8) = h;
-    *reinterpret_cast<uint4*>(lo + pix * 192 + o8 * 8) = l;
-    if (hi2) {   // bf16 twin: the weight-gradient GEMM pairs x with bf16 gradient planes (one format per MMA)
-        split8(v, h, l);
-        *reinterpret_cast<uint4*>(hi2 + pix * 192 + o8 * 8) = h;
-        *reinterpret_cast<uint4*>(lo2 + pix * 192 + o8 * 8) = l;
+    __syncthreads();
+    for (int i = threadIdx.x; i < Wo * 24; i += blockDim.x) {
+        const int ox = i / 24, o8 = i - ox * 24;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = o8 * 8 + j;
+            float r = 0.0f;
+            if (k < 147) {
+                const int c = k / 49, t = k - c * 49;
+                const int ky = t / 7, kx = t - ky * 7;
+                r = tile[(c * 7 + ky) * Wp + 2 * ox + kx];
+            }
+            v[j] = r;
+        }
+        const int64_t pix = ((int64_t)b * Ho + oy) * Wo + ox;
+        uint4 h, l;
+        split8_fmt(v, h, l, fmt);
+        *reinterpret_cast<uint4*>(hi + pix * 192 + o8 * 8) = h;
+        *reinterpret_cast<uint4*>(lo + pix * 192 + o8 * 8) = l;
+        if (hi2) {   // bf16 twin: the weight-gradient GEMM pairs x with bf16 gradient planes (one format per MMA)
+            split8(v, h, l);
+            *reinterpret_cast<uint4*>(hi2 + pix * 192 + o8 * 8) = h;
+            *reinterpret_cast<uint4*>(lo2 + pix * 192 + o8 * 8) = l;
+        }
     }
 }
 
@@ -522,8 +529,8 @@ using namespace v2a;
 int v2a_enc_stem_pack(const float* x, float scale, float shift, int B, int H, int W, void* out_hi, void* out_lo,
                       int plane_fmt, void* twin_hi, void* twin_lo, void* stream) {
     V2A_REQUIRE(B >= 1 && H % 2 == 0 && W % 2 == 0, "enc_stem_pack: bad shape");
-    const int64_t total = (int64_t)B * (H / 2) * (W / 2) * 24;
-    enc_stem_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    V2A_REQUIRE(W <= 1024, "enc_stem_pack: image width %d exceeds the shared-memory row tile", W);
+    enc_stem_pack_kernel<<<(unsigned)(B * (H / 2)), 256, 21 * (W + 6) * sizeof(float), (cudaStream_t)stream>>>(
         x, scale, shift, B, H, W, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, plane_fmt,
         (__nv_bfloat16*)twin_hi, (__nv_bfloat16*)twin_lo);
     V2A_ENC_LAUNCH_OK();
