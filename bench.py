@@ -267,7 +267,7 @@ def run_policy(args, world, rank, local, barrier, max_over_ranks, peaks):
     loss_u = lambda: F.mse_loss(net(noisy, tt, global_cond=gc), noise)
     ms_u, launches_u = timed(lambda: step_u.step(loss_u), steps)
     eng = PU.last_engine(net)
-    flops = sum(gm.flops for gm in eng.igemms)              # forward + dgrad + wgrad GEMMs of one step
+    flops = sum(gm.flops for gm in eng.igemms) + sum(gm.flops for gm in eng.wgrads)   # forward + dgrad + wgrad GEMMs
     # the forward / backward lists replay as CUDA graphs, so count their kernels from the plan (the C-ABI
     # launch counter only sees capture time): planned launches + repack chunks + sumsq + AdamW/EMA
     launches_u = len(eng.fwd) + len(eng.bwd) + len(eng._wchunks) + len(eng._vchunks) + 2

@@ -104,8 +104,8 @@ int64_t v2a_launch_count(void);
  * ResNet18 / keypoint convs   diffusion_policy/common/vision_nets.py:29-39
  *                             diffusion_policy/common/base_nets.py:183
  * `out` is accumulated with fp32 REDs (the pixel reduction is split between
- * CTAs): the caller zeroes it.  v2a_wgrad_scatter adds the [(tap, ci)][co]
- * scratch into a parameter-gradient tensor laid out [co][ci][tap].
+ * CTAs): the caller zeroes it.  v2a_wgrad_scatter writes / adds the [(tap, ci)][co]
+ * scratch into a parameter-gradient tensor laid out [co][ci][tap] (rows ld_dw apart).
  * ---------------------------------------------------------------------- */
 #define V2A_WGRAD_MAX_UNITS 80
 typedef struct v2a_wgrad_unit {
@@ -131,7 +131,8 @@ int v2a_wgrad_plan_create(const v2a_wgrad_desc* desc, void** plan_out);
 int v2a_wgrad_plan_run(void* plan, void* stream);
 int v2a_wgrad_plan_k_splits(void* plan);
 void v2a_wgrad_plan_destroy(void* plan);
-int v2a_wgrad_scatter(const float* wt, int ld, int cout, int cin, int ntaps, float* dw, void* stream);
+int v2a_wgrad_scatter(const float* wt, int ld, int cout, int cin, int ntaps, float* dw, int64_t ld_dw,
+                      int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------
  * GroupNorm statistics + apply (HBM-bound elementwise).

@@ -51,7 +51,7 @@ def main():
     torch.cuda.synchronize()
     print(f"first step (plan build + pack) {time.time() - t0:.2f}s")
     eng = PU.last_engine(net)
-    flops_f = sum(g.flops for g in eng.igemms)
+    flops_f = sum(g.flops for g in eng.igemms) + sum(g.flops for g in eng.wgrads)
     ms_step = timed(lambda: step.step(loss_fn))
     print(f"B={B} full step {ms_step:.3f} ms -> {B / ms_step * 1e3:.0f} samples/s; igemm flops fwd+bwd {flops_f / 1e9:.1f} GF "
           f"-> {flops_f / ms_step / 1e9:.1f} TFLOP/s; launches fwd {len(eng.fwd)} bwd {len(eng.bwd)}")

@@ -171,7 +171,7 @@ SIGNATURES = {
     "v2a_wgrad_plan_run": (_i, [_vp, _vp]),
     "v2a_wgrad_plan_k_splits": (_i, [_vp]),
     "v2a_wgrad_plan_destroy": (None, [_vp]),
-    "v2a_wgrad_scatter": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "v2a_wgrad_scatter": (_i, [_vp, _i, _i, _i, _i, _vp, _i64, _i, _vp]),
     "v2a_gn_finalize": (_i, [_vp, _i, _i64, _i, _i, _i, _i64, _f, _vp, _vp]),
     "v2a_enc_stem_pack": (_i, [_vp, _f, _f, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "v2a_enc_gn_relu_maxpool": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),

@@ -36,8 +36,15 @@ __global__ void __launch_bounds__(256) enc_stem_pack_kernel(const float* __restr
                                                             __nv_bfloat16* __restrict__ hi2,
                                                             __nv_bfloat16* __restrict__ lo2) {
     extern __shared__ float tile[];   // [3][7][W + 6]
+    __shared__ short lut[192];        // k -> offset of (c, ky, kx) in the tile (-1: zero padding of K)
     const int Ho = H >> 1, Wo = W >> 1, Wp = W + 6;
     const int b = blockIdx.x / Ho, oy = blockIdx.x - b * Ho;
+    if (threadIdx.x < 192) {
+        const int k = threadIdx.x;
+        const int c = k / 49, t = k - c * 49;
+        const int ky = t / 7, kx = t - ky * 7;
+        lut[k] = k < 147 ? (short)((c * 7 + ky) * Wp + kx) : (short)-1;
+    }
     for (int i = threadIdx.x; i < 21 * Wp; i += blockDim.x) {
         const int xx = i % Wp, r = (i / Wp) % 7, c = i / (7 * Wp);
         const int iy = 2 * oy + r - 3, ix = xx - 3;
@@ -51,14 +58,8 @@ __global__ void __launch_bounds__(256) enc_stem_pack_kernel(const float* __restr
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int k = o8 * 8 + j;
-            float r = 0.0f;
-            if (k < 147) {
-                const int c = k / 49, t = k - c * 49;
-                const int ky = t / 7, kx = t - ky * 7;
-                r = tile[(c * 7 + ky) * Wp + 2 * ox + kx];
-            }
-            v[j] = r;
+            const int o = lut[o8 * 8 + j];
+            v[j] = o >= 0 ? tile[o + 2 * ox] : 0.0f;
         }
         const int64_t pix = ((int64_t)b * Ho + oy) * Wo + ox;
         uint4 h, l;
@@ -529,7 +530,7 @@ using namespace v2a;
 int v2a_enc_stem_pack(const float* x, float scale, float shift, int B, int H, int W, void* out_hi, void* out_lo,
                       int plane_fmt, void* twin_hi, void* twin_lo, void* stream) {
     V2A_REQUIRE(B >= 1 && H % 2 == 0 && W % 2 == 0, "enc_stem_pack: bad shape");
-    V2A_REQUIRE(W <= 1024, "enc_stem_pack: image width %d exceeds the shared-memory row tile", W);
+    V2A_REQUIRE(W <= 1024, "enc_stem_pack: image width %d exceeds the shared-memory row tile", W);   // lut offsets < 32768
     enc_stem_pack_kernel<<<(unsigned)(B * (H / 2)), 256, 21 * (W + 6) * sizeof(float), (cudaStream_t)stream>>>(
         x, scale, shift, B, H, W, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, plane_fmt,
         (__nv_bfloat16*)twin_hi, (__nv_bfloat16*)twin_lo);

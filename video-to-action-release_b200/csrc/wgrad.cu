@@ -200,17 +200,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     }
 }
 
-// dW[co][ci][tap] += dWT[(tap * nchunk + chunk) * 64 + ci % 64][co]   (ci = chunk * 64 + ci % 64)
+// dW[co][ci][tap] (+)= dWT[(tap * nchunk + chunk) * 64 + ci % 64][co]   (ci = chunk * 64 + ci % 64); dW rows are
+// ld_dw apart (a column window of a wider [cout][cin_total * taps] gradient when the conv input is a concat)
 __global__ void wgrad_scatter_kernel(const float* __restrict__ wt, int ld, int cout, int cin, int ntaps, int nchunk,
-                                     float* __restrict__ dw) {
+                                     float* __restrict__ dw, int64_t ld_dw, int accumulate) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t n = (int64_t)cout * cin * ntaps;
-    if (i >= n) return;
-    const int tap = (int)(i % ntaps);
-    const int ci = (int)((i / ntaps) % cin);
-    const int co = (int)(i / ((int64_t)ntaps * cin));
+    const int64_t per = (int64_t)cin * ntaps;
+    if (i >= cout * per) return;
+    const int co = (int)(i / per);
+    const int rem = (int)(i - co * per);
+    const int tap = rem % ntaps;
+    const int ci = rem / ntaps;
     const int64_t r = ((int64_t)tap * nchunk + (ci >> 6)) * 64 + (ci & 63);
-    dw[i] += wt[r * ld + co];
+    const float v = wt[r * ld + co];
+    float* d = dw + co * ld_dw + rem;
+    *d = accumulate ? *d + v : v;
 }
 
 struct WgradPlan {
@@ -351,11 +355,12 @@ int v2a_wgrad_plan_k_splits(void* plan) { return reinterpret_cast<v2a::WgradPlan
 
 void v2a_wgrad_plan_destroy(void* plan) { delete reinterpret_cast<v2a::WgradPlan*>(plan); }
 
-int v2a_wgrad_scatter(const float* wt, int ld, int cout, int cin, int ntaps, float* dw, void* stream) {
-    V2A_REQUIRE(cout >= 1 && cin >= 1 && ntaps >= 1, "wgrad_scatter: bad shape");
+int v2a_wgrad_scatter(const float* wt, int ld, int cout, int cin, int ntaps, float* dw, int64_t ld_dw,
+                      int accumulate, void* stream) {
+    V2A_REQUIRE(cout >= 1 && cin >= 1 && ntaps >= 1 && ld_dw >= (int64_t)cin * ntaps, "wgrad_scatter: bad shape");
     const int64_t n = (int64_t)cout * cin * ntaps;
     v2a::wgrad_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        wt, ld, cout, cin, ntaps, (cin + 63) / 64, dw);
+        wt, ld, cout, cin, ntaps, (cin + 63) / 64, dw, ld_dw, accumulate);
     V2A_CUDA_OK(cudaGetLastError());
     v2a::g_launches.fetch_add(1);
     return 0;

@@ -217,8 +217,21 @@ class _EncoderEngine(PackedParams):
         self._deferred = []
 
     # ---- launch wrappers (plans are created after the arenas exist) ------------------------------
+    @staticmethod
+    def _block_n(rows: int, cout: int) -> int:
+        """N tile of a forward conv: its epilogue accumulates GroupNorm sums, so it cannot split K to fill the
+        machine; when the widest N tile leaves fewer tiles than SMs (layers 3-4: 64 ... 32 tiles), narrow it."""
+        n = ops.choose_block_n(cout)
+        m_tiles = -(-rows // 128)
+        while n > 64 and n % 32 == 0 and m_tiles * -(-cout // n) < 120:
+            n //= 2
+        return n
+
     def igemm(self, steps, tag="igemm", **kw):
         slot = [None]
+        if kw.get("stats") is not None and "block_n" not in kw:
+            od = kw["out_dims"]
+            kw["block_n"] = self._block_n(od[0] * od[1] * od[2] * od[3], kw["cout"])
 
         def make():
             args = {k: (v[0] if isinstance(v, list) and len(v) == 1 and isinstance(v[0], torch.Tensor) else v)
@@ -241,7 +254,7 @@ class _EncoderEngine(PackedParams):
         self._deferred.append(make)
         steps.add(f"wgrad M{64 * len(units)} N{cout}", lambda: slot[0].run(), lane=1)
         dst = self.pgrad[id(param)]
-        steps.add("wgrad_scatter", lambda: ops.wgrad_scatter(sc[0], cout, cin, ntaps, dst), lane=1)
+        steps.add("wgrad_scatter", lambda: ops.wgrad_scatter(sc[0], cout, cin, ntaps, dst, accumulate=False), lane=1)
 
     def gn_finalize(self, steps, st, N, Cc, groups, HW, eps, mr):
         steps.add("gn_finalize", lambda: _lib.check(self.lib.v2a_gn_finalize(

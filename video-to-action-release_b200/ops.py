@@ -292,12 +292,16 @@ class Wgrad:
             pass
 
 
-def wgrad_scatter(wt: torch.Tensor, cout: int, cin: int, ntaps: int, dw: torch.Tensor) -> None:
-    """dw [cout, cin, taps...] += wt[(tap * ceil(cin/64) + chunk) * 64 + ci % 64, co]."""
+def wgrad_scatter(wt: torch.Tensor, cout: int, cin: int, ntaps: int, dw: torch.Tensor, *, ld_dw: int = 0,
+                  accumulate: bool = True) -> None:
+    """dw [cout, cin, taps...] (+)= wt[(tap * ceil(cin/64) + chunk) * 64 + ci % 64, co]; ``ld_dw``: row pitch of a
+    column window inside a wider [cout, cin_total * taps] gradient (default: contiguous)."""
     _require_cuda(wt, dw)
-    assert dw.is_contiguous() and dw.numel() == cout * cin * ntaps
-    _lib.check(_lib.load().v2a_wgrad_scatter(wt.data_ptr(), wt.stride(0), cout, cin, ntaps, dw.data_ptr(), _stream()),
-               "wgrad_scatter")
+    if not ld_dw:
+        assert dw.is_contiguous() and dw.numel() == cout * cin * ntaps
+        ld_dw = cin * ntaps
+    _lib.check(_lib.load().v2a_wgrad_scatter(wt.data_ptr(), wt.stride(0), cout, cin, ntaps, dw.data_ptr(), ld_dw,
+                                             int(accumulate), _stream()), "wgrad_scatter")
 
 
 # ---------------------------------------------------------------------------

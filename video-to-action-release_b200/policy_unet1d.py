@@ -280,6 +280,10 @@ class _PolicyEngine(PackedParams):
             off += p.numel()
         self._dcat: Dict[tuple, torch.Tensor] = {}
         self._zero_each_bwd: List[torch.Tensor] = [self.gslab]
+        self._mn_wgrad = os.environ.get("V2A_POLICY_WGRAD", "mn") == "mn"   # "im2col": the transposed-im2col path
+        self._wg_arenas: List[torch.Tensor] = []
+        self._wg_used = 0
+        self.wgrads: List[ops.Wgrad] = []
         self._build(model)
         self._trace_packers()
 
@@ -290,6 +294,18 @@ class _PolicyEngine(PackedParams):
     def hlz(self, rows, cols) -> HL:
         return HL(torch.zeros(rows, cols, dtype=torch.bfloat16, device=self.device),
                   torch.zeros(rows, cols, dtype=torch.bfloat16, device=self.device))
+
+    def _wg_scratch(self, rows: int, cols: int) -> torch.Tensor:
+        """[rows, cols] fp32 carved from arenas that are cleared once per backward (the MN-major weight-gradient
+        GEMM accumulates its split pixel reduction with REDs)."""
+        n = rows * cols
+        if not self._wg_arenas or self._wg_used + n > self._wg_arenas[-1].numel():
+            self._wg_arenas.append(torch.zeros(max(n, 32 << 20), dtype=torch.float32, device=self.device))
+            self._zero_each_bwd.append(self._wg_arenas[-1])
+            self._wg_used = 0
+        t = self._wg_arenas[-1][self._wg_used:self._wg_used + n].view(rows, cols)
+        self._wg_used += n
+        return t
 
     # ---- launch wrappers -------------------------------------------------------
     def igemm(self, steps, **kw):
@@ -384,8 +400,21 @@ class _PolicyEngine(PackedParams):
         off = 0
         steps.lane = 1
         for n in ins:
-            col = self.im2col_t(steps, n.hl, n.ld, Bn, T, T, n.C, [j - pad for j in range(k)], 1)
-            self.wgrad(steps, dyT, cout, col, n.C * k, wgrad_target, off * k)
+            units = [(0, (j - pad, 0, 0, 0), ch) for j in range(k) for ch in range(ops.nchunks(n.ld))]
+            if self._mn_wgrad and len(units) <= _lib.V2A_WGRAD_MAX_UNITS:
+                # MN-major tcgen05 weight gradient straight from the channels-last planes of x and dy: no
+                # transposed im2col copy (44 launches, 1.8 ms of the 3.5 ms backward before) and no dy^T operand
+                sc = self._wg_scratch(64 * len(units), ld_dy)
+                wg = ops.Wgrad(srcs=[(n.hl, n.ld, (T, Bn, 1, 1))], units=units, dy=dy, dy_channels=ld_dy,
+                               dy_dims=(T, Bn, 1, 1), cout=ld_dy, out=sc, passes=self.passes)
+                self.wgrads.append(wg)
+                steps.add(f"wgrad M{64 * len(units)} N{ld_dy}", wg.run)
+                win = wgrad_target[:, off * k:(off + n.C) * k]
+                steps.add("wgrad_scatter", lambda sc=sc, n=n, win=win: ops.wgrad_scatter(
+                    sc, cout, n.C, k, win, ld_dw=wgrad_target.stride(0), accumulate=False))
+            else:
+                col = self.im2col_t(steps, n.hl, n.ld, Bn, T, T, n.C, [j - pad for j in range(k)], 1)
+                self.wgrad(steps, dyT, cout, col, n.C * k, wgrad_target, off * k)
             off += n.C
         steps.lane = 0
         progd = convs.conv1d(ld_dy, Bn, T, k, pad)
