@@ -1,11 +1,14 @@
 """Drop the B200 paths into an UNMODIFIED reference checkout.
 
-``install()`` rebinds, inside the reference's own modules, the three classes on the two hot paths:
+``install()`` rebinds, inside the reference's own modules, the classes on the two hot paths:
 
   flowdiffusion.flowdiffusion.goal_diffusion.GoalGaussianDiffusion   -> v2a_b200.GoalGaussianDiffusion
   flowdiffusion.flowdiffusion.unet.Unet_Libero                       -> v2a_b200.Unet_Libero
   diffuser.diffusion_policy.model.conditional_unet1d.ConditionalUnet1D
   (+ the name imported into diffusion_unet_image_policy)             -> v2a_b200.ConditionalUnet1D
+  diffuser.diffusion_policy.common.vision_nets.VisualCore            -> v2a_b200.diffusion_policy.VisualCore
+  diffuser.diffusion_policy.model.multi_image_obs_encoder.MultiImageObsEncoder
+                                                                     -> v2a_b200.diffusion_policy.MultiImageObsEncoder
 
 so ``lb_get_video_model_gcp_v2`` (diffuser/libero/lb_video_model_utils.py:13-66) and
 ``Init_Diffusion_Policy`` (diffuser/diffusion_policy/get_dp.py:27-89) build the CUDA-backed modules
@@ -27,6 +30,9 @@ _TARGETS: List[Tuple[str, str, str]] = [
     ("diffuser.libero.lb_video_model_utils", "Unet_Libero", "unet"),
     ("diffuser.diffusion_policy.model.conditional_unet1d", "ConditionalUnet1D", "policy_unet1d"),
     ("diffuser.diffusion_policy.diffusion_unet_image_policy", "ConditionalUnet1D", "policy_unet1d"),
+    # observation encoder (row P6 / N1): the yaml instantiates both by `_target_` path, i.e. by these names
+    ("diffuser.diffusion_policy.common.vision_nets", "VisualCore", "diffusion_policy"),
+    ("diffuser.diffusion_policy.model.multi_image_obs_encoder", "MultiImageObsEncoder", "diffusion_policy"),
 ]
 _saved: Dict[Tuple[str, str], object] = {}
 
