@@ -59,3 +59,9 @@ def policy_loss_batch(B, seed):
     return {"obs": {"img_obs_1": torch.rand(B, 1, 3, 128, 128, generator=g),
                     "img_goal_1": torch.rand(B, 1, 3, 128, 128, generator=g)},
             "action": torch.rand(B, 16, 7, generator=g) * 2 - 1}
+
+
+def encoder_inputs(B, seed):
+    """One VisualCore's input (already normalised to [-1, 1]) and the weights of the scalar its gradient is taken of."""
+    g = torch.Generator().manual_seed(seed + 7)
+    return torch.rand(B, 3, 128, 128, generator=g) * 2 - 1, torch.randn(B, 64, generator=g)
