@@ -327,6 +327,15 @@ def run_policy(args, world, rank, local, barrier, max_over_ranks, peaks):
                                  "ms_per_step_with_torch_cudnn_encoders_fp32": ms_p_torch},
            "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": sum(v.numel() * 4 for v in host.values()), "d2h_bytes_per_step": 4}}
+    # inference entry: 8-step DDIM predict_action latency at B = 1, device-resident observation
+    policy.eval()
+    obs1 = {"img_obs_1": dev["img_obs_1"][:1], "img_goal_1": dev["img_goal_1"][:1]}
+    with torch.no_grad():
+        ms_pa, _ = timed(lambda: policy.predict_action(obs1, use_ddim=True), 5)
+    out["predict_action"] = {"what": "DiffusionUnetImagePolicy.predict_action(use_ddim=True): 2 encoders + 8 ConditionalUnet1D "
+                                     "forwards + DDIM updates, B = 1 (latency path between simulator steps)",
+                             "ms_per_call": ms_pa, "ddim_steps": 8}
+    policy.train()
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         sec = policy_cpu_reference_step(threads, 64)

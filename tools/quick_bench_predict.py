@@ -1,0 +1,31 @@
+"""Developer timing probe: DiffusionUnetImagePolicy.predict_action (8-step DDIM) latency."""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from v2a_b200 import ops  # noqa: E402
+from v2a_b200.diffusion_policy import build_libero_policy  # noqa: E402
+
+torch.manual_seed(0)
+pol = build_libero_policy().to("cuda").eval()
+for B in (1, 8):
+    obs = {"img_obs_1": torch.rand(B, 1, 3, 128, 128, device="cuda"), "img_goal_1": torch.rand(B, 1, 3, 128, 128, device="cuda")}
+    with torch.no_grad():
+        for _ in range(4):
+            out = pol.predict_action(obs, use_ddim=True)
+        torch.cuda.synchronize()
+        n0 = ops.launch_count()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = 10
+        for _ in range(n):
+            out = pol.predict_action(obs, use_ddim=True)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / n * 1e3
+    print(f"B={B}: predict_action {e0.elapsed_time(e1) / n:.3f} ms GPU, {wall:.3f} ms wall, "
+          f"{(ops.launch_count() - n0) / n:.0f} eager v2a launches per call, action {tuple(out['action'].shape)}")
