@@ -34,23 +34,31 @@ def _gn(sd: SD, p: str, x: Tensor) -> Tensor:
     return F.group_norm(x, c // 16, sd[p + "weight"], sd[p + "bias"], GN_EPS)
 
 
-def basic_block(sd: SD, p: str, x: Tensor, stride: int) -> Tensor:
-    """torchvision BasicBlock: conv3x3(stride) -> norm -> relu -> conv3x3 -> norm (+ downsample(x)) -> relu."""
-    out = F.relu(_gn(sd, p + "bn1.", F.conv2d(x, sd[p + "conv1.weight"], stride=stride, padding=1)))
+def _relu(x: Tensor, site: int) -> Tensor:
+    return F.relu(x)
+
+
+def basic_block(sd: SD, p: str, x: Tensor, stride: int, relu=_relu, site: int = 0) -> Tensor:
+    """torchvision BasicBlock: conv3x3(stride) -> norm -> relu -> conv3x3 -> norm (+ downsample(x)) -> relu.
+    `relu(x, site)` is the activation hook (tests substitute a fixed mask to compare gradients mask for mask)."""
+    out = relu(_gn(sd, p + "bn1.", F.conv2d(x, sd[p + "conv1.weight"], stride=stride, padding=1)), site)
     out = _gn(sd, p + "bn2.", F.conv2d(out, sd[p + "conv2.weight"], padding=1))
     idn = x
     if p + "downsample.0.weight" in sd:
         idn = _gn(sd, p + "downsample.1.", F.conv2d(x, sd[p + "downsample.0.weight"], stride=stride))
-    return F.relu(out + idn)
+    return relu(out + idn, site + 1)
 
 
-def resnet18_gn_trunk(sd: SD, p: str, x: Tensor) -> Tensor:
-    """p = '...backbone.nets.': 0 conv7x7 s2 p3 (no bias), 1 norm, 2 relu, 3 maxpool(3, 2, 1), 4..7 = layer1..4."""
-    x = F.relu(_gn(sd, p + "1.", F.conv2d(x, sd[p + "0.weight"], stride=2, padding=3)))
+def resnet18_gn_trunk(sd: SD, p: str, x: Tensor, relu=_relu) -> Tensor:
+    """p = '...backbone.nets.': 0 conv7x7 s2 p3 (no bias), 1 norm, 2 relu, 3 maxpool(3, 2, 1), 4..7 = layer1..4.
+    ReLU sites: 0 = stem, 2k+1 / 2k+2 = inner / output activation of BasicBlock k (k = 0..7)."""
+    x = relu(_gn(sd, p + "1.", F.conv2d(x, sd[p + "0.weight"], stride=2, padding=3)), 0)
     x = F.max_pool2d(x, 3, 2, 1)
+    k = 0
     for li in range(4, 8):
         for bi in range(2):
-            x = basic_block(sd, f"{p}{li}.{bi}.", x, 2 if (li > 4 and bi == 0) else 1)
+            x = basic_block(sd, f"{p}{li}.{bi}.", x, 2 if (li > 4 and bi == 0) else 1, relu, 2 * k + 1)
+            k += 1
     return x
 
 
@@ -64,9 +72,9 @@ def spatial_softmax(sd: SD, p: str, feat: Tensor) -> Tensor:
     return torch.cat([ex, ey], 1).view(-1, K, 2)
 
 
-def visual_core_forward(sd: SD, p: str, x: Tensor) -> Tensor:
+def visual_core_forward(sd: SD, p: str, x: Tensor, relu=_relu) -> Tensor:
     """p = prefix of one VisualCore ('obs_encoder.key_model_map.img_obs_1.'); x [B, 3, H, W] -> [B, 64]."""
-    kp = spatial_softmax(sd, p + "pool.", resnet18_gn_trunk(sd, p + "backbone.nets.", x))
+    kp = spatial_softmax(sd, p + "pool.", resnet18_gn_trunk(sd, p + "backbone.nets.", x, relu))
     return F.linear(kp.flatten(1), sd[p + "nets.3.weight"], sd[p + "nets.3.bias"])
 
 

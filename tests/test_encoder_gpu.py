@@ -158,9 +158,10 @@ def test_visual_core_forward_backward_matches_torch(monkeypatch, B):
     # 2-5e-4 off the float64 truth here (fp32_err).  Bars: the forward at the north-star 1e-3 (measured 2.4e-5; floor = the
     # tensor core's truncating fp32 accumulate), flip-free parameters sit at ~5e-5 (B = 3: median), and a flip-limited
     # bar on the whole gradient.  (B = 8 on this seed: a flip in layer3 lifts every upstream parameter to ~1e-3.)
-    assert med < 3e-3, f"median per-parameter rel-L2 {med:.3e}\n{report}"
-    assert total < 6e-3, f"whole gradient rel-L2 {total:.3e}\n{report}"
-    assert max(errs.values()) < 2e-2, report
+    # (which elements flip depends on the accumulation order, i.e. on tile shapes and kernel versions: these are
+    # sanity bars against structural errors, which show up as O(1); the mask-for-mask test below is the tight one)
+    assert total < 3e-2, f"whole gradient rel-L2 {total:.3e}\n{report}"
+    assert max(errs.values()) < 6e-2, report
 
 
 def test_visual_core_matches_cpu_oracle_and_reference_golden():
@@ -219,7 +220,67 @@ def test_visual_core_full_batch_is_batch_independent():
     core.zero_grad(set_to_none=True)
     sub = core(x[:8])
     (sub * w[:8]).sum().backward()
-    assert rel_l2(full[:8], sub) < 1e-5
+    assert rel_l2(full[:8], sub) < 1e-4      # different tile shapes -> different fp32 accumulation orders
     num = sum((g_full[n] - p.grad).double().pow(2).sum().item() for n, p in core.named_parameters() if n in g_full)
     den = sum(p.grad.double().pow(2).sum().item() for n, p in core.named_parameters() if n in g_full)
-    assert (num / den) ** 0.5 < 5 * TOL, (num / den) ** 0.5
+    assert (num / den) ** 0.5 < 3e-2, (num / den) ** 0.5     # flip-limited (see above)
+
+
+@pytest.mark.parametrize("B", [3, 8])
+def test_visual_core_gradients_match_float64_mask_for_mask(B):
+    """The tight backward check: the float64 truth is evaluated with OUR forward's ReLU sign patterns (every
+    ReLU of the oracle replaced by multiplication with the mask the CUDA engine produced), so the gradients are
+    comparable element for element and the ReLU discontinuity drops out.  Every parameter gradient then has to
+    meet the 1e-3 tolerance (measured ~5e-5; the stem's three parameters also sit behind the MaxPool arg-max, whose
+    near-ties are left to chance: ~1e-5 of the windows, each worth ~1/sqrt(3M elements))."""
+    from oracle import encoder_oracle as EO
+    from v2a_b200 import obs_encoder as OE
+    core = _seeded_core()
+    core.train()
+    torch.manual_seed(3)
+    x = torch.rand(B, 3, 128, 128, device="cuda") * 2 - 1
+    wout = torch.randn(B, 64, device="cuda")
+    got = core(x)
+    (got * wout).sum().backward()
+    eng = OE.last_engine(core)
+
+    def nchw(t2d, a):
+        return t2d.view(a.N, a.H, a.W, a.C).permute(0, 3, 1, 2)
+    masks = {}
+    for k, (a1, out) in enumerate(zip(eng.inner_acts, eng.acts[1:])):
+        masks[2 * k + 1] = nchw(a1.float() > 0, out).double()
+        masks[2 * k + 2] = nchw(out.f32 > 0, out).double()
+    # stem: sign pattern of GroupNorm(raw0) recomputed from the engine's conv output and statistics
+    sp = eng.stem_probe
+    gn0 = core.backbone.nets[1]
+    raw0 = sp["raw0"].view(B, sp["H"], sp["W"], -1).permute(0, 3, 1, 2).double()
+    mr0 = sp["mr0"].view(B, gn0.num_groups, 2).double()
+    cpg = raw0.shape[1] // gn0.num_groups
+    mean = mr0[:, :, 0].repeat_interleave(cpg, 1)[:, :, None, None]
+    rstd = mr0[:, :, 1].repeat_interleave(cpg, 1)[:, :, None, None]
+    pre0 = (raw0 - mean) * rstd * gn0.weight.detach().double()[None, :, None, None] + gn0.bias.detach().double()[None, :, None, None]
+    masks[0] = (pre0 > 0).double()
+    key = "k."
+    sd = {key + n: p.detach().double().clone().requires_grad_(True) for n, p in core.named_parameters()}
+    sd.update({key + n: b.detach().double() for n, b in core.named_buffers()})
+    relu = lambda t, i: t * masks[i] if i in masks else torch.relu(t)
+    ref = EO.visual_core_forward(sd, key, x.double(), relu)
+    assert rel_l2(got, ref) < TOL
+    (ref * wout.double()).sum().backward()
+    worst, report = 0.0, []
+    scale = max(v.grad.norm().item() for k_, v in sd.items() if v.requires_grad and v.grad is not None)
+    for n, p in core.named_parameters():
+        g = sd[key + n].grad
+        if g is None or p.grad is None:
+            continue
+        err = (p.grad.double() - g).norm().item() / max(g.norm().item(), 1e-4 * scale)
+        report.append(f"{n}: {err:.2e}")
+        if n == "backbone.nets.0.weight":
+            # the stem conv sits behind the MaxPool: a near-tie between two candidates of ONE window (pinned with
+            # tools/debug_stem.py: image 2, pixels (54,34) / (55,35) on this seed) routes that window's gradient to the
+            # other pixel -> 3-5e-3 on this one parameter; the kernels themselves measure 4e-6 on the same operands
+            assert err < 2e-2, report[-1]
+            continue
+        worst = max(worst, err)
+    print(f"VisualCore B={B} mask-for-mask: worst parameter-gradient rel-L2 {worst:.2e}")
+    assert worst < TOL, "\n".join(report)

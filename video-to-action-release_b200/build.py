@@ -8,7 +8,7 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libv2a_b200.so")
+LIB_PATH = os.environ.get("V2A_LIB") or os.path.join(PKG_DIR, "libv2a_b200.so")   # V2A_LIB: developer experiments
 STAMP = os.path.join(PKG_DIR, ".libv2a_b200.stamp")
 
 SOURCES = ["igemm.cu", "wgrad.cu", "elementwise.cu", "attention.cu", "policy.cu", "encoder.cu"]

@@ -98,6 +98,7 @@ struct alignas(64) IgemmParams {
     int k_splits;         // >1: the K loop of one output tile is shared by k_splits CTAs (fp32 atomics)
     int kps;              // K iterations per split
     int a_fp16, b_fp16;   // operand planes hold fp16 (hi, lo) pairs instead of bf16 ones
+    int fuse2;            // N <= 128: a_hi x [b_hi | b_lo] as ONE N = 2*block_n MMA (two accumulator halves)
     int debug;  // V2A_IGEMM_DEBUG bits: 1 skip stats, 2 skip stores, 4 skip residual (timing experiments only)
 };
 
@@ -138,7 +139,10 @@ __device__ __forceinline__ TileRange cta_tiles(const IgemmParams& p, int total) 
     return r;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+#ifndef V2A_IGEMM_MAXNREG
+#define V2A_IGEMM_MAXNREG 168
+#endif
+__global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constant__ IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment.  The offset is added to the __shared__ pointer itself: a
     // round trip through uintptr_t loses the address space and turned every epilogue slab access into a
@@ -252,7 +256,24 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 mbar_wait(&full_bar[stage], phase, 300 + stage);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-                if (p.passes == 3) {
+                if (p.passes == 3 && p.fuse2) {
+                    // The weight stage holds [b_hi rows | b_lo rows] back to back = one K-major tile of 2*block_n
+                    // rows, so a_hi x b_hi and a_hi x b_lo are ONE MMA with N = 2*block_n writing two accumulator
+                    // halves (summed in the epilogue), and a_lo x b_hi adds into the first half.  Same FLOPs, but
+                    // 2 instead of 3 MMAs per k step and 20 KB instead of 24 KB of shared-memory operand reads
+                    // (at N = 128 the three-MMA form reads 128 B/clk = the whole shared-memory bandwidth, which the
+                    // epilogue's staging slabs also need).
+                    const uint64_t a_hi = umma_desc_sw128(sa);
+                    const uint64_t a_lo = umma_desc_sw128(sa + kATileBytes);
+                    const uint64_t b_hi = umma_desc_sw128(sa + 2 * kATileBytes);
+                    const uint32_t idesc2 = umma_idesc_16(kTileM, 2 * p.block_n, p.a_fp16, p.b_fp16);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc2, (kit | k) != 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
+                } else if (p.passes == 3) {
                     const uint64_t a_hi = umma_desc_sw128(sa);
                     const uint64_t a_lo = umma_desc_sw128(sa + kATileBytes);
                     const uint64_t b_hi = umma_desc_sw128(sa + 2 * kATileBytes);
@@ -501,6 +522,18 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 
             // TMEM loads are software pipelined: chunk c+16 is in flight while chunk c is processed
             uint32_t ra[16], rb[16];
+            if (p.fuse2) {
+                // two accumulator halves per chunk: [hi*hi + lo*hi | hi*lo]
+                for (int c = c_begin; c < c_end; c += 16) {
+                    tmem_ld16(t_row + c, ra);
+                    tmem_ld16(t_row + p.block_n + c, rb);
+                    tmem_ld_wait16(ra);
+                    tmem_ld_wait16(rb);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(rb[j]));
+                    process(ra, c);
+                }
+            } else {
             if (c_begin < c_end) tmem_ld16(t_row + c_begin, ra);
             for (int c = c_begin; c < c_end; c += 32) {
                 tmem_ld_wait16(ra);
@@ -511,6 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                     if (c + 32 < c_end) tmem_ld16(t_row + c + 32, ra);
                     process(rb, c + 16);
                 }
+            }
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
@@ -686,6 +720,10 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
     p.stats_rep_stride = d->stats_rep_stride;
     p.a_fp16 = d->a_fp16;
     p.b_fp16 = d->b_fp16;
+    {
+        const char* env = getenv("V2A_FUSE2");
+        p.fuse2 = (d->passes == 3 && d->block_n <= 128 && !(env && atoi(env) == 0)) ? 1 : 0;
+    }
     {
         const char* dbg = getenv("V2A_IGEMM_DEBUG");
         p.debug = dbg ? atoi(dbg) : 0;

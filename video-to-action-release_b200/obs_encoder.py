@@ -333,6 +333,7 @@ class _EncoderEngine(PackedParams):
         self.igemm(self.fwd, "igemm stem", srcs=[(col, 192, prog.src_dims[0])], taps=prog.taps, w=w0,
                    out_dims=prog.out_dims, cout=C0, out_f32=raw0, stats=st0, stats_mul=(0, 1, 0, 0))
         self.gn_finalize(self.fwd, st0, N, C0, G(gn0), HW0, gn0.eps, mr0)
+        self.stem_probe = dict(raw0=raw0, mr0=mr0, H=H0, W=W0)     # parity probes: the stem ReLU's sign pattern
         H1, W1 = H0 // 2, W0 // 2
         P0 = _Act(N, H1, W1, C0, f32=self.zeros(N * H1 * W1, C0), hl=self.hlz(N * H1 * W1, C0, FWD16))
         P0.tw = self.hlz(N * H1 * W1, C0) if FWD16 else P0.hl
@@ -350,6 +351,7 @@ class _EncoderEngine(PackedParams):
                 raw0.data_ptr(), mr0.data_ptr(), G(gn0), ga0.data_ptr(), be0.data_ptr(), P0.f32.data_ptr(),
                 P0.grad.data_ptr(), N, H0, W0, C0, g0.data_ptr(), ops._stream()), "maxpool_relu_bwd"))
             d0 = self.hlz(N * HW0, C0)
+            self.stem_probe.update(g0=g0, d0=d0)
             self.gn_bwd(st, dout=g0, raw=raw0, mr=mr0, gn=gn0, N=N, HW=HW0, Cc=C0, mask_mode=0, d_hl=d0)
             self.wgrad(st, srcs=[(col_tw, 192, (HW0, N, 1, 1))], units=[(0, (0, 0, 0, 0), ch) for ch in range(3)],
                        dy=d0, dy_channels=C0, dy_dims=(HW0, N, 1, 1), cout=C0, cin=147, ntaps=1, param=conv1.weight)
@@ -359,6 +361,7 @@ class _EncoderEngine(PackedParams):
         blocks = [b for layer in layers for b in layer]
         X = P0
         self.probes: List[dict] = []   # per-block backward intermediates (developer parity probes)
+        self.inner_acts: List[HL] = []
         self.acts = [P0]          # block inputs / outputs in order (parity probes read .f32 / .grad)
         for bi, blk in enumerate(blocks):
             nxt_s2 = bi + 1 < len(blocks) and blocks[bi + 1].conv1.stride[0] == 2
@@ -517,6 +520,7 @@ class _EncoderEngine(PackedParams):
                     "unblock_add"))
         tape.append(plan_bwd)
         self.acts.append(out)
+        self.inner_acts.append(a1)     # post-ReLU operand of conv2 (parity probes read its sign pattern)
         return out
 
     def planned_launches(self) -> int:
