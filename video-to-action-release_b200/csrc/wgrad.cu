@@ -150,7 +150,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
             const uint64_t b_hi = umma_desc_mn_sw128(sb, kWgUnitBytes);
             const uint64_t b_lo = umma_desc_mn_sw128(sb + b_plane, kWgUnitBytes);
             // one k step = 16 pixels = 16 rows of 128 B = 2048 B (>> 4 = 128 in the descriptor's address field)
-            if (p.passes == 3) {
+            if (p.passes == 3 && p.block_n <= 128) {
+                // [b_hi blocks | b_lo blocks] are consecutive 64-channel MN atoms (LBO apart): a_hi x b_hi and
+                // a_hi x b_lo are ONE MMA with N = 2*block_n filling two accumulator halves (summed in the epilogue)
+                const uint32_t idesc2 = umma_idesc_16(128, 2 * p.block_n, p.x_fp16, p.x_fp16) | (1u << 15) | (1u << 16);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base, a_hi + 128 * k, b_hi + 128 * k, idesc2, (kit > kb || k != 0));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, a_lo + 128 * k, b_hi + 128 * k, idesc, 1);
+            } else if (p.passes == 3) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     umma_bf16(tmem_base, a_lo + 128 * k, b_hi + 128 * k, idesc, (kit > kb || k != 0));
@@ -177,10 +186,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         mbar_wait(tfull_bar, 0, 700);
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const bool fused = p.passes == 3 && p.block_n <= 128;
         for (int c = 0; c < p.block_n; c += 16) {
             uint32_t r[16];
             tmem_ld16(t_row + c, r);
-            tmem_ld_wait16(r);
+            if (fused) {
+                uint32_t r2[16];
+                tmem_ld16(t_row + p.block_n + c, r2);
+                tmem_ld_wait16(r);
+                tmem_ld_wait16(r2);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            } else {
+                tmem_ld_wait16(r);
+            }
             if (valid) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
