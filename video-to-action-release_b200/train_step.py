@@ -112,6 +112,19 @@ class PolicyTrainStep:
         self.collectives = 0
         self._lib = _lib.load()
 
+    def close(self) -> None:
+        """Hand gradients back to autograd (per-parameter .grad tensors) for anyone who keeps using the modules
+        without this object."""
+        try:
+            policy_unet1d.set_slab_grads(self.unet, False)
+            for core in self.cores:
+                obs_encoder.set_slab_grads(core, False)
+        except Exception:
+            pass
+
+    def __del__(self):
+        self.close()
+
     # ---- pieces (also used one by one in tests) ------------------------------------------------
     def _unet_grad_slab(self) -> torch.Tensor:
         eng = policy_unet1d.last_engine(self.unet)
