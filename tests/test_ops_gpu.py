@@ -6,6 +6,7 @@ relative error of ~2^-16 per operand pair, so tensor-core results are checked
 to 5e-5 of the output scale; fp32 elementwise kernels to 1e-5.
 """
 import math
+import os
 
 import pytest
 import torch
@@ -339,5 +340,10 @@ def test_igemm_cta_pair_multicast_matches_single_cta(N, H, W, ci, co, monkeypatc
     assert _rel(st[..., 0], want_s) < 1e-5 and _rel(st[..., 1], want_ss) < 1e-5
     monkeypatch.setenv("V2A_CLUSTER", "0")
     got1, st1, _ = _run_igemm(prog, [x], convs.spatial3x3_weight(w), co, bias=b, stats_mul=stats_mul)
-    assert torch.equal(got, got1)            # same MMA order per tile: bit identical outputs
-    assert _rel(st, st1) < 1e-12
+    if os.environ.get("V2A_CTA2", "1") != "0" and co <= 128:
+        # cta_group::2 pairs aim the lo*hi MMA at a different accumulator column than the one-CTA plan: the same
+        # terms in another fp32 summation order
+        assert _rel(got, got1) < 1e-6 and _rel(st, st1) < 1e-6
+    else:
+        assert torch.equal(got, got1)            # same MMA order per tile: bit identical outputs
+        assert _rel(st, st1) < 1e-12

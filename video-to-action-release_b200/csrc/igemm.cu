@@ -98,6 +98,7 @@ struct alignas(64) IgemmParams {
     int k_splits;         // >1: the K loop of one output tile is shared by k_splits CTAs (fp32 atomics)
     int kps;              // K iterations per split
     int a_fp16, b_fp16;   // operand planes hold fp16 (hi, lo) pairs instead of bf16 ones
+    int cta2;             // CTA pairs issue ONE cta_group::2 MMA (M = 256, B split between the two SMs)
     int fuse2;            // N <= 128: a_hi x [b_hi | b_lo] as ONE N = 2*block_n MMA (two accumulator halves)
     int debug;  // V2A_IGEMM_DEBUG bits: 1 skip stats, 2 skip stores, 4 skip residual (timing experiments only)
 };
@@ -142,6 +143,9 @@ __device__ __forceinline__ TileRange cta_tiles(const IgemmParams& p, int total) 
 #ifndef V2A_IGEMM_MAXNREG
 #define V2A_IGEMM_MAXNREG 168
 #endif
+// kCta2: the cta_group::2 (CTA-pair MMA) paths exist only in that instantiation -- a kernel that contains
+// cta_group::2 instructions must be launched as a cluster of 2
+template <bool kCta2>
 __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constant__ IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment.  The offset is added to the __shared__ pointer itself: a
@@ -164,11 +168,12 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], p.cluster > 1 ? 2 : 1);   // pair mode: both CTAs must release a stage
+            // multicast pairs: both CTAs' MMA warps release a stage; cta_group::2 pairs: the leader's commit does
+            mbar_init(&empty_bar[s], (p.cluster > 1 && !kCta2) ? 2 : 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], kEpilogueThreads);
+            mbar_init(&tempty_bar[s], kCta2 ? 2 * kEpilogueThreads : kEpilogueThreads);   // cta2: both epilogues
         }
         fence_mbar_init();
     } else if (warp == 1 && lane == 0) {
@@ -179,7 +184,8 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
             tma_prefetch_desc(&p.b_lo);
         }
     } else if (warp == 2) {
-        tmem_alloc(tmem_slot, kTmemCols);
+        if constexpr (kCta2) tmem_alloc_2sm(tmem_slot, kTmemCols);
+        else tmem_alloc(tmem_slot, kTmemCols);
     }
     tc_fence_before();
     __syncthreads();
@@ -212,6 +218,20 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                     if (kit < kb || kit >= ke) continue;
                     mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
                     uint8_t* st = smem + (size_t)stage * p.stage_bytes;
+                    if constexpr (kCta2) {
+                        // each CTA stages its own A tile and ITS HALF of the weight rows in its own shared memory;
+                        // all bytes of the pair are counted on the leader's barrier (the leader alone issues MMAs)
+                        const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                        if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * p.stage_bytes);
+                        tma_load_5d_2sm(st, &p.a_hi[src], lead_full, ch * kChunkK, c1, c2, c3, c4);
+                        tma_load_5d_2sm(st + kATileBytes, &p.a_lo[src], lead_full, ch * kChunkK, c1, c2, c3, c4);
+                        const uint32_t half_rows = p.block_n >> 1, half_bytes = p.b_tile_bytes >> 1;
+                        uint8_t* sb = st + 2 * kATileBytes;
+                        tma_load_2d_2sm(sb, &p.bh_hi, lead_full, kit * kChunkK, n0 + crank * half_rows);
+                        tma_load_2d_2sm(sb + half_bytes, &p.bh_lo, lead_full, kit * kChunkK, n0 + crank * half_rows);
+                        if (++stage == S) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full_bar[stage], p.stage_bytes);
                     if (p.passes == 3 && p.cluster > 1) {
                         tma_load_5d(st, &p.a_hi[src], &full_bar[stage], ch * kChunkK, c1, c2, c3, c4);
@@ -234,6 +254,45 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                         tma_load_5d(st, &p.a_hi[src], &full_bar[stage], ch * kChunkK, c1, c2, c3, c4);
                         tma_load_2d(st + kATileBytes, &p.b_hi, &full_bar[stage], kit * kChunkK, n0);
                     }
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (kCta2 && warp == 1 && lane == 0) {
+        // ===================== MMA issuer of a cta_group::2 pair (leader CTA only) =====================
+        // M = 256 (this CTA's tile + the peer's), N rows of B split between the two shared memories.  With the
+        // fused split product each CTA's weight stage is [b_hi half | b_lo half], so the N = 2*block_n MMA's
+        // columns come out as [hi*hi(c<h) | hi*lo(c<h) | hi*hi(c>=h) | hi*lo(c>=h)] (h = block_n/2) and the
+        // a_lo x b_hi MMA (N = block_n -> [lo*hi(c<h) | lo*hi(c>=h)]) is aimed at column h, where both of its
+        // halves land on accumulators of the same logical columns.  Shared-memory operand reads per SM per k step:
+        // 14 KB instead of 20 KB (24 KB unfused).
+        if constexpr (kCta2) if (crank == 0) {
+            const int hb = p.block_n >> 1;
+            const uint32_t idesc2 = umma_idesc_16(256, 2 * p.block_n, p.a_fp16, p.b_fp16);
+            const uint32_t idesc1 = umma_idesc_16(256, p.block_n, p.a_fp16, p.b_fp16);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < tr.count; ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kAccStride;
+                for (int kit = 0; kit < p.k_iters; ++kit) {
+                    mbar_wait(&full_bar[stage], phase, 300 + stage);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+                    const uint64_t a_hi = umma_desc_sw128(sa);
+                    const uint64_t a_lo = umma_desc_sw128(sa + kATileBytes);
+                    const uint64_t b_hi = umma_desc_sw128(sa + 2 * kATileBytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_2sm(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc2, (kit | k) != 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_2sm(d_tmem + hb, a_lo + 2 * k, b_hi + 2 * k, idesc1, 1);
+                    umma_commit_2sm_mc(&empty_bar[stage], 3);
+                    if (kit == p.k_iters - 1) umma_commit_2sm_mc(&tfull_bar[acc], 3);
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             }
@@ -524,9 +583,13 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
             uint32_t ra[16], rb[16];
             if (p.fuse2) {
                 // two accumulator halves per chunk: [hi*hi + lo*hi | hi*lo]
+                const int hb = p.block_n >> 1;
                 for (int c = c_begin; c < c_end; c += 16) {
-                    tmem_ld16(t_row + c, ra);
-                    tmem_ld16(t_row + p.block_n + c, rb);
+                    // single CTA: [sum | hi*lo]; cta_group::2 pair: [., . | ., .] per half of the columns (see the issuer)
+                    const int ca = kCta2 ? (c >= hb ? p.block_n + (c - hb) : c) : c;
+                    const int cb = kCta2 ? ca + hb : p.block_n + c;
+                    tmem_ld16(t_row + ca, ra);
+                    tmem_ld16(t_row + cb, rb);
                     tmem_ld_wait16(ra);
                     tmem_ld_wait16(rb);
 #pragma unroll
@@ -547,15 +610,18 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
             }
             }
             tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
+            if (kCta2 && crank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+            else mbar_arrive(&tempty_bar[acc]);
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (kCta2) cluster_sync_all();   // the leader's MMAs read the peer's shared memory and write its TMEM
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if constexpr (kCta2) tmem_dealloc_2sm(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
     if (p.cluster > 1) cluster_sync_all();   // no CTA leaves while its peer can still signal its barriers
 }
@@ -816,10 +882,30 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
             }
         }
     }
+    // cta_group::2 pairs: ONE MMA spans the two SMs of a pair (M = 256), each SM reads its own A tile and only
+    // HALF of the weight rows from shared memory: 14 KB of operand reads per SM per k step instead of 20 KB, which
+    // turns the shared-memory-bound N = 128 layers tensor-bound (B = 16, K = 3456: 385 -> 530 TFLOP/s).  Needs the
+    // fused split product (block_n <= 128); short-K launches (temporal / 1x1 convs, whose time is their epilogue)
+    // lose to the lockstep of the two epilogues and stay on multicast pairs.  V2A_CTA2=0 disables, =2 forces.
+    p.cta2 = 0;
+    {
+        const char* env = getenv("V2A_CTA2");
+        const int mode = env ? atoi(env) : 1;
+        if (mode != 0 && p.cluster == 2 && p.fuse2 && d->block_n % 32 == 0 && (p.k_iters >= 16 || mode == 2)) {
+            p.cta2 = 1;
+            p.stage_bytes = 2 * (kATileBytes + p.b_tile_bytes / 2);
+            int stages = (int)((g_max_smem - overhead) / p.stage_bytes);
+            if (stages > 8) stages = 8;
+            p.stages = stages;
+            pl->smem = (size_t)stages * p.stage_bytes + overhead;
+        }
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              g_max_smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
         if (e != cudaSuccess) {
             delete pl;
             V2A_CUDA_OK(e);
@@ -864,9 +950,10 @@ int v2a_igemm_plan_run(void* plan, void* stream) {
         attr.val.clusterDim.z = 1;
         cfg.attrs = &attr;
         cfg.numAttrs = 1;
-        V2A_CUDA_OK(cudaLaunchKernelEx(&cfg, v2a::igemm_kernel, pl->p));
+        if (pl->p.cta2) V2A_CUDA_OK(cudaLaunchKernelEx(&cfg, v2a::igemm_kernel<true>, pl->p));
+        else V2A_CUDA_OK(cudaLaunchKernelEx(&cfg, v2a::igemm_kernel<false>, pl->p));
     } else {
-        v2a::igemm_kernel<<<pl->grid, v2a::kThreads, pl->smem, (cudaStream_t)stream>>>(pl->p);
+        v2a::igemm_kernel<false><<<pl->grid, v2a::kThreads, pl->smem, (cudaStream_t)stream>>>(pl->p);
     }
     V2A_CUDA_OK(cudaGetLastError());
     v2a::g_launches.fetch_add(1);
