@@ -104,6 +104,26 @@ struct alignas(64) IgemmParams {
 };
 
 __device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int& n_idx, int o[4], int& split) {
+    if (p.cluster > 1) {
+        // CTA pairs: tiles 2q and 2q + 1 are the two M tiles of pair-tile q, which share one N tile (so the pair
+        // shares / splits ONE weight tile); q walks the N tiles fastest.  (k_splits == 1 in pair mode.)
+        const int q = tile >> 1;
+        n_idx = q % p.num_n_tiles;
+        int m = (q / p.num_n_tiles) * 2 + (tile & 1);
+        split = 0;
+        if (m >= p.num_m_tiles) {     // ghost tile: a box wholly outside the tensor -> TMA zero fill, no valid row
+            o[0] = o[1] = o[2] = 0;
+            o[3] = p.ntile[3] << p.tile_log2[3];
+            return;
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            int j = m % p.ntile[d];
+            m /= p.ntile[d];
+            o[d] = j << p.tile_log2[d];
+        }
+        return;
+    }
     if (tile >= p.num_m_tiles * p.num_n_tiles * p.k_splits) {
         // ghost tile (cluster mode pads every CTA to the same iteration count): a box wholly outside the
         // tensor -> TMA zero fill, no row is valid in the epilogue
@@ -268,7 +288,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
         // 14 KB instead of 20 KB (24 KB unfused).
         if constexpr (kCta2) if (crank == 0) {
             const int hb = p.block_n >> 1;
-            const uint32_t idesc2 = umma_idesc_16(256, 2 * p.block_n, p.a_fp16, p.b_fp16);
+            const uint32_t idesc2 = umma_idesc_16(256, p.fuse2 ? 2 * p.block_n : p.block_n, p.a_fp16, p.b_fp16);
             const uint32_t idesc1 = umma_idesc_16(256, p.block_n, p.a_fp16, p.b_fp16);
             int stage = 0;
             uint32_t phase = 0;
@@ -285,12 +305,24 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                     const uint64_t a_hi = umma_desc_sw128(sa);
                     const uint64_t a_lo = umma_desc_sw128(sa + kATileBytes);
                     const uint64_t b_hi = umma_desc_sw128(sa + 2 * kATileBytes);
+                    if (p.fuse2) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16_2sm(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc2, (kit | k) != 0);
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_2sm(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc2, (kit | k) != 0);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16_2sm(d_tmem + hb, a_lo + 2 * k, b_hi + 2 * k, idesc1, 1);
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_2sm(d_tmem + hb, a_lo + 2 * k, b_hi + 2 * k, idesc1, 1);
+                    } else {
+                        // block_n > 128: three M = 256 MMAs, columns in natural order (this CTA's half | the peer's)
+                        const uint64_t b_lo = umma_desc_sw128(sa + 2 * kATileBytes + (p.b_tile_bytes >> 1));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_2sm(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc1, (kit | k) != 0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16_2sm(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc1, 1);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16_2sm(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc1, 1);
+                    }
                     umma_commit_2sm_mc(&empty_bar[stage], 3);
                     if (kit == p.k_iters - 1) umma_commit_2sm_mc(&tfull_bar[acc], 3);
                     if (++stage == S) { stage = 0; phase ^= 1; }
@@ -864,13 +896,17 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
     {
         const char* env = getenv("V2A_CLUSTER");
         const bool want = !(env && atoi(env) == 0);
-        if (want && p.num_n_tiles == 1 && p.k_splits == 1 && d->passes == 3 && d->block_n % 16 == 0 &&
+        // pairs over several N tiles are new with the cta_group::2 path and follow its switch
+        const char* env2 = getenv("V2A_CTA2");
+        const int mode2 = env2 ? atoi(env2) : 1;
+        const bool multi_n = mode2 != 0 && mode2 != 3 && p.k_iters >= 16 && d->block_n % 32 == 0;
+        if (want && (p.num_n_tiles == 1 || multi_n) && p.k_splits == 1 && d->passes == 3 && d->block_n % 16 == 0 &&
             p.num_m_tiles >= 4 && g_num_sms >= 2) {
             int grid = (g_num_sms / 2) * 2;
-            const int pairs_needed = ceil_div(p.num_m_tiles, 2);
+            const int pairs_needed = ceil_div(p.num_m_tiles, 2) * p.num_n_tiles;
             if (grid > 2 * pairs_needed) grid = 2 * pairs_needed;
             p.cluster = 2;
-            p.iters_per_cta = ceil_div(p.num_m_tiles, grid);
+            p.iters_per_cta = ceil_div(pairs_needed, grid / 2);
             pl->grid = grid;
             uint64_t dims[2] = {(uint64_t)d->ktot, (uint64_t)d->wrows};
             uint32_t box[2] = {kChunkK, (uint32_t)d->block_n / 2};
@@ -891,7 +927,8 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
     {
         const char* env = getenv("V2A_CTA2");
         const int mode = env ? atoi(env) : 1;
-        if (mode != 0 && p.cluster == 2 && p.fuse2 && d->block_n % 32 == 0 && (p.k_iters >= 16 || mode == 2)) {
+        if (mode != 0 && p.cluster == 2 && d->block_n % 32 == 0 && (p.k_iters >= 16 || mode == 2) &&
+            (p.fuse2 || mode != 3)) {      // mode 3: fused (block_n <= 128) layers only (A/B probes)
             p.cta2 = 1;
             p.stage_bytes = 2 * (kATileBytes + p.b_tile_bytes / 2);
             int stages = (int)((g_max_smem - overhead) / p.stage_bytes);
