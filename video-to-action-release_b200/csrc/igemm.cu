@@ -515,8 +515,17 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                 const int n = n0 + c;
                 if (n >= p.cout) return;  // warp-uniform
                 float v[16];
+                {   // bias (+ shared rowvec row) of these 16 columns: 4 broadcast LDS.128 instead of 16 scalar reads
+                    const float4* a4 = reinterpret_cast<const float4*>(addv + c);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) + addv[c + j];
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 a = a4[q];
+                        v[4 * q] = __uint_as_float(raw[4 * q]) + a.x;
+                        v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + a.y;
+                        v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + a.z;
+                        v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + a.w;
+                    }
+                }
                 if (valid && p.rowvec && !rv_uniform && lead) {
                     const float* rp = p.rowvec + (int64_t)rv * p.ld_rowvec + n;
 #pragma unroll
@@ -534,8 +543,15 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                         srow[q] = x;
                     }
                     __syncwarp();
-                    // C: coalesced residual read + output store: 4 lanes per row, 8 rows per instruction
-                    if (p.out_f32 != nullptr || use_res) {
+                    // C: coalesced residual read + output store: 4 lanes per row, 8 rows per instruction.  The same
+                    // 4 x float4 give this lane's share of the GroupNorm column sums (columns 4*piece .. +3 over
+                    // its 4 rows) for free: the sums used to be a second walk over the slab, 32 shared-memory loads
+                    // per lane and chunk (ncu: the short-K launches spend 45 % of the LSU shared-memory pipe in the
+                    // epilogue, next to the MMAs' operand reads).
+                    const bool fast_stats = stats != nullptr && inst_uniform;
+                    const bool row_back = use_res && (p.out_hi != nullptr || (stats != nullptr && !inst_uniform));
+                    float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (p.out_f32 != nullptr || use_res || fast_stats) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             if (!svalid[i]) continue;
@@ -544,18 +560,21 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                             if (use_res) {
                                 const float4 rr = rres[i];
                                 x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
-                                *sp = x;
+                                if (row_back) *sp = x;
                             }
                             if (p.out_f32 && !(p.debug & 2)) {
                                 float4* op = reinterpret_cast<float4*>(p.out_f32 + spix[i] * p.ldc + n) + piece;
                                 if (p.k_splits > 1) atomicAdd(op, x);   // partial sum of this K range
                                 else *op = x;
                             }
+                            cs[0] += x.x; cs[1] += x.y; cs[2] += x.z; cs[3] += x.w;
+                            cq[0] = fmaf(x.x, x.x, cq[0]); cq[1] = fmaf(x.y, x.y, cq[1]);
+                            cq[2] = fmaf(x.z, x.z, cq[2]); cq[3] = fmaf(x.w, x.w, cq[3]);
                         }
                         if (use_res) {
                             if (c + 16 < c_end) load_res(c + 16);   // next chunk's residual: in flight during the rest
-                            __syncwarp();
-                            if (p.out_hi || (stats && !inst_uniform)) {   // own row again, residual included
+                            if (row_back) {                         // own row again, residual included
+                                __syncwarp();
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
                                     const float4 x = srow[q];
@@ -564,22 +583,33 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                             }
                         }
                     }
-                    // D: GroupNorm partial sums of the 32 x 16 block: lane = (column, sum | sum of squares)
+                    // D: GroupNorm partial sums of the 32 x 16 block
                     if (stats) {
                         if (inst_uniform) {
-                            const int col = lane & 15;
-                            const bool sq = lane >= 16;
-                            float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll 8
-                            for (int rr2 = 0; rr2 < 32; rr2 += 2) {
-                                const float x0 = slab[rr2 * kSlabStride + col];
-                                const float x1 = slab[(rr2 + 1) * kSlabStride + col];
-                                s0 += sq ? x0 * x0 : x0;
-                                s1 += sq ? x1 * x1 : x1;
+                            // recursive halving over the 8 lanes that share `piece` (lane bits 4, 3, 2): 7 shuffles
+                            // leave every lane with ONE finished value -- (sum | sum of squares) of one column
+                            const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+                            float k4[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float send = b4 ? cs[j] : cq[j];
+                                const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+                                k4[j] = (b4 ? cq[j] : cs[j]) + recv;
                             }
+                            float k2[2];
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const float send = b3 ? k4[j] : k4[2 + j];
+                                const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+                                k2[j] = (b3 ? k4[2 + j] : k4[j]) + recv;
+                            }
+                            const float send = b2 ? k2[0] : k2[1];
+                            const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+                            const float tot = (b2 ? k2[1] : k2[0]) + recv;
+                            const int col = 4 * piece + (b3 ? 2 : 0) + (b2 ? 1 : 0);
                             if (n + col < p.cout)
-                                atomicAdd(&stats[((int64_t)inst0 * p.stats_ld + n + col) * 2 + (sq ? 1 : 0)],
-                                          (double)(s0 + s1));
+                                atomicAdd(&stats[((int64_t)inst0 * p.stats_ld + n + col) * 2 + (b4 ? 1 : 0)],
+                                          (double)tot);
                         } else if (valid) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
