@@ -6,6 +6,7 @@
 #include "../../include/v2a_b200.h"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace v2a {
 extern std::atomic<int64_t> g_launches;
@@ -539,7 +540,11 @@ int v2a_prep(const v2a_prep_desc* d, void* stream) {
     const int oct = C / 8;
     V2A_REQUIRE(oct <= 256, "prep: %d channels exceed the 2048-channel block of the kernel", C);
     const int lanes = 256 / oct;
-    int iters = 8;
+    int iters = 16;    // B200 sweep of the B=16 UNet's 74 prep launches (tools/ab_prep.py): 2: 16.2 ms, 4: 14.4, 8: 14.0, 16: 13.5, 32: 14.2
+    {
+        static const int env_iters = getenv("V2A_PREP_ITERS") ? atoi(getenv("V2A_PREP_ITERS")) : 0;   // tuning probe
+        if (env_iters > 0) iters = env_iters;
+    }
     while (iters > 1 && out_pix / ((int64_t)lanes * iters) < 4 * 148) iters >>= 1;
     const int64_t pix_per_block = (int64_t)lanes * iters;
     prep_kernel<<<(unsigned)((out_pix + pix_per_block - 1) / pix_per_block), oct * lanes, 0, (cudaStream_t)stream>>>(
