@@ -295,6 +295,11 @@ class _PolicyEngine(PackedParams):
         return HL(torch.zeros(rows, cols, dtype=torch.bfloat16, device=self.device),
                   torch.zeros(rows, cols, dtype=torch.bfloat16, device=self.device))
 
+    def _needs_dyT(self, k: int, ins) -> bool:
+        """True when a conv over `ins` falls back to the transposed-im2col weight gradient (which wants dy^T);
+        the MN-major weight gradient reads dy itself, so GroupNorm backward need not write the transpose."""
+        return not (self._mn_wgrad and all(k * ops.nchunks(n.ld) <= _lib.V2A_WGRAD_MAX_UNITS for n in ins))
+
     def _wg_scratch(self, rows: int, cols: int) -> torch.Tensor:
         """[rows, cols] fp32 carved from arenas that are cleared once per backward (the MN-major weight-gradient
         GEMM accumulates its split pixel reduction with REDs)."""
@@ -540,12 +545,15 @@ class _PolicyEngine(PackedParams):
                 dO = out.grad
                 assert dO is not None
                 kp = _c64(rows)
-                dy2, dy2T = self.hlz(rows, Co), self.hlz(Co, kp)
+                none = HL(None, None)
+                dy2 = self.hlz(rows, Co)
+                dy2T = self.hlz(Co, kp) if self._needs_dyT(k, [hf]) else none
                 self.gn(st, True, B=Bn, T=Tn, C=Co, groups=G, eps=gn2.eps, y=y2, gamma=ga2, beta=be2, mean_rstd=mr2,
                         dout=dO.ptr, ld_dout=dO.ld, dy_hi=dy2.hi, dy_lo=dy2.lo, dyT_hi=dy2T.hi, dyT_lo=dy2T.lo,
                         ld_T=kp, dbias=g(c2.bias), dgamma=g(gn2.weight), dbeta=g(gn2.bias))
                 self.conv_bwd(st, lambda: c2.weight, g(c2.weight).view(Co, -1), k, pad, [hf], dy2, Co, dy2T, Co)
-                dy1, dy1T = self.hlz(rows, Co), self.hlz(Co, kp)
+                dy1 = self.hlz(rows, Co)
+                dy1T = self.hlz(Co, kp) if self._needs_dyT(k, ins) else none
                 self.gn(st, True, B=Bn, T=Tn, C=Co, groups=G, eps=gn1.eps, y=y1, gamma=ga1, beta=be1, mean_rstd=mr1,
                         film=film_ptr, ld_film=ftot, dout=hf.grad.ptr, ld_dout=hf.grad.ld, dy_hi=dy1.hi, dy_lo=dy1.lo,
                         dyT_hi=dy1T.hi, dyT_lo=dy1T.lo, ld_T=kp, dbias=g(c1.bias), dgamma=g(gn1.weight),
@@ -670,7 +678,8 @@ class _PolicyEngine(PackedParams):
             dOh, ldh, dOT = self.grad_prep(st, dO, rows, colsum=g(fc.bias))
             self.conv_bwd(st, lambda: fc.weight, g(fc.weight).view(din, -1), 1, 0, [hfin], dOh, ldh, dOT, din)
             kp = _c64(rows)
-            dyf, dyfT = self.hlz(rows, Cs), self.hlz(Cs, kp)
+            dyf = self.hlz(rows, Cs)
+            dyfT = self.hlz(Cs, kp) if self._needs_dyT(kf, [x_last]) else HL(None, None)
             self.gn(st, True, B=Bn, T=T, C=Cs, groups=fb[1].num_groups, eps=fb[1].eps, y=yf, gamma=gaf, beta=bef,
                     mean_rstd=mrf, dout=hfin.grad.ptr, ld_dout=hfin.grad.ld, dy_hi=dyf.hi, dy_lo=dyf.lo,
                     dyT_hi=dyfT.hi, dyT_lo=dyfT.lo, ld_T=kp, dbias=g(fb[0].bias), dgamma=g(fb[1].weight),
