@@ -370,8 +370,8 @@ typedef struct v2a_enc_gn_bwd_desc {
     const float* beta;
     int mask_mode;              /* 0 none, 1 outv > 0, 2 GroupNorm(raw) > 0 (recomputed) */
     int groups, C, HW, images;
-    float* sums;                /* scratch [images][C][2], zero on entry, zero on exit */
-    float* coef;                /* scratch [images][groups][2] */
+    float* sums;                /* scratch [images][C][2]: ZERO on entry (the caller clears it once per backward) */
+    float* coef;                /* unused (kept for ABI stability) */
     void* d_hi;                 /* out: gradient wrt raw, bf16 planes */
     void* d_lo;
     float* g_out;               /* optional out: masked dout (identity / downsample branch gradient) */

@@ -280,15 +280,16 @@ struct EncGnBwdParams {
     int mask_mode;                              // 0 none, 1 outv > 0, 2 GN(raw) > 0
     int groups, C, HW;
     int64_t pixels;
-    float* sums;                                // [images][C][2]           (pass 1 out)
-    const float2* coef;                         // [images][groups]         (pass 2 in)
+    float* sums;                                // [images][C][2]           (pass 1 out, pass 2 in)
+    float inv_m;                                // 1 / (HW * C / groups)
+    float* dgamma; float* dbeta;                // parameter gradients, accumulated by block 0 of pass 2
     __nv_bfloat16* d_hi; __nv_bfloat16* d_lo;   // draw planes              (pass 2 out)
     float* g_out;                               // optional fp32 g          (pass 2 out)
 };
 
 template <int PASS>
 __global__ void __launch_bounds__(256, 3) enc_gn_bwd_kernel(const EncGnBwdParams p, int lanes, int iters) {
-    __shared__ float red[2][256][9];   // pass 1 block reduction (padded)
+    __shared__ float red[2][256][9];   // pass 1 block reduction (padded); pass 2: the image's group coefficients
     const int oct = p.C >> 3;
     const int pl = threadIdx.x / oct;
     const int o8 = threadIdx.x - pl * oct;
@@ -299,13 +300,45 @@ __global__ void __launch_bounds__(256, 3) enc_gn_bwd_kernel(const EncGnBwdParams
     const int img = blockIdx.x / bpi;
     const int first = (blockIdx.x - img * bpi) * (lanes * iters);
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (PASS == 2) {
+        // (the former finalize launch) group coefficients of this image from the pass-1 sums:
+        // coef[g] = (sum_c gamma_c sum_g, sum_c gamma_c sum_gxh) / m;  block 0 also reduces the sums over the images
+        // into the parameter gradients
+        float* cf = &red[0][0][0];       // [groups][2]
+        const int cpg = p.C / p.groups;
+        for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
+            float a = 0.f, b2 = 0.f;
+            for (int j = 0; j < cpg; ++j) {
+                const int ch = g * cpg + j;
+                const float gam = __ldg(&p.gamma[ch]);
+                a += gam * p.sums[((int64_t)img * p.C + ch) * 2];
+                b2 += gam * p.sums[((int64_t)img * p.C + ch) * 2 + 1];
+            }
+            cf[2 * g] = a * p.inv_m;
+            cf[2 * g + 1] = b2 * p.inv_m;
+        }
+        if (blockIdx.x == 0) {
+            const int images = (int)(p.pixels / p.HW);
+            for (int ch = threadIdx.x; ch < p.C; ch += blockDim.x) {
+                float a = 0.f, b2 = 0.f;
+                for (int im = 0; im < images; ++im) {
+                    a += p.sums[((int64_t)im * p.C + ch) * 2];
+                    b2 += p.sums[((int64_t)im * p.C + ch) * 2 + 1];
+                }
+                p.dbeta[ch] += a;
+                p.dgamma[ch] += b2;
+            }
+        }
+        __syncthreads();
+    }
     if (active) {
         const int cpg = p.C / p.groups;
         float mean[8], rstd[8], ga[8], be[8], cx[8], cy[8];
         {
             int g = c / cpg, rem = c - g * cpg;
             float2 m = __ldg(&p.mr[(int64_t)img * p.groups + g]);
-            float2 cf = PASS == 2 ? __ldg(&p.coef[(int64_t)img * p.groups + g]) : make_float2(0.f, 0.f);
+            const float* cfs = &red[0][0][0];
+            float2 cf = PASS == 2 ? make_float2(cfs[2 * g], cfs[2 * g + 1]) : make_float2(0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 mean[j] = m.x; rstd[j] = m.y; cx[j] = cf.x; cy[j] = cf.y;
@@ -315,7 +348,7 @@ __global__ void __launch_bounds__(256, 3) enc_gn_bwd_kernel(const EncGnBwdParams
                     rem = 0;
                     ++g;
                     m = __ldg(&p.mr[(int64_t)img * p.groups + g]);
-                    if (PASS == 2) cf = __ldg(&p.coef[(int64_t)img * p.groups + g]);
+                    if (PASS == 2) cf = make_float2(cfs[2 * g], cfs[2 * g + 1]);
                 }
             }
         }
@@ -378,41 +411,6 @@ __global__ void __launch_bounds__(256, 3) enc_gn_bwd_kernel(const EncGnBwdParams
                 atomicAdd(dst + 2 * j + 1, sx[j]);
             }
         }
-    }
-}
-
-// coef[img][grp] = (S1, S2) / m;  dgamma[c] += sum_img sum_gxh;  dbeta[c] += sum_img sum_g;  then the sums are
-// cleared for the next backward.  grid: images blocks of `C` threads + 1 block for the parameter gradients.
-__global__ void enc_gn_bwd_finalize_kernel(float* __restrict__ sums, const float* __restrict__ gamma, int images,
-                                           int C, int groups, float inv_m, float2* __restrict__ coef,
-                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    extern __shared__ float sh[];   // [2 * C]
-    const int c = threadIdx.x;
-    if ((int)blockIdx.x < images) {
-        const int img = blockIdx.x;
-        if (c < C) {
-            const float ga = gamma[c];
-            sh[c] = ga * sums[((int64_t)img * C + c) * 2];
-            sh[C + c] = ga * sums[((int64_t)img * C + c) * 2 + 1];
-        }
-        __syncthreads();
-        if (c < groups) {
-            const int cpg = C / groups;
-            float a = 0.f, b = 0.f;
-            for (int j = 0; j < cpg; ++j) {
-                a += sh[c * cpg + j];
-                b += sh[C + c * cpg + j];
-            }
-            coef[(int64_t)img * groups + c] = make_float2(a * inv_m, b * inv_m);
-        }
-    } else if (c < C) {
-        float a = 0.f, b = 0.f;
-        for (int img = 0; img < images; ++img) {
-            a += sums[((int64_t)img * C + c) * 2];
-            b += sums[((int64_t)img * C + c) * 2 + 1];
-        }
-        dbeta[c] += a;
-        dgamma[c] += b;
     }
 }
 
@@ -593,8 +591,11 @@ int v2a_enc_gn_bwd(const v2a_enc_gn_bwd_desc* d, void* stream) {
     p.dout = d->dout; p.outv = d->outv; p.raw = d->raw; p.mr = reinterpret_cast<const float2*>(d->mean_rstd);
     p.gamma = d->gamma; p.beta = d->beta; p.mask_mode = d->mask_mode; p.groups = d->groups; p.C = d->C;
     p.HW = d->HW; p.pixels = (int64_t)d->images * d->HW;
-    p.sums = d->sums; p.coef = reinterpret_cast<const float2*>(d->coef);
+    p.sums = d->sums;
+    p.inv_m = 1.0f / ((float)d->HW * (float)(d->C / d->groups));
+    p.dgamma = d->dgamma; p.dbeta = d->dbeta;
     p.d_hi = (__nv_bfloat16*)d->d_hi; p.d_lo = (__nv_bfloat16*)d->d_lo; p.g_out = d->g_out;
+    V2A_REQUIRE(d->groups * 2 <= 2 * 256 * 9, "enc_gn_bwd: too many groups");
     int lanes, iters;
     walk_shape(d->C, p.pixels, lanes, iters);
     while (iters > 1 && lanes * iters > d->HW) iters >>= 1;
@@ -602,16 +603,11 @@ int v2a_enc_gn_bwd(const v2a_enc_gn_bwd_desc* d, void* stream) {
     const unsigned grid = (unsigned)(bpi * d->images);
     const int threads = (d->C / 8) * lanes;
     cudaStream_t st = (cudaStream_t)stream;
-    // pass 1 -> finalize -> pass 2
+    // pass 1 (sums; the caller zeroes them once per backward) -> pass 2 (coefficients, parameter gradients, dx)
     enc_gn_bwd_kernel<1><<<grid, threads, 0, st>>>(p, lanes, iters);
-    V2A_ENC_LAUNCH_OK();
-    const float inv_m = 1.0f / ((float)d->HW * (float)(d->C / d->groups));
-    enc_gn_bwd_finalize_kernel<<<d->images + 1, d->C < 32 ? 32 : d->C, 2 * d->C * sizeof(float), st>>>(
-        d->sums, d->gamma, d->images, d->C, d->groups, inv_m, reinterpret_cast<float2*>(d->coef), d->dgamma, d->dbeta);
     V2A_ENC_LAUNCH_OK();
     enc_gn_bwd_kernel<2><<<grid, threads, 0, st>>>(p, lanes, iters);
     V2A_ENC_LAUNCH_OK();
-    V2A_CUDA_OK(cudaMemsetAsync(d->sums, 0, (size_t)d->images * d->C * 2 * sizeof(float), st));
     return 0;
 }
 

@@ -290,13 +290,13 @@ class _EncoderEngine(PackedParams):
     def gn_bwd(self, steps, *, dout, raw, mr, gn: nn.GroupNorm, N, HW, Cc, mask_mode, outv=None, d_hl: HL, g_out=None):
         d = _lib.EncGnBwdDesc()
         ga, ba = self.vec(lambda: gn.weight, Cc), self.vec(lambda: gn.bias, Cc)
-        sums = self.zeros(N * Cc * 2)
-        coef = self.zeros(N * gn.num_groups * 2)
+        sums = self.scratch(N * Cc * 2, 1)      # pass-1 sums: part of the arena cleared once per backward
+        coef = None
         d.dout, d.raw, d.mean_rstd = dout.data_ptr(), raw.data_ptr(), mr.data_ptr()
         d.outv = None if outv is None else outv.data_ptr()
         d.gamma, d.beta = ga.data_ptr(), ba.data_ptr()
         d.mask_mode, d.groups, d.C, d.HW, d.images = mask_mode, gn.num_groups, Cc, HW, N
-        d.sums, d.coef = sums.data_ptr(), coef.data_ptr()
+        self._deferred.append(lambda: setattr(d, "sums", sums[0].data_ptr()))
         d.d_hi, d.d_lo = d_hl.hi.data_ptr(), d_hl.lo.data_ptr()
         d.g_out = None if g_out is None else g_out.data_ptr()
         d.dgamma, d.dbeta = self.pgrad[id(gn.weight)].data_ptr(), self.pgrad[id(gn.bias)].data_ptr()
@@ -524,8 +524,8 @@ class _EncoderEngine(PackedParams):
         return out
 
     def planned_launches(self) -> int:
-        """kernel launches of one forward + backward (gn_bwd = 3 kernels + a memset node; weight repack chunks)"""
-        n = len(self.fwd) + len(self.bwd) + 2 * sum(1 for t in self.bwd.tags if t == "enc_gn_bwd")
+        """kernel launches of one forward + backward (gn_bwd = 2 kernels; + the weight repack chunks)"""
+        n = len(self.fwd) + len(self.bwd) + sum(1 for t in self.bwd.tags if t == "enc_gn_bwd")
         return n + len(self._wchunks) + len(self._vchunks)
 
     # ---- execution -----------------------------------------------------------------------------
