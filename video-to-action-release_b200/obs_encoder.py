@@ -407,7 +407,7 @@ class _EncoderEngine(PackedParams):
                        dy_dims=(X.rows, 1, 1, 1), cout=K, cin=X.C, ntaps=1, param=kconv.weight)
             X.grad = self.zeros(X.rows, X.C)
             progd = convs.pointwise(K, (X.rows,))
-            wd = self.weight(lambda: ops.pack_weight_taps([kconv.weight.reshape(K, X.C).t()]), X.C, progd.ktot)
+            wd = self.weight(lambda: ops.pack_weight_taps([kconv.weight.reshape(K, X.C).t()]), X.C, progd.ktot, bwd=True)
             self.igemm(st, "igemm dgrad kp", srcs=[(dlog, K, progd.src_dims[0])], taps=progd.taps, w=wd,
                        out_dims=progd.out_dims, cout=X.C, out_f32=X.grad)
         tape.append(head_bwd)
@@ -477,7 +477,7 @@ class _EncoderEngine(PackedParams):
                        units=[(0, d, ch) for d in taps9 for ch in range(ops.nchunks(Co))], dy=d2, dy_channels=Co,
                        dy_dims=(Wo, Ho, N, 1), cout=Co, cin=Co, ntaps=9, param=blk.conv2.weight)
             dA1 = self.zeros(rows_o, Co)
-            wd2 = self.weight(lambda: dgrad3x3_weight(blk.conv2.weight), Co, prog2.ktot)
+            wd2 = self.weight(lambda: dgrad3x3_weight(blk.conv2.weight), Co, prog2.ktot, bwd=True)
             self.igemm(st, f"igemm dgrad conv2 C{Co}", srcs=[(d2, Co, prog2.src_dims[0])], taps=prog2.taps, w=wd2,
                        out_dims=prog2.out_dims, cout=Co, out_f32=dA1)
             # relu + GN1 backward
@@ -490,7 +490,7 @@ class _EncoderEngine(PackedParams):
                            units=[(0, d, ch) for d in taps9 for ch in range(ops.nchunks(Ci))], dy=d1, dy_channels=Co,
                            dy_dims=(Wo, Ho, N, 1), cout=Co, cin=Ci, ntaps=9, param=blk.conv1.weight)
                 progd = convs.spatial3x3(Co, N, Ho, Wo)
-                wd1 = self.weight(lambda: dgrad3x3_weight(blk.conv1.weight), Ci, progd.ktot)
+                wd1 = self.weight(lambda: dgrad3x3_weight(blk.conv1.weight), Ci, progd.ktot, bwd=True)
                 self.igemm(st, f"igemm dgrad conv1 C{Co}->{Ci}", srcs=[(d1, Co, progd.src_dims[0])], taps=progd.taps,
                            w=wd1, out_dims=progd.out_dims, cout=Ci, out_f32=X.grad, residual=g)
             else:
@@ -498,7 +498,7 @@ class _EncoderEngine(PackedParams):
                            units=[(0, tuple(t[1]), ch) for t in prog1.taps for ch in range(ops.nchunks(Ci))], dy=d1,
                            dy_channels=Co, dy_dims=(Wo, Ho, 1, N), cout=Co, cin=Ci, ntaps=9, param=blk.conv1.weight)
                 taps4 = [(0, (di, dj, 0, 0), ops.nchunks(Co)) for dj in range(2) for di in range(2)]
-                wd1 = self.weight(lambda: dgrad3x3_s2_weight(blk.conv1.weight), 4 * Ci, 4 * 64 * ops.nchunks(Co))
+                wd1 = self.weight(lambda: dgrad3x3_s2_weight(blk.conv1.weight), 4 * Ci, 4 * 64 * ops.nchunks(Co), bwd=True)
                 blocked = self.zeros(rows_o, 4 * Ci)
                 self.igemm(st, f"igemm dgrad conv1 s2 C{Co}->4x{Ci}", srcs=[(d1, Co, (Wo, Ho, N, 1))], taps=taps4,
                            w=wd1, out_dims=(Wo, Ho, N, 1), cout=4 * Ci, out_f32=blocked)
@@ -512,7 +512,7 @@ class _EncoderEngine(PackedParams):
                            dy_dims=(Wo, Ho, 1, N), cout=Co, cin=Ci, ntaps=1, param=dconv.weight)
                 dxd = self.zeros(rows_o, Ci)
                 progp = convs.pointwise(Co, (rows_o,))
-                wdd = self.weight(lambda: ops.pack_weight_taps([dconv.weight.reshape(Co, Ci).t()]), Ci, progp.ktot)
+                wdd = self.weight(lambda: ops.pack_weight_taps([dconv.weight.reshape(Co, Ci).t()]), Ci, progp.ktot, bwd=True)
                 self.igemm(st, f"igemm dgrad downsample C{Co}->{Ci}", srcs=[(dd, Co, progp.src_dims[0])],
                            taps=progp.taps, w=wdd, out_dims=progp.out_dims, cout=Ci, out_f32=dxd)
                 st.add("unblock_add", lambda: _lib.check(self.lib.v2a_enc_unblock_add(
@@ -577,6 +577,7 @@ class _EncoderEngine(PackedParams):
 
     def backward(self, dfeat: torch.Tensor, clone_param_grads: bool = True):
         self.dfeat.copy_(dfeat)
+        self.wait_bwd_weights()
         self._run("bwd", self.bwd, pre=(self.gslab, self.wg_arena))
         self.done.record(torch.cuda.current_stream())   # consumers of gslab on other streams wait on this
         if clone_param_grads:

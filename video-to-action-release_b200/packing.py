@@ -21,17 +21,20 @@ class PackedParams:
         self._wkey = None
         self._stage = None
         self._trace_checked = False
+        self._pack_stream = None          # side stream for the backward-only packs (data-gradient weights)
+        self._bwd_pack_done = None        # event the backward waits on
 
-    def _carve(self, kind: str, n: int):
+    def _carve(self, kind: str, n: int, bwd: bool = False):
         """n elements (multiple of 128) from the growing weight ('w': bf16 hi/lo planes) or vector ('v': fp32)
         arena; every arena chunk is re-packed by ONE v2a_gather_split launch."""
         n_al = -(-n // 128) * 128
         # 'h': weight planes in the fp16 (hi, lo) format (stored in bf16-typed tensors; only the bits matter)
-        chunks = [c for c in self._wchunks if c["fmt"] == (1 if kind == "h" else 0)] if kind in "wh" else self._vchunks
+        chunks = ([c for c in self._wchunks if c["fmt"] == (1 if kind == "h" else 0) and c["bwd"] == bwd]
+                  if kind in "wh" else self._vchunks)
         if not chunks or chunks[-1]["used"] + n_al > chunks[-1]["cap"]:
             cap = max(n_al, (16 << 20) if kind in "wh" else (1 << 20))
             c = dict(cap=cap, used=0, map=torch.zeros(cap, dtype=torch.int32, device=self.device),
-                     fmt=1 if kind == "h" else 0)
+                     fmt=1 if kind == "h" else 0, bwd=bwd)
             if kind in "wh":
                 c["hi"] = torch.zeros(cap, dtype=torch.bfloat16, device=self.device)
                 c["lo"] = torch.zeros(cap, dtype=torch.bfloat16, device=self.device)
@@ -44,8 +47,10 @@ class PackedParams:
         c["used"] += n_al
         return c, lo, hi
 
-    def weight(self, fn, rows, cols, fp16: bool = False) -> HL:
-        c, lo, hi = self._carve("h" if fp16 else "w", rows * cols)
+    def weight(self, fn, rows, cols, fp16: bool = False, bwd: bool = False) -> HL:
+        """bwd=True: a pack only the backward pass reads (data-gradient layouts) -- re-packed on a side stream
+        while the forward pass runs (`wait_bwd_weights()` before the first backward launch)."""
+        c, lo, hi = self._carve("h" if fp16 else "w", rows * cols, bwd)
         hl = HL(c["hi"][lo:hi].view(rows, cols), c["lo"][lo:hi].view(rows, cols))
         hl.fp16 = fp16
         self.packers.append((fn, hl, c["map"][lo:hi].view(rows, cols)))
@@ -123,12 +128,30 @@ class PackedParams:
             return
         src = self._param_slab()
         st = ops._stream()
-        for c in self._wchunks:
+
+        def pack(c, stream):
             _lib.check(self.lib.v2a_gather_split_fmt(src.data_ptr(), c["map"].data_ptr(), c["used"], c["hi"].data_ptr(),
-                                                     c["lo"].data_ptr(), None, c["fmt"], st), "gather_split")
+                                                     c["lo"].data_ptr(), None, c["fmt"], stream), "gather_split")
+        for c in self._wchunks:
+            if not c["bwd"]:
+                pack(c, st)
         for c in self._vchunks:
             _lib.check(self.lib.v2a_gather_split(src.data_ptr(), c["map"].data_ptr(), c["used"], None, None,
                                                  c["f32"].data_ptr(), st), "gather_split")
+        bwd_chunks = [c for c in self._wchunks if c["bwd"]]
+        if bwd_chunks:
+            # nothing in the forward pass reads these: re-pack them beside it
+            cur = torch.cuda.current_stream()
+            if self._pack_stream is None:
+                self._pack_stream = torch.cuda.Stream(device=self.device)
+            self._pack_stream.wait_stream(cur)
+            with torch.cuda.stream(self._pack_stream):
+                for c in bwd_chunks:
+                    pack(c, self._pack_stream.cuda_stream)
+                self._bwd_pack_done = torch.cuda.Event()
+                self._bwd_pack_done.record(self._pack_stream)
+            if not self._trace_checked:
+                cur.wait_stream(self._pack_stream)
         if not self._trace_checked:   # first pack: the traced gather must reproduce the torch packers bit for bit
             for got, want in self._repack_reference():
                 if not torch.equal(got, want):
@@ -136,3 +159,8 @@ class PackedParams:
             self._trace_checked = True
         self._wkey = key
 
+
+    def wait_bwd_weights(self) -> None:
+        """Order the current stream after the side-stream re-pack of the backward-only weight layouts."""
+        if self._bwd_pack_done is not None:
+            torch.cuda.current_stream().wait_event(self._bwd_pack_done)

@@ -429,7 +429,7 @@ class _PolicyEngine(PackedParams):
             parts = [F.pad(w[:, :, j].t(), (0, ld_dy - cout)) if ld_dy != cout else w[:, :, j].t()
                      for j in reversed(range(k))]
             return ops.pack_weight_taps(parts)
-        wd = self.weight(packed_d, cin_tot, progd.ktot)
+        wd = self.weight(packed_d, cin_tot, progd.ktot, bwd=True)
         src = [(dy, ld_dy, progd.src_dims[0])]
         if len(ins) == 1:
             n = ins[0]
@@ -587,7 +587,7 @@ class _PolicyEngine(PackedParams):
                 self.wgrad(st, dOT, Cc, col, Cc * 3, g(conv.weight).view(Cc, -1), 0)
                 st.lane = 0
                 progd = convs.down1d_dgrad(ldh, Bn, Tn)
-                wd = self.weight(lambda: convs.down1d_dgrad_weight(conv.weight), 2 * Cc, progd.ktot)
+                wd = self.weight(lambda: convs.down1d_dgrad_weight(conv.weight), 2 * Cc, progd.ktot, bwd=True)
                 tmp = self.zeros(rows_o, 2 * Cc)  # == [B*T, C] memory
                 self.igemm(st, srcs=[(dOh, ldh, progd.src_dims[0])], taps=progd.taps, w=wd, out_dims=progd.out_dims,
                            cout=2 * Cc, out_f32=tmp)
@@ -622,7 +622,7 @@ class _PolicyEngine(PackedParams):
                 self.wgrad(st, xT, Cc, col, Cc * 4, g(conv.weight).view(Cc, -1), 0)
                 st.lane = 0
                 progd = convs.up1d_dgrad(ldh, Bn, Tn)
-                wd = self.weight(lambda: convs.up1d_dgrad_weight(conv.weight), Cc, progd.ktot)
+                wd = self.weight(lambda: convs.up1d_dgrad_weight(conv.weight), Cc, progd.ktot, bwd=True)
                 if x.grad is None:
                     x.grad = _Ref(self.zeros(rows, Cc), 0, Cc)
                     res = None
@@ -780,6 +780,7 @@ class _PolicyEngine(PackedParams):
     def backward(self, grad_out, clone_param_grads=True):
         Bn, T = self.B, self.T
         self.dout16[:, :self.x0.C].copy_(grad_out.reshape(Bn * T, -1))
+        self.wait_bwd_weights()
         self._run("bwd", self.bwd, pre=self._zero_each_bwd)
         d_sample = self.x0.grad.win.reshape(Bn, T, -1).clone()
         d_gc = self.dgf[:, self.dgf.shape[1] - self.gc_in.shape[1]:].clone()
