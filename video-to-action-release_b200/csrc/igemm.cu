@@ -98,6 +98,7 @@ struct alignas(64) IgemmParams {
     int k_splits;         // >1: the K loop of one output tile is shared by k_splits CTAs (fp32 atomics)
     int kps;              // K iterations per split
     int a_fp16, b_fp16;   // operand planes hold fp16 (hi, lo) pairs instead of bf16 ones
+    int nacc_log2;        // accumulator ring: 2 x 256 TMEM columns (1) or 4 x 128 (2: block_n <= 128, unfused)
     int cta2;             // CTA pairs issue ONE cta_group::2 MMA (M = 256, B split between the two SMs)
     int fuse2;            // N <= 128: a_hi x [b_hi | b_lo] as ONE N = 2*block_n MMA (two accumulator halves)
     int debug;  // V2A_IGEMM_DEBUG bits: 1 skip stats, 2 skip stores, 4 skip residual (timing experiments only)
@@ -179,9 +180,9 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * p.stage_bytes);
     uint64_t* full_bar = bars;             // [S]
     uint64_t* empty_bar = bars + S;        // [S]
-    uint64_t* tfull_bar = bars + 2 * S;    // [2]
-    uint64_t* tempty_bar = bars + 2 * S + 2;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+    uint64_t* tfull_bar = bars + 2 * S;    // [4]
+    uint64_t* tempty_bar = bars + 2 * S + 4;  // [4]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
     float* warp_add = reinterpret_cast<float*>(bars) + 64;  // 8 epilogue warps x 256 floats, after the 256 B barrier block
     float* stage_slab = warp_add + 8 * 256;   // 8 epilogue warps x [32 rows][kSlabStride] coalescing slabs
 
@@ -191,7 +192,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
             // multicast pairs: both CTAs' MMA warps release a stage; cta_group::2 pairs: the leader's commit does
             mbar_init(&empty_bar[s], (p.cluster > 1 && !kCta2) ? 2 : 1);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < 4; ++s) {
             mbar_init(&tfull_bar[s], 1);
             mbar_init(&tempty_bar[s], kCta2 ? 2 * kEpilogueThreads : kEpilogueThreads);   // cta2: both epilogues
         }
@@ -212,6 +213,8 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
     if (p.cluster > 1) cluster_sync_all();   // the peer's barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int nacc_mask = (1 << p.nacc_log2) - 1;
+    const uint32_t acc_stride = kTmemCols >> p.nacc_log2;
 
     const int total_tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
     const TileRange tr = cta_tiles(p, total_tiles);
@@ -293,11 +296,11 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             for (int it = 0; it < tr.count; ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
+                const int acc = it & nacc_mask;
+                const uint32_t acc_phase = (it >> p.nacc_log2) & 1;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * kAccStride;
+                const uint32_t d_tmem = tmem_base + acc * acc_stride;
                 for (int kit = 0; kit < p.k_iters; ++kit) {
                     mbar_wait(&full_bar[stage], phase, 300 + stage);
                     tc_fence_after();
@@ -336,11 +339,11 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
         uint32_t phase = 0;
         for (int it = 0; it < tr.count; ++it) {
             const int tile = tr.first + it * tr.step;
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
+            const int acc = it & nacc_mask;
+            const uint32_t acc_phase = (it >> p.nacc_log2) & 1;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * kAccStride;
+            const uint32_t d_tmem = tmem_base + acc * acc_stride;
             const int kb = (tile % p.k_splits) * p.kps;
             const int n_it = min(kb + p.kps, p.k_iters) - kb;
             for (int kit = 0; kit < n_it; ++kit) {
@@ -414,8 +417,8 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
         const int piece = lane & 3;
         for (int it = 0; it < tr.count; ++it) {
             const int tile = tr.first + it * tr.step;
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
+            const int acc = it & nacc_mask;
+            const uint32_t acc_phase = (it >> p.nacc_log2) & 1;
             int n_idx, o[4], split;
             decode_tile(p, tile, n_idx, o, split);
             const int n0 = n_idx * p.block_n;
@@ -509,7 +512,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
 
             mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kAccStride;
+            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * acc_stride;
 
             auto process = [&](uint32_t (&raw)[16], int c) {
                 const int n = n0 + c;
@@ -954,10 +957,23 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
     // fused split product (block_n <= 128); short-K launches (temporal / 1x1 convs, whose time is their epilogue)
     // lose to the lockstep of the two epilogues and stay on multicast pairs.  V2A_CTA2=0 disables, =2 forces.
     p.cta2 = 0;
+    p.nacc_log2 = 1;
     {
         const char* env = getenv("V2A_CTA2");
         const int mode = env ? atoi(env) : 1;
-        if (mode != 0 && p.cluster == 2 && d->block_n % 32 == 0 && (p.k_iters >= 16 || mode == 2) &&
+        if (mode == 4 && p.cluster == 2 && d->block_n <= 128 && d->block_n % 32 == 0 && p.k_iters < 16) {
+            // experiment: short-K launches as UNFUSED pairs with a 4-deep accumulator ring (4 x 128 TMEM columns),
+            // so the two epilogues of a pair run up to 3 tiles behind the MMAs instead of in lockstep with them
+            p.cta2 = 1;
+            p.fuse2 = 0;
+            p.nacc_log2 = 2;
+            p.stage_bytes = 2 * (kATileBytes + p.b_tile_bytes / 2);
+            int stages = (int)((g_max_smem - overhead) / p.stage_bytes);
+            if (stages > 8) stages = 8;
+            p.stages = stages;
+            pl->smem = (size_t)stages * p.stage_bytes + overhead;
+        }
+        if (!p.cta2 && mode != 0 && p.cluster == 2 && d->block_n % 32 == 0 && (p.k_iters >= 16 || mode == 2) &&
             (p.fuse2 || mode != 3)) {      // mode 3: fused (block_n <= 128) layers only (A/B probes)
             p.cta2 = 1;
             p.stage_bytes = 2 * (kATileBytes + p.b_tile_bytes / 2);
