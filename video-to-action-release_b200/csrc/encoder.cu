@@ -302,8 +302,7 @@ __global__ void __launch_bounds__(256, 3) enc_gn_bwd_kernel(const EncGnBwdParams
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (PASS == 2) {
         // (the former finalize launch) group coefficients of this image from the pass-1 sums:
-        // coef[g] = (sum_c gamma_c sum_g, sum_c gamma_c sum_gxh) / m;  block 0 also reduces the sums over the images
-        // into the parameter gradients
+        // coef[g] = (sum_c gamma_c sum_g, sum_c gamma_c sum_gxh) / m
         float* cf = &red[0][0][0];       // [groups][2]
         const int cpg = p.C / p.groups;
         for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
@@ -317,16 +316,12 @@ __global__ void __launch_bounds__(256, 3) enc_gn_bwd_kernel(const EncGnBwdParams
             cf[2 * g] = a * p.inv_m;
             cf[2 * g + 1] = b2 * p.inv_m;
         }
-        if (blockIdx.x == 0) {
-            const int images = (int)(p.pixels / p.HW);
+        if (blockIdx.x == img * bpi) {
+            // the first block of every image adds the image's sums into the parameter gradients (a single block
+            // walking all images serially was this launch's critical path: 37 us at 4x4x512)
             for (int ch = threadIdx.x; ch < p.C; ch += blockDim.x) {
-                float a = 0.f, b2 = 0.f;
-                for (int im = 0; im < images; ++im) {
-                    a += p.sums[((int64_t)im * p.C + ch) * 2];
-                    b2 += p.sums[((int64_t)im * p.C + ch) * 2 + 1];
-                }
-                p.dbeta[ch] += a;
-                p.dgamma[ch] += b2;
+                atomicAdd(&p.dbeta[ch], p.sums[((int64_t)img * p.C + ch) * 2]);
+                atomicAdd(&p.dgamma[ch], p.sums[((int64_t)img * p.C + ch) * 2 + 1]);
             }
         }
         __syncthreads();
