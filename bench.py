@@ -235,7 +235,7 @@ def run_policy(args, world, rank, local, barrier, max_over_ranks, peaks):
     torch.manual_seed(77)                                   # same initial weights on every rank (DDP semantics)
     policy = build_libero_policy().to("cuda")
     policy.train()
-    torch.backends.cudnn.allow_tf32 = False                 # fp32 truth setting for the cuDNN encoders
+    torch.backends.cudnn.allow_tf32 = False                 # fp32 setting for the torch/cuDNN encoder A/B leg
     torch.backends.cuda.matmul.allow_tf32 = False
     g = torch.Generator().manual_seed(2000 + rank)
     host = {"img_obs_1": torch.rand(B, 1, 3, 128, 128, generator=g).pin_memory(),

@@ -9,9 +9,10 @@ What runs where:
   * P2-P5  ``self.model`` = v2a_b200 ``ConditionalUnet1D``: planned CUDA forward + backward (the hot path);
   * P7     ``add_noise`` and the scheduler steps: restated here — ``diffusers`` is a third-party
            dependency the reference leaves unpinned (requirements.txt:4) and is absent offline;
-  * P6     the observation encoder (2x ResNet18-GroupNorm + SpatialSoftmax, 80 % of compute_loss FLOPs,
-           not named by north_star) stays on torch/cuDNN this round (row N1 is next): the modules below
-           only restate its structure with the reference's ``state_dict`` names.
+  * P6     the observation encoder (2x ResNet18-GroupNorm + SpatialSoftmax, 80 % of compute_loss FLOPs): the
+           modules below hold its parameters under the reference's ``state_dict`` names; ``VisualCore.forward``
+           runs the planned CUDA engine of ``obs_encoder.py`` (forward and backward).  ``V2A_ENCODER=torch``
+           runs the stock torch modules instead (host-side comparisons / A-B timing).
 
 RNG order of ``compute_loss`` follows the reference: SpatialSoftmax draws (goal, then
 obs encoder, training mode only), ``randn(trajectory.shape)``, ``randint(0, T, (B,))``.
@@ -207,7 +208,8 @@ class ConstNormalizerGroup:
 
 
 # ---------------------------------------------------------------------------
-# observation encoder (row P6 — torch/cuDNN this round; structure + state_dict names of the reference)
+# observation encoder (row P6 / N1): parameter holders with the reference's structure and state_dict names;
+# the math runs in obs_encoder.py
 # ---------------------------------------------------------------------------
 class _AttrMixin(nn.Module):
     """common/module_attr_mixin.py:3-15 — an empty parameter pins .device/.dtype (and is in state_dict)."""

@@ -11,8 +11,8 @@ config/libero/lb_tk8_65to72.py:138-153):
     EMA.update()                                            slabs: p, g, m, v, ema)
 
 Parameters are re-pointed into one flat fp32 slab per segment (their ``state_dict`` names and
-shapes are unchanged); the UNet1D's gradients never leave the engine's gradient slab, other
-parameters (the cuDNN observation encoder) accumulate through autograd into slab views.
+shapes are unchanged); the gradients of the UNet1D and of the observation encoders never leave their
+engines' gradient slabs, any other parameter accumulates through autograd into slab views.
 
 EMA follows ``ema_pytorch`` 0.2.3 as the trainer configures it (``EMA(model, beta=0.9999,
 update_after_step=0, inv_gamma=1, power=0.75, min_value=0, update_every=1)``; third-party, not
