@@ -768,6 +768,12 @@ static int device_props() {
     return 0;
 }
 
+// K steps (of 64) from which a pair launch uses cta_group::2 MMAs (tuning probe: V2A_CTA2_MINK)
+static int cta2_min_k() {
+    static const int v = getenv("V2A_CTA2_MINK") ? atoi(getenv("V2A_CTA2_MINK")) : 12;   // same-box A/B: 16: 97.2 ms, 12: 96.1, 10: 97.0
+    return v;
+}
+
 static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
     if (int rc = device_props()) return rc;
     V2A_REQUIRE(d->nsrc >= 1 && d->nsrc <= V2A_MAX_SRC, "igemm: nsrc %d out of range", d->nsrc);
@@ -932,7 +938,7 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
         // pairs over several N tiles are new with the cta_group::2 path and follow its switch
         const char* env2 = getenv("V2A_CTA2");
         const int mode2 = env2 ? atoi(env2) : 1;
-        const bool multi_n = mode2 != 0 && mode2 != 3 && p.k_iters >= 16 && d->block_n % 32 == 0;
+        const bool multi_n = mode2 != 0 && mode2 != 3 && p.k_iters >= cta2_min_k() && d->block_n % 32 == 0;
         if (want && (p.num_n_tiles == 1 || multi_n) && p.k_splits == 1 && d->passes == 3 && d->block_n % 16 == 0 &&
             p.num_m_tiles >= 4 && g_num_sms >= 2) {
             int grid = (g_num_sms / 2) * 2;
@@ -973,7 +979,7 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
             p.stages = stages;
             pl->smem = (size_t)stages * p.stage_bytes + overhead;
         }
-        if (!p.cta2 && mode != 0 && p.cluster == 2 && d->block_n % 32 == 0 && (p.k_iters >= 16 || mode == 2) &&
+        if (!p.cta2 && mode != 0 && p.cluster == 2 && d->block_n % 32 == 0 && (p.k_iters >= cta2_min_k() || mode == 2) &&
             (p.fuse2 || mode != 3)) {      // mode 3: fused (block_n <= 128) layers only (A/B probes)
             p.cta2 = 1;
             p.stage_bytes = 2 * (kATileBytes + p.b_tile_bytes / 2);
