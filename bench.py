@@ -287,6 +287,34 @@ def run_policy(args, world, rank, local, barrier, max_over_ranks, peaks):
     # (c) the same step with the batch already resident
     batch_dev = {"obs": {"img_obs_1": dev["img_obs_1"], "img_goal_1": dev["img_goal_1"]}, "action": dev["action"]}
     ms_p, _ = timed(lambda: step_p.step(lambda: policy.compute_loss(batch_dev)), steps)
+    # (d) row N4: the same e2e step fed by the HBM-resident replay buffer -- per step the host sends a table of
+    # 3*B device addresses instead of 2*B float images; the batch is gathered from uint8 episodes on the device
+    replay_e2e = None
+    try:
+        import numpy as np
+        from v2a_b200.replay import Global_EnvReplayBuffer_Img
+        rb = Global_EnvReplayBuffer_Img(["synthetic"], 64, 128, T + 1, None, (128, 128),
+                                        env_buf_config={"sample_act_seq_len": T})
+        rng = np.random.default_rng(3000 + rank)
+        for e in range(32):
+            rb.add_one_episode("synthetic", "agentview", e, rng.integers(0, 256, size=(64, 128, 128, 3), dtype=np.uint8),
+                               rng.uniform(-1, 1, size=(63, Da)).astype(np.float32))
+
+        def replay_step():
+            st, gl, acts, _, _ = rb.sample_random_batch_seq(B)
+            b = {"obs": {"img_obs_1": st[:, None], "img_goal_1": gl[:, None]}, "action": acts}   # to_batch_dict
+            loss = step_p.step(lambda: policy.compute_loss(b))
+            loss_host.copy_(loss.reshape(1), non_blocking=True)
+        ms_rb, _ = timed(replay_step, steps)
+        replay_e2e = {"what": "same step, batch assembled on the device from the HBM-resident uint8 replay buffer "
+                              "(v2a_b200.replay, SURVEY.md 8f row N4): sample_random_batch_seq -> to_batch_dict -> "
+                              "compute_loss -> backward -> optimiser -> loss to host",
+                      "value": B * world / (ms_rb * 1e-3), "unit": "samples/s", "ms_per_step": ms_rb,
+                      "h2d_bytes_per_step": 3 * B * 8, "d2h_bytes_per_step": 4,
+                      "replay_bytes_in_hbm": rb.nbytes(), "episodes": len(rb)}
+        del rb
+    except Exception as exc:   # an optional leg must not cost the bench line
+        replay_e2e = {"error": f"{type(exc).__name__}: {exc}"}
     from v2a_b200 import obs_encoder as OE
     enc_flops, enc_launches = 0.0, 0
     for core in step_p.cores:
@@ -326,7 +354,8 @@ def run_policy(args, world, rank, local, barrier, max_over_ranks, peaks):
                                  "frac_of_bf16_peak": (flops + enc_flops) / (ms_p * 1e-3) / 1e12 / peak,
                                  "ms_per_step_with_torch_cudnn_encoders_fp32": ms_p_torch},
            "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
-                   "h2d_bytes_per_step": sum(v.numel() * 4 for v in host.values()), "d2h_bytes_per_step": 4}}
+                   "h2d_bytes_per_step": sum(v.numel() * 4 for v in host.values()), "d2h_bytes_per_step": 4},
+           "e2e_device_replay": replay_e2e}
     # inference entry: 8-step DDIM predict_action latency at B = 1, device-resident observation
     policy.eval()
     obs1 = {"img_obs_1": dev["img_obs_1"][:1], "img_goal_1": dev["img_goal_1"][:1]}

@@ -391,6 +391,20 @@ int v2a_enc_spatial_softmax_bwd(const float* att, const float* kp, const float* 
 int v2a_enc_linear_bwd(const float* x, const float* dy, const float* W, int B, int IN, int OUT, float* dx, float* dW,
                        float* db, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Replay-batch assembly on the device.
+ * Replaces the per-step Python loop + torch.stack + host->device copy of
+ * diffuser/datasets/env_img_replay_buffer.py:68-116 (`sample_random_batch_seq`),
+ * diffuser/datasets/img_utils.py:27-37 (`img_np_toTensor`: uint8 HWC -> float CHW / 255)
+ * and diffuser/libero/lb_online_trainer_v7.py:586 (`to_device_tp`).
+ * ------------------------------------------------------------------------ */
+/* frame_ptrs: DEVICE array of n device addresses, each a uint8 frame [H][W][3] (episodes own their
+ * allocations); out fp32 [n][3][H][W] = float(u8) / 255, IEEE division = the reference's tensors bit for bit */
+int v2a_replay_gather_images(const void* const* frame_ptrs, int n, int H, int W, float* out, void* stream);
+/* row_ptrs: DEVICE array of B device addresses, each the first of T consecutive fp32 action rows [A];
+ * out fp32 [B][T][A] */
+int v2a_replay_gather_actions(const void* const* row_ptrs, int B, int T, int A, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -124,3 +124,16 @@ def GoalGaussianDiffusion():
 
 def ConditionalUnet1D():
     return _imp("diffuser.diffusion_policy.model.conditional_unet1d").ConditionalUnet1D
+
+
+def replay_buffer_module():
+    """diffuser/datasets/env_img_replay_buffer.py (row N4); its simulator import is an inert stub."""
+    install_shims()
+    _stub("environment")
+    _stub("environment.libero")
+    _stub("environment.libero.lb_env_v3", LiberoEnvList_V3=type("LiberoEnvList_V3", (), {}))
+    return _imp("diffuser.datasets.env_img_replay_buffer")
+
+
+def img_utils_module():
+    return _imp("diffuser.datasets.img_utils")

@@ -65,3 +65,22 @@ def encoder_inputs(B, seed):
     """One VisualCore's input (already normalised to [-1, 1]) and the weights of the scalar its gradient is taken of."""
     g = torch.Generator().manual_seed(seed + 7)
     return torch.rand(B, 3, 128, 128, generator=g) * 2 - 1, torch.randn(B, 64, generator=g)
+
+
+# ---- replay buffer (row N4) ----
+REPLAY = dict(max_num_unitBufs=4, max_len_uB=24, min_len_uB=5, act_seq_len=4, H=16, W=20, A=7,
+              episode_lens=(9, 30, 12, 24, 7, 18), batch=32, np_seed=7, py_seed=11)
+
+
+def replay_episodes():
+    """Seeded synthetic episodes: (task, cam, env_idx, uint8 frames [T, H, W, 3], fp32 actions [T - 1, A]).
+    Six episodes into a deque of four (the two oldest are evicted), one longer than max_len_uB (truncated)."""
+    import numpy as np
+    rng = np.random.default_rng(2024)
+    c = REPLAY
+    eps = []
+    for i, T in enumerate(c["episode_lens"]):
+        frames = rng.integers(0, 256, size=(T, c["H"], c["W"], 3), dtype=np.uint8)
+        acts = rng.uniform(-1, 1, size=(T - 1, c["A"])).astype(np.float32)
+        eps.append((f"task_{i % 3}", f"cam_{i % 2}", 100 + i, frames, acts))
+    return eps

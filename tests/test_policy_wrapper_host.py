@@ -3,6 +3,7 @@ reference's (414 keys), scheduler / normaliser restatements, the observation enc
 reference modules (when /root/reference is mounted), install() rebinding."""
 import copy
 import importlib
+import sys
 import json
 import os
 
@@ -110,6 +111,9 @@ def test_encoder_and_install_against_live_reference(policy, monkeypatch):
         assert list(swapped.state_dict().keys()) == list(ref.state_dict().keys())
         gd = importlib.import_module("flowdiffusion.flowdiffusion.goal_diffusion")
         assert gd.GoalGaussianDiffusion.__module__.startswith("v2a_b200")
+        if "diffuser.datasets.env_img_replay_buffer" in sys.modules:        # row N4 (needs the simulator stub)
+            rb = sys.modules["diffuser.datasets.env_img_replay_buffer"]
+            assert rb.Global_EnvReplayBuffer_Img.__module__.startswith("v2a_b200")
     finally:
         install.uninstall()
     pol = importlib.import_module("diffuser.diffusion_policy.diffusion_unet_image_policy")

@@ -9,6 +9,9 @@
   diffuser.diffusion_policy.common.vision_nets.VisualCore            -> v2a_b200.diffusion_policy.VisualCore
   diffuser.diffusion_policy.model.multi_image_obs_encoder.MultiImageObsEncoder
                                                                      -> v2a_b200.diffusion_policy.MultiImageObsEncoder
+  diffuser.datasets.env_img_replay_buffer.Global_EnvReplayBuffer_Img
+  (+ the name imported into lb_online_trainer_v7)                    -> v2a_b200.replay.Global_EnvReplayBuffer_Img
+                                                                        (episodes in HBM, row N4; ``replay=False`` skips it)
 
 so ``lb_get_video_model_gcp_v2`` (diffuser/libero/lb_video_model_utils.py:13-66) and
 ``Init_Diffusion_Policy`` (diffuser/diffusion_policy/get_dp.py:27-89) build the CUDA-backed modules
@@ -34,10 +37,16 @@ _TARGETS: List[Tuple[str, str, str]] = [
     ("diffuser.diffusion_policy.common.vision_nets", "VisualCore", "diffusion_policy"),
     ("diffuser.diffusion_policy.model.multi_image_obs_encoder", "MultiImageObsEncoder", "diffusion_policy"),
 ]
+# replay buffer with HBM-resident episodes (row N4): the trainer touches only add_one_episode /
+# sample_random_batch_seq / len (lb_online_trainer_v7.py:774,797-837,927,975-977)
+_REPLAY_TARGETS: List[Tuple[str, str, str]] = [
+    ("diffuser.datasets.env_img_replay_buffer", "Global_EnvReplayBuffer_Img", "replay"),
+    ("diffuser.libero.lb_online_trainer_v7", "Global_EnvReplayBuffer_Img", "replay"),
+]
 _saved: Dict[Tuple[str, str], object] = {}
 
 
-def install(import_missing: bool = True) -> List[str]:
+def install(import_missing: bool = True, replay: bool = True) -> List[str]:
     """Rebind the hot-path classes; returns the ``module.attr`` names that were patched.
 
     Modules the reference has not imported yet are imported first when ``import_missing`` (so call this
@@ -45,7 +54,7 @@ def install(import_missing: bool = True) -> List[str]:
     cannot be imported (e.g. the Libero helpers without the simulator installed) are skipped.
     """
     patched = []
-    for mod_name, attr, ours in _TARGETS:
+    for mod_name, attr, ours in _TARGETS + (_REPLAY_TARGETS if replay else []):
         mod = sys.modules.get(mod_name)
         if mod is None and import_missing:
             try:
