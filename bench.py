@@ -135,6 +135,108 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_reference_gpu_eager(args):
+    """`--impl reference --reference-device cuda`: the GPU-eager baselines E32 / E16 of BASELINE.md §3 (SURVEY.md
+    §8d) -- the oracle port, i.e. the reference's own torch op sequence (F.conv2d / F.group_norm / softmax attention
+    ...), on cuda:0 through stock PyTorch / cuDNN.  None of this repo's kernels run here.  Not the driver's
+    reference arm (that stays the CPU path); run by hand, its line is committed under profiles/.
+
+    E32: fp32, TF32 off, no autocast (the numerics the 1e-3 parity bar is defined against).
+    E16: as shipped -- TF32 on + torch.autocast(float16) (scripts/train_libero_dp.py:10,25-26)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import encoder_oracle as EO
+    from oracle import policy_oracle as PO
+    from oracle import video_oracle as VO
+    from v2a_b200.diffusion_policy import build_libero_policy   # only for the SpatialSoftmax buffer constants
+    dry = bool(os.environ.get("V2A_EAGER_DRY_RUN"))    # CPU plumbing check of this function (build container)
+    dev = "cpu" if dry else "cuda"
+    torch.backends.cudnn.benchmark = True
+    B = 1 if dry else args.batch
+    sd = {k: v.to(dev) for k, v in synthetic_state_dict().items()}
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, 3 * FRAMES, H, W, generator=g).to(dev)
+    cond = torch.rand(B, 3, H, W, generator=g).to(dev)
+    te = torch.randn(B, TOKENS, 512, generator=g).to(dev)
+    t = torch.full((B,), 50, dtype=torch.long, device=dev)
+
+    def timed(fn, n, warm):
+        if dry:
+            t0 = time.perf_counter()
+            fn()
+            return (time.perf_counter() - t0) * 1e3
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def setting(name):
+        tf32 = name == "E16"
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        return torch.autocast(dev, dtype=torch.bfloat16 if dry else torch.float16, enabled=(name == "E16"))
+
+    def video_step():
+        with torch.no_grad():
+            VO.unet_libero_forward(sd, torch.cat([x, cond], 1), t, te)
+
+    k = max(1, min(args.steps, 3))
+    video = {}
+    for name in ("E32", "E16"):
+        with setting(name):
+            ms = timed(video_step, k, 2)
+        video[name] = {"ms_per_denoise_step": ms, "frames_per_s": B * FRAMES / (ms * 1e-3 * DENOISE_STEPS),
+                       "tflops_algorithmic": B * FLOP_PER_VIDEO_STEP / (ms * 1e-3) / 1e12}
+    del sd, x, cond, te
+    torch.cuda.empty_cache()
+
+    # policy: compute_loss forward + backward (two ResNet18-GN encoders + ConditionalUnet1D), torch autograd, no optimiser
+    with open(os.path.join(ROOT, "tests", "golden", "policy_loss_golden_meta.json")) as f:
+        layout = json.load(f)["layout"]
+    full = dict(build_libero_policy().state_dict())
+    full.update(PO.seeded_full_policy_state_dict(layout, 12))
+    psd = {}
+    for kname, v in full.items():
+        v = v.detach().to(dev)
+        psd[kname] = v.requires_grad_(True) if v.is_floating_point() and v.numel() > 0 and kname.rsplit(".", 1)[-1] in (
+            "weight", "bias") else v
+    usd = {kname[len("model."):]: v for kname, v in psd.items() if kname.startswith("model.")}
+    PB = 2 if dry else POLICY_B
+    obs = {"img_obs_1": torch.rand(PB, 3, 128, 128, generator=g).to(dev),
+           "img_goal_1": torch.rand(PB, 3, 128, 128, generator=g).to(dev)}
+    traj = (torch.rand(PB, POLICY_T, POLICY_DA, generator=g) * 2 - 1).to(dev)
+    noise = torch.randn(PB, POLICY_T, POLICY_DA, generator=g).to(dev)
+    tt = torch.randint(0, 100, (PB,), generator=g).to(dev)
+    acp = PO.ddpm_alphas_cumprod(100).to(dev)
+
+    def policy_step():
+        feat = EO.obs_encoder_forward(psd, "obs_encoder.", {kk: vv * 2 - 1 for kk, vv in obs.items()})
+        PO.epsilon_loss(usd, traj, feat.float(), noise, tt, acp).backward()
+        for v in psd.values():
+            v.grad = None
+
+    policy = {}
+    for name in ("E32", "E16"):
+        with setting(name):
+            ms = timed(policy_step, max(3, args.policy_steps // 4), 2)
+        policy[name] = {"ms_per_fwd_bwd": ms, "samples_per_s": PB / (ms * 1e-3)}
+    line = {"impl": "reference", "device": "cuda", "metric": METRIC, "unit": UNIT, "n_gpus": 1,
+            "value": video["E32"]["frames_per_s"], "steps": k, "warmup": 2, "higher_is_better": True, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(1, B),
+            "what": "GPU-eager baselines: oracle port (the reference's torch op sequence) on stock PyTorch/cuDNN, "
+                    "cudnn.benchmark on; video = UNet forward of one denoise step at B (sampler update excluded), "
+                    "extrapolated x100 steps; policy = compute_loss forward + backward at B=256 (no optimiser)",
+            "gpu_eager": {"video": video, "policy": policy},
+            "torch": torch.__version__, "gpu": "dry run on cpu" if dry else torch.cuda.get_device_name(0)}
+    print(json.dumps(line))
+
+
 def workload_config(n_gpus, batch):
     return {"workload": "Libero goal-video synthesis 128x128x8 (7 generated + 1 cond), 100 denoise steps "
                         "(DDPM ancestral = the shipped config), Unet_Libero 201M params",
@@ -505,8 +607,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-policy", action="store_true", help="skip the policy-samples/s object")
     ap.add_argument("--policy-steps", type=int, default=20)
+    ap.add_argument("--reference-device", default="cpu", choices=["cpu", "cuda"],
+                    help="with --impl reference: cuda = the GPU-eager baselines E32/E16 (BASELINE.md §3), run by hand")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl == "reference" and args.reference_device == "cuda":
+        run_reference_gpu_eager(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
