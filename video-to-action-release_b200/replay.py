@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import random
 from collections import deque
-from typing import List, NamedTuple, Optional, Sequence
+from typing import NamedTuple, Optional
 
 import numpy as np
 import torch
@@ -153,22 +153,23 @@ class Global_EnvReplayBuffer_Img:
         cur_len = len(self.buffers)
         buf_idxs = np.random.randint(0, cur_len, size=batch_size)
         starts = np.empty(batch_size, dtype=np.int64)
-        for i, bf_idx in enumerate(buf_idxs):
-            starts[i] = self.buffers[bf_idx].sample_start(self.sample_act_seq_len)
+        bufs = list(self.buffers)                 # deque indexing walks from an end: O(n) per access
+        for i, bf_idx in enumerate(buf_idxs.tolist()):
+            starts[i] = bufs[bf_idx].sample_start(self.sample_act_seq_len)
         return BatchPlan(buf_idxs, starts, starts + self.sample_act_seq_len)
 
     def address_table(self, plan: BatchPlan) -> np.ndarray:
         """int64 [3B]: device addresses of the start frames, the goal frames and the first action rows."""
-        B = len(plan.buf_idxs)
-        table = np.empty(3 * B, dtype=np.int64)
-        for i in range(B):
-            buf = self.buffers[plan.buf_idxs[i]]
-            fbytes = buf.frames.stride(0)                 # uint8: elements = bytes
-            base = buf.frames.data_ptr()
-            table[i] = base + int(plan.start_idxs[i]) * fbytes
-            table[B + i] = base + int(plan.goal_idxs[i]) * fbytes
-            table[2 * B + i] = buf.acts.data_ptr() + int(plan.start_idxs[i]) * buf.acts.stride(0) * 4
-        return table
+        n = len(self.buffers)
+        fbase = np.fromiter((b.frames.data_ptr() for b in self.buffers), dtype=np.int64, count=n)
+        fstep = np.fromiter((b.frames.stride(0) for b in self.buffers), dtype=np.int64, count=n)   # uint8: bytes
+        abase = np.fromiter((b.acts.data_ptr() for b in self.buffers), dtype=np.int64, count=n)
+        astep = np.fromiter((b.acts.stride(0) * 4 for b in self.buffers), dtype=np.int64, count=n)
+        idx = np.asarray(plan.buf_idxs, dtype=np.int64)
+        start = np.asarray(plan.start_idxs, dtype=np.int64)
+        goal = np.asarray(plan.goal_idxs, dtype=np.int64)
+        return np.concatenate([fbase[idx] + start * fstep[idx], fbase[idx] + goal * fstep[idx],
+                               abase[idx] + start * astep[idx]])
 
     def gather(self, plan: BatchPlan, out_imgs: Optional[torch.Tensor] = None,
                out_acts: Optional[torch.Tensor] = None):
@@ -181,7 +182,7 @@ class Global_EnvReplayBuffer_Img:
         first = self.buffers[plan.buf_idxs[0]] if B else self.buffers[0]
         H, W = int(first.frames.shape[1]), int(first.frames.shape[2])
         A = int(first.acts.shape[1])
-        for i in set(int(b) for b in plan.buf_idxs):
+        for i in np.unique(plan.buf_idxs):
             f = self.buffers[i].frames
             assert tuple(f.shape[1:]) == (H, W, 3) and self.buffers[i].acts.shape[1] == A
         if out_imgs is None:
