@@ -405,6 +405,31 @@ int v2a_replay_gather_images(const void* const* frame_ptrs, int n, int H, int W,
  * out fp32 [B][T][A] */
 int v2a_replay_gather_actions(const void* const* row_ptrs, int B, int T, int A, float* out, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Task-token conditioning (row V13): task_attnpool = PerceiverResampler -> Linear -> mean over latents
+ *   guided_diffusion/unet.py:491-494,671; guided_diffusion/imagen.py:197-211,254-372,1009-1017
+ * Step-invariant (once per sample() call): fp32 CUDA-core kernels; the dense layers between them are v2a_linear.
+ * Token rows are addressed as base + b * batch_stride + i * ld (i < n_tok), so a kernel can write straight into
+ * a slice of a concatenated [B][tokens][D] buffer.
+ * ------------------------------------------------------------------------ */
+/* out = (act(x) (+ pos[i]) - mean) * rsqrt(var + eps) * gamma (+ beta); biased variance over D; act 0 none, 3 GELU(erf);
+ * beta may be NULL (imagen's gain-only LayerNorm), pos [n_tok][D] may be NULL */
+int v2a_pr_layernorm(const float* x, int64_t x_batch, int ldx, const float* pos, int B, int n_tok, int D, int act,
+                     const float* gamma, const float* beta, float eps, float* out, int64_t out_batch, int ld_out,
+                     void* stream);
+/* per (row, head): out = x / max(||x||, 1e-12) * scale[dh]   (F.normalize * q_scale / k_scale, imagen.py:299-303) */
+int v2a_pr_l2norm_scale(const float* x, int ldx, int rows, int heads, int dh, const float* scale, float* out,
+                        int ld_out, void* stream);
+/* out[b][i][h*dh..] = softmax_j(scale * q[b][i][h] . k[b][j][h]) @ v[b][j][h]; rows of q [B*nq], k / v [B*nk] */
+int v2a_pr_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int B, int heads,
+                     int dh, int nq, int nk, float scale, float* out, int ld_out, void* stream);
+/* out[b][c] = mean_i x[b][i][c] */
+int v2a_pr_token_mean(const float* x, int64_t x_batch, int ldx, int B, int n, int D, float* out, int ld_out,
+                      void* stream);
+/* out[b][i][c] = src[i][c] (learned latents broadcast over the batch) */
+int v2a_pr_broadcast_rows(const float* src, int n, int D, int B, float* out, int64_t out_batch, int ld_out,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

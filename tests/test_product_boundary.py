@@ -25,7 +25,8 @@ def test_product_never_touches_the_oracle_or_the_reference_checkout():
 def test_bench_uses_the_oracle_only_in_the_cpu_baseline_and_reference_arm():
     with open(os.path.join(ROOT, "bench.py")) as f:
         src = f.read()
-    allowed = {"synthetic_state_dict", "cpu_reference_step", "policy_cpu_reference_step", "synthetic_policy_state_dict"}
+    allowed = {"synthetic_state_dict", "cpu_reference_step", "policy_cpu_reference_step", "synthetic_policy_state_dict",
+               "run_reference_gpu_eager"}      # the last one = `--impl reference --reference-device cuda` (reference arm)
     for m in re.finditer(r"^\s+from oracle\b.*$", src, re.M):
         head = src[:m.start()]
         fn = re.findall(r"^def (\w+)\(", head, re.M)[-1]

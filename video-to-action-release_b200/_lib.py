@@ -204,6 +204,11 @@ SIGNATURES = {
     "v2a_add_strided": (_i, [_vp, _i, _vp, _i, _i64, _i, _i, _vp]),
     "v2a_grad_sumsq": (_i, [_vp, _i64, _vp, _vp]),
     "v2a_adamw_ema_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _f, _i, _f, _vp]),
+    "v2a_pr_layernorm": (_i, [_vp, _i64, _i, _vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _i64, _i, _vp]),
+    "v2a_pr_l2norm_scale": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "v2a_pr_attention": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _vp]),
+    "v2a_pr_token_mean": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _i, _vp]),
+    "v2a_pr_broadcast_rows": (_i, [_vp, _i, _i, _i, _vp, _i64, _i, _vp]),
     "v2a_replay_gather_images": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "v2a_replay_gather_actions": (_i, [_vp, _i, _i, _i, _vp, _vp]),
 }

@@ -11,7 +11,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("V2A_LIB") or os.path.join(PKG_DIR, "libv2a_b200.so")   # V2A_LIB: developer experiments
 STAMP = os.path.join(PKG_DIR, ".libv2a_b200.stamp")
 
-SOURCES = ["igemm.cu", "wgrad.cu", "elementwise.cu", "attention.cu", "policy.cu", "encoder.cu", "replay.cu"]
+SOURCES = ["igemm.cu", "wgrad.cu", "elementwise.cu", "attention.cu", "policy.cu", "encoder.cu", "replay.cu", "perceiver.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

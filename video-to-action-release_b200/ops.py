@@ -411,5 +411,73 @@ def unnormalize_clamp(x, out) -> None:
                "unnormalize_clamp")
 
 
+# ---- task-token conditioning (row V13): PerceiverResampler pieces, fp32 CUDA cores ----
+ACT_GELU = 3
+
+
+def _rows3(t: torch.Tensor):
+    """[B, n, D] view (last dim contiguous) -> (ptr, batch stride, row stride, B, n, D)."""
+    assert t.dim() == 3 and t.stride(2) == 1 and t.dtype == torch.float32
+    return t.data_ptr(), t.stride(0), t.stride(1), t.shape[0], t.shape[1], t.shape[2]
+
+
+def pr_layernorm(x, gamma, beta, out, *, pos=None, act=ACT_NONE, eps=1e-5) -> None:
+    """out[b, i] = LayerNorm(act(x[b, i]) (+ pos[i])) * gamma (+ beta) over the last dim; x / out [B, n, D] views."""
+    _require_cuda(x, gamma, out)
+    xp, xb, xl, B, n, D = _rows3(x)
+    op, ob, ol, B2, n2, D2 = _rows3(out)
+    assert (B, n, D) == (B2, n2, D2) and gamma.numel() == D and gamma.is_contiguous()
+    if pos is not None:
+        assert pos.is_contiguous() and pos.shape[-1] == D and pos.shape[0] >= n
+    _lib.check(_lib.load().v2a_pr_layernorm(xp, xb, xl, _ptr(pos), B, n, D, act, gamma.data_ptr(), _ptr(beta),
+                                            float(eps), op, ob, ol, _stream()), "pr_layernorm")
+
+
+def pr_l2norm_scale(x, heads: int, scale, out) -> None:
+    """x / out [rows, heads * dh] (row-strided views): per (row, head) x / max(||x||, 1e-12) * scale[dh]."""
+    _require_cuda(x, scale, out)
+    rows, width = x.shape
+    dh = width // heads
+    assert x.stride(1) == 1 and out.stride(1) == 1 and out.shape == x.shape and scale.numel() == dh
+    _lib.check(_lib.load().v2a_pr_l2norm_scale(x.data_ptr(), x.stride(0), rows, heads, dh, scale.data_ptr(),
+                                               out.data_ptr(), out.stride(0), _stream()), "pr_l2norm_scale")
+
+
+def pr_attention(q, k, v, B: int, heads: int, scale: float, out) -> None:
+    """q [B*nq, heads*dh], k / v [B*nk, heads*dh] (row-strided views) -> out [B*nq, heads*dh]."""
+    _require_cuda(q, k, v, out)
+    nq, nk = q.shape[0] // B, k.shape[0] // B
+    dh = q.shape[1] // heads
+    assert all(t.stride(1) == 1 for t in (q, k, v, out)) and k.shape == v.shape and out.shape == q.shape
+    _lib.check(_lib.load().v2a_pr_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+                                            v.stride(0), B, heads, dh, nq, nk, float(scale), out.data_ptr(),
+                                            out.stride(0), _stream()), "pr_attention")
+
+
+def pr_token_mean(x, out) -> None:
+    """out[b] = mean_i x[b, i]; x [B, n, D] view, out [B, D]."""
+    _require_cuda(x, out)
+    xp, xb, xl, B, n, D = _rows3(x)
+    assert out.shape == (B, D) and out.stride(1) == 1
+    _lib.check(_lib.load().v2a_pr_token_mean(xp, xb, xl, B, n, D, out.data_ptr(), out.stride(0), _stream()),
+               "pr_token_mean")
+
+
+def pr_broadcast_rows(src, out) -> None:
+    """out[b, i] = src[i]; src [n, D] contiguous, out [B, n, D] view."""
+    _require_cuda(src, out)
+    op, ob, ol, B, n, D = _rows3(out)
+    assert src.is_contiguous() and tuple(src.shape) == (n, D)
+    _lib.check(_lib.load().v2a_pr_broadcast_rows(src.data_ptr(), n, D, B, op, ob, ol, _stream()), "pr_broadcast_rows")
+
+
+def add_rows_(dst, src) -> None:
+    """dst[r, c] += src[r, c] for row-strided fp32 [rows, C] views."""
+    _require_cuda(dst, src)
+    assert dst.shape == src.shape and dst.stride(1) == 1 and src.stride(1) == 1
+    _lib.check(_lib.load().v2a_add_strided(dst.data_ptr(), dst.stride(0), src.data_ptr(), src.stride(0),
+                                           dst.shape[0], dst.shape[1], 1, _stream()), "add_strided")
+
+
 def launch_count() -> int:
     return int(_lib.load().v2a_launch_count())

@@ -626,7 +626,10 @@ class _UNetEngine:
         if key == self._task_key:
             return
         with torch.no_grad(), torch.autocast("cuda", enabled=False):
-            self.task_emb.copy_(_task_pool(model.task_attnpool, y.float()))
+            if os.environ.get("V2A_ATTNPOOL", "torch") == "cuda":
+                _task_pool_cuda(model.task_attnpool, y.float().contiguous(), self.task_emb)
+            else:
+                self.task_emb.copy_(_task_pool(model.task_attnpool, y.float()))
         self._task_key = key
 
     # ---- execution ---------------------------------------------------------
@@ -653,6 +656,74 @@ class _UNetEngine:
 
     def run_static(self):
         self._launch_all()
+
+
+def _task_pool_cuda(seq: nn.Sequential, y: torch.Tensor, out: torch.Tensor) -> None:
+    """`_task_pool` on the v2a kernels (`csrc/perceiver.cu` + `v2a_linear`): out [B, D] = task_attnpool(y).mean(1).
+
+    Same operation order as the reference (gd/imagen.py:254-372) except the final `Linear(D, D)` and the mean over
+    the latents, which commute (the layer is affine): the mean is taken first, on 68x fewer rows.
+    torch only allocates the scratch buffers here.
+    """
+    pr: PerceiverResampler = seq[0]
+    B, n, D = y.shape
+    dev = y.device
+    f32 = dict(device=dev, dtype=torch.float32)
+    n_pool = 0
+    n_lat = pr.latents.shape[0]
+    mp = pr.to_latents_from_mean_pooled_seq
+    if mp is not None:
+        n_pool = mp[1].weight.shape[0] // D
+    NL = n_pool + n_lat
+    lat = torch.empty(B, NL, D, **f32)
+    ops.pr_broadcast_rows(pr.latents.detach(), lat[:, n_pool:])
+    if mp is not None:
+        ymean = torch.empty(B, D, **f32)
+        ops.pr_token_mean(y, ymean)
+        yn = torch.empty(B, 1, D, **f32)
+        ops.pr_layernorm(ymean.unsqueeze(1), mp[0].g.detach(), None, yn)
+        # [B, n_pool * D] written as the first n_pool latent rows of every sample (row stride NL * D)
+        ops.linear(yn.reshape(B, D), mp[1].weight.detach(), mp[1].bias.detach(), lat.reshape(B, NL * D))
+    pos = pr.pos_emb.weight.detach()
+    for attn, ff in pr.layers:
+        h = attn.heads
+        inner = attn.to_q.weight.shape[0]
+        kvin = torch.empty(B, n + NL, D, **f32)                 # cat([norm(x + pos), norm_latents(lat)], dim=1)
+        ops.pr_layernorm(y, attn.norm.weight.detach(), attn.norm.bias.detach(), kvin[:, :n], pos=pos)
+        ops.pr_layernorm(lat, attn.norm_latents.weight.detach(), attn.norm_latents.bias.detach(), kvin[:, n:])
+        kv = torch.empty(B * (n + NL), 2 * inner, **f32)
+        ops.linear(kvin.reshape(B * (n + NL), D), attn.to_kv.weight.detach(), None, kv)
+        ln_rows = torch.empty(B * NL, D, **f32)                 # the latent rows of kvin, contiguous for to_q
+        ops.pr_layernorm(lat, attn.norm_latents.weight.detach(), attn.norm_latents.bias.detach(),
+                         ln_rows.reshape(B, NL, D))
+        q = torch.empty(B * NL, inner, **f32)
+        ops.linear(ln_rows, attn.to_q.weight.detach(), None, q)
+        qn = torch.empty_like(q)
+        ops.pr_l2norm_scale(q, h, attn.q_scale.detach(), qn)
+        kn = torch.empty(B * (n + NL), inner, **f32)
+        ops.pr_l2norm_scale(kv[:, :inner], h, attn.k_scale.detach(), kn)
+        o = torch.empty(B * NL, inner, **f32)
+        ops.pr_attention(qn, kn, kv[:, inner:], B, h, float(attn.scale), o)
+        po = torch.empty(B * NL, D, **f32)
+        ops.linear(o, attn.to_out[0].weight.detach(), None, po)
+        lat2 = torch.empty(B, NL, D, **f32)
+        ops.pr_layernorm(po.reshape(B, NL, D), attn.to_out[1].weight.detach(), attn.to_out[1].bias.detach(), lat2)
+        ops.add_rows_(lat2.reshape(B * NL, D), lat.reshape(B * NL, D))        # lat = to_out(...) + lat
+        lat = lat2
+        hidden = ff[1].weight.shape[0]
+        g1 = torch.empty(B, NL, D, **f32)
+        ops.pr_layernorm(lat, ff[0].g.detach(), None, g1)
+        hdn = torch.empty(B * NL, hidden, **f32)
+        ops.linear(g1.reshape(B * NL, D), ff[1].weight.detach(), None, hdn)
+        g2 = torch.empty(B, NL, hidden, **f32)
+        ops.pr_layernorm(hdn.reshape(B, NL, hidden), ff[3].g.detach(), None, g2, act=ops.ACT_GELU)
+        lat3 = torch.empty(B * NL, D, **f32)
+        ops.linear(g2.reshape(B * NL, hidden), ff[4].weight.detach(), None, lat3, add=lat.reshape(B * NL, D))
+        lat = lat3.reshape(B, NL, D)
+    lmean = torch.empty(B, D, **f32)
+    ops.pr_token_mean(lat, lmean)
+    assert out.shape == (B, D) and out.stride(1) == 1
+    ops.linear(lmean, seq[1].weight.detach(), seq[1].bias.detach(), out)
 
 
 def _task_pool(seq: nn.Sequential, y: torch.Tensor) -> torch.Tensor:
