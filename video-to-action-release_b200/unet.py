@@ -626,7 +626,7 @@ class _UNetEngine:
         if key == self._task_key:
             return
         with torch.no_grad(), torch.autocast("cuda", enabled=False):
-            if os.environ.get("V2A_ATTNPOOL", "torch") == "cuda":
+            if os.environ.get("V2A_ATTNPOOL", "cuda") != "torch":   # torch = the stock-op version, host comparisons
                 _task_pool_cuda(model.task_attnpool, y.float().contiguous(), self.task_emb)
             else:
                 self.task_emb.copy_(_task_pool(model.task_attnpool, y.float()))
