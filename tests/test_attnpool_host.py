@@ -57,7 +57,7 @@ def test_task_pool_cuda_launch_sequence_matches_oracle(monkeypatch, B, n):
     torch.manual_seed(0)
     seq = torch.nn.Sequential(U.PerceiverResampler(dim=64, depth=2, dim_head=16, heads=4, num_latents=8,
                                                    num_latents_mean_pooled=2, max_seq_len=32),
-                              torch.nn.Linear(64, 64))
+                              torch.nn.Linear(64, 40))     # time_embed_dim != token width (tiny UNet configs)
     with torch.no_grad():
         for p in seq.parameters():                       # gains 1 / biases 0 / scales 1 would hide operand mix-ups
             p.add_(0.3 * torch.randn_like(p))
@@ -67,7 +67,7 @@ def test_task_pool_cuda_launch_sequence_matches_oracle(monkeypatch, B, n):
     for name in ("pr_broadcast_rows", "pr_token_mean", "pr_layernorm", "linear", "pr_l2norm_scale", "pr_attention",
                  "add_rows_"):
         monkeypatch.setattr(U.ops, name, getattr(_TorchOps, name))
-    got = torch.empty(B, 64)
+    got = torch.empty(B, 40)
     with torch.no_grad():
         U._task_pool_cuda(seq, y, got)
         ref_torch = U._task_pool(seq, y)

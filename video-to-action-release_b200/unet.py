@@ -722,7 +722,7 @@ def _task_pool_cuda(seq: nn.Sequential, y: torch.Tensor, out: torch.Tensor) -> N
         lat = lat3.reshape(B, NL, D)
     lmean = torch.empty(B, D, **f32)
     ops.pr_token_mean(lat, lmean)
-    assert out.shape == (B, D) and out.stride(1) == 1
+    assert out.shape == (B, seq[1].weight.shape[0]) and out.stride(1) == 1      # Linear(D, time_embed_dim)
     ops.linear(lmean, seq[1].weight.detach(), seq[1].bias.detach(), out)
 
 
