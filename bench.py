@@ -471,7 +471,7 @@ def run_policy(args, world, rank, local, barrier, max_over_ranks, peaks):
                                      "forwards + DDIM updates, B = 1 (latency path between simulator steps)",
                              "ms_per_call": ms_pa, "ddim_steps": 8}
     policy.train()
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # reported at N = 1 only
         threads = os.cpu_count() or 1
         sec = policy_cpu_reference_step(threads, 64)
         out["cpu_baseline"] = {"value": 64 / sec, "unit": "samples/s", "cores": threads, "kind": "port",
@@ -568,7 +568,7 @@ def run_ours(args):
         roof = measure_kernel_roofline(diff, B, peaks)
         roof["peak_source"] = peak_src
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU baseline is reported at N = 1 only
             threads = os.cpu_count() or 1
             cpu_reference_step(sd, threads)
             ts = cpu_reference_step(sd, threads)
