@@ -13,8 +13,9 @@ fingerprints; tests/test_policy_oracle.py checks this file against them and, whe
 Third-party arithmetic: `diffusers` DDPMScheduler (unpinned in the reference's
 requirements.txt, not installed here) — `ddpm_alphas_cumprod` / `add_noise` restate its
 published squaredcos_cap_v2 schedule (twin in-repo formula:
-flowdiffusion/.../guided_diffusion/gaussian_diffusion.py:45-62); parity unpinned by
-reference tests for that boundary.
+flowdiffusion/.../guided_diffusion/gaussian_diffusion.py:45-62); unpinned against diffusers
+itself, pinned against that vendored twin run unmodified (tests/golden/make_scheduler_golden.py,
+tests/test_scheduler_pin.py: betas, alphas_cumprod, add_noise = q_sample).
 
 dp/ = diffuser/diffusion_policy/model/ in the reference checkout.
 """
