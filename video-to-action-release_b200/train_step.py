@@ -72,6 +72,86 @@ class _Segment:
             off += n
 
 
+# ---------------------------------------------------------------------------------------------------
+# checkpoint / resume: the optimiser and EMA state in the formats the reference trainer saves
+# (lb_online_trainer_v7.py:367-407: data['opt'] = AdamW.state_dict(), data['ema'] = EMA.state_dict())
+# ---------------------------------------------------------------------------------------------------
+def export_optimizer_state(module: nn.Module, segments: Iterable["_Segment"], steps_done: int, *, lr: float, betas,
+                           eps: float, weight_decay: float) -> dict:
+    """``torch.optim.AdamW(module.parameters()).state_dict()`` equivalent of the slab state: per-parameter
+    ``exp_avg`` / ``exp_avg_sq`` / ``step`` indexed by position in ``module.parameters()``."""
+    index = {id(p): i for i, p in enumerate(module.parameters())}
+    state = {}
+    if steps_done > 0:                                   # torch creates the state lazily at the first step
+        for seg in segments:
+            off = 0
+            for p in seg.params:
+                n = p.numel()
+                if n:
+                    state[index[id(p)]] = {"step": torch.tensor(float(steps_done)),
+                                           "exp_avg": seg.m[off:off + n].view(p.shape).clone(),
+                                           "exp_avg_sq": seg.v[off:off + n].view(p.shape).clone()}
+                off += n
+    group = {"lr": lr, "betas": tuple(betas), "eps": eps, "weight_decay": weight_decay, "amsgrad": False,
+             "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+             "params": list(range(len(index)))}
+    return {"state": dict(sorted(state.items())), "param_groups": [group]}
+
+
+def import_optimizer_state(module: nn.Module, segments: Iterable["_Segment"], opt_state: dict) -> int:
+    """Inverse of ``export_optimizer_state`` (accepts a real ``AdamW.state_dict()``); returns the step count."""
+    index = {id(p): i for i, p in enumerate(module.parameters())}
+    state = opt_state["state"]
+    steps = 0
+    with torch.no_grad():
+        for seg in segments:
+            off = 0
+            for p in seg.params:
+                n = p.numel()
+                st = state.get(index[id(p)])
+                if n and st is not None:
+                    seg.m[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                    seg.v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    steps = max(steps, int(float(st["step"])))
+                elif n:
+                    seg.m[off:off + n].zero_()
+                    seg.v[off:off + n].zero_()
+                off += n
+    return steps
+
+
+def export_ema_state(module: nn.Module, segments: Iterable["_Segment"], steps_done: int) -> dict:
+    """``ema_pytorch.EMA(include_online_model=False).state_dict()`` layout: ``ema_model.<name>`` for every
+    parameter (from the EMA slabs) and buffer (from the module), plus ``initted`` and ``step``."""
+    names = {id(p): n for n, p in module.named_parameters()}
+    out = {}
+    for seg in segments:
+        if seg.ema is None:
+            raise RuntimeError("no EMA state: PolicyTrainStep was built with ema=False")
+        for p, e in seg.ema_views():
+            out["ema_model." + names[id(p)]] = e.clone()
+    for n, p in module.named_parameters():                      # zero-size placeholders etc.
+        out.setdefault("ema_model." + n, p.detach().clone())
+    for n, b in module.named_buffers():
+        out["ema_model." + n] = b.detach().clone()
+    out["initted"] = torch.tensor(steps_done > 0)
+    out["step"] = torch.tensor(steps_done)
+    return out
+
+
+def import_ema_state(module: nn.Module, segments: Iterable["_Segment"], ema_state: dict) -> None:
+    names = {id(p): n for n, p in module.named_parameters()}
+    with torch.no_grad():
+        for seg in segments:
+            if seg.ema is None:
+                continue
+            for p, e in seg.ema_views():
+                key = "ema_model." + names[id(p)]
+                if key not in ema_state:
+                    raise KeyError(f"EMA checkpoint lacks {key}")
+                e.copy_(ema_state[key])
+
+
 class PolicyTrainStep:
     """``step(loss_fn)`` = forward + backward + (all-reduce) + clip + AdamW + EMA on CUDA."""
 
@@ -172,6 +252,33 @@ class PolicyTrainStep:
         loss.backward()
         self.optimizer_tail()
         return loss.detach()
+
+    # ---- checkpoint / resume (lb_online_trainer_v7.py:367-407) ----------------------------------
+    def _all_segments(self):
+        return [seg for seg in (self.seg_unet, *self.seg_cores, self.seg_other) if seg is not None]
+
+    def state_dict(self) -> dict:
+        """``{'opt': AdamW-format, 'ema': ema_pytorch-format, 'steps_done': int}`` — what the reference trainer
+        stores under ``data['opt']`` / ``data['ema']``; loadable into the stock ``AdamW`` / ``EMA`` objects."""
+        segs = self._all_segments()
+        out = {"opt": export_optimizer_state(self.module, segs, self.steps_done, lr=self.lr, betas=self.betas,
+                                             eps=self.eps, weight_decay=self.wd),
+               "steps_done": self.steps_done}
+        if self.seg_unet.ema is not None:
+            out["ema"] = export_ema_state(self.module, segs, self.steps_done)
+        return out
+
+    def load_state_dict(self, state: dict) -> None:
+        """Resume from ``state_dict()`` output or from the reference trainer's ``data['opt']`` / ``data['ema']``
+        (pass ``{'opt': ..., 'ema': ...}``).  The module's own weights are loaded separately, as in the trainer."""
+        segs = self._all_segments()
+        steps = import_optimizer_state(self.module, segs, state["opt"])
+        self.steps_done = int(state.get("steps_done", steps))
+        if "ema" in state and self.seg_unet.ema is not None:
+            import_ema_state(self.module, segs, state["ema"])
+        policy_unet1d.invalidate_weights(self.unet)
+        for core in self.cores:
+            obs_encoder.invalidate_weights(core)
 
     def grad_norm(self) -> torch.Tensor:
         """Global gradient L2 norm of the last step (before clipping), as a device tensor."""
