@@ -78,3 +78,30 @@ def test_cabi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.v2a_version() >= 100
+
+
+def test_task_embed_cache_is_exact_per_batch_and_returns_the_same_tensor():
+    """Row N5: CLIP embeddings of the fixed task strings are computed once per distinct batch of strings."""
+    import torch
+    from v2a_b200.text_cache import TaskEmbedCache, install_text_cache
+
+    calls = []
+
+    class FakeVideoModel:
+        def encode_batch_text(self, batch_text):        # pads to the longest string, like the CLIP tokenizer
+            calls.append(tuple(batch_text))
+            L = max(len(s.split()) for s in batch_text) + 2
+            g = torch.Generator().manual_seed(sum(map(len, batch_text)) + 131 * L)
+            return torch.randn(len(batch_text), L, 8, generator=g, requires_grad=True) * 1.0
+
+    vm = FakeVideoModel()
+    cache = install_text_cache(vm, max_entries=2)
+    a1 = vm.encode_batch_text(["open the drawer"])
+    a2 = vm.encode_batch_text(["open the drawer"])
+    assert a1 is a2 and not a1.requires_grad and calls == [("open the drawer",)]
+    b = vm.encode_batch_text(["open the drawer", "put the bowl on the plate"])     # padded differently: own entry
+    assert b.shape[1] == 8 and a1.shape[1] == 5 and len(calls) == 2
+    vm.encode_batch_text(["close it"])                                              # evicts the oldest batch
+    vm.encode_batch_text(["open the drawer"])
+    assert len(calls) == 4 and cache.hits == 1 and cache.misses == 4
+    assert isinstance(cache, TaskEmbedCache)
