@@ -76,6 +76,29 @@ def test_task_pool_cuda_launch_sequence_matches_oracle(monkeypatch, B, n):
     assert rel(ref_torch, want) < 5e-6
 
 
+def test_task_pool_cuda_chunks_large_batches(monkeypatch):
+    """B x (n + latents) token rows above `_POOL_MAX_ROWS` are processed in sample chunks (samples are independent)."""
+    from v2a_b200 import unet as U
+    torch.manual_seed(2)
+    seq = torch.nn.Sequential(U.PerceiverResampler(dim=32, depth=1, dim_head=8, heads=2, num_latents=6,
+                                                   num_latents_mean_pooled=2, max_seq_len=16),
+                              torch.nn.Linear(32, 24))
+    y = torch.randn(7, 4, 32)
+    rows = []
+    for name in ("pr_broadcast_rows", "pr_token_mean", "pr_layernorm", "linear", "pr_l2norm_scale", "pr_attention",
+                 "add_rows_"):
+        monkeypatch.setattr(U.ops, name, getattr(_TorchOps, name))
+    lin = U.ops.linear
+    monkeypatch.setattr(U.ops, "linear", lambda x, *a, **k: (rows.append(x.shape[0]), lin(x, *a, **k))[1])
+    monkeypatch.setattr(U, "_POOL_MAX_ROWS", 40)            # 12 token rows per sample -> 3 samples per call
+    got = torch.empty(7, 24)
+    with torch.no_grad():
+        U._task_pool_cuda(seq, y, got)
+        want = U._task_pool(seq, y)
+    assert ((got - want).norm() / want.norm()).item() < 5e-6
+    assert max(rows) <= 40 and len(rows) == 3 * 7            # 3 chunks (3 + 3 + 1 samples) x 7 linears each
+
+
 def test_task_pool_cuda_without_mean_pooled_latents(monkeypatch):
     from v2a_b200 import unet as U
     torch.manual_seed(1)

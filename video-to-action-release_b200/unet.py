@@ -658,6 +658,9 @@ class _UNetEngine:
         self._launch_all()
 
 
+_POOL_MAX_ROWS = 512
+
+
 def _task_pool_cuda(seq: nn.Sequential, y: torch.Tensor, out: torch.Tensor) -> None:
     """`_task_pool` on the v2a kernels (`csrc/perceiver.cu` + `v2a_linear`): out [B, D] = task_attnpool(y).mean(1).
 
@@ -675,6 +678,13 @@ def _task_pool_cuda(seq: nn.Sequential, y: torch.Tensor, out: torch.Tensor) -> N
     if mp is not None:
         n_pool = mp[1].weight.shape[0] // D
     NL = n_pool + n_lat
+    # samples are independent: keep every dense layer within `_POOL_MAX_ROWS` token rows per launch (the small-batch
+    # `v2a_linear` covers 8 rows x 64 row-blocks per pass), i.e. 6 samples of 12 + 68 tokens at a time
+    per_call = max(1, _POOL_MAX_ROWS // (n + NL))
+    if B > per_call:
+        for b0 in range(0, B, per_call):
+            _task_pool_cuda(seq, y[b0:b0 + per_call], out[b0:b0 + per_call])
+        return
     lat = torch.empty(B, NL, D, **f32)
     ops.pr_broadcast_rows(pr.latents.detach(), lat[:, n_pool:])
     if mp is not None:
