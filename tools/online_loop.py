@@ -53,6 +53,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--denoise-steps", type=int, default=100)
     ap.add_argument("--exec-steps", type=int, default=4, help="actions executed per sub-goal frame")
+    ap.add_argument("--batch-videos", action="store_true",
+                    help="sample the sub-goal videos of all of a rank's tasks in one call instead of one by one")
     args = ap.parse_args()
 
     import torch.distributed as dist
@@ -111,23 +113,33 @@ def main():
         return float(t.item())
 
     def explore(only_first=False):
-        """video_guided_explore for this rank's tasks: returns (#videos, #predict_action calls, #env frames)."""
+        """video_guided_explore for this rank's tasks: returns (#videos, #predict_action calls, #env frames).
+        The reference generates the sub-goal videos one task at a time (bs = 1, trainer :880-891); --batch-videos
+        samples all of a rank's tasks in ONE call (they are independent), which fills the GPU far better."""
         n_vid = n_act = n_frames = 0
         policy.eval()
-        for i, tk in enumerate(tasks):
-            if i % world != rank or (only_first and n_vid):
-                continue
-            env = StubEnv(1000 * (i + 1))
-            frame = env.render()
-            x_cond = (torch.from_numpy(frame).permute(2, 0, 1).float() / 255.0)[None].cuda()
-            video = diff.sample(x_cond, task_embed[tk], batch_size=1)              # [1, 21, H, W] in [0, 1]
-            goals = video.reshape(FRAMES, 3, H, W)
+        mine = [(i, tk) for i, tk in enumerate(tasks) if i % world == rank]
+        if only_first:
+            mine = mine[:1]
+        envs = {i: StubEnv(1000 * (i + 1)) for i, _ in mine}
+        first = {i: envs[i].render() for i, _ in mine}
+        to_cond = lambda fr: torch.from_numpy(fr).permute(2, 0, 1).float() / 255.0
+        videos = {}
+        if args.batch_videos and len(mine) > 1:
+            x_cond = torch.stack([to_cond(first[i]) for i, _ in mine]).cuda()
+            te = torch.cat([task_embed[tk] for _, tk in mine], dim=0)
+            out = diff.sample(x_cond, te, batch_size=len(mine))                    # [n, 21, H, W] in [0, 1]
+            videos = {i: out[j] for j, (i, _) in enumerate(mine)}
+        for i, tk in mine:
+            env, frame = envs[i], first[i]
+            if i not in videos:
+                videos[i] = diff.sample(to_cond(frame)[None].cuda(), task_embed[tk], batch_size=1)[0]
+            goals = videos[i].reshape(FRAMES, 3, H, W)
             n_vid += 1
             frames, acts = [frame], []
             with torch.no_grad():
                 for f in range(FRAMES):
-                    obs = {"img_obs_1": (torch.from_numpy(frames[-1]).cuda().permute(2, 0, 1).float() / 255.0)[None, None],
-                           "img_goal_1": goals[f][None, None]}
+                    obs = {"img_obs_1": to_cond(frames[-1]).cuda()[None, None], "img_goal_1": goals[f][None, None]}
                     a = policy.predict_action(obs, use_ddim=True)["action"][0].cpu().numpy()   # [n_action_steps, 7]
                     n_act += 1
                     for k in range(min(args.exec_steps, len(a))):
@@ -169,7 +181,7 @@ def main():
         print(json.dumps({
             "what": "configs[4] in miniature: per task sample() at B=1 + predict_action rollout on a stub simulator + "
                     "replay insert, then policy optimisation steps fed by the HBM replay buffer (all-reduce for N>1)",
-            "n_gpus": world, "tasks": args.tasks, "iters": args.iters, "denoise_steps": args.denoise_steps,
+            "n_gpus": world, "tasks": args.tasks, "batch_videos": bool(args.batch_videos), "iters": args.iters, "denoise_steps": args.denoise_steps,
             "explore_ms_per_iter": ms_explore / args.iters,
             "videos_per_s": n_vid / (ms_explore * 1e-3), "video_frames_per_s": n_vid * FRAMES / (ms_explore * 1e-3),
             "predict_action_calls_per_task": counts[1] // max(1, counts[0]), "env_frames_per_task": counts[2] // max(1, counts[0]),
