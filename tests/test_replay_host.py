@@ -105,6 +105,24 @@ def test_push_seq_continues_an_episode_like_the_deques():
     assert np.array_equal(ub.frames.numpy(), np.stack(imgs)) and np.array_equal(ub.acts.numpy(), np.stack(acts))
 
 
+def test_unit_buffer_reference_views():
+    """`imgs_buf` / `sample_seq` hand back what the reference's unit buffer holds (CPU float CHW = u8 / 255)."""
+    buf = build_buffer("cpu")
+    ub = buf[1]
+    frames = ub.frames
+    imgs = ub.imgs_buf
+    assert len(imgs) == len(ub) and imgs[0].shape == (3, REPLAY["H"], REPLAY["W"])
+    assert torch.equal(imgs[3], frames[3].permute(2, 0, 1).float() / 255.0)
+    random.seed(5)
+    st, gl, acts, tk, env_idx = ub.sample_seq(REPLAY["act_seq_len"])
+    random.seed(5)
+    s = random.randint(0, len(ub) - REPLAY["act_seq_len"] - 1)
+    assert torch.equal(st, imgs[s]) and torch.equal(gl, imgs[s + REPLAY["act_seq_len"]])
+    assert torch.equal(acts, ub.acts[s:s + REPLAY["act_seq_len"]]) and (tk, env_idx) == (ub.task_name, ub.env_idx)
+    with pytest.raises(IndexError):
+        buf[len(buf)]
+
+
 def test_no_cpu_batch_assembly():
     buf = build_buffer("cpu")
     with pytest.raises(RuntimeError, match="GPU only"):

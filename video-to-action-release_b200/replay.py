@@ -104,6 +104,26 @@ class EnvImg_UnitBuffer:
         assert act_seq_len < cur_len
         return random.randint(0, cur_len - act_seq_len - 1)   # [a, b] inclusive
 
+    def _float_frames(self, idx) -> torch.Tensor:
+        """Frames as the reference stores them: CPU float [.., 3, H, W] = u8 / 255 (divided on the CPU, like
+        img_np_toTensor; torch's CUDA division by a scalar multiplies by the reciprocal instead)."""
+        f = self.frames[idx].cpu()
+        return f.permute(*range(f.dim() - 3), -1, -3, -2).float() / 255.0
+
+    @property
+    def imgs_buf(self):
+        """The reference's attribute (a deque of CPU float [3, H, W] tensors), materialised on demand — the trainer
+        only reads it in its debug image dumps (lb_online_trainer_v7.py:541-546)."""
+        return [] if self.frames is None else list(torch.unbind(self._float_frames(slice(None)), dim=0))
+
+    def sample_seq(self, act_seq_len):
+        """Reference-format single sample (env_img_replay_buffer.py:278-302): CPU tensors, same RNG draw."""
+        start_idx = self.sample_start(act_seq_len)
+        goal_idx = start_idx + act_seq_len
+        ret_acts = self.acts[start_idx:goal_idx].cpu()
+        assert len(ret_acts) == act_seq_len
+        return self._float_frames(start_idx), self._float_frames(goal_idx), ret_acts, self.task_name, self.env_idx
+
     def __len__(self):
         return 0 if self.frames is None else int(self.frames.shape[0])
 
