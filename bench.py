@@ -4,6 +4,8 @@
 
   python bench.py --gpus N --steps K --warmup W          # our arm (one rank per GPU under torchrun for N>1)
   python bench.py --impl reference --steps K --warmup W  # the reference algorithm on the host CPU cores
+  python bench.py --impl reference --reference-device cuda --steps 2   # by hand: the reference's torch op sequence on
+                                                         # stock PyTorch/cuDNN on the GPU (E32 / E16)
 
 One "step" = one GoalGaussianDiffusion.sample() call (100 UNet forwards + sampler updates) on one
 batch of synthetic prompts.  Prints ONE JSON line (contract in the task statement / DESIGN.md §6).
