@@ -70,6 +70,12 @@ def _worker(rank, world, port, tmp):
     n = D.allreduce_mean_([g1, g2], bucket_bytes=4 * 256)
     assert n == 4 + 1
     assert torch.allclose(g1, torch.full((1000,), 1.5)) and torch.allclose(g2, torch.full((37,), 15.0))
+    # split exchange (V2A_OVERLAP_ALLREDUCE): one slab's collectives start early, the rest later, one wait for all
+    e1, e2 = torch.full((600,), float(rank + 1)), torch.full((5,), float(3 * (rank + 1)))
+    early = D.allreduce_mean_start([e1], bucket_bytes=4 * 256)
+    late = D.allreduce_mean_start([e2], bucket_bytes=4 * 256)
+    assert D.allreduce_wait(early + late) == 3 + 1
+    assert torch.allclose(e1, torch.full((600,), 1.5)) and torch.allclose(e2, torch.full((5,), 4.5))
     # prompt sharding: 5 prompts over 2 ranks -> 3 + 2, per-rank seeds, no collective in the loop
     cond = torch.arange(5.0)[:, None].expand(5, 4).contiguous()
     te = torch.zeros(5, 2, 8)

@@ -78,19 +78,15 @@ def bucket_ranges(numel: int, bucket_elems: int) -> List[Tuple[int, int]]:
     return [(lo, min(lo + bucket_elems, numel)) for lo in range(0, numel, bucket_elems)]
 
 
-def allreduce_mean_(slabs: Sequence[torch.Tensor], group=None, bucket_bytes: int = 64 << 20) -> int:
-    """In-place mean over ranks of flat fp32 gradient slabs; returns the number of collectives issued.
-
-    NVSwitch gives every peer full bandwidth and reduces in the switch (NVLS), so the bucket size is
-    chosen for launch latency only: 64 MiB buckets -> 5 collectives for the 259 MB UNet1D slab.  The
-    collectives are asynchronous on the NCCL stream and ordered before the caller's next kernel by
-    ``wait()``; with one rank this is a no-op.
-    """
+def allreduce_mean_start(slabs: Sequence[torch.Tensor], group=None, bucket_bytes: int = 64 << 20) -> list:
+    """Launch the in-place mean over ranks of flat fp32 gradient slabs and return the pending works (empty without
+    a process group or with one rank).  The collectives run on the NCCL stream, ordered after what the current
+    stream holds NOW — kernels enqueued afterwards overlap with them until ``allreduce_wait``."""
     if not dist.is_available() or not dist.is_initialized():
-        return 0
+        return []
     world = dist.get_world_size(group)
     if world == 1:
-        return 0
+        return []
     works = []
     for slab in slabs:
         flat = slab.view(-1)
@@ -99,9 +95,25 @@ def allreduce_mean_(slabs: Sequence[torch.Tensor], group=None, bucket_bytes: int
             # pre-divide: SUM of g/world == mean, and keeps fp32 range for a scaled loss
             chunk.mul_(1.0 / world)
             works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=group, async_op=True))
+    return works
+
+
+def allreduce_wait(works: list) -> int:
+    """Order the pending collectives before the caller's next kernel; returns how many there were."""
     for w in works:
         w.wait()
     return len(works)
+
+
+def allreduce_mean_(slabs: Sequence[torch.Tensor], group=None, bucket_bytes: int = 64 << 20) -> int:
+    """In-place mean over ranks of flat fp32 gradient slabs; returns the number of collectives issued.
+
+    NVSwitch gives every peer full bandwidth and reduces in the switch (NVLS), so the bucket size is
+    chosen for launch latency only: 64 MiB buckets -> 5 collectives for the 259 MB UNet1D slab.  The
+    collectives are asynchronous on the NCCL stream and ordered before the caller's next kernel by
+    ``wait()``; with one rank this is a no-op.
+    """
+    return allreduce_wait(allreduce_mean_start(slabs, group, bucket_bytes))
 
 
 def gather_videos(local: torch.Tensor, group=None) -> torch.Tensor:

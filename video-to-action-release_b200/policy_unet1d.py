@@ -196,6 +196,10 @@ class _UNet1DFunction(torch.autograd.Function):
                                "module/shape — activations live in static buffers (one forward per backward)")
         with torch.autocast("cuda", enabled=False):
             d_sample, d_gc, pgrads = eng.backward(grad_out.float(), clone_param_grads=not ctx.slab)
+        hook = getattr(eng, "on_backward_done", None)
+        if hook is not None:       # one-shot: PolicyTrainStep starts this slab's all-reduce under the encoders' backward
+            eng.on_backward_done = None
+            hook()
         return (None, None, d_sample.to(ctx.in_dtypes[0]), None, d_gc.to(ctx.in_dtypes[1]), *pgrads)
 
 

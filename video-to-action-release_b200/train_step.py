@@ -23,6 +23,7 @@ decay = clamp(1 - (1 + c)^-0.75, 0, beta).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Iterable, List, Optional
 
 import torch
@@ -190,6 +191,10 @@ class PolicyTrainStep:
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.steps_done = 0
         self.collectives = 0
+        self._early_works = None
+        # graph replay joins the weight-gradient side lane before the graph ends, so the slab is complete (in stream
+        # order) when backward returns; the eager-launch debugging mode gives no such guarantee
+        self._overlap = os.environ.get("V2A_OVERLAP_ALLREDUCE", "0") == "1" and not os.environ.get("V2A_NO_GRAPH")
         self._lib = _lib.load()
 
     def close(self) -> None:
@@ -227,7 +232,12 @@ class PolicyTrainStep:
         """all-reduce (mean) -> global grad-norm -> clip + AdamW + EMA, all asynchronous on the stream."""
         st = ops._stream()
         segs = list(self._segments())
-        self.collectives += distributed.allreduce_mean_([g for _, g in segs], self.group, self.bucket_bytes)
+        early, self._early_works = self._early_works, None
+        if early is not None:      # the UNet1D slab's exchange was started from inside backward (segs[0])
+            works = early + distributed.allreduce_mean_start([g for _, g in segs[1:]], self.group, self.bucket_bytes)
+        else:
+            works = distributed.allreduce_mean_start([g for _, g in segs], self.group, self.bucket_bytes)
+        self.collectives += distributed.allreduce_wait(works)
         self.sumsq.zero_()
         for _, g in segs:
             _lib.check(self._lib.v2a_grad_sumsq(g.data_ptr(), g.numel(), self.sumsq.data_ptr(), st), "grad_sumsq")
@@ -249,6 +259,15 @@ class PolicyTrainStep:
         """Run ``loss_fn`` (it must call the module), backward, and the optimiser tail.  Returns the loss
         tensor (device resident; reading it synchronises)."""
         loss = loss_fn()
+        if self._overlap and self.cores:
+            # V2A_OVERLAP_ALLREDUCE=1 (multi-GPU, default off until measured): autograd runs the UNet1D's backward
+            # before the observation encoders'; its gradient slab (260 of the 349 MB) starts its all-reduce the
+            # moment it is complete and travels under the encoders' backward
+            eng = policy_unet1d.last_engine(self.unet)
+            if eng is not None:
+                def start(eng=eng):
+                    self._early_works = distributed.allreduce_mean_start([eng.gslab], self.group, self.bucket_bytes)
+                eng.on_backward_done = start
         loss.backward()
         self.optimizer_tail()
         return loss.detach()
