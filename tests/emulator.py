@@ -44,3 +44,33 @@ def emulate(program, srcs, w, cout):
 def as5d(x2d, channels, dims):
     """[rows, C] channels-last -> [X3, X2, X1, X0, C]."""
     return x2d.reshape(dims[3], dims[2], dims[1], dims[0], channels)
+
+
+def emulate_fused3d(fp, srcs, w_spatial, b_spatial, w_temporal, cout):
+    """Semantics of the planned one-kernel Conv3d (docs/FUSED_CONV3D_PLAN.md): stage 1 = `emulate` of the spatial
+    program + spatial bias, evaluated tile by tile in the kernel's on-chip layout — rows = 16 pixels x 8 frame slots,
+    slots >= F zero — then stage 2 = whole-frame shifts of that tile (16 zero rows on either side) times the temporal
+    tap matrices, plus the extra taps from global memory.  srcs[0]: [B, F, H, W, Cin]; returns [B*F*H*W, cout]."""
+    Wd, Hd, Fd, Bd = fp.out_dims
+    mid = emulate(fp.spatial, [srcs[0]], w_spatial, cout) + b_spatial          # [(b f h w), cout]
+    mid = mid.reshape(Bd, Fd, Hd, Wd, cout)
+    pw, slots = 1 << fp.tile_log2[0], 1 << fp.tile_log2[2]
+    nck = fp.mid_chunks * 64
+    out = torch.zeros(Bd, Fd, Hd, Wd, cout, dtype=mid.dtype)
+    for b in range(Bd):
+        for h in range(Hd):
+            for w0 in range(0, Wd, pw):
+                tile = torch.zeros(pw * (slots + 2), cout, dtype=mid.dtype)     # [16 zero | 128 rows | 16 zero]
+                for f in range(Fd):                                              # row = 16 * (f + 1) + w
+                    tile[pw * (f + 1):pw * (f + 2)] = mid[b, f, h, w0:w0 + pw]
+                acc = torch.zeros(pw * slots, cout, dtype=mid.dtype)
+                for ti, t in enumerate(fp.frame_taps):                           # the SAME buffer at row offset 16 (t + 1)
+                    view = tile[pw * (t + 1):pw * (t + 1) + pw * slots]
+                    acc += view @ w_temporal[:cout, ti * nck:ti * nck + cout].to(mid.dtype).t()
+                out[b, :, h, w0:w0 + pw] = acc.reshape(slots, pw, cout)[:Fd]
+    k0 = len(fp.frame_taps) * nck
+    for (s, off, nch), C in zip(fp.extra, fp.extra_channels):
+        assert off == (0, 0, 0, 0)
+        out += srcs[s] @ w_temporal[:cout, k0:k0 + C].to(mid.dtype).t()
+        k0 += nch * 64
+    return out.reshape(-1, cout)

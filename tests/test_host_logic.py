@@ -1,5 +1,6 @@
 """CPU tests of the host-side conv programs (tap offsets, packing, phase split)
 replayed through tests/emulator.py and compared with torch's own convolutions."""
+import pytest
 import torch
 import torch.nn.functional as F
 
@@ -36,6 +37,28 @@ def test_spatial3x3_stride2_phase_split():
     out = emulate(prog, [xp], convs.spatial3x3_weight(w), Co)
     ref = _nhwc(F.conv2d(x, w, padding=1, stride=2))
     torch.testing.assert_close(out, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_fused_conv3d_program_matches_conv2d_then_padded_conv1d():
+    """The two-stage program of the planned one-kernel Conv3d (docs/FUSED_CONV3D_PLAN.md): 16-pixel x 8-frame-slot
+    tiles, temporal taps as whole-frame shifts of the on-chip tile, spatial bias BEFORE the temporal zero padding
+    (guided_diffusion/nn.py:72-85), optional 1x1 skip conv as extra K."""
+    from tests.emulator import emulate_fused3d
+    B, Fr, H, W, Ci, Co, Cx = 2, 7, 3, 32, 24, 40, 16
+    x = torch.randn(B, Fr, H, W, Ci, dtype=D)
+    xs = torch.randn(B, Fr, H, W, Cx, dtype=D)
+    ws, bs = torch.randn(Co, Ci, 3, 3, dtype=D), torch.randn(Co, dtype=D)
+    wt, wk = torch.randn(Co, Co, 3, dtype=D), torch.randn(Co, Cx, 1, 1, dtype=D)
+    fp = convs.fused3d(Ci, Co, B, Fr, H, W, skip_channels=Cx)
+    assert fp.spatial.ktot == 9 * 64 and fp.ktot2 == 3 * 64 + 64 and fp.tile_log2 == (4, 0, 3, 0)
+    out = emulate_fused3d(fp, [x, xs], convs.spatial3x3_weight(ws), bs, convs.temporal3_weight(wt, wk), Co)
+    y = F.conv2d(x.reshape(B * Fr, H, W, Ci).permute(0, 3, 1, 2), ws, bs, padding=1)          # [(b f), Co, H, W]
+    yy = y.reshape(B, Fr, Co, H, W).permute(0, 3, 4, 2, 1).reshape(B * H * W, Co, Fr)         # '(b h w) c f'
+    ref_t = F.conv1d(F.pad(yy, (1, 1)), wt).reshape(B, H, W, Co, Fr).permute(0, 4, 1, 2, 3)   # [B, F, H, W, Co]
+    ref = ref_t + torch.einsum("bfhwc,oc->bfhwo", xs, wk[:, :, 0, 0])
+    torch.testing.assert_close(out, ref.reshape(-1, Co), rtol=1e-11, atol=1e-11)
+    with pytest.raises(ValueError):
+        convs.fused3d(Ci, Co, B, Fr, H, 8)
 
 
 def test_temporal_with_skip_matches_conv1d_plus_1x1():

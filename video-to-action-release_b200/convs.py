@@ -79,6 +79,40 @@ def temporal3_weight(wt: torch.Tensor, wskip: torch.Tensor | None = None) -> tor
     return pack_weight_taps(parts)
 
 
+@dataclass
+class FusedConv3dProgram:
+    """Two-stage program of ONE Conv3d launch (docs/FUSED_CONV3D_PLAN.md; host description only — the kernel that
+    consumes it is next round's work, nothing on the product path builds one yet).
+
+    stage 1 = ``spatial``: 3x3 taps over the grid (W, H, F, B) into an on-chip tile of 16 pixels x 8 frame slots
+    (``tile_log2``; slot F..7 is out of bounds = zero filled); stage 2 = ``frame_taps`` shifts of that tile by whole
+    frames (zero padded) times the temporal tap matrices, plus ``extra`` taps read from global memory (the
+    ResBlock's 1x1 skip conv).  Weights: ``spatial3x3_weight`` and ``temporal3_weight``, unchanged."""
+    spatial: ConvProgram
+    tile_log2: Tuple[int, int, int, int]
+    frame_taps: Tuple[int, ...]
+    mid_chunks: int
+    extra: List[Tuple[int, Tuple[int, int, int, int], int]]
+    extra_channels: List[int]
+    out_dims: Tuple[int, int, int, int]
+    ktot2: int = field(init=False)
+
+    def __post_init__(self):
+        self.ktot2 = 64 * (len(self.frame_taps) * self.mid_chunks + sum(t[2] for t in self.extra))
+
+
+def fused3d(cin: int, cout: int, B: int, F: int, H: int, W: int, skip_channels: int = 0) -> FusedConv3dProgram:
+    if W % 16 != 0 or F > 8:
+        raise ValueError("fused Conv3d tiles are 16 pixels along W x 8 frame slots")
+    taps = [(0, (kw - 1, kh - 1, 0, 0), nchunks(cin)) for kh in range(3) for kw in range(3)]
+    spatial = ConvProgram([cin], [(W, H, F, B)], taps, (W, H, F, B))
+    extra, extra_ch = [], []
+    if skip_channels:
+        extra.append((1, (0, 0, 0, 0), nchunks(skip_channels)))
+        extra_ch.append(skip_channels)
+    return FusedConv3dProgram(spatial, (4, 0, 3, 0), (-1, 0, 1), nchunks(cout), extra, extra_ch, (W, H, F, B))
+
+
 def pointwise(cin: int, dims: Sequence[int]) -> ConvProgram:
     d = tuple(list(dims) + [1] * (4 - len(dims)))
     return ConvProgram([cin], [d], [(0, (0, 0, 0, 0), nchunks(cin))], d)
