@@ -310,6 +310,13 @@ int v2a_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema,
                        const double* grad_sumsq, float max_norm, float lr, float beta1, float beta2, float eps,
                        float weight_decay, int step, float ema_decay, void* stream);
 
+/* 64-bit content fingerprint of a list of fp32 tensors (no reference counterpart: it guards the packed-weight
+ * caches of the engines against `param.data.copy_()` updates, which bypass autograd's version counter -- what
+ * ema_pytorch.EMA.update() does to the EMA model the reference evaluates, lb_online_trainer_v7.py:624,1077).
+ * items: device array of {const float* ptr; int64_t n; int64_t global_offset} chunks; out[0] = sum over all
+ * elements of bits(x) * (2 * (global_offset + i) + 1) mod 2^64. */
+int v2a_params_fingerprint(const void* items, int nitems, uint64_t* out, void* stream);
+
 /* out[i] = src[map[i] - 1] (0 where map[i] == 0), split into planes of format plane_fmt (0 bf16, 1 fp16) */
 int v2a_gather_split_fmt(const float* src, const int32_t* map, int64_t n, void* hi, void* lo, float* f32,
                          int plane_fmt, void* stream);

@@ -17,6 +17,17 @@ from oracle import policy_oracle as PO  # noqa: E402
 from tests.golden.configs import grad_fingerprint, policy_loss_batch  # noqa: E402
 
 
+_E = "obs_encoder.key_model_map."
+FULL_GRADS = [_E + "img_obs_1.backbone.nets.0.weight", _E + "img_obs_1.backbone.nets.4.0.conv1.weight",
+              _E + "img_obs_1.backbone.nets.5.0.conv1.weight", _E + "img_obs_1.backbone.nets.7.1.conv2.weight",
+              _E + "img_obs_1.pool.nets.weight",
+              _E + "img_obs_1.nets.3.weight", _E + "img_goal_1.backbone.nets.0.weight",
+              "model.down_modules.0.0.blocks.0.block.0.weight", "model.final_conv.1.weight"]
+
+
+FULL_GRAD_ROWS = 16
+
+
 def build_reference_policy():
     R.install_shims()
     from v2a_b200 import diffusion_policy as DP
@@ -56,6 +67,12 @@ def main():
     with torch.no_grad():
         act = policy.predict_action(batch["obs"], use_ddim=True)
     out = {"loss": loss.detach(), "action": act["action"], "action_pred": act["action_pred"]}
+    # whole gradient tensors of a few parameters (a fingerprint = norm + one projection would not catch a
+    # wrong-but-same-norm gradient): the stem, an early and a late ResNet conv, the keypoint conv and the
+    # Linear of one encoder, the stem of the other, and two UNet1D weights
+    grads = dict(policy.named_parameters())
+    for name in FULL_GRADS:
+        out["grad." + name] = grads[name].grad.detach()[:FULL_GRAD_ROWS].clone()   # leading output channels (file size)
     torch.save(out, os.path.join(HERE, "policy_loss_golden.pt"))
     with open(os.path.join(HERE, "policy_loss_golden_meta.json"), "w") as f:
         json.dump({"layout": layout, "grad_fingerprints": fps, "B": B, "seed": seed}, f)

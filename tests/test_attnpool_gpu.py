@@ -2,6 +2,8 @@
 `task_attnpool(y).mean(1)` on them against the CPU oracle at the Libero sizes."""
 import pytest
 import torch
+
+from tests.stock_twins import _task_pool
 import torch.nn.functional as F
 
 from oracle import video_oracle as VO
@@ -73,7 +75,7 @@ def test_task_pool_on_kernels_matches_oracle(B, n):
     n0 = U.ops.launch_count()
     with torch.no_grad():
         U._task_pool_cuda(seq, y.cuda(), got)
-        stock = U._task_pool(seq, y.cuda())
+        stock = _task_pool(seq, y.cuda())
     launches = U.ops.launch_count() - n0
     assert _rel(got.cpu(), want) < 1e-5, _rel(got.cpu(), want)
     assert _rel(got, stock) < 1e-5

@@ -3,6 +3,8 @@ writes, operand order, residuals) evaluated with torch stand-ins for the C-ABI w
 `perceiver_resampler` restatement.  The kernels themselves are checked on the GPU (tests/test_attnpool_gpu.py)."""
 import pytest
 import torch
+
+from tests.stock_twins import _task_pool
 import torch.nn.functional as F
 
 from oracle import video_oracle as VO
@@ -70,7 +72,7 @@ def test_task_pool_cuda_launch_sequence_matches_oracle(monkeypatch, B, n):
     got = torch.empty(B, 40)
     with torch.no_grad():
         U._task_pool_cuda(seq, y, got)
-        ref_torch = U._task_pool(seq, y)
+        ref_torch = _task_pool(seq, y)
     rel = lambda a, b: ((a - b).norm() / b.norm()).item()
     assert rel(got, want) < 5e-6, rel(got, want)      # fp32 re-association only (mean before the last Linear)
     assert rel(ref_torch, want) < 5e-6
@@ -94,7 +96,7 @@ def test_task_pool_cuda_chunks_large_batches(monkeypatch):
     got = torch.empty(7, 24)
     with torch.no_grad():
         U._task_pool_cuda(seq, y, got)
-        want = U._task_pool(seq, y)
+        want = _task_pool(seq, y)
     assert ((got - want).norm() / want.norm()).item() < 5e-6
     assert max(rows) <= 40 and len(rows) == 3 * 7            # 3 chunks (3 + 3 + 1 samples) x 7 linears each
 
@@ -112,5 +114,5 @@ def test_task_pool_cuda_without_mean_pooled_latents(monkeypatch):
     got = torch.empty(2, 32)
     with torch.no_grad():
         U._task_pool_cuda(seq, y, got)
-        want = U._task_pool(seq, y)
+        want = _task_pool(seq, y)
     assert ((got - want).norm() / want.norm()).item() < 5e-6

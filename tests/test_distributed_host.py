@@ -55,6 +55,8 @@ def test_ema_decay_schedule_matches_ema_pytorch_0_2_3():
 class _FakeDiffusion:
     """Stands in for GoalGaussianDiffusion on CPU: 'samples' = cond + per-rank seeded noise."""
 
+    image_size, channels = (1, 4), 1
+
     def sample(self, x_cond, task_embed, batch_size):
         assert x_cond.shape[0] == batch_size == task_embed.shape[0]
         return x_cond + torch.randn(x_cond.shape)
@@ -88,6 +90,12 @@ def _worker(rank, world, port, tmp):
     assert out2.shape == (4, 4)
     torch.manual_seed(7 + 0)
     assert torch.equal(out2[:2], cond[:2] + torch.randn(2, 4))
+    # uneven shards cannot be all-gathered (would error or hang under NCCL) -> refused up front
+    with pytest.raises(ValueError, match="multiple of the world size"):
+        D.sample_sharded(_FakeDiffusion(), cond[:3], te[:3], gather=True)
+    # fewer prompts than ranks: the empty shard returns an empty batch instead of calling sample(batch_size=0)
+    one = D.sample_sharded(_FakeDiffusion(), cond[:1, None], te[:1], seed=3)
+    assert one.shape[0] == (1 if rank == 0 else 0)
     torch.save(out2, os.path.join(tmp, f"g{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()

@@ -116,18 +116,16 @@ def test_visual_core_forward_backward_matches_torch(monkeypatch, B):
     # truth: the same modules through stock torch ops in float64 (cuDNN's fp32 Winograd / FFT algorithms are
     # themselves ~1e-3 off on the 64-channel 32x32 layers, measured here: see the fp32 column of the report)
     import copy
-    monkeypatch.setenv("V2A_ENCODER", "torch")
     core64 = copy.deepcopy(core).double()
-    ref = core64(x.double())
+    ref = core64.nets(x.double())          # stock-op twin on the parameter-holder modules (tests/stock_twins.py)
     (ref * wout.double()).sum().backward()
     want = {n: p.grad.float() for n, p in core64.named_parameters() if p.grad is not None}
     ref = ref.float()
-    ref32 = core(x)
+    ref32 = core.nets(x)
     (ref32 * wout).sum().backward()
     fp32_err = {n: (p.grad - want[n]).norm().item() / max(want[n].norm().item(), 1e-30)
                 for n, p in core.named_parameters() if p.grad is not None}
     core.zero_grad(set_to_none=True)
-    monkeypatch.setenv("V2A_ENCODER", "cuda")
     from v2a_b200 import ops
     n0 = ops.launch_count()
     got = core(x)

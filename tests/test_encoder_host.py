@@ -93,7 +93,6 @@ def test_choose_tile_for_the_64_pixel_reduction_box():
 
 def test_visual_core_cuda_path_fails_loudly_on_cpu(monkeypatch):
     from v2a_b200 import diffusion_policy as DP
-    monkeypatch.delenv("V2A_ENCODER", raising=False)
     pol = DP.build_libero_policy()
     core = pol.obs_encoder.key_model_map["img_obs_1"]
     assert tuple(pol.obs_encoder.output_shape()) == (128,)          # read off the modules, no forward pass

@@ -48,6 +48,19 @@ def test_tiny_forward_and_samplers_match_reference_golden():
         assert rel_l2(s, GOLD["tiny_ddim3of10"]) < 1e-5
 
 
+def test_oracle_100_step_trajectory_matches_reference_golden():
+    """The whole ancestral loop the bench times (100 clamped posterior steps, goal_diffusion.py:582-599):
+    pins the oracle's sampler over the full trajectory, not only 2-4 steps (tests/golden/make_drift_golden.py)."""
+    gold = torch.load(os.path.join(HERE, "golden", "video_drift_golden.pt"))
+    sd = VO.seeded_state_dict(tiny_shapes(), 1)
+    _, _, x_cond, te = tiny_inputs()
+    with torch.no_grad():
+        torch.manual_seed(91)
+        s = VO.ddpm_sample(sd, VO.cosine_schedule_buffers(100), x_cond, te, (2, 9, 16, 16))
+    assert rel_l2(s, gold["tiny_ddpm100"]) < 1e-4
+    assert tuple(gold["tiny_ddpm4_all"].shape) == (2, 5, 9, 16, 16) and tuple(gold["tiny_ddim3_all"].shape) == (2, 4, 9, 16, 16)
+
+
 def test_classifier_free_guidance_samplers_match_reference_golden():
     """guidance_weight > 0: doubled batch, zeroed task tokens, noise-space mixing."""
     gold = torch.load(os.path.join(HERE, "golden", "video_cfg_golden.pt"))

@@ -270,6 +270,17 @@ def test_compute_loss_and_predict_action_match_reference_policy_golden(monkeypat
         worst = max(worst, abs(n2 - norm) / max(norm, floor))
         n += 1
     assert n == len(meta["grad_fingerprints"]) == 276
+    # whole gradient tensors (leading output channels) of a few parameters, element for element: a fingerprint
+    # (norm + one projection) would not catch a wrong-but-same-norm gradient
+    params = dict(pol.named_parameters())
+    full = {k[len("grad."):]: v for k, v in gold.items() if k.startswith("grad.")}
+    assert len(full) >= 8
+    for k, want in full.items():
+        got = params[k].grad[:want.shape[0]]
+        tol = 5 * TOL if k.startswith("obs_encoder.") else TOL
+        e = rel_l2(got, want)
+        print(f"full-gradient rel-L2 {k}: {e:.2e}")
+        assert e < tol, (k, e)
     pol.eval()
     torch.manual_seed(meta["seed"] + 1)
     with torch.no_grad():
@@ -278,3 +289,88 @@ def test_compute_loss_and_predict_action_match_reference_policy_golden(monkeypat
     assert rel_l2(act["action_pred"], gold["action_pred"]) < TOL
     assert rel_l2(act["action"], gold["action"]) < TOL
     print(f"compute_loss {loss.item():.7f} (gold {gold['loss'].item():.7f}); worst gradient-norm deviation {worst:.2e}")
+
+
+def test_unet1d_b256_every_gradient_matches_cpu_oracle_autograd():
+    """configs[2] itself: ConditionalUnet1D forward + backward at B = 256 (horizon 16, 7-DoF, the Libero network)
+    against torch autograd through the CPU oracle (~1 s on the host), EVERY parameter gradient at 1e-3 rel-L2."""
+    from oracle import policy_oracle as PO
+    from tests.golden.configs import POLICY_LIBERO, policy_inputs
+    from v2a_b200.policy_unet1d import ConditionalUnet1D
+    m = _meta()["libero"]
+    B = 256
+    sd = PO.seeded_policy_state_dict({k: tuple(v) for k, v in m["layout"].items()}, m["seed"])
+    net = ConditionalUnet1D(**POLICY_LIBERO)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda()
+    traj, noise, t, gc = policy_inputs(B, POLICY_LIBERO, 31)
+    acp = PO.ddpm_alphas_cumprod(100)
+    noisy = PO.add_noise(acp, traj, noise, t)
+    x_g, gc_g = noisy.cuda().requires_grad_(True), gc.cuda().requires_grad_(True)
+    pred = net(x_g, t.cuda(), global_cond=gc_g)
+    loss = F.mse_loss(pred, noise.cuda(), reduction="none").reshape(B, -1).mean(1).mean()
+    loss.backward()
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    x_r, gc_r = noisy.clone().requires_grad_(True), gc.clone().requires_grad_(True)
+    pr = PO.unet1d_forward(sdr, x_r, t, gc_r)
+    lr = F.mse_loss(pr, noise, reduction="none").reshape(B, -1).mean(1).mean()
+    lr.backward()
+    assert rel_l2(pred, pr) < TOL and abs(loss.item() - lr.item()) < TOL * abs(lr.item())
+    worst = ("", 0.0)
+    for k, p in net.named_parameters():
+        e = rel_l2(p.grad, sdr[k].grad)
+        if e > worst[1]:
+            worst = (k, e)
+        assert e < TOL, (k, e)
+    assert rel_l2(gc_g.grad, gc_r.grad) < TOL and rel_l2(x_g.grad, x_r.grad) < TOL
+    print(f"B=256: pred rel-L2 {rel_l2(pred, pr):.2e}; worst parameter-gradient rel-L2 {worst[1]:.2e} ({worst[0]})")
+
+
+def test_policy_engines_follow_dot_data_updates_and_copy_ema_to():
+    """weights written through `.data` (ema_pytorch.EMA.update, PolicyTrainStep.copy_ema_to)
+    bump no version counter; the UNet1D and encoder engines must repack anyway.  forward -> .data update ->
+    forward has to change the output and match a freshly built policy holding the same values."""
+    import copy
+    from v2a_b200 import diffusion_policy as DP
+    from tests.golden.configs import policy_loss_batch
+    torch.manual_seed(9)
+    pol = DP.build_libero_policy().to("cuda").eval()
+    obs = {k: v.cuda() for k, v in policy_loss_batch(2, 3)["obs"].items()}
+
+    def act(p):
+        torch.manual_seed(4)
+        with torch.no_grad():
+            return p.predict_action(obs, use_ddim=True)["action_pred"].clone()
+
+    a0 = act(pol)
+    versions = [p._version for p in pol.parameters()]
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for p in pol.parameters():
+            if p.numel():
+                p.data.copy_(p.data + 0.02 * torch.randn(p.shape, generator=g).cuda())
+    assert versions == [p._version for p in pol.parameters()]
+    a1 = act(pol)
+    fresh = DP.build_libero_policy()
+    fresh.load_state_dict({k: v.cpu() for k, v in pol.state_dict().items()}, strict=True)
+    a1_want = act(fresh.to("cuda").eval())
+    assert rel_l2(a1, a1_want) < 1e-5, rel_l2(a1, a1_want)
+    assert rel_l2(a0, a1) > 1e-3
+    # copy_ema_to: the EMA model's next forward uses the copied weights
+    from v2a_b200.train_step import PolicyTrainStep
+    online = DP.build_libero_policy().to("cuda")
+    online.train()
+    ema_model = copy.deepcopy(online).eval()
+    a_before = act(ema_model)
+    step = PolicyTrainStep(online, lr=1e-2)
+    batch = policy_loss_batch(4, 6)
+    dev = {"obs": {k: v.cuda() for k, v in batch["obs"].items()}, "action": batch["action"].cuda()}
+    for _ in range(2):
+        step.step(lambda: online.compute_loss(dev))
+    step.copy_ema_to(ema_model)
+    a_after = act(ema_model)
+    ref = DP.build_libero_policy()
+    ref.load_state_dict({k: v.cpu() for k, v in ema_model.state_dict().items()}, strict=True)
+    assert rel_l2(a_after, act(ref.to("cuda").eval())) < 1e-5
+    assert rel_l2(a_before, a_after) > 1e-4
+    step.close()

@@ -72,6 +72,10 @@ def test_train_step_checkpoint_formats_roundtrip_with_stock_adamw():
     ema_sd = TS.export_ema_state(net, segs, steps)
     assert set(ema_sd) == {"ema_model." + k for k in net.state_dict()} | {"initted", "step"}
     assert bool(ema_sd["initted"]) and int(ema_sd["step"]) == 3
+    # ema_pytorch 0.2.3 registers both bookkeeping buffers with shape [1] (float32 flag, int64 counter); the flag
+    # is set by the SECOND update() call
+    assert tuple(ema_sd["initted"].shape) == (1,) and ema_sd["initted"].dtype == torch.float32
+    assert tuple(ema_sd["step"].shape) == (1,) and ema_sd["step"].dtype == torch.int64
     kept = [seg.ema.clone() for seg in segs]
     for seg in segs:
         seg.ema.zero_()

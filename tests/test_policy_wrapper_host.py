@@ -11,6 +11,8 @@ import numpy as np
 import pytest
 import torch
 
+from tests.stock_twins import global_cond_stock
+
 from oracle import policy_oracle as PO
 from oracle import ref_import as R
 from tests.golden.configs import policy_loss_batch
@@ -89,7 +91,6 @@ def test_compute_loss_fails_loudly_without_cuda(policy):
 
 @pytest.mark.skipif(not R.available(), reason="reference checkout not mounted")
 def test_encoder_and_install_against_live_reference(policy, monkeypatch):
-    monkeypatch.setenv("V2A_ENCODER", "torch")   # host-side check of the parameter-holding torch modules
     from tests.golden.make_policy_loss_golden import build_reference_policy
     from v2a_b200 import install
     ref = build_reference_policy()
@@ -98,7 +99,7 @@ def test_encoder_and_install_against_live_reference(policy, monkeypatch):
     mine.load_state_dict(ref.state_dict(), strict=True)
     b = policy_loss_batch(2, 5)
     torch.manual_seed(1)
-    got, B = mine._global_cond(b["obs"])
+    got, B = global_cond_stock(mine, b["obs"])     # the parameter-holding torch modules, evaluated on the host
     nobs = ref.normalizer.normalize_d(b["obs"])
     torch.manual_seed(1)
     want = ref.obs_encoder({k: v[:, :1].reshape(-1, *v.shape[2:]) for k, v in nobs.items()}).reshape(2, -1)

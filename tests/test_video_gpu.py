@@ -192,3 +192,194 @@ def test_full_size_libero_properties():
     d.sampling_timesteps, d.is_ddim_sampling = 3, True  # the eval helper's attribute pokes
     s = d.sample(x[:, -3:].contiguous(), te, batch_size=2)
     assert s.shape == (2, 21, 128, 128) and s.min() >= 0 and s.max() <= 1 and torch.isfinite(s).all()
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: parity AT the benchmarked configuration (VERDICT r1 "weak" 1) and the advisor's cache findings
+# ---------------------------------------------------------------------------------------------------
+def _libero_net():
+    from oracle.video_oracle import seeded_state_dict
+    from v2a_b200.unet import Unet_Libero
+    with open(os.path.join(HERE, "golden", "goal_diffusion_state_dict_layout.json")) as f:
+        lay = json.load(f)
+    shapes = {k[len("model."):]: tuple(v) for k, v in lay.items() if k.startswith("model.")}
+    sd = seeded_state_dict(shapes, 2)
+    net = Unet_Libero()
+    net.load_state_dict(sd, strict=True)
+    return net.cuda(), sd
+
+
+def test_full_size_b1_matches_cpu_oracle():
+    """configs[1] geometry (128x128, 7 + 1 frames), one sample: the CUDA forward against the CPU oracle
+    (the reference's op sequence in fp32; a few seconds on the host cores) at north_star's 1e-3."""
+    from oracle import video_oracle as VO
+    net, sd = _libero_net()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 24, 128, 128, generator=g)
+    x[:, -3:] = torch.rand(1, 3, 128, 128, generator=g)
+    t = torch.tensor([63])
+    te = torch.randn(1, 12, 512, generator=g)
+    out = net(x.cuda(), t.cuda(), te.cuda())
+    with torch.no_grad():
+        ref = VO.unet_libero_forward(sd, x, t, te)
+    assert rel_l2(out, ref) < TOL and max_rel(out, ref) < TOL, (rel_l2(out, ref), max_rel(out, ref))
+
+
+def test_full_size_b16_matches_per_sample_runs():
+    """The benchmarked batch itself: B = 16 at 128x128x7 (1.83 M pixel rows x up to 384 channels = 2.8 GB per
+    plane, the regime where 32-bit pixel arithmetic has to widen) against sixteen B = 1 runs of the same
+    network, per sample.  Different batch -> different tile shapes and summation order, nothing else."""
+    net, _ = _libero_net()
+    g = torch.Generator().manual_seed(12)
+    B = 16
+    x = torch.randn(B, 24, 128, 128, generator=g)
+    x[:, -3:] = torch.rand(B, 3, 128, 128, generator=g)
+    t = torch.randint(0, 100, (B,), generator=g)
+    te = torch.randn(B, 12, 512, generator=g)
+    o = net(x.cuda(), t.cuda(), te.cuda()).cpu()
+    assert torch.isfinite(o).all()
+    worst = 0.0
+    for b in range(B):
+        ob = net(x[b:b + 1].cuda(), t[b:b + 1].cuda(), te[b:b + 1].cuda()).cpu()
+        worst = max(worst, rel_l2(o[b:b + 1], ob))
+    assert worst < 1e-4, worst
+
+
+def test_100_step_ddpm_trajectory_matches_reference_golden(cpu_rng_stream):
+    """Drift over the whole loop the bench times: 100 ancestral steps (timesteps = sampling_timesteps = 100,
+    goal_diffusion.py:582-599) on the tiny UNet with the reference's CPU noise stream replayed, against the
+    unmodified reference (tests/golden/make_drift_golden.py).  The per-forward error (~1e-5) must not compound
+    past the 1e-3 bar over 100 clamped posterior steps."""
+    from tests.golden.configs import tiny_inputs
+    net, _ = _tiny_model(1)
+    _, _, x_cond, te = tiny_inputs()
+    gold = torch.load(os.path.join(HERE, "golden", "video_drift_golden.pt"))
+    d = _diffusion(net, 9, (16, 16), 100, 100)
+    assert not d.is_ddim_sampling
+    torch.manual_seed(91)
+    s = d.sample(x_cond.cuda(), te.cuda(), batch_size=2)
+    err = rel_l2(s, gold["tiny_ddpm100"])
+    print(f"100-step DDPM trajectory rel-L2 vs reference: {err:.3e}, max-rel {max_rel(s, gold['tiny_ddpm100']):.3e}")
+    assert err < TOL and max_rel(s, gold["tiny_ddpm100"]) < 5 * TOL
+
+
+def test_return_all_timesteps_matches_reference_golden(cpu_rng_stream):
+    """`sample(return_all_timesteps=True)` (goal_diffusion.py:596,639): every intermediate image, stacked on dim 1,
+    un-normalised and clamped like the final one -- DDPM and DDIM, fused path and the general (guidance) loop."""
+    from tests.golden.configs import tiny_inputs
+    net, _ = _tiny_model(1)
+    _, _, x_cond, te = tiny_inputs()
+    gold = torch.load(os.path.join(HERE, "golden", "video_drift_golden.pt"))
+    d4 = _diffusion(net, 9, (16, 16), 4, 4)
+    torch.manual_seed(92)
+    a = d4.sample(x_cond.cuda(), te.cuda(), batch_size=2, return_all_timesteps=True)
+    assert a.shape == (2, 5, 9, 16, 16) and a.min() >= 0 and a.max() <= 1
+    assert rel_l2(a, gold["tiny_ddpm4_all"]) < TOL
+    d10 = _diffusion(net, 9, (16, 16), 10, 3)
+    torch.manual_seed(93)
+    b = d10.sample(x_cond.cuda(), te.cuda(), batch_size=2, return_all_timesteps=True)
+    assert b.shape == (2, 4, 9, 16, 16)
+    assert rel_l2(b, gold["tiny_ddim3_all"]) < TOL
+    # the last entry is what sample() returns without the flag
+    torch.manual_seed(92)
+    assert rel_l2(d4.sample(x_cond.cuda(), te.cuda(), batch_size=2), a[:, -1]) < 1e-6
+
+
+def test_task_embedding_cache_keys_on_content_not_address():
+    """prompts are temporaries; the allocator hands the next prompt the previous one's address.
+    Two back-to-back forwards whose embeddings are created and freed inside a function must each be conditioned
+    on their own tokens."""
+    from tests.golden.configs import tiny_inputs
+    net, _ = _tiny_model(1)
+    x, t, x_cond, _ = tiny_inputs()
+    xin = torch.cat([x, x_cond], 1).cuda()
+    tc = t.cuda()
+
+    def run(seed):
+        te = torch.randn(2, 6, 512, generator=torch.Generator().manual_seed(seed)).cuda()   # freed on return
+        ptr = te.data_ptr()
+        return net(xin, tc, te).clone(), ptr
+
+    a, pa = run(1)
+    b, pb = run(2)
+    a2, _ = run(1)
+    fresh, _ = _tiny_model(1)
+    te2 = torch.randn(2, 6, 512, generator=torch.Generator().manual_seed(2)).cuda()
+    want_b = fresh(xin, tc, te2)
+    assert rel_l2(b, want_b) < 1e-6, ("second prompt was conditioned on the first", pa == pb)
+    assert rel_l2(a, b) > 1e-3 and rel_l2(a2, a) < 1e-6
+
+
+def test_weight_cache_sees_updates_through_dot_data():
+    """`p.data.copy_()` / `p.data.lerp_()` (ema_pytorch.EMA.update) bump no version counter; the
+    packed hi/lo weights must follow anyway (content fingerprint in the cache key)."""
+    from oracle import video_oracle as VO
+    from tests.golden.configs import tiny_inputs
+    net, _ = _tiny_model(1)
+    x, t, x_cond, te = tiny_inputs()
+    xin = torch.cat([x, x_cond], 1)
+    o1 = net(xin.cuda(), t.cuda(), te.cuda()).clone()
+    versions = [p._version for p in net.parameters()]
+    with torch.no_grad():
+        for p in net.parameters():
+            p.data.copy_(p.data * 1.02)
+    assert versions == [p._version for p in net.parameters()]          # the premise of the finding
+    o2 = net(xin.cuda(), t.cuda(), te.cuda())
+    sd2 = {k: v.cpu() for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        ref2 = VO.unet_libero_forward(sd2, xin, t, te)
+    assert rel_l2(o2, ref2) < TOL and rel_l2(o1, o2) > 1e-3
+
+
+def test_sampler_clamp_propagates_nan():
+    """torch.clamp keeps NaN (goal_diffusion.py:565-566,650); so must the fused sampler kernels."""
+    from v2a_b200 import ops
+    x = torch.randn(64, device="cuda")
+    v = torch.randn(64, device="cuda")
+    v[5] = float("nan")
+    coef = torch.tensor([0.9, 0.4, 0.3, 0.7, 0.1, 1.0, 0, 0], device="cuda")
+    ops.ddpm_step(x, v, torch.zeros_like(x), coef)
+    assert torch.isnan(x[5]) and torch.isfinite(torch.cat([x[:5], x[6:]])).all()
+    out = torch.empty_like(x)
+    ops.unnormalize_clamp(x, out)
+    assert torch.isnan(out[5]) and out[6:].min() >= 0 and out[6:].max() <= 1
+
+
+FAST_TOL = 2e-2
+
+
+def test_fast_precision_class_is_opt_in_and_within_its_own_tolerance(cpu_rng_stream):
+    """`diffusion.precision = "fast"`: ONE bf16 tensor-core product per contraction instead of the 3-pass split
+    product -- the numerics class the reference itself ships on the GPU (fp16 autocast + TF32,
+    scripts/train_libero_dp.py:10,25-26; ~1e-2).  Never the default and never held to the 1e-3 bar: its own
+    tolerance is 2e-2 on a forward / 3e-2 on a short trajectory against the fp32 reference golden, and it must
+    really be a different numerics class (error well above the strict path's ~1e-5)."""
+    from tests.golden.configs import config1_inputs, tiny_inputs
+    net, _ = _tiny_model(1)
+    x, t, x_cond, te = tiny_inputs()
+    xin = torch.cat([x, x_cond], 1).cuda()
+    gold = _gold()
+    d = _diffusion(net, 9, (16, 16), 4, 4)
+    assert d.precision == "strict" and net.unet.precision == "strict"
+    strict = net(xin, t.cuda(), te.cuda()).clone()
+    d.precision = "fast"
+    assert net.unet.precision == "fast"
+    fast = net(xin, t.cuda(), te.cuda())
+    e_fast, e_strict = rel_l2(fast, gold["tiny_forward"]), rel_l2(strict, gold["tiny_forward"])
+    print(f"tiny forward rel-L2 vs reference: strict {e_strict:.2e}, fast {e_fast:.2e}")
+    assert e_strict < TOL and 20 * e_strict < e_fast < FAST_TOL
+    torch.manual_seed(77)
+    s = d.sample(x_cond.cuda(), te.cuda(), batch_size=2)
+    assert rel_l2(s, gold["tiny_ddpm4"]) < 3e-2
+    d.precision = "strict"                      # and back: the strict engine is untouched
+    assert rel_l2(net(xin, t.cuda(), te.cuda()), strict) < 1e-6
+    with pytest.raises(ValueError):
+        d.precision = "fp8"
+    # the real network at configs[0]
+    big, _ = _libero_net()
+    x, t, x_cond, te = config1_inputs()
+    big.unet.precision = "fast"
+    o = big(torch.cat([x, x_cond], 1).cuda(), t.cuda(), te.cuda())
+    e = rel_l2(o, gold["config1_forward"])
+    print(f"config-1 forward, fast class: rel-L2 {e:.2e}")
+    assert 1e-4 < e < FAST_TOL

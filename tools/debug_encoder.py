@@ -10,7 +10,6 @@ core = _seeded_core(); core.train()
 torch.manual_seed(3)
 x = torch.rand(B, 3, 128, 128, device="cuda") * 2 - 1
 wout = torch.randn(B, 64, device="cuda")
-os.environ["V2A_ENCODER"] = "torch"
 c64 = copy.deepcopy(core).double()
 outs = []
 mods = [c64.backbone.nets[3]] + [b for i in range(4, 8) for b in c64.backbone.nets[i]]
@@ -18,8 +17,7 @@ for m in mods:
     def hook(mod, inp, out, store=outs):
         out.retain_grad(); store.append(out)
     m.register_forward_hook(hook)
-ref = c64(x.double()); (ref * wout.double()).sum().backward()
-os.environ["V2A_ENCODER"] = "cuda"
+ref = c64.nets(x.double()); (ref * wout.double()).sum().backward()
 got = core(x); (got * wout).sum().backward()
 eng = OE.last_engine(core)
 for i, (a, t) in enumerate(zip(eng.acts, outs)):
@@ -40,8 +38,7 @@ def mk(name):
         out.retain_grad(); store[name] = out
     return hook
 h1 = blk.conv1.register_forward_hook(mk("c1")); h2 = blk.conv2.register_forward_hook(mk("c2"))
-os.environ["V2A_ENCODER"] = "torch"
-ref = c64(x.double()); (ref * wout.double()).sum().backward()
+ref = c64.nets(x.double()); (ref * wout.double()).sum().backward()
 pr = eng.probes[-1]   # plans run in reverse: the last probe is block 0
 for name, key in (("c2", "d2"), ("c1", "d1")):
     t = store[name].grad.permute(0, 2, 3, 1).reshape(-1, 64)
@@ -54,7 +51,7 @@ for name, key in (("c2", "raw2"), ("c1", "raw1")):
     print("fwd", name, "rel", rel(pr[key], t), "bad", (d > 1e-3 * t.abs().max()).nonzero()[:8].tolist())
 c64.zero_grad(); store.clear()
 h3 = blk.bn2.register_forward_hook(mk("b2"))
-ref = c64(x.double()); (ref * wout.double()).sum().backward()
+ref = c64.nets(x.double()); (ref * wout.double()).sum().backward()
 tg = store["b2"].grad.permute(0, 2, 3, 1).reshape(-1, 64)
 mine = pr["g"]
 d = (mine.double() - tg).abs().amax(1).view(B, 32, 32)

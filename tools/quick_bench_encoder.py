@@ -45,13 +45,11 @@ def main():
     ms_b = timed(lambda: eng.backward(w, clone_param_grads=False))
     print(f"B={B} engine forward {ms_f:.3f} ms  backward {ms_b:.3f} ms  (fwd {fl_f / 1e9:.0f} GF, all {fl_all / 1e9:.0f} GF -> "
           f"{fl_all / (ms_f + ms_b) / 1e9:.1f} TFLOP/s algorithmic)  launches fwd {len(eng.fwd)} bwd {len(eng.bwd)}")
-    os.environ["V2A_ENCODER"] = "torch"
     def torch_step():
         core.zero_grad(set_to_none=True)
-        o = core(x)
+        o = core.nets(x)          # the stock-op twin on the parameter-holder modules
         (o * w).sum().backward()
     ms_t = timed(torch_step, n=3, warm=1)
-    os.environ["V2A_ENCODER"] = "cuda"
     print(f"torch/cuDNN fp32 (TF32 off) fwd+bwd {ms_t:.3f} ms -> engine speed-up {ms_t / (ms_f + ms_b):.2f}x")
     if "--layers" in sys.argv:
         for name, steps in (("fwd", eng.fwd), ("bwd", eng.bwd)):

@@ -194,6 +194,7 @@ SIGNATURES = {
     "v2a_ddim_step": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "v2a_unnormalize_clamp": (_i, [_vp, _vp, _i64, _vp]),
     "v2a_split_hl": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "v2a_params_fingerprint": (_i, [_vp, _i, _vp, _vp]),
     "v2a_gather_split": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "v2a_policy_gn_act_fwd": (_i, [C.POINTER(PolicyGnDesc), _vp]),
     "v2a_policy_gn_act_bwd": (_i, [C.POINTER(PolicyGnDesc), _vp]),

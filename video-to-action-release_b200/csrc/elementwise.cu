@@ -355,6 +355,12 @@ __global__ void unet_output_head_kernel(const float* __restrict__ y, int ldy, co
 // ---------------------------------------------------------------------------
 // sampler steps (operation order follows the reference's fp32 op chain)
 // ---------------------------------------------------------------------------
+// torch.clamp propagates NaN; fminf / fmaxf return the other operand, which would turn a diverged UNet output
+// into a plausible-looking finite pixel.  Keep the reference's behaviour: NaN in, NaN out.
+__device__ __forceinline__ float clamp_nan(float x, float lo, float hi) {
+    return x != x ? x : fminf(fmaxf(x, lo), hi);
+}
+
 __global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ v,
                                  const float* __restrict__ noise, const float* __restrict__ coef,
                                  int64_t n) {
@@ -363,7 +369,7 @@ __global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict_
     const float sa = coef[0], s1 = coef[1], c1 = coef[2], c2 = coef[3], sigma = coef[4], vt = coef[5];
     const float xt = x[i];
     float x0 = __fsub_rn(__fmul_rn(sa, xt), __fmul_rn(s1, v[i]));  // predict_start_from_v
-    x0 = fminf(fmaxf(x0, -1.0f), 1.0f);                            // clamp_(-1, 1)
+    x0 = clamp_nan(x0, -1.0f, 1.0f);                               // clamp_(-1, 1)
     const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xt));  // q_posterior mean
     const float nz = noise ? __fmul_rn(noise[i], vt) : 0.0f;
     x[i] = __fadd_rn(mean, __fmul_rn(sigma, nz));
@@ -392,7 +398,7 @@ __global__ void unnormalize_clamp_kernel(const float* __restrict__ x, float* __r
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float u = __fmul_rn(__fadd_rn(x[i], 1.0f), 0.5f);
-    out[i] = fminf(fmaxf(u, 0.0f), 1.0f);
+    out[i] = clamp_nan(u, 0.0f, 1.0f);
 }
 
 __global__ void split_hl_kernel(const float* __restrict__ x, int64_t rows, int cols, int ld,
@@ -406,6 +412,29 @@ __global__ void split_hl_kernel(const float* __restrict__ x, int64_t rows, int c
     split_bf16(v, h, l);
     hi[i] = h;
     lo[i] = l;
+}
+
+// ---------------------------------------------------------------------------
+// 64-bit content fingerprint of a list of fp32 tensors: sum over elements of bits(x_i) * (2 * global_index + 1)
+// mod 2^64 (integer addition: exact and order independent, so the grid layout does not matter).  The engines use
+// it to notice parameter updates that bypass autograd's version counter (`p.data.copy_()`, what
+// ema_pytorch.EMA.update() does to the EMA model).
+// ---------------------------------------------------------------------------
+struct FpItem {
+    const uint32_t* ptr;
+    int64_t n;
+    int64_t off;
+};
+__global__ void fingerprint_kernel(const FpItem* __restrict__ items, int nitems, unsigned long long* out) {
+    unsigned long long h = 0;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+        const FpItem item = items[it];
+        for (int64_t i = threadIdx.x; i < item.n; i += blockDim.x)
+            h += (unsigned long long)item.ptr[i] * (unsigned long long)(2 * (item.off + i) + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0 && h) atomicAdd(out, h);
 }
 
 }  // namespace v2a
@@ -643,6 +672,17 @@ int v2a_split_hl(const float* x, int64_t rows, int cols, int ld_out, void* out_h
     const int64_t total = rows * ld_out;
     split_hl_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         x, rows, cols, ld_out, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+    V2A_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_params_fingerprint(const void* items, int nitems, uint64_t* out, void* stream) {
+    V2A_REQUIRE(items && out && nitems >= 0, "params_fingerprint: missing pointers");
+    V2A_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(uint64_t), (cudaStream_t)stream));
+    if (nitems == 0) return 0;
+    const int blocks = nitems < 148 * 8 ? nitems : 148 * 8;
+    fingerprint_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const FpItem*)items, nitems,
+                                                                 (unsigned long long*)out);
     V2A_LAUNCH_OK();
     return 0;
 }

@@ -11,8 +11,7 @@ What runs where:
            dependency the reference leaves unpinned (requirements.txt:4) and is absent offline;
   * P6     the observation encoder (2x ResNet18-GroupNorm + SpatialSoftmax, 80 % of compute_loss FLOPs): the
            modules below hold its parameters under the reference's ``state_dict`` names; ``VisualCore.forward``
-           runs the planned CUDA engine of ``obs_encoder.py`` (forward and backward).  ``V2A_ENCODER=torch``
-           runs the stock torch modules instead (host-side comparisons / A-B timing).
+           runs the planned CUDA engine of ``obs_encoder.py`` (forward and backward) and nothing else.
 
 RNG order of ``compute_loss`` follows the reference: SpatialSoftmax draws (goal, then
 obs encoder, training mode only), ``randn(trajectory.shape)``, ``randint(0, T, (B,))``.
@@ -29,7 +28,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import obs_encoder
+from . import obs_encoder, packing
 from .policy_unet1d import ConditionalUnet1D
 
 
@@ -308,11 +307,9 @@ class VisualCore(nn.Module):
 
     def forward(self, x):
         """Planned CUDA engine (obs_encoder.py: tcgen05 convs + GroupNorm/ReLU/MaxPool/SpatialSoftmax kernels,
-        forward and backward).  ``V2A_ENCODER=torch`` runs the stock torch modules instead (host-side
-        comparisons and A/B timing only)."""
+        forward and backward).  There is no other path: ``self.nets`` only holds the parameters under the
+        reference's names (tests and tools call ``core.nets(x)`` themselves when they want the stock-op twin)."""
         assert tuple(x.shape[-3:]) == self.input_shape
-        if not obs_encoder.enabled():
-            return self.nets(x)
         if self.pool.noise_std != 0.0:
             raise NotImplementedError("the CUDA VisualCore covers noise_std == 0 (the Libero yaml)")
         if self.training:   # the reference draws randn_like(keypoints) * noise_std even for noise_std == 0
@@ -370,7 +367,7 @@ class MultiImageObsEncoder(_AttrMixin):
             assert x.shape[0] == bs and tuple(x.shape[1:]) == self.key_shape_map[key]
             if key not in self.key_model_map:
                 feats.append(x)
-            elif x.is_cuda and obs_encoder.enabled() and i + 1 < len(self.rgb_keys):
+            elif x.is_cuda and i + 1 < len(self.rgb_keys):
                 # independent encoders overlap: all but the last run on side streams (the RNG draws and the
                 # Python-side order stay the reference's; autograd replays the backward on the same streams)
                 s = obs_encoder.side_stream(x.device, i)
@@ -449,6 +446,10 @@ class DiffusionUnetImagePolicy(_AttrMixin):
 
     def predict_action(self, obs_dict: Dict[str, torch.Tensor], use_ddim=False) -> Dict[str, torch.Tensor]:
         assert "past_action" not in obs_dict
+        with packing.one_content_check():       # each engine verifies its packed weights once per call
+            return self._predict_action(obs_dict, use_ddim)
+
+    def _predict_action(self, obs_dict, use_ddim):
         global_cond, B = self._global_cond(obs_dict)
         cond = torch.zeros((B, self.horizon, self.action_dim), device=self.device, dtype=self.dtype)
         nsample = self.conditional_sample(cond, torch.zeros_like(cond, dtype=torch.bool), global_cond=global_cond,

@@ -52,6 +52,10 @@ def init_from_env(backend: Optional[str] = None):
     return rank, local, world
 
 
+def world_size(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous [lo, hi) of ``n`` items for ``rank``; the first ``n % world`` ranks get one extra."""
     if not (0 <= rank < world):
@@ -87,14 +91,19 @@ def allreduce_mean_start(slabs: Sequence[torch.Tensor], group=None, bucket_bytes
     world = dist.get_world_size(group)
     if world == 1:
         return []
+    # NCCL averages inside the collective (ReduceOp.AVG): no extra read + write pass over the 349 MB of gradients.
+    # gloo (the CPU tests) has no AVG: pre-divide, then SUM.
+    avg = dist.get_backend(group) == "nccl"
     works = []
     for slab in slabs:
         flat = slab.view(-1)
         for lo, hi in bucket_ranges(flat.numel(), max(1, bucket_bytes // flat.element_size())):
             chunk = flat[lo:hi]
-            # pre-divide: SUM of g/world == mean, and keeps fp32 range for a scaled loss
-            chunk.mul_(1.0 / world)
-            works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=group, async_op=True))
+            if avg:
+                works.append(dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=group, async_op=True))
+            else:
+                chunk.mul_(1.0 / world)
+                works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=group, async_op=True))
     return works
 
 
@@ -136,7 +145,14 @@ def sample_sharded(diffusion, x_cond: torch.Tensor, task_embed: torch.Tensor, *,
     """
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    n = x_cond.shape[0]
+    if gather and n % world != 0:
+        # all_gather_into_tensor needs equal shards; uneven or empty ones would error or hang under NCCL
+        raise ValueError(f"sample_sharded(gather=True): batch {n} is not a multiple of the world size {world}")
     xc, te = shard_batch([x_cond, task_embed], rank, world)
+    if xc.shape[0] == 0:            # fewer prompts than ranks: this rank has nothing to sample
+        H, W = diffusion.image_size
+        return x_cond.new_zeros((0, diffusion.channels, H, W))
     if seed is not None:
         torch.manual_seed(seed + rank)
     out = diffusion.sample(xc, te, batch_size=xc.shape[0])

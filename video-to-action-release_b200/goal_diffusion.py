@@ -118,6 +118,23 @@ class GoalGaussianDiffusion(nn.Module):
         self.guidance_weight = guidance_weight
         self.var_temp = var_temp
 
+    # numerics class of the UNet's tensor-core contractions ("strict" = fp32-class 3-pass split product, the
+    # default and the only class the 1e-3 parity bar applies to; "fast" = one bf16 product, the class of the
+    # reference's own fp16-autocast GPU path).  Lives on the UNet so a direct `model(...)` call agrees with sample().
+    @property
+    def precision(self) -> str:
+        unet = getattr(self.model, "unet", None)
+        return getattr(unet, "precision", "strict")
+
+    @precision.setter
+    def precision(self, value: str) -> None:
+        from .unet import PRECISIONS
+        if value not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {value!r}")
+        if not isinstance(self.model, Unet_Libero):
+            raise NotImplementedError("precision classes exist for the CUDA Unet_Libero path")
+        self.model.unet.precision = value
+
     # the reference stores these as attributes holding functions
     def normalize(self, img):
         return img * 2 - 1 if self.auto_normalize else img

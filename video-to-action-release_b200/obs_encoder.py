@@ -61,11 +61,6 @@ def invalidate_weights(core: nn.Module) -> None:
         eng._wkey = None
 
 
-def enabled() -> bool:
-    """V2A_ENCODER=torch keeps the stock torch/cuDNN modules (A/B timing only)."""
-    return os.environ.get("V2A_ENCODER", "cuda") != "torch"
-
-
 def encoder_engine(core, B: int, device) -> "_EncoderEngine":
     per = _ENGINES.setdefault(core, {})
     device = torch.device(device)
@@ -108,6 +103,10 @@ class _VisualCoreFunction(torch.autograd.Function):
                                "(activations live in static buffers: one forward per backward)")
         with torch.autocast("cuda", enabled=False):
             pgrads = eng.backward(grad_out.float(), clone_param_grads=not ctx.slab)
+        hook = getattr(eng, "on_backward_done", None)
+        if hook is not None:       # one-shot: PolicyTrainStep starts this slab's all-reduce the moment it is complete
+            eng.on_backward_done = None
+            hook()
         return (None, None, None, *pgrads)
 
 

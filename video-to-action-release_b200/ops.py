@@ -479,5 +479,38 @@ def add_rows_(dst, src) -> None:
                                            dst.shape[0], dst.shape[1], 1, _stream()), "add_strided")
 
 
+# ---- content fingerprint of a parameter list (guards the packed-weight caches, see packing.content_key) ----
+_FP_TABLES: dict = {}
+_FP_CHUNK = 1 << 16
+
+
+def params_fingerprint(params: Sequence[torch.Tensor]) -> int:
+    """64-bit fingerprint of the VALUES of ``params`` (CUDA fp32 tensors): one kernel launch over a cached
+    device table of (pointer, length, global offset) chunks, then an 8-byte read-back (this synchronises)."""
+    ps = [p.detach() for p in params if p.numel()]
+    if not ps:
+        return 0
+    _require_cuda(*ps)
+    dev = ps[0].device
+    key = (str(dev),) + tuple((p.data_ptr(), p.numel()) for p in ps)
+    ent = _FP_TABLES.get(key)
+    if ent is None:
+        rows, off = [], 0
+        for p in ps:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("v2a_b200: engine parameters must be contiguous fp32 tensors")
+            n, base = p.numel(), p.data_ptr()
+            for lo in range(0, n, _FP_CHUNK):
+                rows.append((base + 4 * lo, min(_FP_CHUNK, n - lo), off + lo))
+            off += n
+        table = torch.tensor(rows, dtype=torch.int64).to(dev)
+        if len(_FP_TABLES) >= 32:
+            _FP_TABLES.pop(next(iter(_FP_TABLES)))
+        ent = _FP_TABLES[key] = (table, torch.zeros(1, dtype=torch.int64, device=dev), len(rows))
+    table, out, n = ent
+    _lib.check(_lib.load().v2a_params_fingerprint(table.data_ptr(), n, out.data_ptr(), _stream()), "params_fingerprint")
+    return int(out.item())
+
+
 def launch_count() -> int:
     return int(_lib.load().v2a_launch_count())

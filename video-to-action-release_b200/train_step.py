@@ -122,8 +122,13 @@ def import_optimizer_state(module: nn.Module, segments: Iterable["_Segment"], op
 
 
 def export_ema_state(module: nn.Module, segments: Iterable["_Segment"], steps_done: int) -> dict:
-    """``ema_pytorch.EMA(include_online_model=False).state_dict()`` layout: ``ema_model.<name>`` for every
-    parameter (from the EMA slabs) and buffer (from the module), plus ``initted`` and ``step``."""
+    """``ema_pytorch.EMA(include_online_model=False).state_dict()`` layout (the trainer's setting,
+    config/libero/lb_tk8_65to72.py:145-153: the online model is then held in a plain list and contributes no
+    ``online_model.*`` keys): ``ema_model.<name>`` for every parameter (from the EMA slabs) and buffer (from the
+    module), plus the two bookkeeping buffers as ema_pytorch 0.2.3 registers them -- ``initted`` =
+    ``torch.Tensor([bool])`` (float32, shape [1]; set by the SECOND ``update()`` call when ``update_after_step``
+    is 0) and ``step`` = ``torch.tensor([n])`` (int64, shape [1]).  The package is not installed offline: restated
+    from its published source, unpinned by a round trip through the real class."""
     names = {id(p): n for n, p in module.named_parameters()}
     out = {}
     for seg in segments:
@@ -135,8 +140,8 @@ def export_ema_state(module: nn.Module, segments: Iterable["_Segment"], steps_do
         out.setdefault("ema_model." + n, p.detach().clone())
     for n, b in module.named_buffers():
         out["ema_model." + n] = b.detach().clone()
-    out["initted"] = torch.tensor(steps_done > 0)
-    out["step"] = torch.tensor(steps_done)
+    out["initted"] = torch.Tensor([steps_done >= 2])
+    out["step"] = torch.tensor([steps_done])
     return out
 
 
@@ -174,10 +179,8 @@ class PolicyTrainStep:
         unet_params = list(unet1d.parameters())
         ids = {id(p) for p in unet_params}
         # observation encoders that run on the planned CUDA engine keep their gradients in the engine's slab too
-        self.cores = []
-        if obs_encoder.enabled():
-            from .diffusion_policy import VisualCore
-            self.cores = [m for m in module.modules() if isinstance(m, VisualCore)]
+        from .diffusion_policy import VisualCore
+        self.cores = [m for m in module.modules() if isinstance(m, VisualCore)]
         self.seg_cores = []
         for core in self.cores:
             cp = [p for p in core.parameters()]
@@ -191,10 +194,14 @@ class PolicyTrainStep:
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.steps_done = 0
         self.collectives = 0
-        self._early_works = None
-        # graph replay joins the weight-gradient side lane before the graph ends, so the slab is complete (in stream
-        # order) when backward returns; the eager-launch debugging mode gives no such guarantee
-        self._overlap = os.environ.get("V2A_OVERLAP_ALLREDUCE", "0") == "1" and not os.environ.get("V2A_NO_GRAPH")
+        self._early = {}           # id(gradient slab) -> pending collectives started from inside backward
+        # Multi-GPU: every engine's gradient slab starts its all-reduce the moment that engine's backward has been
+        # enqueued (autograd runs the UNet1D's backward first, then the two encoders'), so the exchange travels
+        # under the rest of backward; only the last encoder's 45 MB is exposed.  Graph replay joins the
+        # weight-gradient side lane before the graph ends, so a slab is complete (in stream order) when its
+        # backward returns; the eager-launch debugging mode gives no such guarantee.  V2A_OVERLAP_ALLREDUCE=0 = one
+        # blocking exchange after backward (A/B probe).
+        self._overlap = os.environ.get("V2A_OVERLAP_ALLREDUCE", "1") != "0" and not os.environ.get("V2A_NO_GRAPH")
         self._lib = _lib.load()
 
     def close(self) -> None:
@@ -232,11 +239,11 @@ class PolicyTrainStep:
         """all-reduce (mean) -> global grad-norm -> clip + AdamW + EMA, all asynchronous on the stream."""
         st = ops._stream()
         segs = list(self._segments())
-        early, self._early_works = self._early_works, None
-        if early is not None:      # the UNet1D slab's exchange was started from inside backward (segs[0])
-            works = early + distributed.allreduce_mean_start([g for _, g in segs[1:]], self.group, self.bucket_bytes)
-        else:
-            works = distributed.allreduce_mean_start([g for _, g in segs], self.group, self.bucket_bytes)
+        early, self._early = self._early, {}
+        works = []
+        for _, g in segs:          # same slab order on every rank; slabs already in flight are not started twice
+            w = early.pop(g.data_ptr(), None)
+            works += w if w is not None else distributed.allreduce_mean_start([g], self.group, self.bucket_bytes)
         self.collectives += distributed.allreduce_wait(works)
         self.sumsq.zero_()
         for _, g in segs:
@@ -259,15 +266,14 @@ class PolicyTrainStep:
         """Run ``loss_fn`` (it must call the module), backward, and the optimiser tail.  Returns the loss
         tensor (device resident; reading it synchronises)."""
         loss = loss_fn()
-        if self._overlap and self.cores:
-            # V2A_OVERLAP_ALLREDUCE=1 (multi-GPU, default off until measured): autograd runs the UNet1D's backward
-            # before the observation encoders'; its gradient slab (260 of the 349 MB) starts its all-reduce the
-            # moment it is complete and travels under the encoders' backward
-            eng = policy_unet1d.last_engine(self.unet)
-            if eng is not None:
-                def start(eng=eng):
-                    self._early_works = distributed.allreduce_mean_start([eng.gslab], self.group, self.bucket_bytes)
-                eng.on_backward_done = start
+        if self._overlap and distributed.world_size(self.group) > 1:
+            engines = [policy_unet1d.last_engine(self.unet)] + [obs_encoder.last_engine(c) for c in self.cores]
+            for eng in engines:
+                if eng is not None:
+                    def start(eng=eng):
+                        self._early[eng.gslab.data_ptr()] = distributed.allreduce_mean_start(
+                            [eng.gslab], self.group, self.bucket_bytes)
+                    eng.on_backward_done = start
         loss.backward()
         self.optimizer_tail()
         return loss.detach()
@@ -318,4 +324,12 @@ class PolicyTrainStep:
                 src[names[id(p)]] = e
         for n, p in target.named_parameters():
             if n in src:
-                p.data.copy_(src[n])
+                p.copy_(src[n])          # in-place through autograd's version counter (under no_grad)
+        # the target's engines key their packed weights on (data_ptr, _version) + a content fingerprint at
+        # inference; drop the caches explicitly as well so the very next forward repacks
+        from .diffusion_policy import VisualCore
+        for m in target.modules():
+            if isinstance(m, policy_unet1d.ConditionalUnet1D):
+                policy_unet1d.invalidate_weights(m)
+            elif isinstance(m, VisualCore):
+                obs_encoder.invalidate_weights(m)
