@@ -85,6 +85,11 @@ typedef struct v2a_igemm_desc {
     int64_t stats_rep_stride;   /* doubles between consecutive copies */
     int a_fp16;             /* source planes are fp16 (hi, lo) pairs instead of bf16 ones (22+ bit operands) */
     int b_fp16;             /* same for the weight planes */
+    int64_t out_pix_mul[4]; /* all zero: output rows follow the grid densely (D0 fastest).  Otherwise the output row */
+    int64_t out_pix_off;    /* (and residual row) of grid point c is out_pix_off + sum c[d] * out_pix_mul[d]: the four
+                               sub-pixel phases of `Upsample` (F.interpolate(nearest, x2) -> 3x3 conv,
+                               guided_diffusion/unet.py:107-114) are 2x2-tap convs over the LOW-resolution grid whose
+                               results interleave on the fine grid */
 } v2a_igemm_desc;
 
 int v2a_igemm_plan_create(const v2a_igemm_desc* desc, void** plan_out);

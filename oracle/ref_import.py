@@ -19,7 +19,15 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("V2A_REFERENCE_ROOT", "/root/reference")
+def _default_root() -> str:
+    """/root/reference in the build container; on the GPU box the copy `oracle/make_ref.py` ships under
+    baseline/_ref (git-ignored, travels with the gpurun snapshot)."""
+    if os.path.isdir("/root/reference/flowdiffusion/flowdiffusion"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+REF_ROOT = os.environ.get("V2A_REFERENCE_ROOT") or _default_root()
 
 
 def available() -> bool:
@@ -137,3 +145,36 @@ def replay_buffer_module():
 
 def img_utils_module():
     return _imp("diffuser.datasets.img_utils")
+
+
+def build_reference_policy():
+    """The reference's own `DiffusionUnetImagePolicy` with the Libero yaml's settings
+    (config/diff_policy/lb_train_diffusion_unet_image_orn10.yaml).  `diffusers` is absent offline: the class
+    receives the restated scheduler objects of v2a_b200.diffusion_policy (third-party boundary)."""
+    install_shims()
+    from v2a_b200 import diffusion_policy as DP
+    pol = importlib.import_module("diffuser.diffusion_policy.diffusion_unet_image_policy")
+    moe = importlib.import_module("diffuser.diffusion_policy.model.multi_image_obs_encoder")
+    vn = importlib.import_module("diffuser.diffusion_policy.common.vision_nets")
+    meta = DP.libero_shape_meta()
+    core = vn.VisualCore(input_shape=[3, 128, 128], backbone_class="ResNet18Conv",
+                         backbone_kwargs=dict(pretrained=None, input_coord_conv=False), pool_class="SpatialSoftmax",
+                         pool_kwargs=dict(num_kp=32, learnable_temperature=False, temperature=1.0, noise_std=0.0,
+                                          output_variance=False), flatten=True, feature_dimension=64)
+    enc = moe.MultiImageObsEncoder(meta, core, use_group_norm=True)
+    sched = dict(num_train_timesteps=100, beta_start=0.0001, beta_end=0.02, beta_schedule="squaredcos_cap_v2",
+                 clip_sample=True, prediction_type="epsilon")
+    return pol.DiffusionUnetImagePolicy(meta, DP.DDPMScheduler(**sched), DP.DDIMScheduler(**sched), enc, horizon=16,
+                                        n_action_steps=8, n_obs_steps=1, num_inference_steps=100,
+                                        diffusion_step_embed_dim=128, down_dims=[256, 512, 1024], kernel_size=5,
+                                        n_groups=8, cond_predict_scale=True)
+
+
+def build_reference_video_diffusion(timesteps: int = 100, sampling_timesteps: int = 100, frames: int = 7,
+                                     image_size=(128, 128)):
+    """The reference's own GoalGaussianDiffusion(Unet_Libero()) at the shipped Libero settings
+    (diffuser/models/video_model.py:15-40: pred_v, cosine schedule, guidance off)."""
+    UL, G = Unet_Libero(), GoalGaussianDiffusion()
+    return G(UL(), image_size=tuple(image_size), channels=3 * frames, timesteps=timesteps,
+             sampling_timesteps=sampling_timesteps, loss_type="l2", objective="pred_v", beta_schedule="cosine",
+             min_snr_loss_weight=True, guidance_weight=0)

@@ -28,24 +28,7 @@ FULL_GRADS = [_E + "img_obs_1.backbone.nets.0.weight", _E + "img_obs_1.backbone.
 FULL_GRAD_ROWS = 16
 
 
-def build_reference_policy():
-    R.install_shims()
-    from v2a_b200 import diffusion_policy as DP
-    pol = importlib.import_module("diffuser.diffusion_policy.diffusion_unet_image_policy")
-    moe = importlib.import_module("diffuser.diffusion_policy.model.multi_image_obs_encoder")
-    vn = importlib.import_module("diffuser.diffusion_policy.common.vision_nets")
-    meta = DP.libero_shape_meta()
-    core = vn.VisualCore(input_shape=[3, 128, 128], backbone_class="ResNet18Conv",
-                         backbone_kwargs=dict(pretrained=None, input_coord_conv=False), pool_class="SpatialSoftmax",
-                         pool_kwargs=dict(num_kp=32, learnable_temperature=False, temperature=1.0, noise_std=0.0,
-                                          output_variance=False), flatten=True, feature_dimension=64)
-    enc = moe.MultiImageObsEncoder(meta, core, use_group_norm=True)
-    sched = dict(num_train_timesteps=100, beta_start=0.0001, beta_end=0.02, beta_schedule="squaredcos_cap_v2",
-                 clip_sample=True, prediction_type="epsilon")
-    return pol.DiffusionUnetImagePolicy(meta, DP.DDPMScheduler(**sched), DP.DDIMScheduler(**sched), enc, horizon=16,
-                                        n_action_steps=8, n_obs_steps=1, num_inference_steps=100,
-                                        diffusion_step_embed_dim=128, down_dims=[256, 512, 1024], kernel_size=5,
-                                        n_groups=8, cond_predict_scale=True)
+build_reference_policy = R.build_reference_policy
 
 
 def main():

@@ -200,3 +200,24 @@ def test_conv1d_wgrad_via_transposed_im2col_and_concat_slices():
     wpk = convs.conv1d_cat_weight(w.detach(), [C0, C1])
     out = emulate(prog, [xl[:, :, :C0].reshape(1, 1, B, T, C0), xl[:, :, C0:].reshape(1, 1, B, T, C1)], wpk, Co)
     torch.testing.assert_close(out, y.permute(0, 2, 1).reshape(-1, Co), rtol=1e-12, atol=1e-12)
+
+
+def test_upsample_subpixel_phases_match_interpolate_then_conv2d():
+    """`Upsample` (guided_diffusion/unet.py:107-114: nearest x2 on (H, W), then 3x3 conv) as four 2x2-tap convs over
+    the coarse grid whose outputs interleave on the fine grid (`out_pix` addressing of the kernel)."""
+    N, Ci, Co, H, W = 2, 24, 40, 5, 6
+    x = torch.randn(N, Ci, H, W, dtype=D)
+    w = torch.randn(Co, Ci, 3, 3, dtype=D)
+    ref = _nhwc(F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1))     # [N*2H*2W, Co]
+    out = torch.full_like(ref, float("nan"))
+    for py in range(2):
+        for px in range(2):
+            prog = convs.upsample3x3_phase(Ci, N, H, W, py, px)
+            assert prog.ktot == 4 * 64 and prog.out_dims == (W, H, N, 1)
+            y = emulate(prog, [as5d(_nhwc(x), Ci, prog.src_dims[0])], convs.upsample3x3_phase_weight(w, py, px), Co)
+            (m0, m1, m2, _), off = convs.upsample3x3_out_pix(H, W, py, px)
+            j, i, n = torch.meshgrid(torch.arange(W), torch.arange(H), torch.arange(N), indexing="ij")
+            rows = (off + j * m0 + i * m1 + n * m2).permute(2, 1, 0).reshape(-1)               # grid order: n, i, j
+            out[rows] = y
+    assert not torch.isnan(out).any()                                                         # every fine pixel written once
+    torch.testing.assert_close(out, ref, rtol=1e-12, atol=1e-12)

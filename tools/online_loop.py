@@ -56,7 +56,25 @@ def main():
     ap.add_argument("--batch-videos", action="store_true",
                     help="sample the sub-goal videos of all of a rank's tasks in one call instead of one by one")
     args = ap.parse_args()
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("online_loop.py needs a CUDA device: the v2a_b200 paths have no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = run_loop(args)
+    if out is not None:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
 
+
+def run_loop(args):
+    """The loop itself on an initialised process group (bench.py calls this in-process so that the N-GPU run of
+    configs[4] is part of the driver-run line).  ``args``: namespace with tasks, iters, policy_steps, batch,
+    denoise_steps, exec_steps, batch_videos.  Returns the result dict on rank 0, None elsewhere."""
     import torch.distributed as dist
     from v2a_b200.diffusion_policy import build_libero_policy
     from v2a_b200.goal_diffusion import GoalGaussianDiffusion
@@ -66,12 +84,6 @@ def main():
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("online_loop.py needs a CUDA device: the v2a_b200 paths have no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     torch.manual_seed(0)                                     # same initial weights on every rank
     net = Unet_Libero()
@@ -177,8 +189,9 @@ def main():
         ms_explore += max_over_ranks(e0.elapsed_time(e1))
         ms_train += max_over_ranks(e1.elapsed_time(e2))
     n_vid = args.tasks * args.iters
+    step.close()
     if rank == 0:
-        print(json.dumps({
+        return ({
             "what": "configs[4] in miniature: per task sample() at B=1 + predict_action rollout on a stub simulator + "
                     "replay insert, then policy optimisation steps fed by the HBM replay buffer (all-reduce for N>1)",
             "n_gpus": world, "tasks": args.tasks, "batch_videos": bool(args.batch_videos), "iters": args.iters, "denoise_steps": args.denoise_steps,
@@ -189,9 +202,8 @@ def main():
             "policy_samples_per_s": args.batch * world * args.iters * args.policy_steps / (ms_train * 1e-3),
             "batch_per_gpu": args.batch, "policy_steps_per_iter": args.policy_steps,
             "replay_episodes": len(replay), "replay_bytes_in_hbm": replay.nbytes(), "loss": float(loss_host.item()),
-            "stubs": "simulator (random uint8 frames), CLIP text encoder (random task embeddings), random-init weights"}))
-    if world > 1:
-        dist.destroy_process_group()
+            "stubs": "simulator (random uint8 frames), CLIP text encoder (random task embeddings), random-init weights"})
+    return None
 
 
 if __name__ == "__main__":

@@ -54,6 +54,8 @@ class IgemmDesc(C.Structure):
         ("stats_rep_stride", C.c_int64),
         ("a_fp16", C.c_int),
         ("b_fp16", C.c_int),
+        ("out_pix_mul", C.c_int64 * 4),
+        ("out_pix_off", C.c_int64),
     ]
 
 

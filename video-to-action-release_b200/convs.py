@@ -60,6 +60,33 @@ def spatial3x3_s2(cin: int, N: int, H: int, W: int) -> ConvProgram:
     return ConvProgram([cin], [(W // 2, H // 2, 4, N)], taps, (W // 2, H // 2, 1, N))
 
 
+# ---- Upsample = nearest x2 on (H, W) then 3x3 conv (guided_diffusion/unet.py:107-114), as four sub-pixel phases ----
+# Output pixel (2i + py, 2j + px) of the fine grid reads fine rows 2i + py + kh - 1, i.e. COARSE rows
+#   py = 0: i - 1 (kh = 0), i (kh = 1, 2)        py = 1: i (kh = 0, 1), i + 1 (kh = 2)
+# and the same along W.  Taps that hit the same coarse pixel share its value, so their weights add: each phase is a
+# 2x2-tap conv over the coarse grid (4 instead of 9 taps: 2.25x fewer MACs than convolving the upsampled tensor, which
+# is never materialised).  The fine grid's zero padding (rows -1 and 2H) falls on coarse rows -1 and H: still the TMA
+# out-of-bounds zero fill.
+_UP_ROWS = {0: ((-1, (0,)), (0, (1, 2))), 1: ((0, (0, 1)), (1, (2,)))}     # phase -> ((coarse offset, kernel taps), ...)
+
+
+def upsample3x3_phase(cin: int, N: int, H: int, W: int, py: int, px: int) -> ConvProgram:
+    """Phase (py, px) over the COARSE grid (H, W = input sizes); tap order (row offset, col offset) row-major."""
+    taps = [(0, (dw, dh, 0, 0), nchunks(cin)) for dh, _ in _UP_ROWS[py] for dw, _ in _UP_ROWS[px]]
+    return ConvProgram([cin], [(W, H, N, 1)], taps, (W, H, N, 1))
+
+
+def upsample3x3_phase_weight(w: torch.Tensor, py: int, px: int) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> [Cout, 4 * pad64(Cin)]: per coarse tap the sum of the kernel taps that land on it."""
+    return pack_weight_taps([sum(w[:, :, kh, kw] for kh in khs for kw in kws)
+                             for _, khs in _UP_ROWS[py] for _, kws in _UP_ROWS[px]])
+
+
+def upsample3x3_out_pix(H: int, W: int, py: int, px: int):
+    """(multipliers, offset) of the fine-grid row written for coarse grid point (j, i, n): ((n*2H + 2i+py)*2W + 2j+px)."""
+    return (2, 4 * W, 4 * H * W, 0), py * 2 * W + px
+
+
 def temporal3(c: int, B: int, F: int, HW: int, skip_channels: int = 0) -> ConvProgram:
     """Conv1d(C, C, 3) over frames, zero padded; optional 1x1 skip conv as extra K."""
     taps = [(0, (0, k - 1, 0, 0), nchunks(c)) for k in range(3)]

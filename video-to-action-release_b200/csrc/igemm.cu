@@ -101,6 +101,8 @@ struct alignas(64) IgemmParams {
     int nacc_log2;        // accumulator ring: 2 x 256 TMEM columns (1) or 4 x 128 (2: block_n <= 128, unfused)
     int cta2;             // CTA pairs issue ONE cta_group::2 MMA (M = 256, B split between the two SMs)
     int fuse2;            // N <= 128: a_hi x [b_hi | b_lo] as ONE N = 2*block_n MMA (two accumulator halves)
+    long long out_mul[4]; // output row of grid point c = out_off + sum c[d] * out_mul[d] (dense by default; the
+    long long out_off;    // sub-pixel phases of the upsample conv write every other row / column of a finer grid)
     int debug;  // V2A_IGEMM_DEBUG bits: 1 skip stats, 2 skip stores, 4 skip residual (timing experiments only)
 };
 
@@ -432,9 +434,8 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                 r >>= p.tile_log2[d];
                 valid = valid && (coord[d] < p.out_dims[d]);
             }
-            const int64_t pix =
-                ((int64_t)(coord[3] * p.out_dims[2] + coord[2]) * p.out_dims[1] + coord[1]) *
-                    p.out_dims[0] + coord[0];
+            const int64_t pix = p.out_off + coord[0] * p.out_mul[0] + coord[1] * p.out_mul[1] +
+                                coord[2] * p.out_mul[2] + coord[3] * p.out_mul[3];
             int rv = 0, inst = 0;
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
@@ -478,15 +479,14 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                 decode_tile(p, tile + tr.step, n_idx2, o2, split2);
                 if (split2 == 0) {
                     int r2 = row;
-                    int64_t pix2 = 0, mul = 1;
+                    int64_t pix2 = p.out_off;
                     bool valid2 = true;
 #pragma unroll
                     for (int d = 0; d < 4; ++d) {
                         const int cd = o2[d] + (r2 & ((1 << p.tile_log2[d]) - 1));
                         r2 >>= p.tile_log2[d];
                         valid2 = valid2 && (cd < p.out_dims[d]);
-                        pix2 += cd * mul;
-                        mul *= p.out_dims[d];
+                        pix2 += cd * p.out_mul[d];
                     }
                     const int cpf = n_idx2 * p.block_n + c_begin + 16 * piece;   // 4 lanes x 64 B = this warp's 64 columns
 #pragma unroll
@@ -857,6 +857,17 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
     p.stats_rep_stride = d->stats_rep_stride;
     p.a_fp16 = d->a_fp16;
     p.b_fp16 = d->b_fp16;
+    if (d->out_pix_mul[0] | d->out_pix_mul[1] | d->out_pix_mul[2] | d->out_pix_mul[3]) {
+        for (int i = 0; i < 4; ++i) p.out_mul[i] = d->out_pix_mul[i];
+        p.out_off = d->out_pix_off;
+    } else {                       // dense: rows in grid order, D0 fastest
+        long long m = 1;
+        for (int i = 0; i < 4; ++i) {
+            p.out_mul[i] = m;
+            m *= d->out_dims[i];
+        }
+        p.out_off = 0;
+    }
     {
         const char* env = getenv("V2A_FUSE2");
         p.fuse2 = (d->passes == 3 && d->block_n <= 128 && !(env && atoi(env) == 0)) ? 1 : 0;

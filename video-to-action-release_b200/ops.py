@@ -130,7 +130,11 @@ class Igemm:
 
     def __init__(self, *, srcs, taps, w: HL, out_dims, cout, ldc=None, out_f32=None, out_hl=None,
                  bias=None, rowvec=None, rowvec_mul=(0, 0, 0, 0), residual=None, stats=None,
-                 stats_mul=(0, 0, 0, 0), block_n=None, passes=3, tile_log2=None):
+                 stats_mul=(0, 0, 0, 0), block_n=None, passes=3, tile_log2=None, out_pix=None, algo_flops_scale=1.0):
+        """out_pix = ((m0, m1, m2, m3), off): the output row of grid point c is off + sum c[d] * m[d] instead of
+        the dense grid order (sub-pixel phases writing into a finer grid); the output tensors are then only
+        checked for covering the largest row.  algo_flops_scale: algorithmic / executed FLOPs of this launch
+        (9/4 for a sub-pixel phase, which does 4 of the reference's 9 taps' worth of work)."""
         lib = _lib.load()
         d = _lib.IgemmDesc()
         self._keep = [srcs, w, out_f32, out_hl, bias, rowvec, residual, stats]
@@ -174,6 +178,14 @@ class Igemm:
         d.passes = passes
         d.cout = cout
         rows = out_dims[0] * out_dims[1] * out_dims[2] * out_dims[3]
+        out_rows = rows
+        if out_pix is not None:
+            mul, off = out_pix
+            out_rows = off + sum((out_dims[k] - 1) * mul[k] for k in range(4)) + 1     # largest row written + 1
+            for k in range(4):
+                d.out_pix_mul[k] = mul[k]
+            d.out_pix_off = off
+            assert any(mul), "out_pix multipliers must not all be zero"
         # outputs may be column windows of wider row-pitched matrices: the pitch is the view's stride(0)
         if ldc is None:
             if out_f32 is not None and out_f32.dim() == 2:
@@ -187,15 +199,17 @@ class Igemm:
         if out_f32 is not None:
             assert out_f32.dtype == torch.float32
             if out_f32.dim() == 2:
-                assert out_f32.shape[0] == rows and out_f32.stride(1) == 1 and out_f32.stride(0) == ldc
+                assert out_f32.shape[0] >= out_rows and out_f32.stride(1) == 1 and out_f32.stride(0) == ldc
+                assert out_pix is not None or out_f32.shape[0] == rows
             else:
-                assert out_f32.numel() == rows * ldc
+                assert out_f32.numel() >= out_rows * ldc
             d.out_f32 = out_f32.data_ptr()
         if out_hl is not None:
             if out_hl.hi.dim() == 2:
-                assert out_hl.hi.shape[0] == rows and out_hl.hi.stride(0) == ldc == out_hl.lo.stride(0)
+                assert out_hl.hi.shape[0] >= out_rows and out_hl.hi.stride(0) == ldc == out_hl.lo.stride(0)
+                assert out_pix is not None or out_hl.hi.shape[0] == rows
             else:
-                assert out_hl.hi.numel() == rows * ldc
+                assert out_hl.hi.numel() >= out_rows * ldc
             d.out_hi, d.out_lo = out_hl.hi.data_ptr(), out_hl.lo.data_ptr()
         if bias is not None:
             assert bias.dtype == torch.float32 and bias.numel() >= cout
@@ -216,7 +230,8 @@ class Igemm:
             d.stats_replicas = stats.shape[0] if stats.dim() == 4 else 1
             d.stats_rep_stride = stats.stride(0) if stats.dim() == 4 else 0
         self.desc = d
-        self.flops = 2.0 * rows * cout * sum(nch * CHUNK_K for _, _, nch in taps)
+        self.flops = 2.0 * rows * cout * sum(nch * CHUNK_K for _, _, nch in taps)    # executed by the tensor cores
+        self.algo_flops = self.flops * algo_flops_scale                               # of the reference's algorithm
         plan = C.c_void_p()
         _lib.check(lib.v2a_igemm_plan_create(C.byref(d), C.byref(plan)), "igemm_plan_create")
         self._plan = plan

@@ -435,20 +435,33 @@ class _UNetEngine:
                 self.igemms.append(g)
         self._pending = []
         self.flops = sum(g.flops for g in self.igemms)
+        self.algo_flops = sum(g.algo_flops for g in self.igemms)
 
     # ---- building blocks ---------------------------------------------------
-    def conv3d(self, m: Conv3d, a_hl: HL, cin, N, H, W, *, stride2=False, rowvec=None, residual=None,
-               skip=None, extra_bias=None) -> _Act:
-        """spatial 3x3 (TMA zero-padded taps) -> hl y -> temporal k3 (+skip K) -> fp32 raw + sums."""
+    def conv3d(self, m: Conv3d, a_hl: HL, cin, N, H, W, *, stride2=False, upsample=False, rowvec=None,
+               residual=None, skip=None, extra_bias=None) -> _Act:
+        """spatial 3x3 (TMA zero-padded taps) -> hl y -> temporal k3 (+skip K) -> fp32 raw + sums.
+        H, W are the sizes of ``a_hl``'s grid; ``upsample``: the conv runs on the nearest-x2 upsampled grid
+        (gd/unet.py:107-114) as four sub-pixel phases over the coarse operand, see convs.upsample3x3_phase."""
         B, Fr = self.B, self.Fr
         cout = m.spatial_conv.out_channels
-        Ho, Wo = (H // 2, W // 2) if stride2 else (H, W)
-        prog = convs.spatial3x3_s2(cin, N, H, W) if stride2 else convs.spatial3x3(cin, N, H, W)
-        w_s = self.weight(lambda: convs.spatial3x3_weight(m.spatial_conv.weight), cout, prog.ktot)
+        Ho, Wo = (H // 2, W // 2) if stride2 else ((2 * H, 2 * W) if upsample else (H, W))
         b_s = self.vec(lambda: m.spatial_conv.bias, cout)
         y_hl, y_st = self.hl(N * Ho * Wo, cout)
-        self.add_igemm(srcs=[(a_hl, cin, prog.src_dims[0])], taps=prog.taps, w=w_s, out_dims=prog.out_dims,
-                       cout=cout, out_hl=y_hl, bias=b_s)
+        if upsample:
+            for py in range(2):
+                for px in range(2):
+                    prog = convs.upsample3x3_phase(cin, N, H, W, py, px)
+                    w_p = self.weight(lambda py=py, px=px: convs.upsample3x3_phase_weight(m.spatial_conv.weight, py, px),
+                                      cout, prog.ktot)
+                    self.add_igemm(srcs=[(a_hl, cin, prog.src_dims[0])], taps=prog.taps, w=w_p,
+                                   out_dims=prog.out_dims, cout=cout, out_hl=y_hl, bias=b_s,
+                                   out_pix=convs.upsample3x3_out_pix(H, W, py, px), algo_flops_scale=9 / 4)
+        else:
+            prog = convs.spatial3x3_s2(cin, N, H, W) if stride2 else convs.spatial3x3(cin, N, H, W)
+            w_s = self.weight(lambda: convs.spatial3x3_weight(m.spatial_conv.weight), cout, prog.ktot)
+            self.add_igemm(srcs=[(a_hl, cin, prog.src_dims[0])], taps=prog.taps, w=w_s, out_dims=prog.out_dims,
+                           cout=cout, out_hl=y_hl, bias=b_s)
         out = _Act(self, N, Ho, Wo, cout)
         HW = Ho * Wo
         srcs = [(y_hl, cout, (HW, Fr, B, 1))]
@@ -533,13 +546,14 @@ class _UNetEngine:
         return out
 
     def resample(self, conv: Conv3d, x: _Act, *, down: bool) -> _Act:
-        rows_out = x.rows * (1 if down else 4)
-        s_hl, s_st = self.hl(rows_out, x.C)
-        self.add_prep(x0=x.raw, mode=2 if down else 1, H=x.H, W=x.W, out_hl=s_hl)
+        s_hl, s_st = self.hl(x.rows, x.C)
+        # down: stride-2 phase split of the operand; up: a plain hi/lo split of the COARSE tensor -- the upsampled
+        # tensor (4x the rows) is never written, the conv's sub-pixel phases read the coarse one
+        self.add_prep(x0=x.raw, mode=2 if down else 0, H=x.H, W=x.W, out_hl=s_hl)
         if down:
             out = self.conv3d(conv, s_hl, x.C, x.N, x.H, x.W, stride2=True)
         else:
-            out = self.conv3d(conv, s_hl, x.C, x.N, 2 * x.H, 2 * x.W)
+            out = self.conv3d(conv, s_hl, x.C, x.N, x.H, x.W, upsample=True)
         self.release(s_st)
         self.free_act(x)
         return out
