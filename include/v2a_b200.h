@@ -217,6 +217,12 @@ int v2a_timestep_embedding(const int64_t* t, int B, int dim, int mode, float* ou
 int v2a_unet_input_pack(const float* x, const int64_t* x_strides, const float* cond,
                         const int64_t* cond_strides, int B, int F, int H, int W, void* out_hi,
                         void* out_lo, void* stream);
+/* Second half of the out head's 3x3 conv (GN -> SiLU -> Conv3d(128, 3), guided_diffusion/unet.py:628-632): the
+ * spatial conv runs as a 1x1 conv to 9*cout columns (P[pix][tap*cout + co], one igemm pass over the activation)
+ * and this kernel gathers the nine taps: y[n,h,w][co] = bias[co] + sum_{kh,kw} P[n,h+kh-1,w+kw-1][(kh*3+kw)*cout+co],
+ * zero outside the image.  cout <= 4. */
+int v2a_stencil9(const float* P, int ldp, const float* bias, int N, int H, int W, int cout, float* y, int ldy,
+                 void* stream);
 /* y fp32 [B][F][H][W][ldy] (3 used) -> temporal Conv1d(3,3,k3)+bias ->
  * out[b*s[0] + f*s[1] + c*s[2] + h*W + w] */
 int v2a_unet_output_head(const float* y, int ldy, const float* wt, const float* bt, int B, int F,

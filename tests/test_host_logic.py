@@ -221,3 +221,28 @@ def test_upsample_subpixel_phases_match_interpolate_then_conv2d():
             out[rows] = y
     assert not torch.isnan(out).any()                                                         # every fine pixel written once
     torch.testing.assert_close(out, ref, rtol=1e-12, atol=1e-12)
+
+
+def stencil9_reference(P, bias, N, H, W, cout):
+    """What `v2a_stencil9` computes, with torch indexing: y[n,h,w,co] = bias[co] + sum_taps P[n,h+kh-1,w+kw-1,tap*cout+co]."""
+    Pp = F.pad(P.reshape(N, H, W, -1), (0, 0, 1, 1, 1, 1))
+    y = bias.to(P.dtype).expand(N, H, W, cout).clone()
+    for kh in range(3):
+        for kw in range(3):
+            t = kh * 3 + kw
+            y = y + Pp[:, kh:kh + H, kw:kw + W, t * cout:(t + 1) * cout]
+    return y.reshape(N * H * W, cout)
+
+
+def test_out_head_as_1x1_conv_plus_nine_tap_gather_matches_conv2d():
+    """The out head's Conv2d(128, 3, 3x3) (guided_diffusion/unet.py:628-632) as a 1x1 conv to 27 columns followed by a
+    9-point gather (`convs.taps_as_columns_weight` + `ops.stencil9`)."""
+    N, Ci, Co, H, W = 3, 72, 3, 6, 5
+    x = torch.randn(N, Ci, H, W, dtype=D)
+    w, b = torch.randn(Co, Ci, 3, 3, dtype=D), torch.randn(Co, dtype=D)
+    prog = convs.pointwise(Ci, (N * H * W,))
+    wp = convs.taps_as_columns_weight(w)
+    assert tuple(wp.shape) == (27, 128)
+    P = emulate(prog, [as5d(_nhwc(x), Ci, prog.src_dims[0])], wp, 27)
+    torch.testing.assert_close(stencil9_reference(P, b, N, H, W, Co), _nhwc(F.conv2d(x, w, b, padding=1)),
+                               rtol=1e-12, atol=1e-12)

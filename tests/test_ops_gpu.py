@@ -347,3 +347,18 @@ def test_igemm_cta_pair_multicast_matches_single_cta(N, H, W, ci, co, monkeypatc
     else:
         assert torch.equal(got, got1)            # same MMA order per tile: bit identical outputs
         assert _rel(st, st1) < 1e-12
+
+
+def test_stencil9_matches_its_torch_restatement():
+    """`v2a_stencil9` (second half of the out head's 3x3 conv) against the indexing restatement that
+    tests/test_host_logic.py pins against F.conv2d; ragged image sizes, per-image zero padding."""
+    from tests.test_host_logic import stencil9_reference
+    from v2a_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for (N, H, W) in ((3, 6, 5), (2, 16, 16), (7, 1, 9)):
+        P = torch.randn(N * H * W, 32, generator=g).cuda()
+        bias = torch.randn(3, generator=g).cuda()
+        y = torch.full((N * H * W, 4), float("nan"), device="cuda")
+        ops.stencil9(P, bias, N, H, W, 3, y)
+        want = stencil9_reference(P.double(), bias.double(), N, H, W, 3)
+        assert torch.allclose(y[:, :3].double(), want, rtol=1e-6, atol=1e-6)

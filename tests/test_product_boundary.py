@@ -25,10 +25,15 @@ def test_product_never_touches_the_oracle_or_the_reference_checkout():
 def test_bench_uses_the_oracle_only_in_the_cpu_baseline_and_reference_arm():
     with open(os.path.join(ROOT, "bench.py")) as f:
         src = f.read()
-    allowed = {"synthetic_state_dict", "cpu_reference_step", "policy_cpu_reference_step", "synthetic_policy_state_dict",
-               "run_reference_gpu_eager"}      # the last one = `--impl reference --reference-device cuda` (reference arm)
+    # the helpers of the reference arms (`--impl reference`, cpu or cuda) and of the `cpu_baseline` leg; our arm's
+    # measured path (run_ours / run_policy / measure_kernel_roofline) must stay free of them
+    allowed = {"_reference_modules", "_port_video_step", "_policy_step_fn"}
     for m in re.finditer(r"^\s+from oracle\b.*$", src, re.M):
         head = src[:m.start()]
         fn = re.findall(r"^def (\w+)\(", head, re.M)[-1]
         assert fn in allowed, f"bench.py imports the oracle inside {fn}()"
     assert not re.search(r"^(from|import) oracle", src, re.M)
+    for fn in ("run_ours", "run_policy", "measure_kernel_roofline"):
+        body = src[src.index(f"def {fn}("):]
+        body = body[:body.index("\ndef ", 1)]
+        assert "oracle" not in body and "_video_step_fn" not in body and "_policy_step_fn" not in body, fn

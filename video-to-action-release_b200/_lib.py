@@ -191,6 +191,7 @@ SIGNATURES = {
     "v2a_linear": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "v2a_timestep_embedding": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "v2a_unet_input_pack": (_i, [_vp, C.POINTER(_i64), _vp, C.POINTER(_i64), _i, _i, _i, _i, _vp, _vp, _vp]),
+    "v2a_stencil9": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "v2a_unet_output_head": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, C.POINTER(_i64), _vp]),
     "v2a_ddpm_step": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "v2a_ddim_step": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),

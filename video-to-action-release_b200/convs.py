@@ -149,6 +149,13 @@ def pointwise_weight(w: torch.Tensor) -> torch.Tensor:
     return pack_weight_taps([w.reshape(w.shape[0], w.shape[1])])
 
 
+def taps_as_columns_weight(w: torch.Tensor) -> torch.Tensor:
+    """Out head: [Cout, Cin, 3, 3] (Cout tiny) -> [9 * Cout, pad64(Cin)], row = (kh*3 + kw) * Cout + co: the 3x3 conv as a
+    1x1 conv to 9*Cout columns whose taps `ops.stencil9` gathers afterwards."""
+    cout, cin = w.shape[:2]
+    return pack_weight_taps([w.permute(2, 3, 0, 1).reshape(9 * cout, cin)])
+
+
 def input_conv_weight(w: torch.Tensor) -> torch.Tensor:
     """First conv [Cout, 6, 3, 3] against the im2col'd 64-wide operand: k = tap*6 + c."""
     cout = w.shape[0]

@@ -405,6 +405,14 @@ def unet_input_pack(x, x_strides, cond, cond_strides, B, F, H, W, out: HL) -> No
                "unet_input_pack")
 
 
+def stencil9(P, bias, N, H, W, cout, y) -> None:
+    """y[pix][co] = bias[co] + sum over the 3x3 neighbourhood of P[pix + d(tap)][tap * cout + co] (zero padded per image)."""
+    _require_cuda(P, y)
+    assert P.dim() == 2 and y.dim() == 2 and P.shape[0] == y.shape[0] == N * H * W
+    _lib.check(_lib.load().v2a_stencil9(P.data_ptr(), P.stride(0), _ptr(bias), N, H, W, cout, y.data_ptr(), y.stride(0),
+                                        _stream()), "stencil9")
+
+
 def unet_output_head(y, ldy, wt, bt, B, F, H, W, out, out_strides) -> None:
     _lib.check(_lib.load().v2a_unet_output_head(y.data_ptr(), ldy, wt.data_ptr(), bt.data_ptr(), B, F,
                                                 H, W, out.data_ptr(), _i64x3(out_strides), _stream()),

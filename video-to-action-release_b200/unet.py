@@ -630,20 +630,26 @@ class _UNetEngine:
         h = self.run_block(model.middle_block, [h])
         for block in model.output_blocks:
             h = self.run_block(block, [h, hs.pop()])
-        # out head: GN -> SiLU -> 3x3 conv to 3 channels (N tile 16) -> temporal conv + layout kernel
+        # out head: GN -> SiLU -> 3x3 conv to 3 channels -> temporal conv + layout kernel.  With 3 output channels the
+        # nine-tap implicit GEMM re-reads the 128-channel operand nine times to feed a 16-wide N tile (1.29 ms at
+        # 9.8 TFLOP/s in round 1); instead ONE 1x1 GEMM to 27 columns P[pix][tap*3 + co], then a 9-point gather.
         a, a_st, _, _, C = self.gn_prep([h], model.out[0], per_frame=False, act=ops.ACT_SILU)
         convo: Conv3d = model.out[2]
-        prog = convs.spatial3x3(C, N, H, W)
-        wo = self.weight(lambda: convs.spatial3x3_weight(convo.spatial_conv.weight), 3, prog.ktot)
+        prog = convs.pointwise(C, (N * H * W,))
+        wo = self.weight(lambda: convs.taps_as_columns_weight(convo.spatial_conv.weight), 27, prog.ktot)
         bo = self.vec(lambda: convo.spatial_conv.bias, 3)
-        self.y_out = torch.empty(N * H * W, 16, dtype=torch.float32, device=dev)
-        self.add_igemm(srcs=[(a, C, prog.src_dims[0])], taps=prog.taps, w=wo, out_dims=prog.out_dims, cout=3,
-                       ldc=16, out_f32=self.y_out, bias=bo)
+        p_out = self.pool.get(N * H * W * 32 * 4)
+        self.p_out = p_out.view(torch.float32).view(N * H * W, 32)
+        self.y_out = torch.empty(N * H * W, 4, dtype=torch.float32, device=dev)
+        self.add_igemm(srcs=[(a, C, prog.src_dims[0])], taps=prog.taps, w=wo, out_dims=prog.out_dims, cout=27,
+                       ldc=32, out_f32=self.p_out, block_n=32, algo_flops_scale=1.0)
+        self._step(lambda: ops.stencil9(self.p_out, bo, N, H, W, 3, self.y_out), "stencil9")
         self.wt_out = self.vec(lambda: convo.temporal_conv.weight, 27)
         self.bt_out = self.vec(lambda: convo.temporal_conv.bias, 3)
-        self._step(lambda: ops.unet_output_head(self.y_out, 16, self.wt_out, self.bt_out, B, Fr, H, W,
+        self._step(lambda: ops.unet_output_head(self.y_out, 4, self.wt_out, self.bt_out, B, Fr, H, W,
                                                 self.io["o"], self.io["os"]), "output_head")
         self.release(a_st)
+        self.pool.put(p_out)
         self.free_act(h)
 
     # ---- conditioning (step-invariant): PerceiverResampler on the text tokens ---
