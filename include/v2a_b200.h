@@ -303,6 +303,13 @@ int v2a_policy_im2col_t(const void* x_hi, const void* x_lo, int ld_x, int c_off,
 /* dy fp32 [rows][ld] (C used) -> hl [rows][ld_hl] (zero padded), hl^T [C][rows], colsum[C] += */
 int v2a_grad_prep(const float* dy, int64_t rows, int C, int ld, void* hi, void* lo, int ld_hl, void* t_hi,
                   void* t_lo, int64_t ld_T, float* colsum, void* stream);
+/* In-place DDIM update (eta = 0) of the action trajectory x [rows][ldx] (C used) from the model output [rows][ldm]:
+ *   epsilon prediction: x0 = clip((x - sqrt_1m_at * eps) / sqrt_at);  sample prediction: x0 = clip(model_out),
+ *   eps = (x - sqrt_at * x0) / sqrt_1m_at;   x <- sqrt_aprev * x0 + coef_eps * eps
+ * replaces diffusers' DDIMScheduler.step as predict_action drives it
+ * (diffuser/diffusion_policy/diffusion_unet_image_policy.py:124-128) */
+int v2a_policy_ddim_step(float* x, int ldx, const float* model_out, int ldm, int64_t rows, int C, float sqrt_1m_at,
+                         float sqrt_at, float sqrt_aprev, float coef_eps, int pred_sample, int clip, void* stream);
 /* dx = dy * act'(x), act 1 SiLU / 2 Mish; optional fp32 and hi/lo outputs */
 int v2a_act_bwd(const float* x, const float* dy, float* dx, void* hi, void* lo, int64_t n, int act,
                 void* stream);

@@ -203,6 +203,7 @@ SIGNATURES = {
     "v2a_policy_gn_act_bwd": (_i, [C.POINTER(PolicyGnDesc), _vp]),
     "v2a_policy_im2col_t": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _vp, _vp, _i64, _vp]),
     "v2a_grad_prep": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _i64, _vp, _vp]),
+    "v2a_policy_ddim_step": (_i, [_vp, _i, _vp, _i, _i64, _i, _f, _f, _f, _f, _i, _i, _vp]),
     "v2a_act_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "v2a_scatter_rows": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp]),
     "v2a_add_strided": (_i, [_vp, _i, _vp, _i, _i64, _i, _i, _vp]),

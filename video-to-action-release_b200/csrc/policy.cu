@@ -511,6 +511,30 @@ __global__ void adamw_ema_kernel(float* __restrict__ p, const float* __restrict_
                       ema_decay);
 }
 
+// DDIM update of the action trajectory, in place (diffusers DDIMScheduler.step with eta = 0, restated in
+// diffusion_policy.DDIMScheduler.step; one launch instead of ~10 elementwise torch kernels per denoise step).
+// Operation order follows that torch chain (separate roundings, no FMA contraction).
+__global__ void policy_ddim_step_kernel(float* __restrict__ x, int ldx, const float* __restrict__ mo, int ldm,
+                                        int64_t rows, int C, float c1, float c2, float c3, float c4,
+                                        int pred_sample, int clip) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * C) return;
+    const int64_t r = i / C;
+    const int c = (int)(i - r * C);
+    const float xt = x[r * ldx + c], m = mo[r * ldm + c];
+    float x0, eps;
+    if (pred_sample) {
+        x0 = m;
+        if (clip) x0 = x0 != x0 ? x0 : fminf(fmaxf(x0, -1.0f), 1.0f);
+        eps = __fdiv_rn(__fsub_rn(xt, __fmul_rn(c2, x0)), c1);     // (sample - sqrt(a_t) x0) / sqrt(1 - a_t)
+    } else {
+        eps = m;
+        x0 = __fdiv_rn(__fsub_rn(xt, __fmul_rn(c1, m)), c2);        // (sample - sqrt(1 - a_t) eps) / sqrt(a_t)
+        if (clip) x0 = x0 != x0 ? x0 : fminf(fmaxf(x0, -1.0f), 1.0f);
+    }
+    x[r * ldx + c] = __fadd_rn(__fmul_rn(c3, x0), __fmul_rn(c4, eps));   // sqrt(a_prev) x0 + sqrt(1 - a_prev) eps
+}
+
 }  // namespace v2a
 
 using namespace v2a;
@@ -619,6 +643,17 @@ int v2a_grad_prep(const float* dy, int64_t rows, int C, int ld, void* hi, void* 
     grad_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, rows, C, ld, (__nv_bfloat16*)hi,
                                                              (__nv_bfloat16*)lo, ld_hl, (__nv_bfloat16*)t_hi,
                                                              (__nv_bfloat16*)t_lo, ld_T > 0 ? ld_T : rows, colsum);
+    POL_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_policy_ddim_step(float* x, int ldx, const float* model_out, int ldm, int64_t rows, int C, float sqrt_1m_at,
+                         float sqrt_at, float sqrt_aprev, float coef_eps, int pred_sample, int clip, void* stream) {
+    V2A_REQUIRE(x && model_out && rows >= 0 && C >= 1 && ldx >= C && ldm >= C, "policy_ddim_step: bad arguments");
+    const int64_t n = rows * C;
+    if (n == 0) return 0;
+    policy_ddim_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x, ldx, model_out, ldm, rows, C, sqrt_1m_at, sqrt_at, sqrt_aprev, coef_eps, pred_sample, clip);
     POL_LAUNCH_OK();
     return 0;
 }

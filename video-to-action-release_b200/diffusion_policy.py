@@ -20,6 +20,8 @@ from __future__ import annotations
 
 import copy
 import math
+import os
+import weakref
 from types import SimpleNamespace
 from typing import Dict, Optional
 
@@ -28,7 +30,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import obs_encoder, packing
+from . import _lib, obs_encoder, ops, packing
 from .policy_unet1d import ConditionalUnet1D
 
 
@@ -450,6 +452,12 @@ class DiffusionUnetImagePolicy(_AttrMixin):
             return self._predict_action(obs_dict, use_ddim)
 
     def _predict_action(self, obs_dict, use_ddim):
+        plan = _predict_plan_for(self, obs_dict, use_ddim)
+        if plan is not None:                     # the latency path: encoders + 8 DDIM steps as ONE CUDA graph
+            nsample = plan.run(obs_dict)
+            action_pred = self.normalizer["action"].unnormalize(nsample[..., :self.action_dim]).detach()
+            start = self.n_obs_steps - 1
+            return {"action": action_pred[:, start:start + self.n_action_steps], "action_pred": action_pred}
         global_cond, B = self._global_cond(obs_dict)
         cond = torch.zeros((B, self.horizon, self.action_dim), device=self.device, dtype=self.dtype)
         nsample = self.conditional_sample(cond, torch.zeros_like(cond, dtype=torch.bool), global_cond=global_cond,
@@ -482,6 +490,138 @@ class DiffusionUnetImagePolicy(_AttrMixin):
         super().to(*args, **kwargs)
         self.normalizer.to_device(*args, **kwargs)
         return self
+
+
+# ---------------------------------------------------------------------------
+# predict_action(use_ddim=True) as ONE CUDA graph
+# ---------------------------------------------------------------------------
+# The reference calls this 28-42x per exploration rollout and 75x per evaluation episode, between simulator steps
+# (lb_online_trainer_v7.py:1060-1079, lb_eval_helper.py:238-298): a pure latency path.  Unfused it is 2 encoder
+# graph replays + 8 x (UNet1D graph replay + ~15 elementwise torch kernels of the scheduler) + the host work
+# between them.  Here the whole chain -- image normalisation, both encoders (on two streams), 8 x [timestep fill,
+# UNet1D forward, fused DDIM update] -- is captured once per (policy, batch) into one graph over static buffers; a
+# call copies the observation and the initial noise in, replays, and reads the trajectory out.
+_PREDICT_PLANS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _predict_plan_for(policy, obs_dict, use_ddim):
+    """The graph plan for this call, or None when the call is outside what it covers (DDPM sampling, eta > 0 or other
+    scheduler kwargs, low-dim observation keys, encoders in training mode -- they draw SpatialSoftmax noise there --
+    or V2A_NO_GRAPH): those take the general loop below, on the same kernels."""
+    enc = policy.obs_encoder
+    if not use_ddim or policy.kwargs or enc.low_dim_keys or os.environ.get("V2A_NO_GRAPH", "0") == "1":
+        return None
+    if any(enc.key_model_map[k].training for k in enc.rgb_keys):
+        return None
+    x = obs_dict[enc.rgb_keys[0]]
+    if not x.is_cuda:
+        return None              # the general path raises the "CUDA only" error
+    sched = policy.noise_scheduler_ddim
+    sig = (x.shape[0], str(x.device), policy.num_inference_steps_ddim, sched.config.prediction_type,
+           bool(sched.config.clip_sample), policy.horizon, policy.n_obs_steps)
+    per = _PREDICT_PLANS.setdefault(policy, {})
+    plan = per.get(sig)
+    if plan is None:
+        if len(per) >= 3:
+            per.pop(next(iter(per)))
+        plan = per[sig] = _PredictPlan(policy, x.shape[0], x.device)
+    return plan
+
+
+class _PredictPlan:
+    def __init__(self, policy, B: int, device):
+        from . import policy_unet1d
+        self.policy = weakref.ref(policy)
+        enc = policy.obs_encoder
+        self.B, self.device = B, device
+        self.keys = list(enc.rgb_keys)
+        To = policy.n_obs_steps
+        self.obs = {k: torch.zeros(B, To, *enc.key_shape_map[k], dtype=torch.float32, device=device) for k in self.keys}
+        self.enc = [obs_encoder.encoder_engine(enc.key_model_map[k], B * To, device) for k in self.keys]
+        self.unet = policy_unet1d._policy_engine(policy.model, B, policy.horizon, device)
+        sched = policy.noise_scheduler_ddim
+        sched.set_timesteps(policy.num_inference_steps_ddim)
+        self.steps = []          # (t, sqrt(1 - a_t), sqrt(a_t), sqrt(a_prev), sqrt(1 - a_prev)) as the scheduler's fp32 scalars
+        T = sched.config.num_train_timesteps
+        for t in sched.timesteps.tolist():
+            prev = t - T // sched.num_inference_steps
+            a_t = sched.alphas_cumprod[t]
+            a_prev = sched.alphas_cumprod[prev] if prev >= 0 else sched.final_alpha_cumprod
+            self.steps.append((int(t), float((1 - a_t) ** 0.5), float(a_t ** 0.5), float(a_prev ** 0.5),
+                               float((1 - a_prev) ** 0.5)))
+        self.pred_sample = int(sched.config.prediction_type == "sample")
+        self.clip = int(bool(sched.config.clip_sample))
+        self.out = torch.zeros(B, policy.horizon, policy.action_dim, dtype=torch.float32, device=device)
+        self.graph = None
+        self._warm = False
+
+    def _body(self):
+        policy = self.policy()
+        To, unet = policy.n_obs_steps, self.unet
+        cur = torch.cuda.current_stream()
+        nobs = policy.normalizer.normalize_d(self.obs)
+        off, joined = 0, []
+        for i, (k, eng) in enumerate(zip(self.keys, self.enc)):
+            x = nobs[k][:, :To].reshape(-1, *nobs[k].shape[2:])
+            width = eng.feat.shape[1]
+            dst = unet.gc_in[:, off:off + width]
+            off += width
+
+            def run(eng=eng, x=x, dst=dst):
+                eng.x_in.copy_(x)
+                eng._run("fwd", eng.fwd, pre=(eng.stats_arena,), force_eager=True)
+                eng.fwd_token += 1
+                dst.copy_(eng.feat.reshape(self.B, -1))
+            if i + 1 < len(self.keys):       # independent encoders overlap (fork / join inside the capture)
+                s = obs_encoder.side_stream(self.device, i)
+                s.wait_stream(cur)
+                with torch.cuda.stream(s):
+                    run()
+                joined.append(s)
+            else:
+                run()
+        for s in joined:
+            cur.wait_stream(s)
+        assert off == unet.gc_in.shape[1], "global_cond width disagrees with the encoders' features"
+        din, rows = unet.x0.C, self.B * unet.T
+        for (t, c1, c2, c3, c4) in self.steps:
+            unet.t_buf.fill_(t)
+            unet._run("fwd", unet.fwd, force_eager=True)
+            _lib.check(_lib.load().v2a_policy_ddim_step(unet.x_in_base.data_ptr(), unet.x_in_base.stride(0),
+                                                        unet.out16.data_ptr(), unet.out16.stride(0), rows, din,
+                                                        c1, c2, c3, c4, self.pred_sample, self.clip, ops._stream()),
+                       "policy_ddim_step")
+        unet.fwd_token += 1
+        self.out.copy_(unet.x_in.reshape(self.B, unet.T, din))
+
+    def run(self, obs_dict):
+        policy = self.policy()
+        for eng in self.enc:
+            eng.refresh_weights()
+        self.unet.refresh_weights()
+        for k in self.keys:
+            self.obs[k].copy_(obs_dict[k][:, :policy.n_obs_steps])
+        # RNG order of the reference: the encoders draw nothing in eval mode, then ONE randn for the trajectory
+        noise = _randn((self.B, policy.horizon, policy.action_dim), self.device, torch.float32)
+        self.unet.x_in.copy_(noise.reshape(self.B * self.unet.T, -1))
+        if not self._warm:            # first call: eager (lazy module loads / plan-time launches must not be captured)
+            self._body()
+            self._warm = True
+        else:
+            if self.graph is None:
+                saved = self.unet.x_in_base.clone()
+                g = torch.cuda.CUDAGraph()
+                cur = torch.cuda.current_stream()
+                side = torch.cuda.Stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(g, stream=side):
+                        self._body()
+                cur.wait_stream(side)
+                self.unet.x_in_base.copy_(saved)      # capture does not execute, but keep the inputs explicit
+                self.graph = g
+            self.graph.replay()
+        return self.out.clone()
 
 
 # ---------------------------------------------------------------------------

@@ -528,7 +528,7 @@ class _EncoderEngine(PackedParams):
         return n + len(self._wchunks) + len(self._vchunks)
 
     # ---- execution -----------------------------------------------------------------------------
-    def _run(self, name: str, steps, pre=()):
+    def _run(self, name: str, steps, pre=(), force_eager: bool = False):
         """Launch a planned list.  Every buffer is static, so after one eager (warm-up) run the list is captured
         into a CUDA graph and replayed (V2A_NO_GRAPH=1 disables).  Lane 1 = weight-gradient GEMMs + their scatter:
         nothing on the main chain reads their results, so they run on a side stream beside the data-gradient chain."""
@@ -549,7 +549,7 @@ class _EncoderEngine(PackedParams):
                     fn()
             if used_side:
                 main.wait_stream(self._side)
-        if os.environ.get("V2A_NO_GRAPH", "0") == "1":
+        if force_eager or os.environ.get("V2A_NO_GRAPH", "0") == "1":   # force_eager: the caller captures a larger graph
             return eager()
         seen = self._graphs.get(name)
         if seen is None:            # first call: eager (lazy CUDA module loads must not happen under capture)

@@ -730,7 +730,7 @@ class _PolicyEngine(PackedParams):
         self.conv_bwd(st, lambda: lin1.weight.unsqueeze(-1), g(lin1.weight), 1, 0, [n_temb], d1h, ld1, d1T, 4 * dsed)
 
     # ---- execution -----------------------------------------------------------------
-    def _run(self, name: str, steps, pre=()):
+    def _run(self, name: str, steps, pre=(), force_eager: bool = False):
         """Launch a planned list.  Every buffer is static, so after one eager (warm-up) run the list is
         captured into a CUDA graph and replayed (one launch instead of 68 / 169; V2A_NO_GRAPH=1 disables)."""
         def eager():
@@ -752,7 +752,7 @@ class _PolicyEngine(PackedParams):
                     fn()
             if used_side:
                 main.wait_stream(self._side)
-        if os.environ.get("V2A_NO_GRAPH", "0") == "1":
+        if force_eager or os.environ.get("V2A_NO_GRAPH", "0") == "1":   # force_eager: the caller captures a larger graph
             return eager()
         seen = self._graphs.get(name)
         if seen is None:            # first call: eager (lazy CUDA module loads must not happen under capture)
