@@ -275,12 +275,16 @@ def test_compute_loss_and_predict_action_match_reference_policy_golden(monkeypat
     params = dict(pol.named_parameters())
     full = {k[len("grad."):]: v for k, v in gold.items() if k.startswith("grad.")}
     assert len(full) >= 8
+    # Encoder gradients are ReLU-flip limited (see above).  At B = 2 one flipped element weighs ~1/sqrt(2 * H * W * C)
+    # of a layer's gradient and every flip downstream of the stem lands in the stem's weight gradient, so whole
+    # tensors are held to 2e-2 there (tests/test_encoder_gpu.py measures the same figure against float64) -- two
+    # orders of magnitude below what a wrong-but-same-norm gradient (rel-L2 ~ 1.4) would show.  UNet1D: 1e-3.
+    errs = {}
     for k, want in full.items():
-        got = params[k].grad[:want.shape[0]]
-        tol = 5 * TOL if k.startswith("obs_encoder.") else TOL
-        e = rel_l2(got, want)
-        print(f"full-gradient rel-L2 {k}: {e:.2e}")
-        assert e < tol, (k, e)
+        errs[k] = rel_l2(params[k].grad[:want.shape[0]], want)
+        print(f"full-gradient rel-L2 {k}: {errs[k]:.2e}")
+    for k, e in errs.items():
+        assert e < (2e-2 if k.startswith("obs_encoder.") else TOL), (k, e)
     pol.eval()
     torch.manual_seed(meta["seed"] + 1)
     with torch.no_grad():

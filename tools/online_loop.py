@@ -172,7 +172,7 @@ def run_loop(args):
         loss_host.copy_(loss.reshape(1), non_blocking=True)
 
     # warm-up: builds the plans / CUDA graphs of every engine at its batch size (B = 1 video + policy, B = batch train)
-    explore(only_first=True)
+    explore(only_first=not args.batch_videos)     # batched: the timed call must find its B = len(tasks) engine built
     train(3)
     barrier()
     ms_explore = ms_train = 0.0

@@ -356,14 +356,16 @@ __global__ void unet_output_head_kernel(const float* __restrict__ y, int ldy, co
 // conv to 9*cout columns, P[pix][tap*cout + co] = sum_c a[pix][c] W[co][c][tap] (ONE pass over the activation on
 // the tensor cores instead of nine TMA taps feeding a 16-wide N tile), this kernel gathers the nine taps:
 //   y[n,h,w][co] = bias[co] + sum_{kh,kw} P[n, h+kh-1, w+kw-1][(kh*3+kw)*cout + co]      (zero outside the image)
+template <int kCout>
 __global__ void stencil9_kernel(const float* __restrict__ P, int ldp, const float* __restrict__ bias, int N, int H,
-                                int W, int cout, float* __restrict__ y, int ldy) {
+                                int W, float* __restrict__ y, int ldy) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (int64_t)N * H * W) return;
     const int w = (int)(gid % W);
     const int h = (int)((gid / W) % H);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int co = 0; co < cout; ++co) acc[co] = bias ? bias[co] : 0.f;
+    float acc[kCout];
+#pragma unroll
+    for (int co = 0; co < kCout; ++co) acc[co] = bias ? __ldg(bias + co) : 0.f;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
         const int hh = h + kh - 1;
@@ -372,11 +374,13 @@ __global__ void stencil9_kernel(const float* __restrict__ P, int ldp, const floa
         for (int kw = 0; kw < 3; ++kw) {
             const int ww = w + kw - 1;
             if (ww < 0 || ww >= W) continue;
-            const float* pp = P + (gid + (int64_t)(kh - 1) * W + (kw - 1)) * ldp + (kh * 3 + kw) * cout;
-            for (int co = 0; co < cout; ++co) acc[co] += __ldg(pp + co);
+            const float* pp = P + (gid + (int64_t)(kh - 1) * W + (kw - 1)) * ldp + (kh * 3 + kw) * kCout;
+#pragma unroll
+            for (int co = 0; co < kCout; ++co) acc[co] += __ldg(pp + co);
         }
     }
-    for (int co = 0; co < cout; ++co) y[gid * ldy + co] = acc[co];
+#pragma unroll
+    for (int co = 0; co < kCout; ++co) y[gid * ldy + co] = acc[co];
 }
 
 // ---------------------------------------------------------------------------
@@ -656,8 +660,14 @@ int v2a_stencil9(const float* P, int ldp, const float* bias, int N, int H, int W
                  void* stream) {
     V2A_REQUIRE(P && y && cout >= 1 && cout <= 4 && ldp >= 9 * cout && ldy >= cout, "stencil9: bad arguments");
     const int64_t total = (int64_t)N * H * W;
-    stencil9_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P, ldp, bias, N, H, W, cout, y,
-                                                                                     ldy);
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (cout) {
+        case 1: stencil9_kernel<1><<<blocks, 256, 0, st>>>(P, ldp, bias, N, H, W, y, ldy); break;
+        case 2: stencil9_kernel<2><<<blocks, 256, 0, st>>>(P, ldp, bias, N, H, W, y, ldy); break;
+        case 3: stencil9_kernel<3><<<blocks, 256, 0, st>>>(P, ldp, bias, N, H, W, y, ldy); break;
+        default: stencil9_kernel<4><<<blocks, 256, 0, st>>>(P, ldp, bias, N, H, W, y, ldy); break;
+    }
     V2A_LAUNCH_OK();
     return 0;
 }

@@ -554,6 +554,8 @@ class _PredictPlan:
         self.out = torch.zeros(B, policy.horizon, policy.action_dim, dtype=torch.float32, device=device)
         self.graph = None
         self._warm = False
+        self._params = [p for eng in (*self.enc, self.unet) for p in eng.params if p.numel()]
+        self._key = None
 
     def _body(self):
         policy = self.policy()
@@ -596,9 +598,16 @@ class _PredictPlan:
 
     def run(self, obs_dict):
         policy = self.policy()
-        for eng in self.enc:
-            eng.refresh_weights()
-        self.unet.refresh_weights()
+        # ONE content check for the three engines: (data_ptr, _version) of every parameter + one fingerprint launch
+        # over all of them (a `.data` write bumps no version, packing.content_key); the engines re-pack only when
+        # that key moves or one of them was invalidated explicitly (fused optimiser step)
+        ptrs = tuple(p.data_ptr() for p in self._params)
+        key = (ptrs, tuple(p._version for p in self._params), ops.params_fingerprint(self._params, key=ptrs))
+        if key != self._key or any(eng._wkey is None for eng in (*self.enc, self.unet)):
+            for eng in (*self.enc, self.unet):
+                eng._wkey = None
+                eng.refresh_weights()
+            self._key = key
         for k in self.keys:
             self.obs[k].copy_(obs_dict[k][:, :policy.n_obs_steps])
         # RNG order of the reference: the encoders draw nothing in eval mode, then ONE randn for the trajectory

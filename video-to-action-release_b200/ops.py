@@ -507,15 +507,17 @@ _FP_TABLES: dict = {}
 _FP_CHUNK = 1 << 16
 
 
-def params_fingerprint(params: Sequence[torch.Tensor]) -> int:
+def params_fingerprint(params: Sequence[torch.Tensor], key=None) -> int:
     """64-bit fingerprint of the VALUES of ``params`` (CUDA fp32 tensors): one kernel launch over a cached
-    device table of (pointer, length, global offset) chunks, then an 8-byte read-back (this synchronises)."""
+    device table of (pointer, length, global offset) chunks, then an 8-byte read-back (this synchronises).
+    ``key``: any hashable that changes whenever a parameter's storage does (callers that already hold the
+    (data_ptr, _version) tuple pass it to save a second walk over the parameters)."""
     ps = [p.detach() for p in params if p.numel()]
     if not ps:
         return 0
     _require_cuda(*ps)
     dev = ps[0].device
-    key = (str(dev),) + tuple((p.data_ptr(), p.numel()) for p in ps)
+    key = (str(dev), key) if key is not None else (str(dev),) + tuple((p.data_ptr(), p.numel()) for p in ps)
     ent = _FP_TABLES.get(key)
     if ent is None:
         rows, off = [], 0
