@@ -238,6 +238,13 @@ int v2a_ddpm_step(float* x, const float* v, const float* noise, const float* coe
                   void* stream);
 int v2a_ddim_step(float* x, const float* v, const float* noise, const float* coef, int64_t n,
                   void* stream);
+/* Sampler update under classifier-free guidance (guidance_weight > 0, pred_v; goal_diffusion.py:503-514,536-548):
+ * x and v hold the doubled batch [conditional | unconditional] (n_half elements each); the guided noise estimate is
+ * mixed in noise space, the DDPM (ddim = 0) or eta-DDIM (ddim = 1) update applied, the result written to both
+ * halves of x.  coef = the 8 floats of the plain step + coef[8] = guidance weight; for DDPM coef[6], coef[7] =
+ * sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod of the step. */
+int v2a_cfg_step(float* x, const float* v, const float* noise, const float* coef, int64_t n_half, int ddim,
+                 void* stream);
 /* out = clamp((x + 1) / 2, 0, 1)   goal_diffusion.py:598,650 */
 int v2a_unnormalize_clamp(const float* x, float* out, int64_t n, void* stream);
 

@@ -358,7 +358,7 @@ def test_policy_engines_follow_dot_data_updates_and_copy_ema_to():
     fresh = DP.build_libero_policy()
     fresh.load_state_dict({k: v.cpu() for k, v in pol.state_dict().items()}, strict=True)
     a1_want = act(fresh.to("cuda").eval())
-    assert rel_l2(a1, a1_want) < 1e-5, rel_l2(a1, a1_want)
+    assert rel_l2(a1, a1_want) < 1e-4, rel_l2(a1, a1_want)     # graph replay vs eager: fp32 atomics reorder
     assert rel_l2(a0, a1) > 1e-3
     # copy_ema_to: the EMA model's next forward uses the copied weights
     from v2a_b200.train_step import PolicyTrainStep
@@ -375,6 +375,6 @@ def test_policy_engines_follow_dot_data_updates_and_copy_ema_to():
     a_after = act(ema_model)
     ref = DP.build_libero_policy()
     ref.load_state_dict({k: v.cpu() for k, v in ema_model.state_dict().items()}, strict=True)
-    assert rel_l2(a_after, act(ref.to("cuda").eval())) < 1e-5
+    assert rel_l2(a_after, act(ref.to("cuda").eval())) < 1e-4
     assert rel_l2(a_before, a_after) > 1e-4
     step.close()

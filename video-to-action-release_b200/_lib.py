@@ -195,6 +195,7 @@ SIGNATURES = {
     "v2a_unet_output_head": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, C.POINTER(_i64), _vp]),
     "v2a_ddpm_step": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "v2a_ddim_step": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "v2a_cfg_step": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "v2a_unnormalize_clamp": (_i, [_vp, _vp, _i64, _vp]),
     "v2a_split_hl": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp]),
     "v2a_params_fingerprint": (_i, [_vp, _i, _vp, _vp]),

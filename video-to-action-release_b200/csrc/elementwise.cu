@@ -425,6 +425,40 @@ __global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict_
     x[i] = __fadd_rn(__fadd_rn(__fmul_rn(x0, san), __fmul_rn(cc, eps)), __fmul_rn(sigma, nz));
 }
 
+// Classifier-free guidance (guidance_weight > 0, objective pred_v; goal_diffusion.py:503-514,536-548): the UNet ran
+// on the doubled batch [conditional | unconditional]; v holds both halves.  Mixing happens in NOISE space:
+//   x0_c = sa x - s1 v_c,  x0_u = sa x - s1 v_u,  eps_* = (sr x - x0_*) / srm1,  eps = (1 + w) eps_c - w eps_u,
+//   x0 = sr x - srm1 eps, then the ancestral (DDPM) or the eta-DDIM update; the new x is written to BOTH halves
+// (the next UNet call reads the same image twice).  coef[8] = guidance weight; coef[6], coef[7] of the DDPM table
+// carry sqrt_recip / sqrt_recipm1 (the DDIM table has them at [2], [3]).  n = elements of ONE half.
+template <bool kDdim>
+__global__ void cfg_step_kernel(float* __restrict__ x, const float* __restrict__ v, const float* __restrict__ noise,
+                                const float* __restrict__ coef, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float sa = coef[0], s1 = coef[1], gw = coef[8];
+    const float sr = kDdim ? coef[2] : coef[6], srm1 = kDdim ? coef[3] : coef[7];
+    const float xt = x[i];
+    const float x0c = __fsub_rn(__fmul_rn(sa, xt), __fmul_rn(s1, v[i]));
+    const float x0u = __fsub_rn(__fmul_rn(sa, xt), __fmul_rn(s1, v[n + i]));
+    const float srx = __fmul_rn(sr, xt);
+    const float ec = __fdiv_rn(__fsub_rn(srx, x0c), srm1), eu = __fdiv_rn(__fsub_rn(srx, x0u), srm1);
+    const float eps = __fsub_rn(__fmul_rn(1.0f + gw, ec), __fmul_rn(gw, eu));
+    float x0 = __fsub_rn(srx, __fmul_rn(srm1, eps));
+    const float nz = noise ? noise[i] : 0.0f;
+    float out;
+    if (kDdim) {
+        const float san = coef[4], cc = coef[5], sigma = coef[6], last = coef[7];
+        out = last != 0.0f ? x0 : __fadd_rn(__fadd_rn(__fmul_rn(x0, san), __fmul_rn(cc, eps)), __fmul_rn(sigma, nz));
+    } else {
+        const float c1 = coef[2], c2 = coef[3], sigma = coef[4], vt = coef[5];
+        x0 = clamp_nan(x0, -1.0f, 1.0f);
+        out = __fadd_rn(__fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xt)), __fmul_rn(sigma, __fmul_rn(nz, vt)));
+    }
+    x[i] = out;
+    x[n + i] = out;
+}
+
 __global__ void unnormalize_clamp_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -682,6 +716,15 @@ int v2a_ddpm_step(float* x, const float* v, const float* noise, const float* coe
 int v2a_ddim_step(float* x, const float* v, const float* noise, const float* coef, int64_t n,
                   void* stream) {
     ddim_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, v, noise, coef, n);
+    V2A_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_cfg_step(float* x, const float* v, const float* noise, const float* coef, int64_t n_half, int ddim,
+                 void* stream) {
+    const unsigned blocks = (unsigned)((n_half + 255) / 256);
+    if (ddim) cfg_step_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, v, noise, coef, n_half);
+    else cfg_step_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, v, noise, coef, n_half);
     V2A_LAUNCH_OK();
     return 0;
 }

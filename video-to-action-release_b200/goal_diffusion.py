@@ -261,11 +261,13 @@ class GoalGaussianDiffusion(nn.Module):
 
     # ---- the hot path ---------------------------------------------------------------------
     def _fast_path_ok(self) -> bool:
-        return (isinstance(self.model, Unet_Libero) and self.objective == "pred_v"
-                and not self.guidance_weight > 0.0 and self.auto_normalize)
+        """The fused, graph-captured sampler covers the shipped objective (pred_v) with and without classifier-free
+        guidance; pred_noise / pred_x0 and auto_normalize=False take the general loop."""
+        return isinstance(self.model, Unet_Libero) and self.objective == "pred_v" and self.auto_normalize
 
     def _ddpm_coef_table(self):
-        """[T, 8] fp32: sqrt_ac, sqrt_1m_ac, coef1, coef2, exp(0.5*logvar), var_temp."""
+        """[T, 8] fp32: sqrt_ac, sqrt_1m_ac, coef1, coef2, exp(0.5*logvar), var_temp, sqrt_recip_ac, sqrt_recipm1_ac
+        (the last two are read by the guided step only)."""
         T = self.num_timesteps
         tab = torch.zeros(T, 8, dtype=torch.float32)
         tab[:, 0] = self.sqrt_alphas_cumprod.cpu()
@@ -274,6 +276,8 @@ class GoalGaussianDiffusion(nn.Module):
         tab[:, 3] = self.posterior_mean_coef2.cpu()
         tab[:, 4] = (0.5 * self.posterior_log_variance_clipped.cpu()).exp()
         tab[:, 5] = float(self.var_temp)
+        tab[:, 6] = self.sqrt_recip_alphas_cumprod.cpu()
+        tab[:, 7] = self.sqrt_recipm1_alphas_cumprod.cpu()
         return tab.to(self.betas.device)
 
     def _ddim_plan(self):
@@ -308,28 +312,42 @@ class GoalGaussianDiffusion(nn.Module):
         H, W = self.image_size
         C3 = self.channels
         unet: UNetModel = self.model.unet
+        gw = float(self.guidance_weight)
+        cfg = gw > 0.0
+        # classifier-free guidance (:503-514): ONE UNet call on the doubled batch [conditional | unconditional (task
+        # tokens zeroed)], then a fused guided update that writes the new image into both halves
+        EB = 2 * batch_size if cfg else batch_size
         with torch.autocast("cuda", enabled=False):
             x_cond = x_cond.to(dev, torch.float32).contiguous()
-            eng = unet.engine(batch_size, C3 // 3, H, W, dev)
+            eng = unet.engine(EB, C3 // 3, H, W, dev)
             eng.refresh_weights(unet)
-            eng.set_task_embed(unet, task_embed.to(dev))
+            te = task_embed.to(dev, torch.float32)
+            eng.set_task_embed(unet, torch.cat([te, torch.zeros_like(te)], dim=0) if cfg else te)
             st = _sampler_state(eng, C3, H, W)
-            st["cond"].copy_(x_cond)
+            st["cond"][:batch_size].copy_(x_cond)
+            if cfg:
+                st["cond"][batch_size:].copy_(x_cond)
             if ddim:
                 times, tab = self._ddim_plan()
-                step_fn = ops.ddim_step
+                step_fn = ops.cfg_ddim_step if cfg else ops.ddim_step
             else:
                 times, tab = list(reversed(range(self.num_timesteps))), self._ddpm_coef_table().flip(0)
-                step_fn = ops.ddpm_step
-            t_tab = torch.tensor(times, dtype=torch.int64, device=dev)[:, None].expand(-1, batch_size).contiguous()
-            x, noise, coef, v = st["x"], st["noise"], st["coef"], st["v"]
-            x.copy_(_initial_noise((batch_size, C3, H, W), dev))  # RNG draw #0 (:586 / :610)
-            imgs = [x.clone()] if return_all_timesteps else None
-            graph = _step_graph(eng, st, step_fn)
+                step_fn = ops.cfg_ddpm_step if cfg else ops.ddpm_step
+            t_tab = torch.tensor(times, dtype=torch.int64, device=dev)[:, None].expand(-1, EB).contiguous()
+            x, coef = st["x"], st["coef"]
+            noise = st["noise"][:batch_size]
+            x0 = _initial_noise((batch_size, C3, H, W), dev)  # RNG draw #0 (:586 / :610)
+            x[:batch_size].copy_(x0)
+            if cfg:
+                x[batch_size:].copy_(x0)
+                coef[8] = gw
+            xb = x[:batch_size]
+            imgs = [xb.clone()] if return_all_timesteps else None
+            graph = _step_graph(eng, st, step_fn, noise)
             n = len(times)
             for i in range(n):
                 eng.t_buf.copy_(t_tab[i])
-                coef.copy_(tab[i])
+                coef[:8].copy_(tab[i])
                 last = i == n - 1
                 if ddim:
                     if not last:
@@ -340,12 +358,12 @@ class GoalGaussianDiffusion(nn.Module):
                     noise.zero_()
                 graph()
                 if imgs is not None:
-                    imgs.append(x.clone())
+                    imgs.append(xb.clone())
             if imgs is not None:
                 ret = torch.stack(imgs, dim=1)
                 return ((ret + 1) * 0.5).clamp(min=0, max=1)
-            out = torch.empty_like(x)
-            ops.unnormalize_clamp(x, out)  # unnormalize (:598) + clamp(0, 1) (:650)
+            out = torch.empty_like(xb)
+            ops.unnormalize_clamp(xb, out)  # unnormalize (:598) + clamp(0, 1) (:650)
             return out
 
     @torch.no_grad()
@@ -365,7 +383,7 @@ class GoalGaussianDiffusion(nn.Module):
         """goal_diffusion.py:643-650.  Returns [B, channels, H, W] in [0, 1]."""
         if not isinstance(self.model, Unet_Libero):
             raise NotImplementedError("v2a_b200 sample(): the CUDA path is built for Unet_Libero")
-        if not self._fast_path_ok():   # classifier-free guidance etc.: general loop around the CUDA UNet
+        if not self._fast_path_ok():   # pred_noise / pred_x0 objectives etc.: general loop around the CUDA UNet
             return self._sample_general(x_cond, task_embed, batch_size, bool(self.is_ddim_sampling),
                                         return_all_timesteps)
         return self._sample_fast(x_cond, task_embed, batch_size, bool(self.is_ddim_sampling), return_all_timesteps)
@@ -385,17 +403,18 @@ def _sampler_state(eng, C3, H, W):
         f32 = dict(dtype=torch.float32, device=eng.device)
         st = dict(x=torch.zeros(eng.B, C3, H, W, **f32), cond=torch.zeros(eng.B, 3, H, W, **f32),
                   v=torch.zeros(eng.B, C3, H, W, **f32), noise=torch.zeros(eng.B, C3, H, W, **f32),
-                  coef=torch.zeros(8, **f32), graphs={})
+                  coef=torch.zeros(16, **f32), graphs={})
         eng._sampler = st
     return st
 
 
-def _step_graph(eng, st, step_fn):
-    """Callable running UNet + sampler update on the static buffers; CUDA graph unless V2A_NO_GRAPH=1."""
+def _step_graph(eng, st, step_fn, noise):
+    """Callable running UNet + sampler update on the static buffers; CUDA graph unless V2A_NO_GRAPH=1.
+    ``noise``: the step's noise buffer (the whole static buffer, or its first half under guidance)."""
     def eager():
         eng.bind_static(st["x"], st["cond"], st["v"])
         eng.run_static()
-        step_fn(st["x"], st["v"], st["noise"], st["coef"])
+        step_fn(st["x"], st["v"], noise, st["coef"])
 
     if os.environ.get("V2A_NO_GRAPH", "0") == "1":
         return eager

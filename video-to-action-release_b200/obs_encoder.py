@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib, convs, ops
+from . import _lib, convs, ops, packing
 from .ops import HL
 from .packing import PackedParams
 from .policy_unet1d import _Steps
@@ -81,6 +81,7 @@ def visual_core_forward(core, x: torch.Tensor) -> torch.Tensor:
     if not x.is_cuda:
         raise RuntimeError("v2a_b200 VisualCore runs on CUDA only (no CPU fallback)")
     eng = encoder_engine(core, x.shape[0], x.device)
+    eng.training_call = packing.training_call(eng.params)
     _LAST_ENGINE[core] = eng
     return _VisualCoreFunction.apply(core, eng, x, *list(core.parameters()))
 

@@ -429,6 +429,17 @@ def ddim_step(x, v, noise, coef) -> None:
                                          x.numel(), _stream()), "ddim_step")
 
 
+def cfg_ddpm_step(x, v, noise, coef) -> None:
+    """x, v: doubled batch [cond | uncond]; noise: one half; coef: 9+ floats (coef[8] = guidance weight)."""
+    _lib.check(_lib.load().v2a_cfg_step(x.data_ptr(), v.data_ptr(), _ptr(noise), coef.data_ptr(), x.numel() // 2, 0,
+                                        _stream()), "cfg_step")
+
+
+def cfg_ddim_step(x, v, noise, coef) -> None:
+    _lib.check(_lib.load().v2a_cfg_step(x.data_ptr(), v.data_ptr(), _ptr(noise), coef.data_ptr(), x.numel() // 2, 1,
+                                        _stream()), "cfg_step")
+
+
 def unnormalize_clamp(x, out) -> None:
     _lib.check(_lib.load().v2a_unnormalize_clamp(x.data_ptr(), out.data_ptr(), x.numel(), _stream()),
                "unnormalize_clamp")

@@ -23,7 +23,8 @@ from .ops import HL
 # fused optimiser invalidates explicitly.  Writes through `.data` (`p.data.copy_()`, `p.data.lerp_()`: how
 # ema_pytorch.EMA.update() maintains the EMA model the reference evaluates, lb_online_trainer_v7.py:624,1077) bump
 # nothing, so every INFERENCE forward also keys on a 64-bit fingerprint of the parameter values (one launch over
-# the parameters + an 8-byte read-back).  Training forwards (grad enabled on trainable parameters) skip it.
+# the parameters + an 8-byte read-back, which synchronises).  Training forwards (grad enabled on trainable
+# parameters) skip it: their optimiser either bumps the versions or invalidates explicitly.
 _SCOPE = [None]
 _SCOPE_SEQ = [0]
 
@@ -40,8 +41,16 @@ def one_content_check():
         _SCOPE[0] = prev
 
 
+def training_call(params) -> bool:
+    """True when the caller runs a TRAINING forward (grad mode on and something to train).  Must be evaluated in the
+    module's forward, not inside a torch.autograd.Function.forward (grad mode is always off in there)."""
+    return torch.is_grad_enabled() and any(p.requires_grad for p in params)
+
+
 def content_key(engine, params):
-    if (torch.is_grad_enabled() and any(p.requires_grad for p in params)) or not all(p.is_cuda for p in params):
+    """Fingerprint part of an engine's weight-cache key; engines set ``engine.training_call`` per forward (engines
+    that never train -- the video UNet -- leave it False and always check)."""
+    if getattr(engine, "training_call", False) or not all(p.is_cuda for p in params):
         return getattr(engine, "_last_fp", None)
     scope = _SCOPE[0]
     if scope is not None and getattr(engine, "_fp_scope", None) == scope:

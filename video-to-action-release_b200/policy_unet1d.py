@@ -30,7 +30,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib, convs, ops
+from . import _lib, convs, ops, packing
 from .ops import HL
 from .packing import PackedParams
 
@@ -158,6 +158,7 @@ class ConditionalUnet1D(nn.Module):
         t = t.expand(B).to(torch.int64)
         gc = global_cond if global_cond is not None else sample.new_zeros(B, 0)
         eng = _policy_engine(self, B, T, sample.device)
+        eng.training_call = packing.training_call(eng.params)
         _LAST_ENGINE[self] = eng
         return _UNet1DFunction.apply(self, eng, sample, t, gc, *list(self.parameters()))
 
