@@ -97,6 +97,16 @@ int v2a_igemm_plan_run(void* plan, void* stream);
 void v2a_igemm_plan_destroy(void* plan);
 /* how many CTAs share one output tile's K loop (1 = no split-K); introspection for tests / probes */
 int v2a_igemm_plan_k_splits(void* plan);
+/* Conv3d as ONE launch (guided_diffusion/nn.py:53-87: Conv2d on every frame, then the zero-padded Conv1d(k = 3) over
+ * frames): the spatial program and the temporal program that consumes its output planes, interleaved tile by tile
+ * in one persistent kernel so the temporal conv's epilogue runs under the spatial conv's MMAs.  Both descriptors
+ * must be pair launches with the fused split product (passes 3, block_n <= 128, one N tile) over the SAME dense
+ * row space cut into the same 128-row tiles; `tiles_per_frame` = tiles of one (sample, frame) = the distance between
+ * the tiles the temporal taps read; `flags` = caller-allocated uint32 [tiles] scratch (cleared by every run). */
+int v2a_igemm_dual_plan_create(const v2a_igemm_desc* spatial, const v2a_igemm_desc* temporal, int frames,
+                               int tiles_per_frame, void* flags, void** plan_out);
+int v2a_igemm_dual_plan_run(void* plan, void* stream);
+void v2a_igemm_dual_plan_destroy(void* plan);
 /* kernel launches performed by v2a_* calls since process start */
 int64_t v2a_launch_count(void);
 

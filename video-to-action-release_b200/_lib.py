@@ -169,6 +169,9 @@ SIGNATURES = {
     "v2a_igemm_plan_run": (_i, [_vp, _vp]),
     "v2a_igemm_plan_destroy": (None, [_vp]),
     "v2a_igemm_plan_k_splits": (_i, [_vp]),
+    "v2a_igemm_dual_plan_create": (_i, [C.POINTER(IgemmDesc), C.POINTER(IgemmDesc), _i, _i, _vp, C.POINTER(_vp)]),
+    "v2a_igemm_dual_plan_run": (_i, [_vp, _vp]),
+    "v2a_igemm_dual_plan_destroy": (None, [_vp]),
     "v2a_wgrad_plan_create": (_i, [C.POINTER(WgradDesc), C.POINTER(_vp)]),
     "v2a_wgrad_plan_run": (_i, [_vp, _vp]),
     "v2a_wgrad_plan_k_splits": (_i, [_vp]),

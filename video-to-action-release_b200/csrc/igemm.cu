@@ -691,6 +691,468 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
     if (p.cluster > 1) cluster_sync_all();   // no CTA leaves while its peer can still signal its barriers
 }
 
+
+// ===========================================================================
+// Conv3d as ONE launch: the spatial conv and the temporal conv that consumes it, interleaved tile by tile
+// (guided_diffusion/nn.py:53-87: Conv2d on every frame, then a zero-padded Conv1d(k = 3) over the frame axis).
+//
+// The temporal conv of a narrow layer (Cout <= 128) is bound by its epilogue, not by its 6-12 k-steps of MMA
+// (0.9 ms against 0.39 ms of tensor time at 1.8 M rows), and the spatial conv before it is bound by its MMAs.  Run
+// back to back as two launches the two phases cannot hide each other.  Here every CTA pair walks ONE sequence of
+// work items that alternates a spatial pair-tile S(i) with the temporal pair-tile T(i - lag): the long spatial
+// K loops keep the tensor pipe busy while the epilogue warps drain the temporal tiles (fp32 store, GroupNorm sums,
+// residual / embedding add), and the short temporal K loops ride on the same operand ring.
+//
+//   * both programs are cta_group::2 pair MMAs with the fused split product (block_n <= 128), same stage layout;
+//   * both tile the SAME dense row space into the same 128-row blocks (the host checks this), so temporal tile m
+//     reads the spatial output rows of tiles m - tpf, m, m + tpf (tpf = tiles per frame) and nothing else;
+//   * the intermediate y (bf16 hi/lo planes) goes through global memory, but `lag` keeps only ~30 MB of it in
+//     flight, i.e. it is produced into and consumed from the 126 MB L2;
+//   * ordering: the spatial epilogue publishes tile m with bar.sync (its 8 warps) -> __threadfence ->
+//     st.release.gpu flags[m]; the temporal producer acquires the three flags it depends on and issues
+//     fence.proxy.async before the TMA reads.  lag >= tpf/2 + (pairs in the grid) makes every dependency an item
+//     of an EARLIER iteration of some pair, and spatial items never wait, so the walk cannot deadlock; a bounded
+//     spin traps instead of hanging if that reasoning is ever wrong.
+// ===========================================================================
+struct alignas(64) DualParams {
+    IgemmParams g[2];      // 0 = spatial (writes y planes), 1 = temporal (reads them)
+    unsigned int* flags;   // [tiles] spatial tile m is complete (zeroed before every launch)
+    int lag;               // pair-tiles between S(i) and the temporal item issued with it
+    int tpf;               // 128-row tiles per (sample, frame): dependency distance of the temporal taps
+    int frames;            // F
+    int tiles;             // 128-row tiles of the row space (both programs)
+    int mp;                // pair-tiles = ceil(tiles / 2)
+    int iters;             // iterations of every pair: ceil((mp + lag) / pairs)
+};
+
+__device__ __forceinline__ void dual_tile_origin(const IgemmParams& p, int m, int o[4]) {
+    if (m >= p.num_m_tiles) {   // ghost tile of an odd tile count: a box wholly outside the tensor
+        o[0] = o[1] = o[2] = 0;
+        o[3] = p.ntile[3] << p.tile_log2[3];
+        return;
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        const int j = m % p.ntile[d];
+        m /= p.ntile[d];
+        o[d] = j << p.tile_log2[d];
+    }
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void dual_wait_flag(const unsigned int* f, int tag) {
+    if (ld_acquire_gpu(f)) return;
+    const long long t0 = clock64();
+    while (!ld_acquire_gpu(f)) {
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000LL) {
+            printf("v2a: dual-conv dependency timeout tile=%d block=%d\n", tag, (int)blockIdx.x);
+            __trap();
+        }
+    }
+}
+
+__global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_constant__ DualParams dp) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int S = dp.g[0].stages;
+    const uint32_t stage_bytes = dp.g[0].stage_bytes;
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + S;
+    uint64_t* tfull_bar = bars + 2 * S;
+    uint64_t* tempty_bar = bars + 2 * S + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
+    float* warp_add = reinterpret_cast<float*>(bars) + 64;
+    float* stage_slab = warp_add + 8 * 256;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 2 * kEpilogueThreads);
+        }
+        fence_mbar_init();
+    } else if (warp == 1 && lane == 0) {
+        for (int w = 0; w < 2; ++w) {
+            tma_prefetch_desc(&dp.g[w].a_hi[0]);
+            tma_prefetch_desc(&dp.g[w].a_lo[0]);
+            tma_prefetch_desc(&dp.g[w].bh_hi);
+            tma_prefetch_desc(&dp.g[w].bh_lo);
+        }
+    } else if (warp == 2) {
+        tmem_alloc_2sm(tmem_slot, kTmemCols);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc_stride = kTmemCols >> 1;       // two accumulators of 256 columns
+    const uint32_t crank = cluster_ctarank();
+    const int pairs = gridDim.x >> 1;
+    const int pr = blockIdx.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int k = 0; k < dp.iters; ++k) {
+            const int i = pr + k * pairs;
+            for (int which = 0; which < 2; ++which) {
+                const int q = which == 0 ? i : i - dp.lag;
+                if (q < 0 || q >= dp.mp) continue;
+                const IgemmParams& p = dp.g[which];
+                const int m = 2 * q + (int)crank;
+                int o[4];
+                dual_tile_origin(p, m, o);
+                if (which == 1 && m < dp.tiles) {
+                    // the three spatial tiles this temporal tile reads (frames f - 1, f, f + 1 of the same pixels)
+                    const int f = (m / dp.tpf) % dp.frames;
+                    dual_wait_flag(dp.flags + m, m);
+                    if (f > 0) dual_wait_flag(dp.flags + m - dp.tpf, m);
+                    if (f + 1 < dp.frames) dual_wait_flag(dp.flags + m + dp.tpf, m);
+                    fence_proxy_async_all();      // generic-proxy stores of other CTAs -> this thread's TMA reads
+                }
+                const uint32_t half_rows = p.block_n >> 1, half_bytes = p.b_tile_bytes >> 1;
+                int kit = 0;
+                for (int e = 0; e < p.ntaps; ++e) {
+                    const int src = p.tap_src[e];
+                    const int c1 = o[0] + p.tap_d[e][0], c2 = o[1] + p.tap_d[e][1];
+                    const int c3 = o[2] + p.tap_d[e][2], c4 = o[3] + p.tap_d[e][3];
+                    for (int ch = 0; ch < p.tap_chunks[e]; ++ch, ++kit) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+                        uint8_t* st = smem + (size_t)stage * stage_bytes;
+                        const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                        if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
+                        tma_load_5d_2sm(st, &p.a_hi[src], lead_full, ch * kChunkK, c1, c2, c3, c4);
+                        tma_load_5d_2sm(st + kATileBytes, &p.a_lo[src], lead_full, ch * kChunkK, c1, c2, c3, c4);
+                        uint8_t* sb = st + 2 * kATileBytes;
+                        tma_load_2d_2sm(sb, &p.bh_hi, lead_full, kit * kChunkK, crank * half_rows);
+                        tma_load_2d_2sm(sb + half_bytes, &p.bh_lo, lead_full, kit * kChunkK, crank * half_rows);
+                        if (++stage == S) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================== MMA issuer (leader CTA of the pair) =====================
+        if (crank == 0) {
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int k = 0; k < dp.iters; ++k) {
+                const int i = pr + k * pairs;
+                for (int which = 0; which < 2; ++which) {
+                    const int q = which == 0 ? i : i - dp.lag;
+                    if (q < 0 || q >= dp.mp) continue;
+                    const IgemmParams& p = dp.g[which];
+                    const int hb = p.block_n >> 1;
+                    const uint32_t idesc2 = umma_idesc_16(256, 2 * p.block_n, 0, 0);
+                    const uint32_t idesc1 = umma_idesc_16(256, p.block_n, 0, 0);
+                    const int acc = it & 1;
+                    const uint32_t acc_phase = (it >> 1) & 1;
+                    ++it;
+                    mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * acc_stride;
+                    for (int kit = 0; kit < p.k_iters; ++kit) {
+                        mbar_wait(&full_bar[stage], phase, 300 + stage);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                        const uint64_t a_hi = umma_desc_sw128(sa);
+                        const uint64_t a_lo = umma_desc_sw128(sa + kATileBytes);
+                        const uint64_t b_hi = umma_desc_sw128(sa + 2 * kATileBytes);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16_2sm(d_tmem, a_hi + 2 * kk, b_hi + 2 * kk, idesc2, (kit | kk) != 0);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16_2sm(d_tmem + hb, a_lo + 2 * kk, b_hi + 2 * kk, idesc1, 1);
+                        umma_commit_2sm_mc(&empty_bar[stage], 3);
+                        if (kit == p.k_iters - 1) umma_commit_2sm_mc(&tfull_bar[acc], 3);
+                        if (++stage == S) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs; the code of igemm_kernel's epilogue, per work item) ==========
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int half = (warp - 4) >> 2;
+        float* addv = warp_add + (warp - 4) * 256;
+        float* slab = stage_slab + (warp - 4) * (32 * kSlabStride);
+        const int srow0 = lane >> 2;
+        const int piece = lane & 3;
+        int it = 0;
+        for (int k = 0; k < dp.iters; ++k) {
+            const int i = pr + k * pairs;
+            for (int which = 0; which < 2; ++which) {
+                const int q = which == 0 ? i : i - dp.lag;
+                if (q < 0 || q >= dp.mp) continue;
+                const IgemmParams& p = dp.g[which];
+                const int m = 2 * q + (int)crank;
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                ++it;
+                const int nch = p.block_n >> 4;
+                const int c_begin = half == 0 ? 0 : ((nch + 1) >> 1) << 4;
+                const int c_end = half == 0 ? ((nch + 1) >> 1) << 4 : p.block_n;
+                double* const stats = p.stats ? p.stats + (long long)(blockIdx.x % p.stats_replicas) * p.stats_rep_stride
+                                              : nullptr;
+                int o[4];
+                dual_tile_origin(p, m, o);
+                int r = row, coord[4];
+                bool valid = true;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    coord[d] = o[d] + (r & ((1 << p.tile_log2[d]) - 1));
+                    r >>= p.tile_log2[d];
+                    valid = valid && (coord[d] < p.out_dims[d]);
+                }
+                const int64_t pix = p.out_off + coord[0] * p.out_mul[0] + coord[1] * p.out_mul[1] +
+                                    coord[2] * p.out_mul[2] + coord[3] * p.out_mul[3];
+                int rv = 0, inst = 0;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    rv += coord[d] * p.rowvec_mul[d];
+                    inst += coord[d] * p.stats_mul[d];
+                }
+                const bool any_valid = __any_sync(0xffffffffu, valid);
+                const int rv0 = __shfl_sync(0xffffffffu, rv, 0);
+                const bool rv_uniform = p.rowvec == nullptr || __all_sync(0xffffffffu, !valid || rv == rv0);
+                const int inst0 = __shfl_sync(0xffffffffu, valid ? inst : -1, 0);
+                const bool inst_uniform =
+                    stats != nullptr && __all_sync(0xffffffffu, !valid || inst == inst0) && inst0 >= 0;
+                int64_t spix[4];
+                bool svalid[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    spix[j] = __shfl_sync(0xffffffffu, pix, srow0 + 8 * j);
+                    svalid[j] = __shfl_sync(0xffffffffu, (int)valid, srow0 + 8 * j) != 0;
+                }
+                __syncwarp();
+                for (int c = c_begin + lane; c < c_end; c += 32) {
+                    float a = 0.0f;
+                    if (any_valid && c < p.cout) {
+                        if (p.bias) a = __ldg(&p.bias[c]);
+                        if (p.rowvec && rv_uniform) a += __ldg(&p.rowvec[(int64_t)rv0 * p.ld_rowvec + c]);
+                    }
+                    addv[c] = a;
+                }
+                __syncwarp();
+                const bool use_res = p.residual != nullptr;
+                if (use_res) {      // pull the residual window of this warp's NEXT temporal tile into L2
+                    const int m2 = m + 2 * pairs;
+                    if (m2 < p.num_m_tiles) {
+                        int o2[4];
+                        dual_tile_origin(p, m2, o2);
+                        int r2 = row;
+                        int64_t pix2 = p.out_off;
+                        bool valid2 = true;
+#pragma unroll
+                        for (int d = 0; d < 4; ++d) {
+                            const int cd = o2[d] + (r2 & ((1 << p.tile_log2[d]) - 1));
+                            r2 >>= p.tile_log2[d];
+                            valid2 = valid2 && (cd < p.out_dims[d]);
+                            pix2 += cd * p.out_mul[d];
+                        }
+                        const int cpf = c_begin + 16 * piece;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int64_t sp2 = __shfl_sync(0xffffffffu, pix2, srow0 + 8 * j);
+                            const bool sv2 = __shfl_sync(0xffffffffu, (int)valid2, srow0 + 8 * j) != 0;
+                            if (sv2 && cpf < p.cout && cpf < c_end) prefetch_l2(p.residual + sp2 * p.ld_res + cpf);
+                        }
+                    }
+                }
+                float4 rres[4];
+                auto load_res = [&](int c) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        rres[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (svalid[j] && c < p.cout) rres[j] = ld_nc_f4(p.residual + spix[j] * p.ld_res + c + 4 * piece);
+                    }
+                };
+                if (use_res && c_begin < c_end) load_res(c_begin);
+
+                mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * acc_stride;
+
+                auto process = [&](uint32_t (&raw)[16], int c) {
+                    const int n = c;
+                    if (n >= p.cout) return;
+                    float v[16];
+                    {
+                        const float4* a4 = reinterpret_cast<const float4*>(addv + c);
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            const float4 a = a4[qq];
+                            v[4 * qq] = __uint_as_float(raw[4 * qq]) + a.x;
+                            v[4 * qq + 1] = __uint_as_float(raw[4 * qq + 1]) + a.y;
+                            v[4 * qq + 2] = __uint_as_float(raw[4 * qq + 2]) + a.z;
+                            v[4 * qq + 3] = __uint_as_float(raw[4 * qq + 3]) + a.w;
+                        }
+                    }
+                    if (valid && p.rowvec && !rv_uniform) {
+                        const float* rp = p.rowvec + (int64_t)rv * p.ld_rowvec + n;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n + j < p.cout) v[j] += __ldg(&rp[j]);
+                    }
+                    const bool need_f32_phase = (p.out_f32 != nullptr) || use_res || (stats != nullptr);
+                    if (need_f32_phase) {
+                        float4* srow = reinterpret_cast<float4*>(slab + lane * kSlabStride);
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            float4 x = make_float4(v[4 * qq], v[4 * qq + 1], v[4 * qq + 2], v[4 * qq + 3]);
+                            if (!valid) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                            srow[qq] = x;
+                        }
+                        __syncwarp();
+                        const bool fast_stats = stats != nullptr && inst_uniform;
+                        const bool row_back = use_res && (p.out_hi != nullptr || (stats != nullptr && !inst_uniform));
+                        float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (p.out_f32 != nullptr || use_res || fast_stats) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (!svalid[j]) continue;
+                                float4* sp = reinterpret_cast<float4*>(slab + (srow0 + 8 * j) * kSlabStride) + piece;
+                                float4 x = *sp;
+                                if (use_res) {
+                                    const float4 rr = rres[j];
+                                    x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+                                    if (row_back) *sp = x;
+                                }
+                                if (p.out_f32)
+                                    *(reinterpret_cast<float4*>(p.out_f32 + spix[j] * p.ldc + n) + piece) = x;
+                                cs[0] += x.x; cs[1] += x.y; cs[2] += x.z; cs[3] += x.w;
+                                cq[0] = fmaf(x.x, x.x, cq[0]); cq[1] = fmaf(x.y, x.y, cq[1]);
+                                cq[2] = fmaf(x.z, x.z, cq[2]); cq[3] = fmaf(x.w, x.w, cq[3]);
+                            }
+                            if (use_res) {
+                                if (c + 16 < c_end) load_res(c + 16);
+                                if (row_back) {
+                                    __syncwarp();
+#pragma unroll
+                                    for (int qq = 0; qq < 4; ++qq) {
+                                        const float4 x = srow[qq];
+                                        v[4 * qq] = x.x; v[4 * qq + 1] = x.y; v[4 * qq + 2] = x.z; v[4 * qq + 3] = x.w;
+                                    }
+                                }
+                            }
+                        }
+                        if (stats) {
+                            if (inst_uniform) {
+                                const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+                                float k4[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float send = b4 ? cs[j] : cq[j];
+                                    const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+                                    k4[j] = (b4 ? cq[j] : cs[j]) + recv;
+                                }
+                                float k2[2];
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    const float send = b3 ? k4[j] : k4[2 + j];
+                                    const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+                                    k2[j] = (b3 ? k4[2 + j] : k4[j]) + recv;
+                                }
+                                const float send = b2 ? k2[0] : k2[1];
+                                const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+                                const float tot = (b2 ? k2[1] : k2[0]) + recv;
+                                const int col = 4 * piece + (b3 ? 2 : 0) + (b2 ? 1 : 0);
+                                if (n + col < p.cout)
+                                    atomicAdd(&stats[((int64_t)inst0 * p.stats_ld + n + col) * 2 + (b4 ? 1 : 0)],
+                                              (double)tot);
+                            } else if (valid) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (n + j < p.cout) {
+                                        double* sp = &stats[((int64_t)inst * p.stats_ld + n + j) * 2];
+                                        atomicAdd(sp, (double)v[j]);
+                                        atomicAdd(sp + 1, (double)v[j] * (double)v[j]);
+                                    }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    if (p.out_hi) {
+                        uint4 h0, l0, h1, l1;
+                        split8(v, h0, l0);
+                        split8(v + 8, h1, l1);
+                        uint4* srow = reinterpret_cast<uint4*>(slab + lane * kSlabStride);
+                        srow[0] = h0; srow[1] = h1; srow[2] = l0; srow[3] = l1;
+                        __syncwarp();
+                        __nv_bfloat16* plane = piece < 2 ? p.out_hi : p.out_lo;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (!svalid[j]) continue;
+                            const uint4 x = *(reinterpret_cast<const uint4*>(slab + (srow0 + 8 * j) * kSlabStride) + piece);
+                            *reinterpret_cast<uint4*>(plane + spix[j] * p.ldc + n + 8 * (piece & 1)) = x;
+                        }
+                        __syncwarp();
+                    }
+                };
+
+                // fused split product of a cta_group::2 pair: columns [hi*hi + lo*hi | hi*lo] per half of the N rows
+                uint32_t ra[16], rb[16];
+                const int hb = p.block_n >> 1;
+                for (int c = c_begin; c < c_end; c += 16) {
+                    const int ca = c >= hb ? p.block_n + (c - hb) : c;
+                    const int cb = ca + hb;
+                    tmem_ld16(t_row + ca, ra);
+                    tmem_ld16(t_row + cb, rb);
+                    tmem_ld_wait16(ra);
+                    tmem_ld_wait16(rb);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(rb[j]));
+                    process(ra, c);
+                }
+                tc_fence_before();
+                if (crank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+                else mbar_arrive(&tempty_bar[acc]);
+                if (which == 0) {
+                    // publish the spatial tile: every epilogue warp's stores are done (bar.sync over the 256 epilogue
+                    // threads), made visible GPU-wide, then the flag is released
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (warp == 4 && lane == 0 && m < dp.tiles) {
+                        __threadfence();
+                        fence_proxy_async_all();
+                        st_release_gpu(dp.flags + m, 1u);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, kTmemCols);
+    }
+    cluster_sync_all();
+}
+
 // ---------------------------------------------------------------------------
 // host side: tensor maps + plan
 // ---------------------------------------------------------------------------
@@ -774,7 +1236,7 @@ static int cta2_min_k() {
     return v;
 }
 
-static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
+static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out, bool force_cta2 = false) {
     if (int rc = device_props()) return rc;
     V2A_REQUIRE(d->nsrc >= 1 && d->nsrc <= V2A_MAX_SRC, "igemm: nsrc %d out of range", d->nsrc);
     V2A_REQUIRE(d->ntaps >= 1 && d->ntaps <= V2A_MAX_TAPS, "igemm: ntaps %d out of range", d->ntaps);
@@ -990,7 +1452,8 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
             p.stages = stages;
             pl->smem = (size_t)stages * p.stage_bytes + overhead;
         }
-        if (!p.cta2 && mode != 0 && p.cluster == 2 && d->block_n % 32 == 0 && (p.k_iters >= cta2_min_k() || mode == 2) &&
+        if (!p.cta2 && (mode != 0 || force_cta2) && p.cluster == 2 && d->block_n % 32 == 0 &&
+            (p.k_iters >= cta2_min_k() || mode == 2 || force_cta2) &&
             (p.fuse2 || mode != 3)) {      // mode 3: fused (block_n <= 128) layers only (A/B probes)
             p.cta2 = 1;
             p.stage_bytes = 2 * (kATileBytes + p.b_tile_bytes / 2);
@@ -1006,6 +1469,8 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
                                              g_max_smem);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(igemm_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
         if (e != cudaSuccess) {
             delete pl;
             V2A_CUDA_OK(e);
@@ -1016,9 +1481,103 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out) {
     return 0;
 }
 
+
+struct DualPlan {
+    DualParams dp;
+    int grid;
+    size_t smem;
+};
+
+static int dual_plan_create(const v2a_igemm_desc* ds, const v2a_igemm_desc* dt, int frames, int tiles_per_frame,
+                            unsigned int* flags, DualPlan** out) {
+    V2A_REQUIRE(flags != nullptr && frames >= 1 && tiles_per_frame >= 1, "igemm_dual: missing flags / geometry");
+    IgemmPlan *ps = nullptr, *pt = nullptr;
+    int rc = plan_create(ds, &ps, true);
+    if (!rc) rc = plan_create(dt, &pt, true);
+    auto fail = [&](const char* why) {
+        delete ps;
+        delete pt;
+        set_error("igemm_dual: %s", why);
+        return 2;
+    };
+    if (rc) {
+        delete ps;
+        delete pt;
+        return rc;
+    }
+    const IgemmParams &a = ps->p, &b = pt->p;
+    for (const IgemmParams* p : {&a, &b})
+        if (!(p->cta2 && p->fuse2 && p->cluster == 2 && p->num_n_tiles == 1 && p->k_splits == 1 && p->passes == 3 &&
+              p->nacc_log2 == 1 && !p->a_fp16 && !p->b_fp16))
+            return fail("both programs must be cta_group::2 pair launches with the fused split product "
+                        "(3 passes, block_n <= 128 and a multiple of 32, one N tile, no split-K)");
+    if (a.block_n != b.block_n || a.stage_bytes != b.stage_bytes || a.stages != b.stages)
+        return fail("the two programs must share block_n (one operand ring serves both)");
+    if (a.num_m_tiles != b.num_m_tiles) return fail("the two programs must tile the same row space");
+    if (a.num_m_tiles % (tiles_per_frame * frames) != 0 || a.out_hi == nullptr)
+        return fail("tiles must be whole (sample, frame) blocks and the spatial program must write hi/lo planes");
+    DualPlan* pl = new DualPlan();
+    memset(&pl->dp, 0, sizeof(pl->dp));
+    pl->dp.g[0] = a;
+    pl->dp.g[1] = b;
+    pl->dp.flags = flags;
+    pl->dp.tpf = tiles_per_frame;
+    pl->dp.frames = frames;
+    pl->dp.tiles = a.num_m_tiles;
+    pl->dp.mp = ceil_div(a.num_m_tiles, 2);
+    int grid = (g_num_sms / 2) * 2;
+    if (grid > 2 * pl->dp.mp) grid = 2 * pl->dp.mp;
+    const int pairs = grid / 2;
+    // every dependency of T(q) (pair-tiles up to q + ceil(tpf / 2)) must belong to an EARLIER iteration of its pair
+    // than the one that issues T(q): lag >= ceil(tpf / 2) + pairs; one more round of pairs gives the producers'
+    // epilogues time to publish, so the temporal producer normally finds its flags set
+    const char* env = getenv("V2A_DUAL_LAG");
+    const int rounds = env ? atoi(env) : 2;
+    pl->dp.lag = (tiles_per_frame + 1) / 2 + 1 + pairs * (rounds < 1 ? 1 : rounds);
+    pl->dp.iters = ceil_div(pl->dp.mp + pl->dp.lag, pairs);
+    pl->grid = grid;
+    pl->smem = ps->smem;
+    delete ps;
+    delete pt;
+    *out = pl;
+    return 0;
+}
+
 }  // namespace v2a
 
 extern "C" {
+
+int v2a_igemm_dual_plan_create(const v2a_igemm_desc* spatial, const v2a_igemm_desc* temporal, int frames,
+                               int tiles_per_frame, void* flags, void** plan_out) {
+    v2a::DualPlan* pl = nullptr;
+    int rc = v2a::dual_plan_create(spatial, temporal, frames, tiles_per_frame, (unsigned int*)flags, &pl);
+    if (rc) return rc;
+    *plan_out = pl;
+    return 0;
+}
+
+int v2a_igemm_dual_plan_run(void* plan, void* stream) {
+    v2a::DualPlan* pl = reinterpret_cast<v2a::DualPlan*>(plan);
+    V2A_CUDA_OK(cudaMemsetAsync(pl->dp.flags, 0, sizeof(unsigned int) * (size_t)pl->dp.tiles, (cudaStream_t)stream));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)pl->grid);
+    cfg.blockDim = dim3(v2a::kThreads);
+    cfg.dynamicSmemBytes = pl->smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    V2A_CUDA_OK(cudaLaunchKernelEx(&cfg, v2a::igemm_dual_kernel, pl->dp));
+    V2A_CUDA_OK(cudaGetLastError());
+    v2a::g_launches.fetch_add(1);
+    return 0;
+}
+
+void v2a_igemm_dual_plan_destroy(void* plan) { delete reinterpret_cast<v2a::DualPlan*>(plan); }
 
 const char* v2a_last_error(void) { return v2a::get_error(); }
 int v2a_version(void) { return 100; }
