@@ -362,3 +362,74 @@ def test_stencil9_matches_its_torch_restatement():
         ops.stencil9(P, bias, N, H, W, 3, y)
         want = stencil9_reference(P.double(), bias.double(), N, H, W, 3)
         assert torch.allclose(y[:, :3].double(), want, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,Fr,H,W,ci,co,cx,res", [(2, 3, 16, 16, 64, 64, 0, False), (2, 7, 16, 16, 72, 64, 40, False),
+                                                  (3, 7, 16, 32, 128, 128, 0, True), (1, 4, 64, 64, 128, 128, 256, False),
+                                                  (3, 3, 8, 16, 64, 64, 0, True)])
+def test_conv3d_dual_launch_matches_float64_and_the_two_launch_path(B, Fr, H, W, ci, co, cx, res):
+    """`ops.IgemmDual`: the spatial 3x3 program and the temporal k3 program (+ 1x1 skip K, + bias, + per-sample
+    embedding row, + residual, + GroupNorm sums) as ONE interleaved launch, against (a) float64 torch convolutions of
+    the same operands (guided_diffusion/nn.py:53-87 order: spatial bias BEFORE the temporal zero padding) and (b)
+    the two separate launches the engine uses for wide layers.  Odd tile counts (ghost tile), every temporal
+    boundary frame, tiles-per-frame 1 / 2 / 4 / 32."""
+    ops, convs = _ops()
+    g = torch.Generator().manual_seed(B * 100 + Fr)
+    N, HW = B * Fr, H * W
+    x = torch.randn(N * HW, ci, generator=g).to(DEV)
+    ws = (torch.randn(co, ci, 3, 3, generator=g) / (3 * ci ** 0.5)).to(DEV)
+    bs = torch.randn(co, generator=g).to(DEV)
+    wt = (torch.randn(co, co, 3, generator=g) / (3 * co) ** 0.5).to(DEV)
+    bt = torch.randn(co, generator=g).to(DEV)
+    emb = torch.randn(B, co, generator=g).to(DEV)
+    xs = torch.randn(N * HW, cx, generator=g).to(DEV) if cx else None
+    wk = (torch.randn(co, cx, 1, 1, generator=g) / cx ** 0.5).to(DEV) if cx else None
+    resid = torch.randn(N * HW, co, generator=g).to(DEV) if res else None
+    progs = convs.spatial3x3(ci, N, H, W)
+    progt = convs.temporal3(co, B, Fr, HW, skip_channels=cx)
+    assert ops.dual_conv3d_ok(progs.out_dims, progt.out_dims, co, 3, Fr)
+    a_hl = ops.split_hl(x)
+    w_s = ops.split_hl_torch(convs.spatial3x3_weight(ws))
+    w_t = ops.split_hl_torch(convs.temporal3_weight(wt, wk))
+    bn = ops.choose_block_n(co)
+
+    def run(dual):
+        y_hl = ops.HL.empty(N * HW, co, DEV)
+        out = torch.full((N * HW, co), float("nan"), device=DEV)
+        stats = torch.zeros(2, N, co, 2, dtype=torch.float64, device=DEV)
+        srcs = [(y_hl, co, (HW, Fr, B, 1))]
+        if cx:
+            srcs.append((ops.split_hl(xs), cx, (HW, Fr, B, 1)))
+        skw = dict(srcs=[(a_hl, ci, progs.src_dims[0])], taps=progs.taps, w=w_s, out_dims=progs.out_dims, cout=co,
+                   out_hl=y_hl, bias=bs, block_n=bn)
+        tkw = dict(srcs=srcs, taps=progt.taps, w=w_t, out_dims=progt.out_dims, cout=co, out_f32=out, bias=bt,
+                   rowvec=emb, rowvec_mul=(0, 0, 1, 0), residual=resid, stats=stats, stats_mul=(0, 1, Fr, 0), block_n=bn)
+        if dual:
+            gd = ops.IgemmDual(skw, tkw, Fr)
+            for _ in range(2):          # twice: the completion flags are re-armed by every run
+                stats.zero_()
+                gd.run()
+        else:
+            ops.Igemm(**skw).run()
+            ops.Igemm(**tkw).run()
+        torch.cuda.synchronize()
+        return out, stats.sum(0)
+
+    got, st = run(True)
+    two, st2 = run(False)
+    # float64 truth
+    xd = x.double().reshape(N, H, W, ci).permute(0, 3, 1, 2)
+    y = F.conv2d(xd, ws.double(), bs.double(), padding=1)                                   # [(b f), co, H, W]
+    yy = y.reshape(B, Fr, co, H, W).permute(0, 3, 4, 2, 1).reshape(B * HW, co, Fr)
+    ref = F.conv1d(F.pad(yy, (1, 1)), wt.double(), bt.double()).reshape(B, H, W, co, Fr).permute(0, 4, 1, 2, 3)
+    ref = ref + emb.double()[:, None, None, None, :]
+    if cx:
+        ref = ref + torch.einsum("bfhwc,oc->bfhwo", xs.double().reshape(B, Fr, H, W, cx), wk.double()[:, :, 0, 0])
+    ref = ref.reshape(N * HW, co)
+    if res:
+        ref = ref + resid.double()
+    assert torch.isfinite(got).all()
+    assert _rel(got, ref) < 5e-5, _rel(got, ref)
+    assert _rel(got, two) < 1e-6, _rel(got, two)            # same products, same accumulation order
+    ref_st = torch.stack([ref.reshape(N, HW, co).sum(1), (ref * ref).reshape(N, HW, co).sum(1)], dim=-1)
+    assert _rel(st, ref_st) < 1e-4 and _rel(st2, ref_st) < 1e-4

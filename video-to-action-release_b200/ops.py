@@ -125,113 +125,122 @@ def pack_weight_taps(per_tap: Sequence[torch.Tensor]) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 # implicit GEMM plan
 # ---------------------------------------------------------------------------
-class Igemm:
-    """One planned tcgen05 implicit-GEMM launch (TMA descriptors built once)."""
+def _igemm_desc(*, srcs, taps, w: HL, out_dims, cout, ldc=None, out_f32=None, out_hl=None,
+                bias=None, rowvec=None, rowvec_mul=(0, 0, 0, 0), residual=None, stats=None,
+                stats_mul=(0, 0, 0, 0), block_n=None, passes=3, tile_log2=None, out_pix=None, algo_flops_scale=1.0):
+    """Fill a `v2a_igemm_desc` from torch tensors.  Returns (desc, keep-alive list, meta dict).
 
-    def __init__(self, *, srcs, taps, w: HL, out_dims, cout, ldc=None, out_f32=None, out_hl=None,
-                 bias=None, rowvec=None, rowvec_mul=(0, 0, 0, 0), residual=None, stats=None,
-                 stats_mul=(0, 0, 0, 0), block_n=None, passes=3, tile_log2=None, out_pix=None, algo_flops_scale=1.0):
-        """out_pix = ((m0, m1, m2, m3), off): the output row of grid point c is off + sum c[d] * m[d] instead of
-        the dense grid order (sub-pixel phases writing into a finer grid); the output tensors are then only
-        checked for covering the largest row.  algo_flops_scale: algorithmic / executed FLOPs of this launch
-        (9/4 for a sub-pixel phase, which does 4 of the reference's 9 taps' worth of work)."""
-        lib = _lib.load()
-        d = _lib.IgemmDesc()
-        self._keep = [srcs, w, out_f32, out_hl, bias, rowvec, residual, stats]
-        assert 1 <= len(srcs) <= _lib.V2A_MAX_SRC
-        for i, (hl, channels, dims) in enumerate(srcs):
-            _require_cuda(hl.hi, hl.lo)
-            dims = list(dims) + [1] * (4 - len(dims))
-            need = channels * dims[0] * dims[1] * dims[2] * dims[3]
-            assert hl.hi.numel() == need, f"src {i}: {hl.hi.numel()} elements, dims say {need}"
-            d.src[i].hi = hl.hi.data_ptr()
-            d.src[i].lo = hl.lo.data_ptr()
-            d.src[i].channels = channels
-            for k in range(4):
-                d.src[i].dims[k] = dims[k]
-        d.nsrc = len(srcs)
-        fmts = {bool(hl.fp16) for hl, _, _ in srcs}
-        assert fmts == {bool(w.fp16)}, "sources and weights of one igemm share a plane format"
-        d.a_fp16 = d.b_fp16 = int(bool(w.fp16))
-        assert 1 <= len(taps) <= _lib.V2A_MAX_TAPS
-        ktot = 0
-        for i, (src, off, nch) in enumerate(taps):
-            off = list(off) + [0] * (4 - len(off))
-            d.taps[i].src = src
-            for k in range(4):
-                d.taps[i].d[k] = off[k]
-            d.taps[i].nchunks = nch
-            ktot += nch * CHUNK_K
-        d.ntaps = len(taps)
-        assert w.hi.shape[1] == ktot, f"weight K {w.hi.shape[1]} != tap program K {ktot}"
-        d.w_hi, d.w_lo = w.hi.data_ptr(), w.lo.data_ptr()
-        d.wrows = w.hi.shape[0]
-        d.ktot = ktot
-        out_dims = list(out_dims) + [1] * (4 - len(out_dims))
-        tile_log2 = tile_log2 or choose_tile(out_dims)
+    out_pix = ((m0, m1, m2, m3), off): the output row of grid point c is off + sum c[d] * m[d] instead of
+    the dense grid order (sub-pixel phases writing into a finer grid); the output tensors are then only
+    checked for covering the largest row.  algo_flops_scale: algorithmic / executed FLOPs of this launch
+    (9/4 for a sub-pixel phase, which does 4 of the reference's 9 taps' worth of work)."""
+    d = _lib.IgemmDesc()
+    keep = [srcs, w, out_f32, out_hl, bias, rowvec, residual, stats]
+    assert 1 <= len(srcs) <= _lib.V2A_MAX_SRC
+    for i, (hl, channels, dims) in enumerate(srcs):
+        _require_cuda(hl.hi, hl.lo)
+        dims = list(dims) + [1] * (4 - len(dims))
+        need = channels * dims[0] * dims[1] * dims[2] * dims[3]
+        assert hl.hi.numel() == need, f"src {i}: {hl.hi.numel()} elements, dims say {need}"
+        d.src[i].hi = hl.hi.data_ptr()
+        d.src[i].lo = hl.lo.data_ptr()
+        d.src[i].channels = channels
         for k in range(4):
-            d.out_dims[k] = out_dims[k]
-            d.tile_log2[k] = tile_log2[k]
-            d.rowvec_mul[k] = rowvec_mul[k]
-            d.stats_mul[k] = stats_mul[k]
-        d.block_n = block_n or choose_block_n(cout)
-        d.passes = passes
-        d.cout = cout
-        rows = out_dims[0] * out_dims[1] * out_dims[2] * out_dims[3]
-        out_rows = rows
-        if out_pix is not None:
-            mul, off = out_pix
-            out_rows = off + sum((out_dims[k] - 1) * mul[k] for k in range(4)) + 1     # largest row written + 1
-            for k in range(4):
-                d.out_pix_mul[k] = mul[k]
-            d.out_pix_off = off
-            assert any(mul), "out_pix multipliers must not all be zero"
-        # outputs may be column windows of wider row-pitched matrices: the pitch is the view's stride(0)
-        if ldc is None:
-            if out_f32 is not None and out_f32.dim() == 2:
-                ldc = out_f32.stride(0)
-            elif out_hl is not None and out_hl.hi.dim() == 2:
-                ldc = out_hl.hi.stride(0)
-            else:
-                ldc = -(-cout // 16) * 16
-        d.ldc = ldc
-        self.rows, self.cout, self.ldc, self.ktot = rows, cout, ldc, ktot
-        if out_f32 is not None:
-            assert out_f32.dtype == torch.float32
-            if out_f32.dim() == 2:
-                assert out_f32.shape[0] >= out_rows and out_f32.stride(1) == 1 and out_f32.stride(0) == ldc
-                assert out_pix is not None or out_f32.shape[0] == rows
-            else:
-                assert out_f32.numel() >= out_rows * ldc
-            d.out_f32 = out_f32.data_ptr()
-        if out_hl is not None:
-            if out_hl.hi.dim() == 2:
-                assert out_hl.hi.shape[0] >= out_rows and out_hl.hi.stride(0) == ldc == out_hl.lo.stride(0)
-                assert out_pix is not None or out_hl.hi.shape[0] == rows
-            else:
-                assert out_hl.hi.numel() >= out_rows * ldc
-            d.out_hi, d.out_lo = out_hl.hi.data_ptr(), out_hl.lo.data_ptr()
-        if bias is not None:
-            assert bias.dtype == torch.float32 and bias.numel() >= cout
-            d.bias = bias.data_ptr()
-        if rowvec is not None:
-            assert rowvec.dtype == torch.float32 and rowvec.dim() == 2
-            d.rowvec = rowvec.data_ptr()
-            d.ld_rowvec = rowvec.stride(0)
-        if residual is not None:
-            assert residual.dtype == torch.float32
-            d.residual = residual.data_ptr()
-            d.ld_res = residual.stride(0) if residual.dim() == 2 else residual.shape[-1]
-        if stats is not None:
-            assert stats.dtype == torch.float64
-            d.stats = stats.data_ptr()
-            d.stats_ld = stats.shape[-2]
-            # optional leading replica dim: [R, instances, C, 2]
-            d.stats_replicas = stats.shape[0] if stats.dim() == 4 else 1
-            d.stats_rep_stride = stats.stride(0) if stats.dim() == 4 else 0
+            d.src[i].dims[k] = dims[k]
+    d.nsrc = len(srcs)
+    fmts = {bool(hl.fp16) for hl, _, _ in srcs}
+    assert fmts == {bool(w.fp16)}, "sources and weights of one igemm share a plane format"
+    d.a_fp16 = d.b_fp16 = int(bool(w.fp16))
+    assert 1 <= len(taps) <= _lib.V2A_MAX_TAPS
+    ktot = 0
+    for i, (src, off, nch) in enumerate(taps):
+        off = list(off) + [0] * (4 - len(off))
+        d.taps[i].src = src
+        for k in range(4):
+            d.taps[i].d[k] = off[k]
+        d.taps[i].nchunks = nch
+        ktot += nch * CHUNK_K
+    d.ntaps = len(taps)
+    assert w.hi.shape[1] == ktot, f"weight K {w.hi.shape[1]} != tap program K {ktot}"
+    d.w_hi, d.w_lo = w.hi.data_ptr(), w.lo.data_ptr()
+    d.wrows = w.hi.shape[0]
+    d.ktot = ktot
+    out_dims = list(out_dims) + [1] * (4 - len(out_dims))
+    tile_log2 = tile_log2 or choose_tile(out_dims)
+    for k in range(4):
+        d.out_dims[k] = out_dims[k]
+        d.tile_log2[k] = tile_log2[k]
+        d.rowvec_mul[k] = rowvec_mul[k]
+        d.stats_mul[k] = stats_mul[k]
+    d.block_n = block_n or choose_block_n(cout)
+    d.passes = passes
+    d.cout = cout
+    rows = out_dims[0] * out_dims[1] * out_dims[2] * out_dims[3]
+    out_rows = rows
+    if out_pix is not None:
+        mul, off = out_pix
+        out_rows = off + sum((out_dims[k] - 1) * mul[k] for k in range(4)) + 1     # largest row written + 1
+        for k in range(4):
+            d.out_pix_mul[k] = mul[k]
+        d.out_pix_off = off
+        assert any(mul), "out_pix multipliers must not all be zero"
+    # outputs may be column windows of wider row-pitched matrices: the pitch is the view's stride(0)
+    if ldc is None:
+        if out_f32 is not None and out_f32.dim() == 2:
+            ldc = out_f32.stride(0)
+        elif out_hl is not None and out_hl.hi.dim() == 2:
+            ldc = out_hl.hi.stride(0)
+        else:
+            ldc = -(-cout // 16) * 16
+    d.ldc = ldc
+    if out_f32 is not None:
+        assert out_f32.dtype == torch.float32
+        if out_f32.dim() == 2:
+            assert out_f32.shape[0] >= out_rows and out_f32.stride(1) == 1 and out_f32.stride(0) == ldc
+            assert out_pix is not None or out_f32.shape[0] == rows
+        else:
+            assert out_f32.numel() >= out_rows * ldc
+        d.out_f32 = out_f32.data_ptr()
+    if out_hl is not None:
+        if out_hl.hi.dim() == 2:
+            assert out_hl.hi.shape[0] >= out_rows and out_hl.hi.stride(0) == ldc == out_hl.lo.stride(0)
+            assert out_pix is not None or out_hl.hi.shape[0] == rows
+        else:
+            assert out_hl.hi.numel() >= out_rows * ldc
+        d.out_hi, d.out_lo = out_hl.hi.data_ptr(), out_hl.lo.data_ptr()
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() >= cout
+        d.bias = bias.data_ptr()
+    if rowvec is not None:
+        assert rowvec.dtype == torch.float32 and rowvec.dim() == 2
+        d.rowvec = rowvec.data_ptr()
+        d.ld_rowvec = rowvec.stride(0)
+    if residual is not None:
+        assert residual.dtype == torch.float32
+        d.residual = residual.data_ptr()
+        d.ld_res = residual.stride(0) if residual.dim() == 2 else residual.shape[-1]
+    if stats is not None:
+        assert stats.dtype == torch.float64
+        d.stats = stats.data_ptr()
+        d.stats_ld = stats.shape[-2]
+        # optional leading replica dim: [R, instances, C, 2]
+        d.stats_replicas = stats.shape[0] if stats.dim() == 4 else 1
+        d.stats_rep_stride = stats.stride(0) if stats.dim() == 4 else 0
+    flops = 2.0 * rows * cout * ktot                    # executed by the tensor cores
+    meta = dict(rows=rows, cout=cout, ldc=ldc, ktot=ktot, flops=flops, algo_flops=flops * algo_flops_scale,
+                out_dims=tuple(out_dims), tile_log2=tuple(tile_log2))
+    return d, keep, meta
+
+
+class Igemm:
+    """One planned tcgen05 implicit-GEMM launch (TMA descriptors built once); keyword arguments: `_igemm_desc`."""
+
+    def __init__(self, **kw):
+        lib = _lib.load()
+        d, self._keep, meta = _igemm_desc(**kw)
+        self.rows, self.cout, self.ldc, self.ktot = meta["rows"], meta["cout"], meta["ldc"], meta["ktot"]
         self.desc = d
-        self.flops = 2.0 * rows * cout * sum(nch * CHUNK_K for _, _, nch in taps)    # executed by the tensor cores
-        self.algo_flops = self.flops * algo_flops_scale                               # of the reference's algorithm
+        self.flops, self.algo_flops = meta["flops"], meta["algo_flops"]
         plan = C.c_void_p()
         _lib.check(lib.v2a_igemm_plan_create(C.byref(d), C.byref(plan)), "igemm_plan_create")
         self._plan = plan
@@ -245,6 +254,71 @@ class Igemm:
         try:
             if getattr(self, "_plan", None):
                 self._lib.v2a_igemm_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:
+            pass
+
+
+def _contiguous_tiling(out_dims, tile_log2) -> bool:
+    """True when the 128-row tile boxes cut the dense row space (D0 fastest) into consecutive 128-row blocks, in tile
+    order: every box divides its dim, and once a box is narrower than its dim all higher dims have box 1."""
+    partial = False
+    for dim, l in zip(out_dims, tile_log2):
+        box = 1 << l
+        if dim % box != 0 or (partial and box != 1):
+            return False
+        if box != dim:
+            partial = True
+    return True
+
+
+def dual_conv3d_ok(spatial_out_dims, temporal_out_dims, cout: int, passes: int, frames: int) -> bool:
+    """Can a Conv3d (spatial program -> temporal program) run as ONE dual launch?  Narrow layers only (the fused
+    split product needs block_n <= 128), and both programs must cut the same dense row space into the same blocks."""
+    if passes != 3 or cout > 128 or cout % 32 != 0:
+        return False
+    sd = list(spatial_out_dims) + [1] * (4 - len(spatial_out_dims))
+    td = list(temporal_out_dims) + [1] * (4 - len(temporal_out_dims))
+    rows_s, rows_t = sd[0] * sd[1] * sd[2] * sd[3], td[0] * td[1] * td[2] * td[3]
+    if rows_s != rows_t or td[1] != frames or td[0] % 128 != 0 or (rows_s // 128) < 8:
+        return False
+    return _contiguous_tiling(sd, choose_tile(sd)) and _contiguous_tiling(td, choose_tile(td))
+
+
+class IgemmDual:
+    """Conv3d as ONE launch: the spatial implicit GEMM and the temporal one that consumes its hi/lo output planes,
+    interleaved tile by tile in one persistent kernel (`v2a_igemm_dual_plan_*`, csrc/igemm.cu `igemm_dual_kernel`)."""
+
+    def __init__(self, spatial: dict, temporal: dict, frames: int):
+        lib = _lib.load()
+        ds, keep_s, ms = _igemm_desc(**spatial)
+        dt, keep_t, mt = _igemm_desc(**temporal)
+        assert ds.block_n == dt.block_n and ms["rows"] == mt["rows"]
+        assert _contiguous_tiling(ms["out_dims"], ms["tile_log2"]) and _contiguous_tiling(mt["out_dims"], mt["tile_log2"])
+        tiles = mt["rows"] // 128
+        tpf = mt["out_dims"][0] // 128                   # temporal grid = (H*W, F, B): tiles of one (sample, frame)
+        assert mt["out_dims"][1] == frames and tiles % (tpf * frames) == 0
+        dev = spatial["w"].hi.device
+        self.flags = torch.zeros(tiles, dtype=torch.int32, device=dev)
+        self._keep = [keep_s, keep_t, self.flags]
+        self.desc, self.desc_t = ds, dt
+        self.rows, self.cout, self.ldc = mt["rows"], mt["cout"], mt["ldc"]
+        self.ktot = ms["ktot"] + mt["ktot"]
+        self.flops = ms["flops"] + mt["flops"]
+        self.algo_flops = ms["algo_flops"] + mt["algo_flops"]
+        self.k_splits = 1
+        plan = C.c_void_p()
+        _lib.check(lib.v2a_igemm_dual_plan_create(C.byref(ds), C.byref(dt), frames, tpf, self.flags.data_ptr(),
+                                                  C.byref(plan)), "igemm_dual_plan_create")
+        self._plan, self._lib = plan, lib
+
+    def run(self) -> None:
+        _lib.check(self._lib.v2a_igemm_dual_plan_run(self._plan, _stream()), "igemm_dual_plan_run")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None):
+                self._lib.v2a_igemm_dual_plan_destroy(self._plan)
                 self._plan = None
         except Exception:
             pass

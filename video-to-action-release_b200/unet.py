@@ -414,6 +414,14 @@ class _UNetEngine:
         self._step(lambda s=slot: s[0].run(), "igemm")
         return slot
 
+    def add_igemm_dual(self, spatial_kw: dict, temporal_kw: dict):
+        """One launch for a Conv3d: the spatial and the temporal implicit GEMM interleaved (ops.IgemmDual)."""
+        self._pending = getattr(self, "_pending", [])
+        slot = [None]
+        self._pending.append((slot, ("dual", spatial_kw, temporal_kw)))
+        self._step(lambda s=slot: s[0].run(), "igemm")
+        return slot
+
     def add_prep(self, **kw):
         self._pending = getattr(self, "_pending", [])
         slot = [None]
@@ -425,7 +433,13 @@ class _UNetEngine:
         def res(v):
             return v[0] if isinstance(v, list) and len(v) == 1 and isinstance(v[0], torch.Tensor) else v
         for slot, kw in self._pending:
-            if isinstance(kw, tuple):
+            if isinstance(kw, tuple) and kw[0] == "dual":
+                skw = {k: res(v) for k, v in kw[1].items()}
+                tkw = {k: res(v) for k, v in kw[2].items()}
+                g = ops.IgemmDual(dict(passes=self.passes, **skw), dict(passes=self.passes, **tkw), self.Fr)
+                slot[0] = g
+                self.igemms.append(g)
+            elif isinstance(kw, tuple):
                 args = {k: res(v) for k, v in kw[1].items()}
                 slot[0] = ops.Prep(**args)
             else:
@@ -457,11 +471,12 @@ class _UNetEngine:
                     self.add_igemm(srcs=[(a_hl, cin, prog.src_dims[0])], taps=prog.taps, w=w_p,
                                    out_dims=prog.out_dims, cout=cout, out_hl=y_hl, bias=b_s,
                                    out_pix=convs.upsample3x3_out_pix(H, W, py, px), algo_flops_scale=9 / 4)
-        else:
+        spatial_kw = None
+        if not upsample:
             prog = convs.spatial3x3_s2(cin, N, H, W) if stride2 else convs.spatial3x3(cin, N, H, W)
             w_s = self.weight(lambda: convs.spatial3x3_weight(m.spatial_conv.weight), cout, prog.ktot)
-            self.add_igemm(srcs=[(a_hl, cin, prog.src_dims[0])], taps=prog.taps, w=w_s, out_dims=prog.out_dims,
-                           cout=cout, out_hl=y_hl, bias=b_s)
+            spatial_kw = dict(srcs=[(a_hl, cin, prog.src_dims[0])], taps=prog.taps, w=w_s, out_dims=prog.out_dims,
+                              cout=cout, out_hl=y_hl, bias=b_s)
         out = _Act(self, N, Ho, Wo, cout)
         HW = Ho * Wo
         srcs = [(y_hl, cout, (HW, Fr, B, 1))]
@@ -476,9 +491,20 @@ class _UNetEngine:
             progt = convs.temporal3(cout, B, Fr, HW)
             w_t = self.weight(lambda: convs.temporal3_weight(m.temporal_conv.weight), cout, progt.ktot)
             b_t = self.vec(lambda: m.temporal_conv.bias, cout)
-        self.add_igemm(srcs=srcs, taps=progt.taps, w=w_t, out_dims=progt.out_dims, cout=cout, out_f32=out.raw,
-                       bias=b_t, rowvec=rowvec, rowvec_mul=(0, 0, 1, 0), residual=residual, stats=out.stats,
-                       stats_mul=(0, 1, Fr, 0))
+        temporal_kw = dict(srcs=srcs, taps=progt.taps, w=w_t, out_dims=progt.out_dims, cout=cout, out_f32=out.raw,
+                           bias=b_t, rowvec=rowvec, rowvec_mul=(0, 0, 1, 0), residual=residual, stats=out.stats,
+                           stats_mul=(0, 1, Fr, 0))
+        # Narrow layers (Cout <= 128): the temporal conv is bound by its epilogue, the spatial conv by its MMAs --
+        # ONE dual launch interleaves them tile by tile so each hides the other (ops.IgemmDual); V2A_DUAL=0 = two
+        # launches (A/B probe)
+        if spatial_kw is not None and os.environ.get("V2A_DUAL", "1") != "0" and \
+                ops.dual_conv3d_ok(spatial_kw["out_dims"], progt.out_dims, cout, self.passes, Fr):
+            bn = ops.choose_block_n(cout)
+            self.add_igemm_dual(dict(block_n=bn, **spatial_kw), dict(block_n=bn, **temporal_kw))
+        else:
+            if spatial_kw is not None:
+                self.add_igemm(**spatial_kw)
+            self.add_igemm(**temporal_kw)
         self.release(y_st)
         return out
 
