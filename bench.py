@@ -364,22 +364,27 @@ def measure_kernel_roofline(diff, batch, peaks):
     eng.bind_static(st["x"], st["cond"], st["v"])
     evs = []
     from v2a_b200 import ops
-    orig_run = ops.Igemm.run
+    classes = [ops.Igemm, ops.IgemmDual]       # IgemmDual = a Conv3d's spatial + temporal GEMM in one launch
+    orig = {c: c.run for c in classes}
 
-    def timed_run(self):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        orig_run(self)
-        e1.record()
-        evs.append((self, e0, e1))
-    ops.Igemm.run = timed_run
+    def wrap(cls):
+        def timed_run(self):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            orig[cls](self)
+            e1.record()
+            evs.append((self, e0, e1))
+        return timed_run
+    for c in classes:
+        c.run = wrap(c)
     try:
         for _ in range(3):
             evs.clear()
             eng.run_static()
             torch.cuda.synchronize()
     finally:
-        ops.Igemm.run = orig_run
+        for c in classes:
+            c.run = orig[c]
     tot_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in evs)
     executed = sum(g.flops for g, _, _ in evs)          # what the tensor cores did (sub-pixel upsample: 4 of 9 taps)
     algorithmic = sum(g.algo_flops for g, _, _ in evs)  # what the reference's algorithm asks of these launches

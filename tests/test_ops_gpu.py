@@ -430,6 +430,48 @@ def test_conv3d_dual_launch_matches_float64_and_the_two_launch_path(B, Fr, H, W,
         ref = ref + resid.double()
     assert torch.isfinite(got).all()
     assert _rel(got, ref) < 5e-5, _rel(got, ref)
-    assert _rel(got, two) < 1e-6, _rel(got, two)            # same products, same accumulation order
+    assert _rel(got, two) < 1e-5, _rel(got, two)            # same products (pair MMAs group the split product differently)
     ref_st = torch.stack([ref.reshape(N, HW, co).sum(1), (ref * ref).reshape(N, HW, co).sum(1)], dim=-1)
     assert _rel(st, ref_st) < 1e-4 and _rel(st2, ref_st) < 1e-4
+
+
+@pytest.mark.parametrize("B,T,cins,co,k,res,hl", [(1, 16, (256,), 256, 5, True, True), (1, 4, (1024,), 1024, 5, False, True),
+                                                  (1, 8, (512, 512), 512, 5, False, False), (2, 16, (7 + 9,), 256, 5, False, True),
+                                                  (1, 1, (256,), 1000, 1, False, False), (2, 4, (1024,), 24, 3, True, False)])
+def test_igemm_small_m_backend_matches_float64(B, T, cins, co, k, res, hl, monkeypatch):
+    """GEMMs of <= 32 output rows (the policy UNet at batch 1-2: `predict_action` between simulator steps) run on the
+    CUDA-core weight-streaming backend of the same plan (csrc/igemm.cu `igemm_smallm_kernel`): Conv1d k5 / k3 / Linear
+    programs incl. a two-source channel concat, zero padding at both ends of the horizon, bias, residual, fp32 and
+    hi/lo outputs -- against float64 and against the tensor-core kernel (V2A_SMALLM=0)."""
+    ops, convs = _ops()
+    g = torch.Generator().manual_seed(T * 10 + co)
+    xs = [torch.randn(B * T, c, generator=g).to(DEV) for c in cins]
+    prog = convs.conv1d_cat(list(cins), B, T, k, k // 2)
+    w = (torch.randn(co, sum(cins), k, generator=g) / (k * sum(cins)) ** 0.5).to(DEV)
+    wp = convs.conv1d_cat_weight(w, list(cins))
+    bias = torch.randn(co, generator=g).to(DEV)
+    resid = torch.randn(B * T, co, generator=g).to(DEV) if res else None
+
+    def run():
+        srcs = [(ops.split_hl(x), c, d) for x, c, d in zip(xs, prog.src_channels, prog.src_dims)]
+        ldc = -(-co // 16) * 16
+        out = torch.zeros(B * T, ldc, device=DEV)
+        ohl = ops.HL(torch.zeros(B * T, ldc, dtype=torch.bfloat16, device=DEV),
+                     torch.zeros(B * T, ldc, dtype=torch.bfloat16, device=DEV)) if hl else None
+        gm = ops.Igemm(srcs=srcs, taps=prog.taps, w=ops.split_hl_torch(wp), out_dims=prog.out_dims, cout=co, ldc=ldc,
+                       out_f32=out, out_hl=ohl, bias=bias, residual=resid)
+        gm.run()
+        torch.cuda.synchronize()
+        return out[:, :co], (ohl.float()[:, :co] if hl else None)
+
+    got, got_hl = run()
+    monkeypatch.setenv("V2A_SMALLM", "0")
+    tc, _ = run()
+    xcat = torch.cat([x.double().reshape(B, T, -1) for x in xs], dim=2).permute(0, 2, 1)
+    ref = F.conv1d(xcat, w.double(), bias.double(), padding=k // 2).permute(0, 2, 1).reshape(B * T, co)
+    if res:
+        ref = ref + resid.double()
+    assert _rel(got, ref) < 2e-5, _rel(got, ref)           # exact hi + lo operands, fp32 FMA accumulation
+    assert _rel(tc, ref) < 5e-5 and _rel(got, tc) < 5e-5
+    if hl:
+        assert _rel(got_hl, ref) < 5e-5

@@ -749,16 +749,31 @@ __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) 
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-__device__ __forceinline__ void dual_wait_flag(const unsigned int* f, int tag) {
-    if (ld_acquire_gpu(f)) return;
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Wait until the spatial tiles a temporal tile reads (frames f - 1, f, f + 1 of the same pixels) are published.
+// The three flags are read with independent relaxed loads (one L2 round trip, not three) and ordered by ONE acquire
+// fence; in steady state they were set iterations ago, so this costs ~1 us of the producer thread's slack.
+__device__ __forceinline__ void dual_wait_deps(const DualParams& dp, int m) {
+    const int f = (m / dp.tpf) % dp.frames;
+    const unsigned int* f0 = dp.flags + m;
+    const unsigned int* f1 = f > 0 ? f0 - dp.tpf : f0;
+    const unsigned int* f2 = f + 1 < dp.frames ? f0 + dp.tpf : f0;
     const long long t0 = clock64();
-    while (!ld_acquire_gpu(f)) {
+    for (;;) {
+        const unsigned int a = ld_relaxed_gpu(f0), b = ld_relaxed_gpu(f1), c = ld_relaxed_gpu(f2);
+        if (a & b & c) break;
         __nanosleep(64);
         if (clock64() - t0 > 4000000000LL) {
-            printf("v2a: dual-conv dependency timeout tile=%d block=%d\n", tag, (int)blockIdx.x);
+            printf("v2a: dual-conv dependency timeout tile=%d block=%d\n", m, (int)blockIdx.x);
             __trap();
         }
     }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    fence_proxy_async_all();      // generic-proxy stores of other CTAs -> this thread's TMA reads
 }
 
 __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_constant__ DualParams dp) {
@@ -814,20 +829,22 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
         uint32_t phase = 0;
         for (int k = 0; k < dp.iters; ++k) {
             const int i = pr + k * pairs;
+            // the temporal item of this iteration: its dependencies are checked while the spatial item's loads are
+            // queued behind a full operand ring (the producer thread has nothing else to do there), not in the gap
+            // between the two items where every microsecond of this thread stalls the MMAs
+            const int qt = i - dp.lag;
+            const int mt = 2 * qt + (int)crank;
+            bool t_pending = qt >= 0 && qt < dp.mp && mt < dp.tiles;
             for (int which = 0; which < 2; ++which) {
-                const int q = which == 0 ? i : i - dp.lag;
+                const int q = which == 0 ? i : qt;
                 if (q < 0 || q >= dp.mp) continue;
                 const IgemmParams& p = dp.g[which];
                 const int m = 2 * q + (int)crank;
                 int o[4];
                 dual_tile_origin(p, m, o);
-                if (which == 1 && m < dp.tiles) {
-                    // the three spatial tiles this temporal tile reads (frames f - 1, f, f + 1 of the same pixels)
-                    const int f = (m / dp.tpf) % dp.frames;
-                    dual_wait_flag(dp.flags + m, m);
-                    if (f > 0) dual_wait_flag(dp.flags + m - dp.tpf, m);
-                    if (f + 1 < dp.frames) dual_wait_flag(dp.flags + m + dp.tpf, m);
-                    fence_proxy_async_all();      // generic-proxy stores of other CTAs -> this thread's TMA reads
+                if (which == 1 && t_pending) {
+                    dual_wait_deps(dp, mt);
+                    t_pending = false;
                 }
                 const uint32_t half_rows = p.block_n >> 1, half_bytes = p.b_tile_bytes >> 1;
                 int kit = 0;
@@ -846,6 +863,10 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
                         tma_load_2d_2sm(sb, &p.bh_hi, lead_full, kit * kChunkK, crank * half_rows);
                         tma_load_2d_2sm(sb + half_bytes, &p.bh_lo, lead_full, kit * kChunkK, crank * half_rows);
                         if (++stage == S) { stage = 0; phase ^= 1; }
+                        if (which == 0 && t_pending && kit == 1) {
+                            dual_wait_deps(dp, mt);
+                            t_pending = false;
+                        }
                     }
                 }
             }
@@ -1153,6 +1174,154 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
     cluster_sync_all();
 }
 
+
+// ===========================================================================
+// Small-M backend: the same tap program on CUDA cores for GEMMs of at most 32 output rows.
+//
+// `predict_action` runs the policy UNet at batch 1 between simulator steps (diffusion_unet_image_policy.py:88-201):
+// M = B*T = 4 .. 16 rows against 65 M weights.  A 128-row tensor-core tile is then > 87 % padding and every launch
+// costs ~10-40 us of fixed pipeline set-up (TMEM allocation, barrier rings, split-K memset + atomics) for a few
+// microseconds of weight streaming.  Here one warp owns one output channel: it streams that channel's K-major weight
+// row (hi + lo planes, 16-byte loads) exactly once and multiplies it with the im2col'd activation rows staged in shared
+// memory (fp32, exact hi + lo), fp32 FMA accumulation -- the activation operand is tiny, the weights are the traffic.
+// Same descriptor, same epilogue subset (bias, residual, fp32 and/or hi/lo output); chosen by the plan, not the caller.
+// ===========================================================================
+constexpr int kSmallMaxRows = 32;
+constexpr int kSmallWarps = 4;                // output channels per block
+constexpr int kSmallRoundElems = 20480;       // staged activation elements per round (80 KB fp32)
+
+struct SmallMParams {
+    const __nv_bfloat16* a_hi[V2A_MAX_SRC];
+    const __nv_bfloat16* a_lo[V2A_MAX_SRC];
+    int src_ch[V2A_MAX_SRC];
+    int src_dims[V2A_MAX_SRC][4];
+    int tap_src[V2A_MAX_TAPS];
+    int tap_d[V2A_MAX_TAPS][4];
+    int tap_chunk0[V2A_MAX_TAPS + 1];         // first 64-wide K chunk of every tap (prefix sums)
+    int ntaps;
+    const __nv_bfloat16* w_hi;
+    const __nv_bfloat16* w_lo;
+    int ktot, wrows;
+    int out_dims[4];
+    int rows, cout, ldc;
+    float* out_f32;
+    __nv_bfloat16* out_hi;
+    __nv_bfloat16* out_lo;
+    const float* bias;
+    const float* residual;
+    int ld_res;
+    long long out_mul[4], out_off;
+    int kround;                               // K elements staged per round (multiple of 256)
+};
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& h, const uint4& l, float* f) {
+    const uint32_t hv[4] = {h.x, h.y, h.z, h.w}, lv[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(hv[i] << 16) + __uint_as_float(lv[i] << 16);
+        f[2 * i + 1] = __uint_as_float(hv[i] & 0xffff0000u) + __uint_as_float(lv[i] & 0xffff0000u);
+    }
+}
+
+__global__ void __launch_bounds__(kSmallWarps * 32) igemm_smallm_kernel(const __grid_constant__ SmallMParams p) {
+    extern __shared__ float4 xs4[];           // [rows][2][kround / 8]: the two float4 halves of every 8-element group
+    __shared__ int s_coord[kSmallMaxRows][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * kSmallWarps + warp;
+    if (threadIdx.x < p.rows) {
+        int m = threadIdx.x;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            s_coord[threadIdx.x][d] = m % p.out_dims[d];
+            m /= p.out_dims[d];
+        }
+    }
+    __syncthreads();
+    float acc[kSmallMaxRows];
+#pragma unroll
+    for (int m = 0; m < kSmallMaxRows; ++m) acc[m] = 0.0f;
+    const int gpr = p.kround >> 3;            // 8-element groups per staged row
+    for (int k0 = 0; k0 < p.ktot; k0 += p.kround) {
+        const int kr = min(p.kround, p.ktot - k0);
+        const int groups = kr >> 3;
+        // ---- stage the im2col'd activation rows of this K range (zero where a tap falls outside its source) ----
+        for (int idx = threadIdx.x; idx < p.rows * groups; idx += blockDim.x) {
+            const int m = idx / groups, g8 = idx - m * groups;
+            const int k = k0 + g8 * 8;
+            const int chunk = k >> 6;
+            int e = 0;
+            while (e + 1 < p.ntaps && chunk >= p.tap_chunk0[e + 1]) ++e;
+            const int c = ((chunk - p.tap_chunk0[e]) << 6) + (k & 63);
+            const int src = p.tap_src[e];
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = 0.0f;
+            const int s0 = s_coord[m][0] + p.tap_d[e][0], s1 = s_coord[m][1] + p.tap_d[e][1];
+            const int s2 = s_coord[m][2] + p.tap_d[e][2], s3 = s_coord[m][3] + p.tap_d[e][3];
+            if (c < p.src_ch[src] && s0 >= 0 && s0 < p.src_dims[src][0] && s1 >= 0 && s1 < p.src_dims[src][1] &&
+                s2 >= 0 && s2 < p.src_dims[src][2] && s3 >= 0 && s3 < p.src_dims[src][3]) {
+                const int64_t r = (((int64_t)s3 * p.src_dims[src][2] + s2) * p.src_dims[src][1] + s1) *
+                                      p.src_dims[src][0] + s0;
+                const uint4 h = *reinterpret_cast<const uint4*>(p.a_hi[src] + r * p.src_ch[src] + c);
+                const uint4 l = *reinterpret_cast<const uint4*>(p.a_lo[src] + r * p.src_ch[src] + c);
+                bf16x8_to_f32(h, l, f);
+            }
+            float4* dst = xs4 + (size_t)m * 2 * gpr;
+            dst[g8] = make_float4(f[0], f[1], f[2], f[3]);
+            dst[gpr + g8] = make_float4(f[4], f[5], f[6], f[7]);
+        }
+        __syncthreads();
+        // ---- one warp per output channel: stream its weight row once ----
+        if (n < p.cout) {
+            const __nv_bfloat16* wh = p.w_hi + (size_t)n * p.ktot + k0;
+            const __nv_bfloat16* wl = p.w_lo + (size_t)n * p.ktot + k0;
+            for (int g8 = lane; g8 < groups; g8 += 32) {
+                const uint4 h = __ldg(reinterpret_cast<const uint4*>(wh) + g8);
+                const uint4 l = __ldg(reinterpret_cast<const uint4*>(wl) + g8);
+                float w[8];
+                bf16x8_to_f32(h, l, w);
+#pragma unroll
+                for (int m = 0; m < kSmallMaxRows; ++m) {
+                    if (m < p.rows) {
+                        const float4 xa = xs4[(size_t)m * 2 * gpr + g8], xb = xs4[(size_t)m * 2 * gpr + gpr + g8];
+                        float a = acc[m];
+                        a = fmaf(xa.x, w[0], a); a = fmaf(xa.y, w[1], a); a = fmaf(xa.z, w[2], a); a = fmaf(xa.w, w[3], a);
+                        a = fmaf(xb.x, w[4], a); a = fmaf(xb.y, w[5], a); a = fmaf(xb.z, w[6], a); a = fmaf(xb.w, w[7], a);
+                        acc[m] = a;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (n >= p.cout) return;
+    // ---- reduce over the lanes; lane m keeps row m ----
+    float mine = 0.0f;
+#pragma unroll
+    for (int m = 0; m < kSmallMaxRows; ++m) {
+        if (m < p.rows) {
+            float v = acc[m];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == m) mine = v;
+        }
+    }
+    if (lane < p.rows) {
+        const int* cd = s_coord[lane];
+        const int64_t row = p.out_off + cd[0] * p.out_mul[0] + cd[1] * p.out_mul[1] + cd[2] * p.out_mul[2] +
+                            cd[3] * p.out_mul[3];
+        float v = mine + (p.bias ? __ldg(p.bias + n) : 0.0f);
+        if (p.residual) v += p.residual[row * p.ld_res + n];
+        if (p.out_f32) p.out_f32[row * p.ldc + n] = v;
+        if (p.out_hi) {
+            __nv_bfloat16 h, l;
+            split_bf16(v, h, l);
+            p.out_hi[row * p.ldc + n] = h;
+            p.out_lo[row * p.ldc + n] = l;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // host side: tensor maps + plan
 // ---------------------------------------------------------------------------
@@ -1211,6 +1380,8 @@ int make_tensor_map_bf16(CUtensorMap* m, const void* base, int rank, const uint6
 
 struct IgemmPlan {
     IgemmParams p;
+    bool smallm;          // <= 32 output rows: the CUDA-core weight-streaming backend (igemm_smallm_kernel)
+    SmallMParams sp;
     int grid;
     size_t smem;
     bool zero_out;        // split-K: clear the output window before the launch
@@ -1278,6 +1449,77 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out, bool force_cta2
     }
     p.ntaps = d->ntaps;
     p.k_iters = k_iters;
+    pl->smallm = false;
+    {
+        const int64_t rows = (int64_t)d->out_dims[0] * d->out_dims[1] * d->out_dims[2] * d->out_dims[3];
+        const char* env = getenv("V2A_SMALLM");
+        bool ok = rows <= kSmallMaxRows && d->passes == 3 && !d->stats && !d->rowvec && !d->a_fp16 && !d->b_fp16 &&
+                  d->w_hi && d->w_lo && !force_cta2 && !(env && atoi(env) == 0);
+        for (int s = 0; s < d->nsrc && ok; ++s) ok = d->src[s].channels % 8 == 0 && d->src[s].hi && d->src[s].lo;
+        if (ok) {
+            SmallMParams& sp = pl->sp;
+            memset(&sp, 0, sizeof(sp));
+            for (int s = 0; s < d->nsrc; ++s) {
+                sp.a_hi[s] = reinterpret_cast<const __nv_bfloat16*>(d->src[s].hi);
+                sp.a_lo[s] = reinterpret_cast<const __nv_bfloat16*>(d->src[s].lo);
+                sp.src_ch[s] = d->src[s].channels;
+                for (int i = 0; i < 4; ++i) sp.src_dims[s][i] = d->src[s].dims[i];
+            }
+            int c0 = 0;
+            for (int e = 0; e < d->ntaps; ++e) {
+                sp.tap_src[e] = d->taps[e].src;
+                for (int i = 0; i < 4; ++i) sp.tap_d[e][i] = d->taps[e].d[i];
+                sp.tap_chunk0[e] = c0;
+                c0 += d->taps[e].nchunks;
+            }
+            sp.tap_chunk0[d->ntaps] = c0;
+            sp.ntaps = d->ntaps;
+            sp.w_hi = reinterpret_cast<const __nv_bfloat16*>(d->w_hi);
+            sp.w_lo = reinterpret_cast<const __nv_bfloat16*>(d->w_lo);
+            sp.ktot = d->ktot;
+            sp.wrows = d->wrows;
+            long long mul = 1;
+            for (int i = 0; i < 4; ++i) {
+                sp.out_dims[i] = d->out_dims[i];
+                sp.out_mul[i] = mul;
+                mul *= d->out_dims[i];
+            }
+            if (d->out_pix_mul[0] | d->out_pix_mul[1] | d->out_pix_mul[2] | d->out_pix_mul[3]) {
+                for (int i = 0; i < 4; ++i) sp.out_mul[i] = d->out_pix_mul[i];
+                sp.out_off = d->out_pix_off;
+            }
+            sp.rows = (int)rows;
+            sp.cout = d->cout < d->wrows ? d->cout : d->wrows;
+            sp.ldc = d->ldc;
+            sp.out_f32 = d->out_f32;
+            sp.out_hi = reinterpret_cast<__nv_bfloat16*>(d->out_hi);
+            sp.out_lo = reinterpret_cast<__nv_bfloat16*>(d->out_lo);
+            sp.bias = d->bias;
+            sp.residual = d->residual;
+            sp.ld_res = d->ld_res;
+            int kround = (kSmallRoundElems / (int)rows) / 256 * 256;
+            if (kround > d->ktot) kround = ((d->ktot + 255) / 256) * 256;
+            if (kround < 256) kround = 256;
+            sp.kround = kround;
+            pl->smallm = true;
+            pl->grid = ceil_div(sp.cout, kSmallWarps);
+            pl->smem = (size_t)rows * kround * sizeof(float);
+            pl->zero_out = false;
+            p.k_splits = 1;
+            static bool small_attr = false;
+            if (!small_attr) {
+                cudaError_t e = cudaFuncSetAttribute(igemm_smallm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     kSmallRoundElems * (int)sizeof(float) + 32 * 256 * (int)sizeof(float));
+                if (e != cudaSuccess) {
+                    delete pl;
+                    V2A_CUDA_OK(e);
+                }
+                small_attr = true;
+            }
+            *out = pl;
+            return 0;
+        }
+    }
     p.num_m_tiles = 1;
     for (int i = 0; i < 4; ++i) {
         p.tile_log2[i] = d->tile_log2[i];
@@ -1593,6 +1835,12 @@ int v2a_igemm_plan_create(const v2a_igemm_desc* desc, void** plan_out) {
 
 int v2a_igemm_plan_run(void* plan, void* stream) {
     v2a::IgemmPlan* pl = reinterpret_cast<v2a::IgemmPlan*>(plan);
+    if (pl->smallm) {
+        v2a::igemm_smallm_kernel<<<pl->grid, v2a::kSmallWarps * 32, pl->smem, (cudaStream_t)stream>>>(pl->sp);
+        V2A_CUDA_OK(cudaGetLastError());
+        v2a::g_launches.fetch_add(1);
+        return 0;
+    }
     if (pl->zero_out)
         V2A_CUDA_OK(cudaMemset2DAsync(pl->p.out_f32, (size_t)pl->p.ldc * sizeof(float), 0, pl->zero_width,
                                       (size_t)pl->zero_rows, (cudaStream_t)stream));
