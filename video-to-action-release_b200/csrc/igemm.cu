@@ -647,19 +647,39 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
             // TMEM loads are software pipelined: chunk c+16 is in flight while chunk c is processed
             uint32_t ra[16], rb[16];
             if (p.fuse2) {
-                // two accumulator halves per chunk: [hi*hi + lo*hi | hi*lo]
+                // two accumulator halves per chunk: [hi*hi + lo*hi | hi*lo].  single CTA: [sum | hi*lo]; cta_group::2
+                // pair: [., . | ., .] per half of the columns (see the issuer).  The TMEM reads of chunk c + 16 are in
+                // flight while chunk c is processed (three register arrays: current, next, shared second half) -- an
+                // unpipelined load -> wait -> process chain made the epilogue latency-bound (~7 us per 128 x 128 tile).
                 const int hb = p.block_n >> 1;
-                for (int c = c_begin; c < c_end; c += 16) {
-                    // single CTA: [sum | hi*lo]; cta_group::2 pair: [., . | ., .] per half of the columns (see the issuer)
-                    const int ca = kCta2 ? (c >= hb ? p.block_n + (c - hb) : c) : c;
-                    const int cb = kCta2 ? ca + hb : p.block_n + c;
-                    tmem_ld16(t_row + ca, ra);
-                    tmem_ld16(t_row + cb, rb);
+                auto col_a = [&](int c) { return kCta2 ? (c >= hb ? p.block_n + (c - hb) : c) : c; };
+                auto col_b = [&](int c) { return kCta2 ? col_a(c) + hb : p.block_n + c; };
+                uint32_t rt[16];
+                if (c_begin < c_end) {
+                    tmem_ld16(t_row + col_a(c_begin), ra);
+                    tmem_ld16(t_row + col_b(c_begin), rt);
+                }
+                for (int c = c_begin; c < c_end; c += 32) {
                     tmem_ld_wait16(ra);
-                    tmem_ld_wait16(rb);
+                    tmem_ld_wait16(rt);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(rb[j]));
+                    for (int j = 0; j < 16; ++j) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(rt[j]));
+                    if (c + 16 < c_end) {
+                        tmem_ld16(t_row + col_a(c + 16), rb);
+                        tmem_ld16(t_row + col_b(c + 16), rt);
+                    }
                     process(ra, c);
+                    if (c + 16 < c_end) {
+                        tmem_ld_wait16(rb);
+                        tmem_ld_wait16(rt);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) rb[j] = __float_as_uint(__uint_as_float(rb[j]) + __uint_as_float(rt[j]));
+                        if (c + 32 < c_end) {
+                            tmem_ld16(t_row + col_a(c + 32), ra);
+                            tmem_ld16(t_row + col_b(c + 32), rt);
+                        }
+                        process(rb, c + 16);
+                    }
                 }
             } else {
             if (c_begin < c_end) tmem_ld16(t_row + c_begin, ra);
@@ -1133,19 +1153,36 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
                     }
                 };
 
-                // fused split product of a cta_group::2 pair: columns [hi*hi + lo*hi | hi*lo] per half of the N rows
-                uint32_t ra[16], rb[16];
+                // fused split product of a cta_group::2 pair: columns [hi*hi + lo*hi | hi*lo] per half of the N rows; the
+                // TMEM reads of the next chunk are in flight while this one is processed (see igemm_kernel)
+                uint32_t ra[16], rb[16], rt[16];
                 const int hb = p.block_n >> 1;
-                for (int c = c_begin; c < c_end; c += 16) {
-                    const int ca = c >= hb ? p.block_n + (c - hb) : c;
-                    const int cb = ca + hb;
-                    tmem_ld16(t_row + ca, ra);
-                    tmem_ld16(t_row + cb, rb);
+                auto col_a = [&](int c) { return c >= hb ? p.block_n + (c - hb) : c; };
+                if (c_begin < c_end) {
+                    tmem_ld16(t_row + col_a(c_begin), ra);
+                    tmem_ld16(t_row + col_a(c_begin) + hb, rt);
+                }
+                for (int c = c_begin; c < c_end; c += 32) {
                     tmem_ld_wait16(ra);
-                    tmem_ld_wait16(rb);
+                    tmem_ld_wait16(rt);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(rb[j]));
+                    for (int j = 0; j < 16; ++j) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(rt[j]));
+                    if (c + 16 < c_end) {
+                        tmem_ld16(t_row + col_a(c + 16), rb);
+                        tmem_ld16(t_row + col_a(c + 16) + hb, rt);
+                    }
                     process(ra, c);
+                    if (c + 16 < c_end) {
+                        tmem_ld_wait16(rb);
+                        tmem_ld_wait16(rt);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) rb[j] = __float_as_uint(__uint_as_float(rb[j]) + __uint_as_float(rt[j]));
+                        if (c + 32 < c_end) {
+                            tmem_ld16(t_row + col_a(c + 32), ra);
+                            tmem_ld16(t_row + col_a(c + 32) + hb, rt);
+                        }
+                        process(rb, c + 16);
+                    }
                 }
                 tc_fence_before();
                 if (crank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
@@ -1187,8 +1224,8 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
 // Same descriptor, same epilogue subset (bias, residual, fp32 and/or hi/lo output); chosen by the plan, not the caller.
 // ===========================================================================
 constexpr int kSmallMaxRows = 32;
-constexpr int kSmallWarps = 4;                // output channels per block
-constexpr int kSmallRoundElems = 20480;       // staged activation elements per round (80 KB fp32)
+constexpr int kSmallWarps = 8;                // warps per block = (output channels per block) x (K slices per channel)
+constexpr int kSmallUnroll = 4;               // 256-element weight groups in flight per warp
 
 struct SmallMParams {
     const __nv_bfloat16* a_hi[V2A_MAX_SRC];
@@ -1211,7 +1248,8 @@ struct SmallMParams {
     const float* residual;
     int ld_res;
     long long out_mul[4], out_off;
-    int kround;                               // K elements staged per round (multiple of 256)
+    int slices;                               // K slices per output channel (1, 2, 4 or 8 warps share a channel)
+    int slice_groups;                         // 8-element groups per slice
 };
 
 __device__ __forceinline__ void bf16x8_to_f32(const uint4& h, const uint4& l, float* f) {
@@ -1223,102 +1261,110 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& h, const uint4& l, fl
     }
 }
 
+// One warp = one (output channel, K slice): it streams that slice of the channel's K-major weight row once
+// (kSmallUnroll independent 16-byte loads per plane in flight) and reads the matching activation elements of every
+// output row straight from global memory (a few KB, L1 resident: every warp of the SM reads the same rows); the
+// im2col shift of a tap is a per-(row, tap) source-row offset looked up in shared memory (-1 = zero padding).
+template <int kRows>
 __global__ void __launch_bounds__(kSmallWarps * 32) igemm_smallm_kernel(const __grid_constant__ SmallMParams p) {
-    extern __shared__ float4 xs4[];           // [rows][2][kround / 8]: the two float4 halves of every 8-element group
-    __shared__ int s_coord[kSmallMaxRows][4];
+    __shared__ long long s_off[kSmallMaxRows][V2A_MAX_TAPS];     // element offset of (row, tap) in its source, or -1
+    __shared__ long long s_out[kSmallMaxRows];
+    __shared__ float s_part[kSmallWarps][kSmallMaxRows];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.x * kSmallWarps + warp;
-    if (threadIdx.x < p.rows) {
-        int m = threadIdx.x;
+    const int cpb = kSmallWarps / p.slices;                       // channels per block
+    const int n = blockIdx.x * cpb + warp / p.slices;
+    const int slice = warp % p.slices;
+    for (int idx = threadIdx.x; idx < p.rows * p.ntaps; idx += blockDim.x) {
+        const int m = idx / p.ntaps, e = idx - m * p.ntaps;
+        int c[4], mm = m;
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-            s_coord[threadIdx.x][d] = m % p.out_dims[d];
-            m /= p.out_dims[d];
+            c[d] = mm % p.out_dims[d];
+            mm /= p.out_dims[d];
         }
+        if (e == 0)
+            s_out[m] = p.out_off + c[0] * p.out_mul[0] + c[1] * p.out_mul[1] + c[2] * p.out_mul[2] + c[3] * p.out_mul[3];
+        const int src = p.tap_src[e];
+        const int s0 = c[0] + p.tap_d[e][0], s1 = c[1] + p.tap_d[e][1], s2 = c[2] + p.tap_d[e][2], s3 = c[3] + p.tap_d[e][3];
+        long long off = -1;
+        if (s0 >= 0 && s0 < p.src_dims[src][0] && s1 >= 0 && s1 < p.src_dims[src][1] && s2 >= 0 &&
+            s2 < p.src_dims[src][2] && s3 >= 0 && s3 < p.src_dims[src][3])
+            off = ((((long long)s3 * p.src_dims[src][2] + s2) * p.src_dims[src][1] + s1) * p.src_dims[src][0] + s0) *
+                  p.src_ch[src];
+        s_off[m][e] = off;
     }
     __syncthreads();
-    float acc[kSmallMaxRows];
+    float acc[kRows];
 #pragma unroll
-    for (int m = 0; m < kSmallMaxRows; ++m) acc[m] = 0.0f;
-    const int gpr = p.kround >> 3;            // 8-element groups per staged row
-    for (int k0 = 0; k0 < p.ktot; k0 += p.kround) {
-        const int kr = min(p.kround, p.ktot - k0);
-        const int groups = kr >> 3;
-        // ---- stage the im2col'd activation rows of this K range (zero where a tap falls outside its source) ----
-        for (int idx = threadIdx.x; idx < p.rows * groups; idx += blockDim.x) {
-            const int m = idx / groups, g8 = idx - m * groups;
-            const int k = k0 + g8 * 8;
-            const int chunk = k >> 6;
-            int e = 0;
-            while (e + 1 < p.ntaps && chunk >= p.tap_chunk0[e + 1]) ++e;
-            const int c = ((chunk - p.tap_chunk0[e]) << 6) + (k & 63);
-            const int src = p.tap_src[e];
-            float f[8];
+    for (int m = 0; m < kRows; ++m) acc[m] = 0.0f;
+    if (n < p.cout) {
+        const int g_begin = slice * p.slice_groups;
+        const int g_end = min(g_begin + p.slice_groups, p.ktot >> 3);
+        const uint4* wh = reinterpret_cast<const uint4*>(p.w_hi + (size_t)n * p.ktot);
+        const uint4* wl = reinterpret_cast<const uint4*>(p.w_lo + (size_t)n * p.ktot);
+        for (int g0 = g_begin + lane; g0 < g_end; g0 += 32 * kSmallUnroll) {
+            uint4 h[kSmallUnroll], l[kSmallUnroll];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = 0.0f;
-            const int s0 = s_coord[m][0] + p.tap_d[e][0], s1 = s_coord[m][1] + p.tap_d[e][1];
-            const int s2 = s_coord[m][2] + p.tap_d[e][2], s3 = s_coord[m][3] + p.tap_d[e][3];
-            if (c < p.src_ch[src] && s0 >= 0 && s0 < p.src_dims[src][0] && s1 >= 0 && s1 < p.src_dims[src][1] &&
-                s2 >= 0 && s2 < p.src_dims[src][2] && s3 >= 0 && s3 < p.src_dims[src][3]) {
-                const int64_t r = (((int64_t)s3 * p.src_dims[src][2] + s2) * p.src_dims[src][1] + s1) *
-                                      p.src_dims[src][0] + s0;
-                const uint4 h = *reinterpret_cast<const uint4*>(p.a_hi[src] + r * p.src_ch[src] + c);
-                const uint4 l = *reinterpret_cast<const uint4*>(p.a_lo[src] + r * p.src_ch[src] + c);
-                bf16x8_to_f32(h, l, f);
+            for (int u = 0; u < kSmallUnroll; ++u) {
+                const int g = g0 + 32 * u;
+                if (g < g_end) {
+                    h[u] = __ldg(wh + g);
+                    l[u] = __ldg(wl + g);
+                }
             }
-            float4* dst = xs4 + (size_t)m * 2 * gpr;
-            dst[g8] = make_float4(f[0], f[1], f[2], f[3]);
-            dst[gpr + g8] = make_float4(f[4], f[5], f[6], f[7]);
-        }
-        __syncthreads();
-        // ---- one warp per output channel: stream its weight row once ----
-        if (n < p.cout) {
-            const __nv_bfloat16* wh = p.w_hi + (size_t)n * p.ktot + k0;
-            const __nv_bfloat16* wl = p.w_lo + (size_t)n * p.ktot + k0;
-            for (int g8 = lane; g8 < groups; g8 += 32) {
-                const uint4 h = __ldg(reinterpret_cast<const uint4*>(wh) + g8);
-                const uint4 l = __ldg(reinterpret_cast<const uint4*>(wl) + g8);
-                float w[8];
-                bf16x8_to_f32(h, l, w);
 #pragma unroll
-                for (int m = 0; m < kSmallMaxRows; ++m) {
-                    if (m < p.rows) {
-                        const float4 xa = xs4[(size_t)m * 2 * gpr + g8], xb = xs4[(size_t)m * 2 * gpr + gpr + g8];
-                        float a = acc[m];
-                        a = fmaf(xa.x, w[0], a); a = fmaf(xa.y, w[1], a); a = fmaf(xa.z, w[2], a); a = fmaf(xa.w, w[3], a);
-                        a = fmaf(xb.x, w[4], a); a = fmaf(xb.y, w[5], a); a = fmaf(xb.z, w[6], a); a = fmaf(xb.w, w[7], a);
-                        acc[m] = a;
-                    }
+            for (int u = 0; u < kSmallUnroll; ++u) {
+                const int g = g0 + 32 * u;
+                if (g >= g_end) continue;
+                float w[8];
+                bf16x8_to_f32(h[u], l[u], w);
+                const int k = g << 3, chunk = k >> 6;
+                int e = 0;
+                while (e + 1 < p.ntaps && chunk >= p.tap_chunk0[e + 1]) ++e;
+                const int c = ((chunk - p.tap_chunk0[e]) << 6) + (k & 63);
+                const int src = p.tap_src[e];
+                if (c >= p.src_ch[src]) continue;            // zero padding of the last chunk of a tap
+                const __nv_bfloat16* ah = p.a_hi[src] + c;
+                const __nv_bfloat16* al = p.a_lo[src] + c;
+#pragma unroll
+                for (int m = 0; m < kRows; ++m) {
+                    if (m >= p.rows) break;
+                    const long long off = s_off[m][e];
+                    if (off < 0) continue;
+                    const uint4 xh = __ldg(reinterpret_cast<const uint4*>(ah + off));
+                    const uint4 xl = __ldg(reinterpret_cast<const uint4*>(al + off));
+                    float x[8];
+                    bf16x8_to_f32(xh, xl, x);
+                    float a = acc[m];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a = fmaf(x[j], w[j], a);
+                    acc[m] = a;
                 }
             }
         }
-        __syncthreads();
     }
-    if (n >= p.cout) return;
-    // ---- reduce over the lanes; lane m keeps row m ----
-    float mine = 0.0f;
+    // ---- reduce over the lanes, then over the K slices of the channel ----
 #pragma unroll
-    for (int m = 0; m < kSmallMaxRows; ++m) {
-        if (m < p.rows) {
-            float v = acc[m];
+    for (int m = 0; m < kRows; ++m) {
+        if (m >= p.rows) break;
+        float v = acc[m];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == m) mine = v;
-        }
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_part[warp][m] = v;
     }
-    if (lane < p.rows) {
-        const int* cd = s_coord[lane];
-        const int64_t row = p.out_off + cd[0] * p.out_mul[0] + cd[1] * p.out_mul[1] + cd[2] * p.out_mul[2] +
-                            cd[3] * p.out_mul[3];
-        float v = mine + (p.bias ? __ldg(p.bias + n) : 0.0f);
-        if (p.residual) v += p.residual[row * p.ld_res + n];
-        if (p.out_f32) p.out_f32[row * p.ldc + n] = v;
-        if (p.out_hi) {
-            __nv_bfloat16 h, l;
-            split_bf16(v, h, l);
-            p.out_hi[row * p.ldc + n] = h;
-            p.out_lo[row * p.ldc + n] = l;
-        }
+    __syncthreads();
+    if (slice != 0 || n >= p.cout || lane >= p.rows) return;
+    float v = 0.0f;
+    for (int s2 = 0; s2 < p.slices; ++s2) v += s_part[warp + s2][lane];
+    const long long row = s_out[lane];
+    v += p.bias ? __ldg(p.bias + n) : 0.0f;
+    if (p.residual) v += p.residual[row * p.ld_res + n];
+    if (p.out_f32) p.out_f32[row * p.ldc + n] = v;
+    if (p.out_hi) {
+        __nv_bfloat16 hh, ll;
+        split_bf16(v, hh, ll);
+        p.out_hi[row * p.ldc + n] = hh;
+        p.out_lo[row * p.ldc + n] = ll;
     }
 }
 
@@ -1497,25 +1543,16 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out, bool force_cta2
             sp.bias = d->bias;
             sp.residual = d->residual;
             sp.ld_res = d->ld_res;
-            int kround = (kSmallRoundElems / (int)rows) / 256 * 256;
-            if (kround > d->ktot) kround = ((d->ktot + 255) / 256) * 256;
-            if (kround < 256) kround = 256;
-            sp.kround = kround;
+            // 1, 2, 4 or 8 warps share one output channel: slices of ~1024 K elements (4 groups of 256 in flight)
+            int slices = 1;
+            while (slices < kSmallWarps && d->ktot > 1024 * slices) slices *= 2;
+            sp.slices = slices;
+            sp.slice_groups = ceil_div(d->ktot / 8, slices);
             pl->smallm = true;
-            pl->grid = ceil_div(sp.cout, kSmallWarps);
-            pl->smem = (size_t)rows * kround * sizeof(float);
+            pl->grid = ceil_div(sp.cout, kSmallWarps / slices);
+            pl->smem = 0;
             pl->zero_out = false;
             p.k_splits = 1;
-            static bool small_attr = false;
-            if (!small_attr) {
-                cudaError_t e = cudaFuncSetAttribute(igemm_smallm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     kSmallRoundElems * (int)sizeof(float) + 32 * 256 * (int)sizeof(float));
-                if (e != cudaSuccess) {
-                    delete pl;
-                    V2A_CUDA_OK(e);
-                }
-                small_attr = true;
-            }
             *out = pl;
             return 0;
         }
@@ -1836,7 +1873,14 @@ int v2a_igemm_plan_create(const v2a_igemm_desc* desc, void** plan_out) {
 int v2a_igemm_plan_run(void* plan, void* stream) {
     v2a::IgemmPlan* pl = reinterpret_cast<v2a::IgemmPlan*>(plan);
     if (pl->smallm) {
-        v2a::igemm_smallm_kernel<<<pl->grid, v2a::kSmallWarps * 32, pl->smem, (cudaStream_t)stream>>>(pl->sp);
+        if (pl->sp.rows <= 4)
+            v2a::igemm_smallm_kernel<4><<<pl->grid, v2a::kSmallWarps * 32, 0, (cudaStream_t)stream>>>(pl->sp);
+        else if (pl->sp.rows <= 8)
+            v2a::igemm_smallm_kernel<8><<<pl->grid, v2a::kSmallWarps * 32, 0, (cudaStream_t)stream>>>(pl->sp);
+        else if (pl->sp.rows <= 16)
+            v2a::igemm_smallm_kernel<16><<<pl->grid, v2a::kSmallWarps * 32, 0, (cudaStream_t)stream>>>(pl->sp);
+        else
+            v2a::igemm_smallm_kernel<32><<<pl->grid, v2a::kSmallWarps * 32, 0, (cudaStream_t)stream>>>(pl->sp);
         V2A_CUDA_OK(cudaGetLastError());
         v2a::g_launches.fetch_add(1);
         return 0;
