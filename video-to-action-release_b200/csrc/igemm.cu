@@ -168,8 +168,16 @@ __device__ __forceinline__ TileRange cta_tiles(const IgemmParams& p, int total) 
 #endif
 // kCta2: the cta_group::2 (CTA-pair MMA) paths exist only in that instantiation -- a kernel that contains
 // cta_group::2 instructions must be launched as a cluster of 2
-template <bool kCta2>
+//
+// kEpi: what the epilogue writes, fixed at compile time (bit 0: fp32 output, bit 1: hi/lo planes, bit 2: GroupNorm
+// sums; such launches have no split-K and no debug switches) or -1 = decided at run time.  ncu source counters
+// (round 2) showed the run-time version executing ~900 warp instructions per 16-column chunk, ~150 of which do the
+// work -- the rest re-evaluate feature tests, predicates and 64-bit addresses per chunk (IMAD + ISETP + BRA = 36 %
+// of everything executed) -- and with only the 8 epilogue warps resident that instruction stream, not TMEM, shared
+// memory or HBM, bounded every short-K launch (8.2 us per 128 x 128 tile against 2.5 us of MMA for a temporal conv).
+template <bool kCta2, int kEpi>
 __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constant__ IgemmParams p) {
+    constexpr bool kFixed = kEpi >= 0;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment.  The offset is added to the __shared__ pointer itself: a
     // round trip through uintptr_t loses the address space and turned every epilogue slab access into a
@@ -408,7 +416,12 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
         const int c_begin = half == 0 ? 0 : ((nch + 1) >> 1) << 4;
         const int c_end = half == 0 ? ((nch + 1) >> 1) << 4 : p.block_n;
         // same-address atomic contention is spread over `stats_replicas` copies of the sums
-        double* const stats = (p.stats && !(p.debug & 1)) ? p.stats + (long long)(blockIdx.x % p.stats_replicas) * p.stats_rep_stride : nullptr;
+        const bool has_f32 = kFixed ? (kEpi & 1) != 0 : p.out_f32 != nullptr;
+        const bool has_hl = kFixed ? (kEpi & 2) != 0 : p.out_hi != nullptr;
+        const bool has_stats = kFixed ? (kEpi & 4) != 0 : (p.stats && !(p.debug & 1));
+        const bool splitk = kFixed ? false : p.k_splits > 1;
+        const int dbg = kFixed ? 0 : p.debug;
+        double* const stats = has_stats ? p.stats + (long long)(blockIdx.x % p.stats_replicas) * p.stats_rep_stride : nullptr;
         // Per-warp staging slab [32 rows][16 words + 4 pad].  TMEM hands each lane one ROW (16 consecutive
         // columns); storing that directly makes every 16-byte store instruction touch 32 different 128-byte
         // lines and bounded the whole kernel on the narrow layers.  Staged through the slab, 4 lanes write one
@@ -468,13 +481,13 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                 addv[c] = a;
             }
             __syncwarp();
-            const bool use_res = p.residual != nullptr && lead && !(p.debug & 4);
+            const bool use_res = p.residual != nullptr && lead && !(dbg & 4);
             // The residual used to be loaded where it is consumed: an exposed HBM round trip per 16-column
             // chunk that made the residual-carrying temporal convs 2x slower than the same launch without it
             // (1.20 vs 0.71 ms at 1.8 M rows x 128 channels).  Now (a) the NEXT tile's residual window of this
             // warp is pulled into L2 one whole tile period ahead, and (b) the chunk's values travel one chunk
             // ahead in registers (`rres`), the first chunk being requested before the wait on the MMAs.
-            if (p.residual != nullptr && !(p.debug & 4) && it + 1 < tr.count) {
+            if (p.residual != nullptr && !(dbg & 4) && it + 1 < tr.count) {
                 int n_idx2, o2[4], split2;
                 decode_tile(p, tile + tr.step, n_idx2, o2, split2);
                 if (split2 == 0) {
@@ -535,7 +548,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                     for (int j = 0; j < 16; ++j)
                         if (n + j < p.cout) v[j] += __ldg(&rp[j]);
                 }
-                const bool need_f32_phase = (p.out_f32 != nullptr) || use_res || (stats != nullptr);
+                const bool need_f32_phase = has_f32 || use_res || has_stats;
                 if (need_f32_phase) {
                     // A: own row -> slab (rows / columns that do not exist are staged as 0 for the column sums)
                     float4* srow = reinterpret_cast<float4*>(slab + lane * kSlabStride);
@@ -551,10 +564,10 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                     // its 4 rows) for free: the sums used to be a second walk over the slab, 32 shared-memory loads
                     // per lane and chunk (ncu: the short-K launches spend 45 % of the LSU shared-memory pipe in the
                     // epilogue, next to the MMAs' operand reads).
-                    const bool fast_stats = stats != nullptr && inst_uniform;
-                    const bool row_back = use_res && (p.out_hi != nullptr || (stats != nullptr && !inst_uniform));
+                    const bool fast_stats = has_stats && inst_uniform;
+                    const bool row_back = use_res && (has_hl || (has_stats && !inst_uniform));
                     float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (p.out_f32 != nullptr || use_res || fast_stats) {
+                    if (has_f32 || use_res || fast_stats) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             if (!svalid[i]) continue;
@@ -565,9 +578,9 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                                 x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
                                 if (row_back) *sp = x;
                             }
-                            if (p.out_f32 && !(p.debug & 2)) {
+                            if (has_f32 && !(dbg & 2)) {
                                 float4* op = reinterpret_cast<float4*>(p.out_f32 + spix[i] * p.ldc + n) + piece;
-                                if (p.k_splits > 1) atomicAdd(op, x);   // partial sum of this K range
+                                if (splitk) atomicAdd(op, x);   // partial sum of this K range
                                 else *op = x;
                             }
                             cs[0] += x.x; cs[1] += x.y; cs[2] += x.z; cs[3] += x.w;
@@ -587,7 +600,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                         }
                     }
                     // D: GroupNorm partial sums of the 32 x 16 block
-                    if (stats) {
+                    if (has_stats) {
                         if (inst_uniform) {
                             // recursive halving over the 8 lanes that share `piece` (lane bits 4, 3, 2): 7 shuffles
                             // leave every lane with ONE finished value -- (sum | sum of squares) of one column
@@ -625,7 +638,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                     }
                     __syncwarp();
                 }
-                if (p.out_hi && !(p.debug & 2)) {
+                if (has_hl && !(dbg & 2)) {
                     // bf16 planes: one slab row = [16 hi | 16 lo] = 64 bytes; pieces 0,1 -> hi plane, 2,3 -> lo
                     uint4 h0, l0, h1, l1;
                     split8(v, h0, l0);
@@ -943,10 +956,15 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
         int it = 0;
         for (int k = 0; k < dp.iters; ++k) {
             const int i = pr + k * pairs;
-            for (int which = 0; which < 2; ++which) {
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {     // unrolled: each program's epilogue is specialised below
                 const int q = which == 0 ? i : i - dp.lag;
                 if (q < 0 || q >= dp.mp) continue;
                 const IgemmParams& p = dp.g[which];
+                // the spatial program writes hi/lo planes and nothing else, the temporal one fp32 (+ sums): fixed by
+                // the plan, so the feature tests below fold at compile time (see igemm_kernel's kEpi)
+                const bool has_f32 = which == 1, has_hl = which == 0;
+                const bool has_stats = which == 1 && p.stats != nullptr;
                 const int m = 2 * q + (int)crank;
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
@@ -954,8 +972,8 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
                 const int nch = p.block_n >> 4;
                 const int c_begin = half == 0 ? 0 : ((nch + 1) >> 1) << 4;
                 const int c_end = half == 0 ? ((nch + 1) >> 1) << 4 : p.block_n;
-                double* const stats = p.stats ? p.stats + (long long)(blockIdx.x % p.stats_replicas) * p.stats_rep_stride
-                                              : nullptr;
+                double* const stats = has_stats ? p.stats + (long long)(blockIdx.x % p.stats_replicas) * p.stats_rep_stride
+                                                : nullptr;
                 int o[4];
                 dual_tile_origin(p, m, o);
                 int r = row, coord[4];
@@ -997,7 +1015,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
                     addv[c] = a;
                 }
                 __syncwarp();
-                const bool use_res = p.residual != nullptr;
+                const bool use_res = which == 1 && p.residual != nullptr;
                 if (use_res) {      // pull the residual window of this warp's NEXT temporal tile into L2
                     const int m2 = m + 2 * pairs;
                     if (m2 < p.num_m_tiles) {
@@ -1051,13 +1069,13 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
                             v[4 * qq + 3] = __uint_as_float(raw[4 * qq + 3]) + a.w;
                         }
                     }
-                    if (valid && p.rowvec && !rv_uniform) {
+                    if (which == 1 && valid && p.rowvec && !rv_uniform) {
                         const float* rp = p.rowvec + (int64_t)rv * p.ld_rowvec + n;
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             if (n + j < p.cout) v[j] += __ldg(&rp[j]);
                     }
-                    const bool need_f32_phase = (p.out_f32 != nullptr) || use_res || (stats != nullptr);
+                    const bool need_f32_phase = has_f32 || use_res || has_stats;
                     if (need_f32_phase) {
                         float4* srow = reinterpret_cast<float4*>(slab + lane * kSlabStride);
 #pragma unroll
@@ -1067,10 +1085,10 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
                             srow[qq] = x;
                         }
                         __syncwarp();
-                        const bool fast_stats = stats != nullptr && inst_uniform;
-                        const bool row_back = use_res && (p.out_hi != nullptr || (stats != nullptr && !inst_uniform));
+                        const bool fast_stats = has_stats && inst_uniform;
+                        const bool row_back = use_res && (has_hl || (has_stats && !inst_uniform));
                         float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (p.out_f32 != nullptr || use_res || fast_stats) {
+                        if (has_f32 || use_res || fast_stats) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 if (!svalid[j]) continue;
@@ -1081,7 +1099,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
                                     x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
                                     if (row_back) *sp = x;
                                 }
-                                if (p.out_f32)
+                                if (has_f32)
                                     *(reinterpret_cast<float4*>(p.out_f32 + spix[j] * p.ldc + n) + piece) = x;
                                 cs[0] += x.x; cs[1] += x.y; cs[2] += x.z; cs[3] += x.w;
                                 cq[0] = fmaf(x.x, x.x, cq[0]); cq[1] = fmaf(x.y, x.y, cq[1]);
@@ -1099,7 +1117,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
                                 }
                             }
                         }
-                        if (stats) {
+                        if (has_stats) {
                             if (inst_uniform) {
                                 const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
                                 float k4[4];
@@ -1135,7 +1153,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
                         }
                         __syncwarp();
                     }
-                    if (p.out_hi) {
+                    if (has_hl) {
                         uint4 h0, l0, h1, l1;
                         split8(v, h0, l0);
                         split8(v + 8, h1, l1);
@@ -1426,6 +1444,7 @@ int make_tensor_map_bf16(CUtensorMap* m, const void* base, int rank, const uint6
 
 struct IgemmPlan {
     IgemmParams p;
+    int epi;              // compile-time epilogue class of the launch (bit 0 fp32, bit 1 hi/lo, bit 2 sums) or -1
     bool smallm;          // <= 32 output rows: the CUDA-core weight-streaming backend (igemm_smallm_kernel)
     SmallMParams sp;
     int grid;
@@ -1437,6 +1456,17 @@ struct IgemmPlan {
 
 static int g_num_sms = 0;
 static int g_max_smem = 0;
+
+typedef void (*IgemmKernelFn)(const IgemmParams);
+static IgemmKernelFn igemm_fn(bool cta2, int epi) {
+    switch (epi) {
+        case 1: return cta2 ? igemm_kernel<true, 1> : igemm_kernel<false, 1>;   // fp32
+        case 2: return cta2 ? igemm_kernel<true, 2> : igemm_kernel<false, 2>;   // hi/lo planes
+        case 3: return cta2 ? igemm_kernel<true, 3> : igemm_kernel<false, 3>;   // fp32 + hi/lo planes
+        case 5: return cta2 ? igemm_kernel<true, 5> : igemm_kernel<false, 5>;   // fp32 + GroupNorm sums
+        default: return cta2 ? igemm_kernel<true, -1> : igemm_kernel<false, -1>;
+    }
+}
 
 static int device_props() {
     if (g_num_sms) return 0;
@@ -1499,7 +1529,7 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out, bool force_cta2
     {
         const int64_t rows = (int64_t)d->out_dims[0] * d->out_dims[1] * d->out_dims[2] * d->out_dims[3];
         const char* env = getenv("V2A_SMALLM");
-        bool ok = rows <= kSmallMaxRows && d->passes == 3 && !d->stats && !d->rowvec && !d->a_fp16 && !d->b_fp16 &&
+        bool ok = rows <= 16 && d->passes == 3 && !d->stats && !d->rowvec && !d->a_fp16 && !d->b_fp16 &&
                   d->w_hi && d->w_lo && !force_cta2 && !(env && atoi(env) == 0);
         for (int s = 0; s < d->nsrc && ok; ++s) ok = d->src[s].channels % 8 == 0 && d->src[s].hi && d->src[s].lo;
         if (ok) {
@@ -1742,12 +1772,22 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out, bool force_cta2
             pl->smem = (size_t)stages * p.stage_bytes + overhead;
         }
     }
+    {
+        // epilogue class: fixed at compile time when nothing run-time-only is involved
+        const char* fe = getenv("V2A_FAST_EPILOGUE");
+        const int bits = (p.out_f32 ? 1 : 0) | (p.out_hi ? 2 : 0) | (p.stats ? 4 : 0);
+        const bool fixed = p.k_splits == 1 && p.debug == 0 && (bits == 1 || bits == 2 || bits == 3 || bits == 5) &&
+                           !(fe && atoi(fe) == 0);
+        pl->epi = fixed ? bits : -1;
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaSuccess;
+        for (int c2 = 0; c2 < 2 && e == cudaSuccess; ++c2)
+            for (int epi : {-1, 1, 2, 3, 5})
+                if (e == cudaSuccess)
+                    e = cudaFuncSetAttribute(igemm_fn(c2 != 0, epi), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              g_max_smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(igemm_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
         if (e != cudaSuccess) {
@@ -1793,8 +1833,11 @@ static int dual_plan_create(const v2a_igemm_desc* ds, const v2a_igemm_desc* dt, 
     if (a.block_n != b.block_n || a.stage_bytes != b.stage_bytes || a.stages != b.stages)
         return fail("the two programs must share block_n (one operand ring serves both)");
     if (a.num_m_tiles != b.num_m_tiles) return fail("the two programs must tile the same row space");
-    if (a.num_m_tiles % (tiles_per_frame * frames) != 0 || a.out_hi == nullptr)
-        return fail("tiles must be whole (sample, frame) blocks and the spatial program must write hi/lo planes");
+    if (a.num_m_tiles % (tiles_per_frame * frames) != 0)
+        return fail("tiles must be whole (sample, frame) blocks");
+    if (!a.out_hi || a.out_f32 || a.stats || a.residual || a.rowvec || !b.out_f32 || b.out_hi)
+        return fail("the spatial program writes hi/lo planes only (bias allowed), the temporal program fp32 "
+                    "(+ bias / embedding row / residual / GroupNorm sums): the kernel's epilogues are specialised on that");
     DualPlan* pl = new DualPlan();
     memset(&pl->dp, 0, sizeof(pl->dp));
     pl->dp.g[0] = a;
@@ -1901,10 +1944,9 @@ int v2a_igemm_plan_run(void* plan, void* stream) {
         attr.val.clusterDim.z = 1;
         cfg.attrs = &attr;
         cfg.numAttrs = 1;
-        if (pl->p.cta2) V2A_CUDA_OK(cudaLaunchKernelEx(&cfg, v2a::igemm_kernel<true>, pl->p));
-        else V2A_CUDA_OK(cudaLaunchKernelEx(&cfg, v2a::igemm_kernel<false>, pl->p));
+        V2A_CUDA_OK(cudaLaunchKernelEx(&cfg, v2a::igemm_fn(pl->p.cta2 != 0, pl->epi), pl->p));
     } else {
-        v2a::igemm_kernel<false><<<pl->grid, v2a::kThreads, pl->smem, (cudaStream_t)stream>>>(pl->p);
+        v2a::igemm_fn(false, pl->epi)<<<pl->grid, v2a::kThreads, pl->smem, (cudaStream_t)stream>>>(pl->p);
     }
     V2A_CUDA_OK(cudaGetLastError());
     v2a::g_launches.fetch_add(1);
