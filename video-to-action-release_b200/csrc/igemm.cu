@@ -104,9 +104,17 @@ struct alignas(64) IgemmParams {
     long long out_mul[4]; // output row of grid point c = out_off + sum c[d] * out_mul[d] (dense by default; the
     long long out_off;    // sub-pixel phases of the upsample conv write every other row / column of a finer grid)
     int debug;  // V2A_IGEMM_DEBUG bits: 1 skip stats, 2 skip stores, 4 skip residual (timing experiments only)
+    int linear; // tile m = rows [128 m, 128 m + 128) of the dense row space, every tile full, one embedding row and one
+                // GroupNorm instance per tile: the epilogue's per-tile set-up needs no votes / shuffles / row decode
 };
 
-__device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int& n_idx, int o[4], int& split) {
+__device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int& n_idx, int o[4], int& split,
+                                            int* m_out = nullptr) {
+    if (m_out) {   // M-tile index (>= num_m_tiles for a ghost tile)
+        *m_out = p.cluster > 1 ? ((tile >> 1) / p.num_n_tiles) * 2 + (tile & 1)
+                               : (tile >= p.num_m_tiles * p.num_n_tiles * p.k_splits ? p.num_m_tiles
+                                                                                      : tile / p.k_splits / p.num_n_tiles);
+    }
     if (p.cluster > 1) {
         // CTA pairs: tiles 2q and 2q + 1 are the two M tiles of pair-tile q, which share one N tile (so the pair
         // shares / splits ONE weight tile); q walks the N tiles fastest.  (k_splits == 1 in pair mode.)
@@ -434,41 +442,63 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
             const int tile = tr.first + it * tr.step;
             const int acc = it & nacc_mask;
             const uint32_t acc_phase = (it >> p.nacc_log2) & 1;
-            int n_idx, o[4], split;
-            decode_tile(p, tile, n_idx, o, split);
+            int n_idx, o[4], split, mt;
+            decode_tile(p, tile, n_idx, o, split, &mt);
             const int n0 = n_idx * p.block_n;
             const bool lead = split == 0;   // bias / rowvec / residual enter the sum exactly once
+            bool valid, any_valid, rv_uniform, inst_uniform;
+            int rv, inst, rv0, inst0;
+            int64_t pix, spix[4];
+            bool svalid[4];
+            if (p.linear) {
+                // dense, contiguous tiling (every large layer): everything about the tile is warp-uniform
+                valid = any_valid = mt < p.num_m_tiles;
+                pix = (int64_t)mt * kTileM + row;
+                rv = inst = 0;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    rv += o[d] * p.rowvec_mul[d];
+                    inst += o[d] * p.stats_mul[d];
+                }
+                rv0 = rv;
+                inst0 = inst;
+                rv_uniform = true;
+                inst_uniform = stats != nullptr && valid;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    spix[i] = (int64_t)mt * kTileM + quad * 32 + srow0 + 8 * i;
+                    svalid[i] = valid;
+                }
+            } else {
             // row -> output pixel
             int r = row, coord[4];
-            bool valid = true;
+            valid = true;
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
                 coord[d] = o[d] + (r & ((1 << p.tile_log2[d]) - 1));
                 r >>= p.tile_log2[d];
                 valid = valid && (coord[d] < p.out_dims[d]);
             }
-            const int64_t pix = p.out_off + coord[0] * p.out_mul[0] + coord[1] * p.out_mul[1] +
-                                coord[2] * p.out_mul[2] + coord[3] * p.out_mul[3];
-            int rv = 0, inst = 0;
+            pix = p.out_off + coord[0] * p.out_mul[0] + coord[1] * p.out_mul[1] +
+                  coord[2] * p.out_mul[2] + coord[3] * p.out_mul[3];
+            rv = 0, inst = 0;
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
                 rv += coord[d] * p.rowvec_mul[d];
                 inst += coord[d] * p.stats_mul[d];
             }
-            const bool any_valid = __any_sync(0xffffffffu, valid);   // false for a whole ghost / padding warp
+            any_valid = __any_sync(0xffffffffu, valid);   // false for a whole ghost / padding warp
             // warp-uniform row group / stats instance?  (true for every large layer)
-            const int rv0 = __shfl_sync(0xffffffffu, rv, 0);
-            const bool rv_uniform = p.rowvec == nullptr || !lead || __all_sync(0xffffffffu, !valid || rv == rv0);
-            const int inst0 = __shfl_sync(0xffffffffu, valid ? inst : -1, 0);
-            const bool inst_uniform =
-                stats != nullptr && __all_sync(0xffffffffu, !valid || inst == inst0) && inst0 >= 0;
+            rv0 = __shfl_sync(0xffffffffu, rv, 0);
+            rv_uniform = p.rowvec == nullptr || !lead || __all_sync(0xffffffffu, !valid || rv == rv0);
+            inst0 = __shfl_sync(0xffffffffu, valid ? inst : -1, 0);
+            inst_uniform = stats != nullptr && __all_sync(0xffffffffu, !valid || inst == inst0) && inst0 >= 0;
             // the 4 rows this lane stores: their pixel index / validity come from the lanes that own them
-            int64_t spix[4];
-            bool svalid[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 spix[i] = __shfl_sync(0xffffffffu, pix, srow0 + 8 * i);
                 svalid[i] = __shfl_sync(0xffffffffu, (int)valid, srow0 + 8 * i) != 0;
+            }
             }
             // stage bias (+ the shared rowvec row) for this N tile: overlaps the tile's MMAs
             __syncwarp();
@@ -488,9 +518,16 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
             // warp is pulled into L2 one whole tile period ahead, and (b) the chunk's values travel one chunk
             // ahead in registers (`rres`), the first chunk being requested before the wait on the MMAs.
             if (p.residual != nullptr && !(dbg & 4) && it + 1 < tr.count) {
-                int n_idx2, o2[4], split2;
-                decode_tile(p, tile + tr.step, n_idx2, o2, split2);
-                if (split2 == 0) {
+                int n_idx2, o2[4], split2, mt2;
+                decode_tile(p, tile + tr.step, n_idx2, o2, split2, &mt2);
+                const int cpf = n_idx2 * p.block_n + c_begin + 16 * piece;   // 4 lanes x 64 B = this warp's 64 columns
+                if (p.linear) {
+                    if (split2 == 0 && mt2 < p.num_m_tiles && cpf < p.cout && c_begin + 16 * piece < c_end) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            prefetch_l2(p.residual + ((int64_t)mt2 * kTileM + quad * 32 + srow0 + 8 * i) * p.ld_res + cpf);
+                    }
+                } else if (split2 == 0) {
                     int r2 = row;
                     int64_t pix2 = p.out_off;
                     bool valid2 = true;
@@ -501,7 +538,6 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                         valid2 = valid2 && (cd < p.out_dims[d]);
                         pix2 += cd * p.out_mul[d];
                     }
-                    const int cpf = n_idx2 * p.block_n + c_begin + 16 * piece;   // 4 lanes x 64 B = this warp's 64 columns
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int64_t sp2 = __shfl_sync(0xffffffffu, pix2, srow0 + 8 * i);
@@ -1648,6 +1684,23 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out, bool force_cta2
         p.debug = dbg ? atoi(dbg) : 0;
     }
 
+    {
+        // linear tiling: boxes divide their dims, and once a box is narrower than its dim all higher dims have box 1
+        // => tile m is rows [128 m, 128 m + 128) of the dense row space; rows of one tile share the embedding row and
+        // the GroupNorm instance when the multipliers vanish on every dim the box spans
+        const char* env = getenv("V2A_LINEAR");
+        bool lin = !(env && atoi(env) == 0) &&
+                   !(d->out_pix_mul[0] | d->out_pix_mul[1] | d->out_pix_mul[2] | d->out_pix_mul[3]);
+        bool partial = false;
+        for (int i = 0; i < 4; ++i) {
+            const int box = 1 << d->tile_log2[i];
+            if (d->out_dims[i] % box != 0 || (partial && box != 1)) lin = false;
+            if (box != d->out_dims[i]) partial = true;
+            if (d->tile_log2[i] > 0 && ((d->rowvec && d->rowvec_mul[i] != 0) || (d->stats && d->stats_mul[i] != 0)))
+                lin = false;
+        }
+        p.linear = lin ? 1 : 0;
+    }
     // tensor maps: A boxes follow the output tile box; every source shares it
     int rc = 0;
     for (int s = 0; s < d->nsrc && !rc; ++s) {
