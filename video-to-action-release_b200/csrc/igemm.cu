@@ -792,6 +792,9 @@ struct alignas(64) DualParams {
     int tiles;             // 128-row tiles of the row space (both programs)
     int mp;                // pair-tiles = ceil(tiles / 2)
     int iters;             // iterations of every pair: ceil((mp + lag) / pairs)
+    int acc4;              // four 128-column accumulators (two per program, unfused MMAs) instead of two fused 256-column
+                           // ones shared by strict S / T alternation -- with those each program effectively owns ONE
+                           // accumulator and MMA(S k+1) waits for the epilogue of S k
 };
 
 __device__ __forceinline__ void dual_tile_origin(const IgemmParams& p, int m, int o[4]) {
@@ -943,7 +946,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
     } else if (warp == 1 && lane == 0) {
         // ===================== MMA issuer (leader CTA of the pair) =====================
         if (crank == 0) {
-            int stage = 0, it = 0;
+            int stage = 0, it = 0, its[2] = {0, 0};
             uint32_t phase = 0;
             for (int k = 0; k < dp.iters; ++k) {
                 const int i = pr + k * pairs;
@@ -954,12 +957,14 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
                     const int hb = p.block_n >> 1;
                     const uint32_t idesc2 = umma_idesc_16(256, 2 * p.block_n, 0, 0);
                     const uint32_t idesc1 = umma_idesc_16(256, p.block_n, 0, 0);
-                    const int acc = it & 1;
-                    const uint32_t acc_phase = (it >> 1) & 1;
+                    const int cnt = dp.acc4 ? its[which] : it;
+                    const int acc = dp.acc4 ? 2 * which + (cnt & 1) : (cnt & 1);
+                    const uint32_t acc_phase = (cnt >> 1) & 1;
                     ++it;
+                    ++its[which];
                     mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc * acc_stride;
+                    const uint32_t d_tmem = tmem_base + acc * (dp.acc4 ? 128u : acc_stride);
                     for (int kit = 0; kit < p.k_iters; ++kit) {
                         mbar_wait(&full_bar[stage], phase, 300 + stage);
                         tc_fence_after();
@@ -967,12 +972,25 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
                         const uint64_t a_hi = umma_desc_sw128(sa);
                         const uint64_t a_lo = umma_desc_sw128(sa + kATileBytes);
                         const uint64_t b_hi = umma_desc_sw128(sa + 2 * kATileBytes);
+                        if (dp.acc4) {
+                            // three M = 256 MMAs into ONE 128-column accumulator, columns in natural order (this CTA's
+                            // half of the weight rows | the peer's)
+                            const uint64_t b_lo = umma_desc_sw128(sa + 2 * kATileBytes + (p.b_tile_bytes >> 1));
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_bf16_2sm(d_tmem, a_lo + 2 * kk, b_hi + 2 * kk, idesc1, (kit | kk) != 0);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) umma_bf16_2sm(d_tmem, a_hi + 2 * kk, b_lo + 2 * kk, idesc1, 1);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) umma_bf16_2sm(d_tmem, a_hi + 2 * kk, b_hi + 2 * kk, idesc1, 1);
+                        } else {
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk)
                             umma_bf16_2sm(d_tmem, a_hi + 2 * kk, b_hi + 2 * kk, idesc2, (kit | kk) != 0);
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk)
                             umma_bf16_2sm(d_tmem + hb, a_lo + 2 * kk, b_hi + 2 * kk, idesc1, 1);
+                        }
                         umma_commit_2sm_mc(&empty_bar[stage], 3);
                         if (kit == p.k_iters - 1) umma_commit_2sm_mc(&tfull_bar[acc], 3);
                         if (++stage == S) { stage = 0; phase ^= 1; }
@@ -989,7 +1007,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
         float* slab = stage_slab + (warp - 4) * (32 * kSlabStride);
         const int srow0 = lane >> 2;
         const int piece = lane & 3;
-        int it = 0;
+        int it = 0, its[2] = {0, 0};
         for (int k = 0; k < dp.iters; ++k) {
             const int i = pr + k * pairs;
 #pragma unroll
@@ -1002,9 +1020,11 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
                 const bool has_f32 = which == 1, has_hl = which == 0;
                 const bool has_stats = which == 1 && p.stats != nullptr;
                 const int m = 2 * q + (int)crank;
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
+                const int cnt = dp.acc4 ? its[which] : it;
+                const int acc = dp.acc4 ? 2 * which + (cnt & 1) : (cnt & 1);
+                const uint32_t acc_phase = (cnt >> 1) & 1;
                 ++it;
+                ++its[which];
                 const int nch = p.block_n >> 4;
                 const int c_begin = half == 0 ? 0 : ((nch + 1) >> 1) << 4;
                 const int c_end = half == 0 ? ((nch + 1) >> 1) << 4 : p.block_n;
@@ -1088,7 +1108,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
 
                 mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
                 tc_fence_after();
-                const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * acc_stride;
+                const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (dp.acc4 ? 128u : acc_stride);
 
                 auto process = [&](uint32_t (&raw)[16], int c) {
                     const int n = c;
@@ -1212,6 +1232,19 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
                 uint32_t ra[16], rb[16], rt[16];
                 const int hb = p.block_n >> 1;
                 auto col_a = [&](int c) { return c >= hb ? p.block_n + (c - hb) : c; };
+                if (dp.acc4) {      // plain 128-column accumulator: chunk c + 16 in flight while chunk c is processed
+                    if (c_begin < c_end) tmem_ld16(t_row + c_begin, ra);
+                    for (int c = c_begin; c < c_end; c += 32) {
+                        tmem_ld_wait16(ra);
+                        if (c + 16 < c_end) tmem_ld16(t_row + c + 16, rb);
+                        process(ra, c);
+                        if (c + 16 < c_end) {
+                            tmem_ld_wait16(rb);
+                            if (c + 32 < c_end) tmem_ld16(t_row + c + 32, ra);
+                            process(rb, c + 16);
+                        }
+                    }
+                } else {
                 if (c_begin < c_end) {
                     tmem_ld16(t_row + col_a(c_begin), ra);
                     tmem_ld16(t_row + col_a(c_begin) + hb, rt);
@@ -1237,6 +1270,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
                         }
                         process(rb, c + 16);
                     }
+                }
                 }
                 tc_fence_before();
                 if (crank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
@@ -1910,6 +1944,10 @@ static int dual_plan_create(const v2a_igemm_desc* ds, const v2a_igemm_desc* dt, 
     const int rounds = env ? atoi(env) : 2;
     pl->dp.lag = (tiles_per_frame + 1) / 2 + 1 + pairs * (rounds < 1 ? 1 : rounds);
     pl->dp.iters = ceil_div(pl->dp.mp + pl->dp.lag, pairs);
+    {
+        const char* a4 = getenv("V2A_DUAL_ACC4");
+        pl->dp.acc4 = (a4 && atoi(a4) == 0) ? 0 : 1;
+    }
     pl->grid = grid;
     pl->smem = ps->smem;
     delete ps;
