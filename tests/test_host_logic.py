@@ -246,3 +246,33 @@ def test_out_head_as_1x1_conv_plus_nine_tap_gather_matches_conv2d():
     P = emulate(prog, [as5d(_nhwc(x), Ci, prog.src_dims[0])], wp, 27)
     torch.testing.assert_close(stencil9_reference(P, b, N, H, W, Co), _nhwc(F.conv2d(x, w, b, padding=1)),
                                rtol=1e-12, atol=1e-12)
+
+
+def test_dual_conv3d_eligibility_and_contiguous_tilings():
+    """`ops.dual_conv3d_ok` decides whether a Conv3d's spatial and temporal programs may share ONE dual launch: both
+    must cut the same dense row space into the same consecutive 128-row blocks (the temporal tile m then depends on the
+    spatial tiles m - tpf, m, m + tpf only) and the layer must be narrow enough for the fused split product."""
+    # Libero levels: 128x128, 64x64 (stride-2 output grid), tiny-model 16x16
+    assert ops.dual_conv3d_ok((128, 128, 112, 1), (16384, 7, 16, 1), 128, 3, 7)
+    assert ops.dual_conv3d_ok((64, 64, 1, 112), (4096, 7, 16, 1), 128, 3, 7)
+    assert ops.dual_conv3d_ok((16, 16, 6, 1), (256, 3, 2, 1), 64, 3, 3)
+    assert not ops.dual_conv3d_ok((128, 128, 112, 1), (16384, 7, 16, 1), 256, 3, 7)      # wide layer: two launches
+    assert not ops.dual_conv3d_ok((128, 128, 112, 1), (16384, 7, 16, 1), 128, 1, 7)      # one-pass class
+    assert not ops.dual_conv3d_ok((8, 8, 112, 1), (64, 7, 16, 1), 128, 3, 7)             # tiles straddle frames
+    assert not ops.dual_conv3d_ok((24, 16, 6, 1), (384, 3, 2, 1), 64, 3, 3)              # ragged boxes
+    # contiguous tiling <=> tile m covers dense rows [128 m, 128 m + 128)
+    for dims in [(128, 128, 5, 1), (64, 64, 3, 2), (16, 16, 6, 1), (4096, 7, 2, 1), (32, 8, 4, 3)]:
+        tl = ops.choose_tile(dims)
+        if not ops._contiguous_tiling(dims, tl):
+            continue
+        ntile = [d >> l for d, l in zip(dims, tl)]
+        idx = torch.arange(dims[0] * dims[1] * dims[2] * dims[3]).reshape(dims[3], dims[2], dims[1], dims[0])
+        m = 0
+        for j3 in range(ntile[3]):
+            for j2 in range(ntile[2]):
+                for j1 in range(ntile[1]):
+                    for j0 in range(ntile[0]):
+                        box = idx[j3 << tl[3]:(j3 + 1) << tl[3], j2 << tl[2]:(j2 + 1) << tl[2],
+                                  j1 << tl[1]:(j1 + 1) << tl[1], j0 << tl[0]:(j0 + 1) << tl[0]].reshape(-1)
+                        assert box.tolist() == list(range(128 * m, 128 * m + 128)), (dims, tl, m)
+                        m += 1

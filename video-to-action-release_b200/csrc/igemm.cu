@@ -1945,8 +1945,11 @@ static int dual_plan_create(const v2a_igemm_desc* ds, const v2a_igemm_desc* dt, 
     pl->dp.lag = (tiles_per_frame + 1) / 2 + 1 + pairs * (rounds < 1 ? 1 : rounds);
     pl->dp.iters = ceil_div(pl->dp.mp + pl->dp.lag, pairs);
     {
+        // measured (gpurun_out/r2c12_ab.txt, B = 16 forward, same box): fused two-accumulator form 90.28 ms, this
+        // four-accumulator unfused form 91.79 ms (the N = 128 layers are shared-memory-operand bound: three MMAs per k
+        // step read 72 KB per SM instead of 56 KB) -- kept as an opt-in probe
         const char* a4 = getenv("V2A_DUAL_ACC4");
-        pl->dp.acc4 = (a4 && atoi(a4) == 0) ? 0 : 1;
+        pl->dp.acc4 = (a4 && atoi(a4) == 1) ? 1 : 0;
     }
     pl->grid = grid;
     pl->smem = ps->smem;
