@@ -355,8 +355,10 @@ def test_stencil9_matches_its_torch_restatement():
     from tests.test_host_logic import stencil9_reference
     from v2a_b200 import ops
     g = torch.Generator().manual_seed(0)
-    for (N, H, W) in ((3, 6, 5), (2, 16, 16), (7, 1, 9)):
-        P = torch.randn(N * H * W, 32, generator=g).cuda()
+    # ldp = 32 takes the shared-memory tiled kernel (tiles of 8 x 32 pixels: sizes below, at and across a tile),
+    # ldp = 27 the direct one
+    for (N, H, W, ldp) in ((3, 6, 5, 32), (2, 16, 16, 32), (7, 1, 9, 32), (2, 19, 70, 32), (1, 8, 32, 32), (2, 9, 33, 27)):
+        P = torch.randn(N * H * W, ldp, generator=g).cuda()
         bias = torch.randn(3, generator=g).cuda()
         y = torch.full((N * H * W, 4), float("nan"), device="cuda")
         ops.stencil9(P, bias, N, H, W, 3, y)
@@ -475,3 +477,23 @@ def test_igemm_small_m_backend_matches_float64(B, T, cins, co, k, res, hl, monke
     assert _rel(tc, ref) < 5e-5 and _rel(got, tc) < 5e-5
     if hl:
         assert _rel(got_hl, ref) < 5e-5
+
+
+def test_params_fingerprint_matches_its_integer_definition():
+    """sum_i bits(x_i) * (2 i + 1) mod 2^64 over the concatenated tensors, for lengths and base alignments that
+    exercise the scalar head / 16-byte body / scalar tail of the kernel; a one-ulp change of one element moves it."""
+    import numpy as np
+    from v2a_b200 import ops
+    torch.manual_seed(3)
+    store = torch.randn(1 << 18, device="cuda")
+    views, pos = [], 0
+    for n, skew in [(1, 0), (3, 1), (5, 2), (70001, 3), (65536, 0), (65537, 1), (131075, 2), (17, 3)]:
+        pos = (pos + 3) // 4 * 4 + skew          # base pointer = 16-byte aligned + 4 * skew
+        views.append(store[pos:pos + n])
+        pos += n
+    got = ops.params_fingerprint(views) & (2**64 - 1)
+    bits = np.concatenate([v.cpu().numpy().view(np.uint32) for v in views]).astype(object)
+    want = sum(int(b) * (2 * i + 1) for i, b in enumerate(bits)) & (2**64 - 1)
+    assert got == want
+    views[3][12345] = torch.nextafter(views[3][12345], torch.tensor(float("inf"), device="cuda"))
+    assert ops.params_fingerprint(views) & (2**64 - 1) != want
