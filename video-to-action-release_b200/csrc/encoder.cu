@@ -11,7 +11,6 @@
 #include "../../include/v2a_b200.h"
 
 #include <atomic>
-#include <cooperative_groups.h>
 
 namespace v2a {
 extern std::atomic<int64_t> g_launches;
@@ -410,145 +409,6 @@ __global__ void __launch_bounds__(256, 3) enc_gn_bwd_kernel(const EncGnBwdParams
     }
 }
 
-// One-pass form of the same backward: ONE thread-block cluster per image keeps the image's (g, xh) in registers
-// (kGnOct octets = 32 values of each per thread), reduces the per-channel sums in shared memory, exchanges the
-// per-group partials through distributed shared memory, and writes draw straight from the registers -- dout / raw
-// (/ out) are read from HBM once instead of twice and the two launches become one.  Used when the image fits
-// 8 blocks x 256 threads x 32 values (every ResNet18 stage after the stem at 128 x 128 input).
-constexpr int kGnOct = 4;
-__global__ void __launch_bounds__(256) enc_gn_bwd_cluster_kernel(const EncGnBwdParams p, int oct_per_img) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cl = cg::this_cluster();
-    const int nb = (int)cl.num_blocks();
-    const int rank = (int)cl.block_rank();
-    const int img = blockIdx.x / nb;
-    __shared__ float ch_s[2 * 512];     // [C][2]: (sum g, sum g * xh) over this block's pixels
-    __shared__ float grp_s[2 * 64];     // [groups][2]: gamma-weighted group partials of this block
-    __shared__ float coef_s[2 * 64];    // [groups][2]: the image's coefficients
-    const int oct = p.C >> 3;
-    const int o8 = threadIdx.x & (oct - 1);          // 256 % oct == 0: the channel octet is the same for every `it`
-    const int c = o8 * 8;
-    const int cpg = p.C / p.groups;
-    for (int i = threadIdx.x; i < 2 * p.C; i += 256) ch_s[i] = 0.f;
-    __syncthreads();
-    float mean[8], rstd[8], ga[8], be[8];
-    {
-        int g = c / cpg, rem = c - g * cpg;
-        float2 m = __ldg(&p.mr[(int64_t)img * p.groups + g]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            mean[j] = m.x; rstd[j] = m.y;
-            ga[j] = __ldg(&p.gamma[c + j]);
-            be[j] = __ldg(&p.beta[c + j]);
-            if (++rem == cpg && j < 7) {
-                rem = 0;
-                ++g;
-                m = __ldg(&p.mr[(int64_t)img * p.groups + g]);
-            }
-        }
-    }
-    float gv[kGnOct][8], xh[kGnOct][8];
-    const int64_t base = (int64_t)img * oct_per_img;
-    const int o0 = rank * (256 * kGnOct) + threadIdx.x;
-    // all loads of the thread are issued before the first use
-    float rv[kGnOct][8], ov[kGnOct][8];
-#pragma unroll
-    for (int it = 0; it < kGnOct; ++it) {
-        const int o = o0 + it * 256;
-        if (o < oct_per_img) {
-            const int64_t e = (base + o) * 8;
-            load8(p.dout + e, gv[it]);
-            load8(p.raw + e, rv[it]);
-            if (p.mask_mode == 1) load8(p.outv + e, ov[it]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) gv[it][j] = rv[it][j] = ov[it][j] = 0.f;
-        }
-    }
-    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int it = 0; it < kGnOct; ++it) {
-        const bool live = o0 + it * 256 < oct_per_img;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float x = (rv[it][j] - mean[j]) * rstd[j];
-            float g = gv[it][j];
-            if (p.mask_mode == 1) g = ov[it][j] > 0.0f ? g : 0.0f;
-            else if (p.mask_mode == 2) g = fmaf(x, ga[j], be[j]) > 0.0f ? g : 0.0f;
-            if (!live) g = 0.f;
-            gv[it][j] = g;
-            xh[it][j] = x;
-            s[j] += g;
-            sx[j] = fmaf(g, x, sx[j]);
-        }
-    }
-    // block reduction: the 32 / oct ... 256 / oct threads of one octet meet in shared memory
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        atomicAdd(&ch_s[2 * (c + j)], s[j]);
-        atomicAdd(&ch_s[2 * (c + j) + 1], sx[j]);
-    }
-    __syncthreads();
-    for (int g = threadIdx.x; g < p.groups; g += 256) {
-        float a = 0.f, b2 = 0.f;
-        for (int j = 0; j < cpg; ++j) {
-            const int ch = g * cpg + j;
-            const float gam = __ldg(&p.gamma[ch]);
-            a = fmaf(gam, ch_s[2 * ch], a);
-            b2 = fmaf(gam, ch_s[2 * ch + 1], b2);
-        }
-        grp_s[2 * g] = a;
-        grp_s[2 * g + 1] = b2;
-    }
-    cl.sync();
-    for (int g = threadIdx.x; g < p.groups; g += 256) {
-        float a = 0.f, b2 = 0.f;
-        for (int r = 0; r < nb; ++r) {
-            const float* peer = cl.map_shared_rank(grp_s, r);
-            a += peer[2 * g];
-            b2 += peer[2 * g + 1];
-        }
-        coef_s[2 * g] = a * p.inv_m;
-        coef_s[2 * g + 1] = b2 * p.inv_m;
-    }
-    if (rank == 0) {
-        // the image's per-channel sums -> parameter gradients (one atomic per channel and image, as before)
-        for (int i = threadIdx.x; i < 2 * p.C; i += 256) {
-            float v = 0.f;
-            for (int r = 0; r < nb; ++r) v += cl.map_shared_rank(ch_s, r)[i];
-            atomicAdd((i & 1) ? &p.dgamma[i >> 1] : &p.dbeta[i >> 1], v);
-        }
-    }
-    cl.sync();   // peers' shared memory stays alive until every remote read is done; coef_s is visible block-wide
-    float cx[8], cy[8];
-    {
-        int g = c / cpg, rem = c - g * cpg;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            cx[j] = coef_s[2 * g];
-            cy[j] = coef_s[2 * g + 1];
-            if (++rem == cpg) {
-                rem = 0;
-                ++g;
-            }
-        }
-    }
-#pragma unroll
-    for (int it = 0; it < kGnOct; ++it) {
-        const int o = o0 + it * 256;
-        if (o >= oct_per_img) continue;
-        const int64_t e = (base + o) * 8;
-        float r[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = rstd[j] * (ga[j] * gv[it][j] - cx[j] - xh[it][j] * cy[j]);
-        uint4 h, l;
-        split8(r, h, l);
-        *reinterpret_cast<uint4*>(p.d_hi + e) = h;
-        *reinterpret_cast<uint4*>(p.d_lo + e) = l;
-        if (p.g_out) store8(p.g_out + e, gv[it]);
-    }
-}
-
 // ---------------------------------------------------------------------------
 // data gradient of a stride-2 3x3 conv arrives phase-blocked [img][H/2][W/2][(py, px)][C]; the 1x1 stride-2
 // downsample path adds at phase (0, 0).  -> dx [img][H][W][C]
@@ -731,37 +591,13 @@ int v2a_enc_gn_bwd(const v2a_enc_gn_bwd_desc* d, void* stream) {
     p.dgamma = d->dgamma; p.dbeta = d->dbeta;
     p.d_hi = (__nv_bfloat16*)d->d_hi; p.d_lo = (__nv_bfloat16*)d->d_lo; p.g_out = d->g_out;
     V2A_REQUIRE(d->groups * 2 <= 2 * 256 * 9, "enc_gn_bwd: too many groups");
-    cudaStream_t st = (cudaStream_t)stream;
-    {
-        // one-pass cluster form when one image fits 8 blocks' registers (V2A_ENC_GN_CLUSTER=0: two-pass A/B probe)
-        static const bool allow = [] { const char* e = getenv("V2A_ENC_GN_CLUSTER"); return !(e && atoi(e) == 0); }();
-        const int oct = d->C / 8;
-        const int64_t oct_per_img = (int64_t)d->HW * oct;
-        const int64_t nb = (oct_per_img + 256 * kGnOct - 1) / (256 * kGnOct);
-        if (allow && nb <= 8 && (oct & (oct - 1)) == 0 && oct <= 64 && d->C <= 512 && d->groups <= 64 &&
-            (nb & (nb - 1)) == 0) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)(nb * d->images));
-            cfg.blockDim = dim3(256);
-            cfg.stream = st;
-            cudaLaunchAttribute attr;
-            attr.id = cudaLaunchAttributeClusterDimension;
-            attr.val.clusterDim.x = (unsigned)nb;
-            attr.val.clusterDim.y = 1;
-            attr.val.clusterDim.z = 1;
-            cfg.attrs = &attr;
-            cfg.numAttrs = 1;
-            V2A_CUDA_OK(cudaLaunchKernelEx(&cfg, enc_gn_bwd_cluster_kernel, p, (int)oct_per_img));
-            V2A_ENC_LAUNCH_OK();
-            return 0;
-        }
-    }
     int lanes, iters;
     walk_shape(d->C, p.pixels, lanes, iters);
     while (iters > 1 && lanes * iters > d->HW) iters >>= 1;
     const int bpi = ceil_div(d->HW, lanes * iters);
     const unsigned grid = (unsigned)(bpi * d->images);
     const int threads = (d->C / 8) * lanes;
+    cudaStream_t st = (cudaStream_t)stream;
     // pass 1 (sums; the caller zeroes them once per backward) -> pass 2 (coefficients, parameter gradients, dx)
     enc_gn_bwd_kernel<1><<<grid, threads, 0, st>>>(p, lanes, iters);
     V2A_ENC_LAUNCH_OK();

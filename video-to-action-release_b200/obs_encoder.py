@@ -301,13 +301,7 @@ class _EncoderEngine(PackedParams):
         d.g_out = None if g_out is None else g_out.data_ptr()
         d.dgamma, d.dbeta = self.pgrad[id(gn.weight)].data_ptr(), self.pgrad[id(gn.bias)].data_ptr()
         self.keep.append((d, [dout, raw, mr, outv, ga, ba, sums, coef, d_hl, g_out]))
-        # one cluster launch when an image fits 8 blocks' registers, else two passes (same test as csrc/encoder.cu)
-        oct_ = Cc // 8
-        nb = -(-HW * oct_ // 1024)
-        one = (os.environ.get("V2A_ENC_GN_CLUSTER", "1") != "0" and nb <= 8 and nb & (nb - 1) == 0
-               and oct_ & (oct_ - 1) == 0 and oct_ <= 64 and gn.num_groups <= 64)
-        steps.add("enc_gn_bwd_cluster" if one else "enc_gn_bwd",
-                  lambda: _lib.check(self.lib.v2a_enc_gn_bwd(C.byref(d), ops._stream()), "enc_gn_bwd"))
+        steps.add("enc_gn_bwd", lambda: _lib.check(self.lib.v2a_enc_gn_bwd(C.byref(d), ops._stream()), "enc_gn_bwd"))
 
     # ---- network plan --------------------------------------------------------------------------
     def _build(self, core):
