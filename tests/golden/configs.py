@@ -18,6 +18,14 @@ def tiny_inputs():
     return x, t, x_cond, te
 
 
+def p_losses_inputs():
+    """img in [0, 1] and noise for the denoising-loss golden (tests/golden/make_p_losses_golden.py)."""
+    g = torch.Generator().manual_seed(4321)
+    img = torch.rand(2, 9, 16, 16, generator=g)
+    noise = torch.randn(2, 9, 16, 16, generator=g)
+    return img, noise
+
+
 def config1_inputs():
     """BASELINE.json configs[0]: Unet_Libero, 64x64, 4 frames, batch 1."""
     g = torch.Generator().manual_seed(123)

@@ -383,3 +383,26 @@ def test_fast_precision_class_is_opt_in_and_within_its_own_tolerance(cpu_rng_str
     e = rel_l2(o, gold["config1_forward"])
     print(f"config-1 forward, fast class: rel-L2 {e:.2e}")
     assert 1e-4 < e < FAST_TOL
+
+
+def test_p_losses_value_matches_reference_golden():
+    """goal_diffusion.py:689-724: the min-SNR weighted denoising loss (value only, under no_grad) against the
+    unmodified reference (tests/golden/make_p_losses_golden.py); with autograd on it must refuse, not return a loss
+    that does not reach the parameters."""
+    from tests.golden.configs import p_losses_inputs, tiny_inputs
+    gold = torch.load(os.path.join(HERE, "golden", "video_p_losses_golden.pt"))
+    net, _ = _tiny_model(1)
+    d = _diffusion(net, 9, (16, 16), 100, 100)
+    _, _, x_cond, te = tiny_inputs()
+    img, noise = p_losses_inputs()
+    with torch.no_grad():
+        for name, t in (("t_37_4", [37, 4]), ("t_0_99", [0, 99])):
+            tt = torch.tensor(t, dtype=torch.long, device="cuda")
+            got = d.p_losses(d.normalize(img.cuda()), tt, x_cond.cuda(), te.cuda(), noise=noise.cuda())
+            want = float(gold[name])
+            print(f"p_losses {name}: {float(got):.8f} vs reference {want:.8f}")
+            assert abs(float(got) - want) <= TOL * abs(want)
+        loss = d(img.cuda(), x_cond.cuda(), te.cuda())          # forward(): random t, device RNG
+        assert loss.dim() == 0 and torch.isfinite(loss)
+    with pytest.raises(NotImplementedError):
+        d(img.cuda(), x_cond.cuda(), te.cuda())

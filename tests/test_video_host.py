@@ -105,3 +105,44 @@ def test_task_embed_cache_is_exact_per_batch_and_returns_the_same_tensor():
     vm.encode_batch_text(["open the drawer"])
     assert len(calls) == 4 and cache.hits == 1 and cache.misses == 4
     assert isinstance(cache, TaskEmbedCache)
+
+
+class _StubDenoiser(torch.nn.Module):
+    """Parameter-free stand-in for the UNet: the loss arithmetic around it is what this test pins."""
+
+    def forward(self, x, t, task_embed=None):
+        return torch.tanh(x[:, :-3] * 0.7 + x[:, -3:].repeat(1, (x.shape[1] - 3) // 3, 1, 1) * 0.1) + \
+            task_embed.mean(dim=(1, 2)).reshape(-1, 1, 1, 1) + t.reshape(-1, 1, 1, 1).float() * 0.01
+
+
+@pytest.mark.parametrize("objective,loss_type,min_snr", [("pred_v", "l2", True), ("pred_noise", "l1", False),
+                                                         ("pred_x0", "l2", True)])
+def test_p_losses_arithmetic_is_bit_exact_vs_reference(objective, loss_type, min_snr):
+    """q_sample -> model -> target (pred_v / pred_noise / pred_x0) -> l1 / l2 -> per-sample mean -> loss weight
+    (goal_diffusion.py:689-716), same stub denoiser on both sides, CPU fp32: every op is the reference's op."""
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference sources not present")
+    kw = dict(image_size=(16, 16), channels=9, timesteps=100, sampling_timesteps=100, loss_type=loss_type,
+              objective=objective, beta_schedule="cosine", min_snr_loss_weight=min_snr, guidance_weight=0)
+    ours = GoalGaussianDiffusion(_StubDenoiser(), **kw)
+    ref = ref_import.GoalGaussianDiffusion()(_StubDenoiser(), **kw)
+    g = torch.Generator().manual_seed(8)
+    img, noise = torch.rand(3, 9, 16, 16, generator=g), torch.randn(3, 9, 16, 16, generator=g)
+    cond, te = torch.rand(3, 3, 16, 16, generator=g), torch.randn(3, 5, 512, generator=g)
+    t = torch.tensor([0, 41, 99])
+    a = ours.p_losses(ours.normalize(img), t, cond, te, noise=noise)
+    b = ref.p_losses(ref.normalize(img), t, cond, te, noise=noise)
+    assert torch.equal(a, b)
+    torch.manual_seed(5)
+    fa = ours(img, cond, te)
+    torch.manual_seed(5)
+    fb = ref(img, cond, te)
+    assert torch.equal(fa, fb)
+
+
+def test_p_losses_refuses_autograd_through_the_cuda_unet():
+    d = GoalGaussianDiffusion(Unet_Libero(), image_size=(16, 16), channels=9, timesteps=4, sampling_timesteps=4,
+                              objective="pred_v", beta_schedule="cosine", guidance_weight=0)
+    with pytest.raises(NotImplementedError, match="no_grad"):
+        d(torch.rand(1, 9, 16, 16), torch.rand(1, 3, 16, 16), torch.randn(1, 4, 512))

@@ -388,10 +388,49 @@ class GoalGaussianDiffusion(nn.Module):
                                         return_all_timesteps)
         return self._sample_fast(x_cond, task_embed, batch_size, bool(self.is_ddim_sampling), return_all_timesteps)
 
+    @property
+    def loss_fn(self):
+        if self.loss_type == "l1":
+            return F.l1_loss
+        if self.loss_type == "l2":
+            return F.mse_loss
+        raise ValueError(f"invalid loss type {self.loss_type}")
+
+    def p_losses(self, x_start, t, x_cond, task_embed, noise=None):
+        """goal_diffusion.py:689-716: the denoising loss at timestep ``t`` (min-SNR weighted).  The CUDA UNet here has
+        no backward (training the video model is outside SURVEY.md §8a rows V1-V14), so this is the loss VALUE --
+        validation / monitoring under ``torch.no_grad()``; asking for it with autograd on raises instead of handing
+        back a loss that silently does not reach the parameters."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
+            raise NotImplementedError(
+                "v2a_b200 GoalGaussianDiffusion computes the training loss without a backward pass (hot-path scope: "
+                "sampling, SURVEY.md §8a); call it under torch.no_grad(), or train the video model with the reference "
+                "module (same state_dict)")
+        noise = torch.randn_like(x_start) if noise is None else noise
+        x = self.q_sample(x_start=x_start, t=t, noise=noise)
+        model_out = self.model(torch.cat([x, x_cond], dim=1), t, task_embed)
+        if self.objective == "pred_noise":
+            target = noise
+        elif self.objective == "pred_x0":
+            target = x_start
+        elif self.objective == "pred_v":
+            target = self.predict_v(x_start, t, noise)
+        else:
+            raise ValueError(f"unknown objective {self.objective}")
+        loss = self.loss_fn(model_out, target, reduction="none")
+        # the reference's `reduce(loss, 'b ... -> b (...)', 'mean')` reduces nothing (every axis is kept on the right):
+        # it is a reshape to [b, C*H*W]; the weight then broadcasts per sample and ONE mean runs over everything
+        loss = loss.reshape(loss.shape[0], -1)
+        loss = loss * _extract(self.loss_weight, t, loss.shape)
+        return loss.mean()
+
     def forward(self, img, img_cond, task_embed):
-        raise NotImplementedError(
-            "training the video model (p_losses, goal_diffusion.py:689-724) is outside the hot-path scope "
-            "(SURVEY.md §8a rows V1-V14 cover sampling); use the reference module for video-model training")
+        """goal_diffusion.py:718-724."""
+        b, c, h, w = img.shape
+        assert h == self.image_size[0] and w == self.image_size[1], \
+            f"height and width of image must be {self.image_size}, got({h}, {w})"
+        t = torch.randint(0, self.num_timesteps, (b,), device=img.device).long()
+        return self.p_losses(self.normalize(img), t, img_cond, task_embed)
 
 
 # ---------------------------------------------------------------------------
