@@ -139,6 +139,13 @@ def test_p_losses_arithmetic_is_bit_exact_vs_reference(objective, loss_type, min
     torch.manual_seed(5)
     fb = ref(img, cond, te)
     assert torch.equal(fa, fb)
+    if objective == "pred_v":   # p_sample / p_mean_variance (:561-580) with the same stub: one ancestral step, t > 0 and t = 0
+        for step in (7, 0):
+            torch.manual_seed(6)
+            pa, xa = ours.p_sample(noise, step, cond, te)
+            torch.manual_seed(6)
+            pb, xb = ref.p_sample(noise, step, cond, te)
+            assert torch.equal(pa, pb) and torch.equal(xa, xb)
 
 
 def test_p_losses_refuses_autograd_through_the_cuda_unet():

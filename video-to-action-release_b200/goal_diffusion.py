@@ -208,6 +208,24 @@ class GoalGaussianDiffusion(nn.Module):
         return mean, _extract(self.posterior_variance, t, x_t.shape), \
             _extract(self.posterior_log_variance_clipped, t, x_t.shape)
 
+    def p_mean_variance(self, x, t, x_cond, task_embed, clip_denoised=False):
+        """goal_diffusion.py:561-569."""
+        x_start = self.model_predictions(x, t, x_cond, task_embed).pred_x_start
+        if clip_denoised:
+            x_start = x_start.clamp(-1.0, 1.0)
+        mean, var, logvar = self.q_posterior(x_start=x_start, x_t=x, t=t)
+        return mean, var, logvar, x_start
+
+    @torch.no_grad()
+    def p_sample(self, x, t: int, x_cond, task_embed):
+        """goal_diffusion.py:571-580: one ancestral step as a standalone call (the loops in `sample()` run the fused
+        step kernel instead; this is the reference's method for callers that drive the loop themselves)."""
+        tc = torch.full((x.shape[0],), t, device=x.device, dtype=torch.long)
+        mean, _, logvar, x_start = self.p_mean_variance(x, tc, x_cond, task_embed, clip_denoised=True)
+        noise = torch.randn_like(x) if t > 0 else 0.0
+        noise = noise * self.var_temp
+        return mean + (0.5 * logvar).exp() * noise, x_start
+
     @torch.no_grad()
     def _sample_general(self, x_cond, task_embed, batch_size, ddim: bool, return_all_timesteps=False):
         """Every setting the fused sampler does not cover (classifier-free guidance, pred_noise / pred_x0
