@@ -439,7 +439,8 @@ def test_conv3d_dual_launch_matches_float64_and_the_two_launch_path(B, Fr, H, W,
 
 @pytest.mark.parametrize("B,T,cins,co,k,res,hl", [(1, 16, (256,), 256, 5, True, True), (1, 4, (1024,), 1024, 5, False, True),
                                                   (1, 8, (512, 512), 512, 5, False, False), (2, 8, (7 + 9,), 256, 5, False, True),
-                                                  (1, 1, (256,), 1000, 1, False, False), (2, 4, (1024,), 24, 3, True, False)])
+                                                  (1, 1, (256,), 1000, 1, False, False), (2, 4, (1024,), 24, 3, True, False),
+                                                  (1, 2, (64,), 258, 3, True, True)])
 def test_igemm_small_m_backend_matches_float64(B, T, cins, co, k, res, hl, monkeypatch):
     """GEMMs of <= 32 output rows (the policy UNet at batch 1-2: `predict_action` between simulator steps) run on the
     CUDA-core weight-streaming backend of the same plan (csrc/igemm.cu `igemm_smallm_kernel`): Conv1d k5 / k3 / Linear
@@ -452,7 +453,7 @@ def test_igemm_small_m_backend_matches_float64(B, T, cins, co, k, res, hl, monke
     w = (torch.randn(co, sum(cins), k, generator=g) / (k * sum(cins)) ** 0.5).to(DEV)
     wp = convs.conv1d_cat_weight(w, list(cins))
     bias = torch.randn(co, generator=g).to(DEV)
-    resid = torch.randn(B * T, co, generator=g).to(DEV) if res else None
+    resid = torch.randn(B * T, -(-co // 16) * 16, generator=g).to(DEV)[:, :co] if res else None   # row stride % 4 == 0
 
     def run():
         srcs = [(ops.split_hl(x), c, d) for x, c, d in zip(xs, prog.src_channels, prog.src_dims)]

@@ -1311,23 +1311,19 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
 // memory (fp32, exact hi + lo), fp32 FMA accumulation -- the activation operand is tiny, the weights are the traffic.
 // Same descriptor, same epilogue subset (bias, residual, fp32 and/or hi/lo output); chosen by the plan, not the caller.
 // ===========================================================================
-constexpr int kSmallMaxRows = 32;
-constexpr int kSmallWarps = 8;                // warps per block = (output channels per block) x (K slices per channel)
-constexpr int kSmallUnroll = 4;               // 256-element weight groups in flight per warp
+constexpr int kSmallMaxRows = 16;
+constexpr int kSmallWarps = 8;                // warps per block = (channel groups per block) x (K slices per group)
 
 struct SmallMParams {
     const __nv_bfloat16* a_hi[V2A_MAX_SRC];
     const __nv_bfloat16* a_lo[V2A_MAX_SRC];
     int src_ch[V2A_MAX_SRC];
-    int src_dims[V2A_MAX_SRC][4];
     int tap_src[V2A_MAX_TAPS];
-    int tap_d[V2A_MAX_TAPS][4];
     int tap_chunk0[V2A_MAX_TAPS + 1];         // first 64-wide K chunk of every tap (prefix sums)
     int ntaps;
     const __nv_bfloat16* w_hi;
     const __nv_bfloat16* w_lo;
     int ktot, wrows;
-    int out_dims[4];
     int rows, cout, ldc;
     float* out_f32;
     __nv_bfloat16* out_hi;
@@ -1335,9 +1331,12 @@ struct SmallMParams {
     const float* bias;
     const float* residual;
     int ld_res;
-    long long out_mul[4], out_off;
-    int slices;                               // K slices per output channel (1, 2, 4 or 8 warps share a channel)
+    int slices;                               // K slices per channel group (1, 2, 4 or 8 warps share a group)
     int slice_groups;                         // 8-element groups per slice
+    // the im2col shift of every (output row, tap) as an element offset into the tap's source (-1 = zero padding) and
+    // the output row of every GEMM row: computed once by the host at plan time (they depend on the shape only)
+    int off[kSmallMaxRows][V2A_MAX_TAPS];
+    int out_row[kSmallMaxRows];
 };
 
 __device__ __forceinline__ void bf16x8_to_f32(const uint4& h, const uint4& l, float* f) {
@@ -1348,111 +1347,125 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& h, const uint4& l, fl
         f[2 * i + 1] = __uint_as_float(hv[i] & 0xffff0000u) + __uint_as_float(lv[i] & 0xffff0000u);
     }
 }
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {   // read-once weights: do not displace x in L1
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
 
-// One warp = one (output channel, K slice): it streams that slice of the channel's K-major weight row once
-// (kSmallUnroll independent 16-byte loads per plane in flight) and reads the matching activation elements of every
-// output row straight from global memory (a few KB, L1 resident: every warp of the SM reads the same rows); the
-// im2col shift of a tap is a per-(row, tap) source-row offset looked up in shared memory (-1 = zero padding).
-template <int kRows>
+// One warp = (kCh consecutive output channels, one K slice): it streams that slice of the channels' K-major weight
+// rows once (2 * kCh independent 16-byte loads in flight per lane, the next group's requested before the current one
+// is used) and reads the matching activation elements of every output row straight from global memory (a few KB, L1
+// resident: every warp of the SM reads the same rows) ONCE for its kCh channels.  The first weight loads are issued
+// before the block's only barrier (the offset table's way into shared memory), so HBM latency overlaps the set-up.
+template <int kRows, int kCh>
 __global__ void __launch_bounds__(kSmallWarps * 32) igemm_smallm_kernel(const __grid_constant__ SmallMParams p) {
-    __shared__ long long s_off[kSmallMaxRows][V2A_MAX_TAPS];     // element offset of (row, tap) in its source, or -1
-    __shared__ long long s_out[kSmallMaxRows];
-    __shared__ float s_part[kSmallWarps][kSmallMaxRows];
+    __shared__ int s_off[kSmallMaxRows][V2A_MAX_TAPS];
+    __shared__ float s_part[kSmallWarps][kRows][kCh];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cpb = kSmallWarps / p.slices;                       // channels per block
-    const int n = blockIdx.x * cpb + warp / p.slices;
+    const int gpb = kSmallWarps / p.slices;                       // channel groups per block
+    const int n0 = (blockIdx.x * gpb + warp / p.slices) * kCh;
     const int slice = warp % p.slices;
-    for (int idx = threadIdx.x; idx < p.rows * p.ntaps; idx += blockDim.x) {
-        const int m = idx / p.ntaps, e = idx - m * p.ntaps;
-        int c[4], mm = m;
+    const int g_begin = slice * p.slice_groups;
+    const int g_end = min(g_begin + p.slice_groups, p.ktot >> 3);
+    const bool live = n0 < p.cout;
+    const uint4* wh[kCh];
+    const uint4* wl[kCh];
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            c[d] = mm % p.out_dims[d];
-            mm /= p.out_dims[d];
-        }
-        if (e == 0)
-            s_out[m] = p.out_off + c[0] * p.out_mul[0] + c[1] * p.out_mul[1] + c[2] * p.out_mul[2] + c[3] * p.out_mul[3];
-        const int src = p.tap_src[e];
-        const int s0 = c[0] + p.tap_d[e][0], s1 = c[1] + p.tap_d[e][1], s2 = c[2] + p.tap_d[e][2], s3 = c[3] + p.tap_d[e][3];
-        long long off = -1;
-        if (s0 >= 0 && s0 < p.src_dims[src][0] && s1 >= 0 && s1 < p.src_dims[src][1] && s2 >= 0 &&
-            s2 < p.src_dims[src][2] && s3 >= 0 && s3 < p.src_dims[src][3])
-            off = ((((long long)s3 * p.src_dims[src][2] + s2) * p.src_dims[src][1] + s1) * p.src_dims[src][0] + s0) *
-                  p.src_ch[src];
-        s_off[m][e] = off;
+    for (int j = 0; j < kCh; ++j) {
+        const int n = min(n0 + j, p.wrows - 1);                   // rows past cout: re-read a valid row, never stored
+        wh[j] = reinterpret_cast<const uint4*>(p.w_hi + (size_t)n * p.ktot);
+        wl[j] = reinterpret_cast<const uint4*>(p.w_lo + (size_t)n * p.ktot);
     }
+    uint4 h[kCh], l[kCh];
+    int g = g_begin + lane;
+    if (live && g < g_end) {
+#pragma unroll
+        for (int j = 0; j < kCh; ++j) {
+            h[j] = ld_stream_u4(wh[j] + g);
+            l[j] = ld_stream_u4(wl[j] + g);
+        }
+    }
+    for (int idx = threadIdx.x; idx < kSmallMaxRows * V2A_MAX_TAPS; idx += blockDim.x)
+        (&s_off[0][0])[idx] = (&p.off[0][0])[idx];
     __syncthreads();
-    float acc[kRows];
+    float acc[kRows][kCh];
 #pragma unroll
-    for (int m = 0; m < kRows; ++m) acc[m] = 0.0f;
-    if (n < p.cout) {
-        const int g_begin = slice * p.slice_groups;
-        const int g_end = min(g_begin + p.slice_groups, p.ktot >> 3);
-        const uint4* wh = reinterpret_cast<const uint4*>(p.w_hi + (size_t)n * p.ktot);
-        const uint4* wl = reinterpret_cast<const uint4*>(p.w_lo + (size_t)n * p.ktot);
-        for (int g0 = g_begin + lane; g0 < g_end; g0 += 32 * kSmallUnroll) {
-            uint4 h[kSmallUnroll], l[kSmallUnroll];
+    for (int m = 0; m < kRows; ++m)
 #pragma unroll
-            for (int u = 0; u < kSmallUnroll; ++u) {
-                const int g = g0 + 32 * u;
-                if (g < g_end) {
-                    h[u] = __ldg(wh + g);
-                    l[u] = __ldg(wl + g);
+        for (int j = 0; j < kCh; ++j) acc[m][j] = 0.0f;
+    if (live) {
+        for (; g < g_end; g += 32) {
+            float w[kCh][8];
+#pragma unroll
+            for (int j = 0; j < kCh; ++j) bf16x8_to_f32(h[j], l[j], w[j]);
+            if (g + 32 < g_end) {
+#pragma unroll
+                for (int j = 0; j < kCh; ++j) {
+                    h[j] = ld_stream_u4(wh[j] + g + 32);
+                    l[j] = ld_stream_u4(wl[j] + g + 32);
                 }
             }
+            const int k = g << 3, chunk = k >> 6;
+            int e = 0;
+            while (e + 1 < p.ntaps && chunk >= p.tap_chunk0[e + 1]) ++e;
+            const int c = ((chunk - p.tap_chunk0[e]) << 6) + (k & 63);
+            const int src = p.tap_src[e];
+            if (c >= p.src_ch[src]) continue;                // zero padding of the last chunk of a tap
+            const __nv_bfloat16* ah = p.a_hi[src] + c;
+            const __nv_bfloat16* al = p.a_lo[src] + c;
 #pragma unroll
-            for (int u = 0; u < kSmallUnroll; ++u) {
-                const int g = g0 + 32 * u;
-                if (g >= g_end) continue;
-                float w[8];
-                bf16x8_to_f32(h[u], l[u], w);
-                const int k = g << 3, chunk = k >> 6;
-                int e = 0;
-                while (e + 1 < p.ntaps && chunk >= p.tap_chunk0[e + 1]) ++e;
-                const int c = ((chunk - p.tap_chunk0[e]) << 6) + (k & 63);
-                const int src = p.tap_src[e];
-                if (c >= p.src_ch[src]) continue;            // zero padding of the last chunk of a tap
-                const __nv_bfloat16* ah = p.a_hi[src] + c;
-                const __nv_bfloat16* al = p.a_lo[src] + c;
+            for (int m = 0; m < kRows; ++m) {
+                if (m >= p.rows) break;
+                const int off = s_off[m][e];
+                if (off < 0) continue;
+                const uint4 xh = __ldg(reinterpret_cast<const uint4*>(ah + off));
+                const uint4 xl = __ldg(reinterpret_cast<const uint4*>(al + off));
+                float x[8];
+                bf16x8_to_f32(xh, xl, x);
 #pragma unroll
-                for (int m = 0; m < kRows; ++m) {
-                    if (m >= p.rows) break;
-                    const long long off = s_off[m][e];
-                    if (off < 0) continue;
-                    const uint4 xh = __ldg(reinterpret_cast<const uint4*>(ah + off));
-                    const uint4 xl = __ldg(reinterpret_cast<const uint4*>(al + off));
-                    float x[8];
-                    bf16x8_to_f32(xh, xl, x);
-                    float a = acc[m];
+                for (int j = 0; j < kCh; ++j) {
+                    float a = acc[m][j];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) a = fmaf(x[j], w[j], a);
-                    acc[m] = a;
+                    for (int i = 0; i < 8; ++i) a = fmaf(x[i], w[j][i], a);
+                    acc[m][j] = a;
                 }
             }
         }
     }
-    // ---- reduce over the lanes, then over the K slices of the channel ----
+    // ---- reduce over the lanes, then over the K slices of the channel group ----
 #pragma unroll
     for (int m = 0; m < kRows; ++m) {
         if (m >= p.rows) break;
-        float v = acc[m];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_part[warp][m] = v;
+        for (int j = 0; j < kCh; ++j) {
+            float v = acc[m][j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_part[warp][m][j] = v;
+        }
     }
     __syncthreads();
-    if (slice != 0 || n >= p.cout || lane >= p.rows) return;
-    float v = 0.0f;
-    for (int s2 = 0; s2 < p.slices; ++s2) v += s_part[warp + s2][lane];
-    const long long row = s_out[lane];
-    v += p.bias ? __ldg(p.bias + n) : 0.0f;
-    if (p.residual) v += p.residual[row * p.ld_res + n];
-    if (p.out_f32) p.out_f32[row * p.ldc + n] = v;
-    if (p.out_hi) {
-        __nv_bfloat16 hh, ll;
-        split_bf16(v, hh, ll);
-        p.out_hi[row * p.ldc + n] = hh;
-        p.out_lo[row * p.ldc + n] = ll;
+    if (slice != 0 || !live) return;
+    // lanes walk the (row, channel) outputs of the group
+    for (int idx = lane; idx < p.rows * kCh; idx += 32) {
+        const int m = idx / kCh, j = idx - m * kCh;
+        const int n = n0 + j;
+        if (n >= p.cout) continue;
+        float v = 0.0f;
+        for (int s2 = 0; s2 < p.slices; ++s2) v += s_part[warp + s2][m][j];
+        const long long row = p.out_row[m];
+        v += p.bias ? __ldg(p.bias + n) : 0.0f;
+        if (p.residual) v += p.residual[row * p.ld_res + n];
+        if (p.out_f32) p.out_f32[row * p.ldc + n] = v;
+        if (p.out_hi) {
+            __nv_bfloat16 hh, ll;
+            split_bf16(v, hh, ll);
+            p.out_hi[row * p.ldc + n] = hh;
+            p.out_lo[row * p.ldc + n] = ll;
+        }
     }
 }
 
@@ -1515,7 +1528,8 @@ int make_tensor_map_bf16(CUtensorMap* m, const void* base, int rank, const uint6
 struct IgemmPlan {
     IgemmParams p;
     int epi;              // compile-time epilogue class of the launch (bit 0 fp32, bit 1 hi/lo, bit 2 sums) or -1
-    bool smallm;          // <= 32 output rows: the CUDA-core weight-streaming backend (igemm_smallm_kernel)
+    bool smallm;          // <= 16 output rows: the CUDA-core weight-streaming backend (igemm_smallm_kernel)
+    int small_ch;         // output channels per warp there (1 or 4)
     SmallMParams sp;
     int grid;
     size_t smem;
@@ -1609,12 +1623,10 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out, bool force_cta2
                 sp.a_hi[s] = reinterpret_cast<const __nv_bfloat16*>(d->src[s].hi);
                 sp.a_lo[s] = reinterpret_cast<const __nv_bfloat16*>(d->src[s].lo);
                 sp.src_ch[s] = d->src[s].channels;
-                for (int i = 0; i < 4; ++i) sp.src_dims[s][i] = d->src[s].dims[i];
             }
             int c0 = 0;
             for (int e = 0; e < d->ntaps; ++e) {
                 sp.tap_src[e] = d->taps[e].src;
-                for (int i = 0; i < 4; ++i) sp.tap_d[e][i] = d->taps[e].d[i];
                 sp.tap_chunk0[e] = c0;
                 c0 += d->taps[e].nchunks;
             }
@@ -1624,15 +1636,38 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out, bool force_cta2
             sp.w_lo = reinterpret_cast<const __nv_bfloat16*>(d->w_lo);
             sp.ktot = d->ktot;
             sp.wrows = d->wrows;
-            long long mul = 1;
+            long long out_mul[4], out_off = 0, mul = 1;
             for (int i = 0; i < 4; ++i) {
-                sp.out_dims[i] = d->out_dims[i];
-                sp.out_mul[i] = mul;
+                out_mul[i] = mul;
                 mul *= d->out_dims[i];
             }
             if (d->out_pix_mul[0] | d->out_pix_mul[1] | d->out_pix_mul[2] | d->out_pix_mul[3]) {
-                for (int i = 0; i < 4; ++i) sp.out_mul[i] = d->out_pix_mul[i];
-                sp.out_off = d->out_pix_off;
+                for (int i = 0; i < 4; ++i) out_mul[i] = d->out_pix_mul[i];
+                out_off = d->out_pix_off;
+            }
+            // (row, tap) -> element offset into the tap's source, or -1 where the tap falls into the zero padding
+            for (int m = 0; m < (int)rows; ++m) {
+                int c[4], mm = m;
+                for (int i = 0; i < 4; ++i) {
+                    c[i] = mm % d->out_dims[i];
+                    mm /= d->out_dims[i];
+                }
+                const long long orow = out_off + c[0] * out_mul[0] + c[1] * out_mul[1] + c[2] * out_mul[2] + c[3] * out_mul[3];
+                V2A_REQUIRE(orow >= 0 && orow < ((long long)1 << 31), "igemm (small M): output row index out of range");
+                sp.out_row[m] = (int)orow;
+                for (int e = 0; e < d->ntaps; ++e) {
+                    const v2a_igemm_src& sr = d->src[d->taps[e].src];
+                    long long off = -1;
+                    bool in = true;
+                    int sc[4];
+                    for (int i = 0; i < 4; ++i) {
+                        sc[i] = c[i] + d->taps[e].d[i];
+                        in = in && sc[i] >= 0 && sc[i] < sr.dims[i];
+                    }
+                    if (in) off = ((((long long)sc[3] * sr.dims[2] + sc[2]) * sr.dims[1] + sc[1]) * sr.dims[0] + sc[0]) * sr.channels;
+                    V2A_REQUIRE(off < ((long long)1 << 31), "igemm (small M): source offset out of range");
+                    sp.off[m][e] = (int)off;
+                }
             }
             sp.rows = (int)rows;
             sp.cout = d->cout < d->wrows ? d->cout : d->wrows;
@@ -1643,13 +1678,16 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out, bool force_cta2
             sp.bias = d->bias;
             sp.residual = d->residual;
             sp.ld_res = d->ld_res;
-            // 1, 2, 4 or 8 warps share one output channel: slices of ~1024 K elements (4 groups of 256 in flight)
+            // 1, 2, 4 or 8 warps share one channel group: at most ~2 weight groups (of 8 elements) per lane and slice
             int slices = 1;
-            while (slices < kSmallWarps && d->ktot > 1024 * slices) slices *= 2;
+            while (slices < kSmallWarps && d->ktot / 8 > 64 * slices) slices *= 2;
             sp.slices = slices;
             sp.slice_groups = ceil_div(d->ktot / 8, slices);
+            // four channels per warp share every activation read (wide layers); one channel per warp keeps the grid
+            // large on narrow ones
+            pl->small_ch = sp.cout >= 256 ? 4 : 1;
             pl->smallm = true;
-            pl->grid = ceil_div(sp.cout, kSmallWarps / slices);
+            pl->grid = ceil_div(ceil_div(sp.cout, pl->small_ch), kSmallWarps / slices);
             pl->smem = 0;
             pl->zero_out = false;
             p.k_splits = 1;
@@ -2010,14 +2048,18 @@ int v2a_igemm_plan_create(const v2a_igemm_desc* desc, void** plan_out) {
 int v2a_igemm_plan_run(void* plan, void* stream) {
     v2a::IgemmPlan* pl = reinterpret_cast<v2a::IgemmPlan*>(plan);
     if (pl->smallm) {
-        if (pl->sp.rows <= 4)
-            v2a::igemm_smallm_kernel<4><<<pl->grid, v2a::kSmallWarps * 32, 0, (cudaStream_t)stream>>>(pl->sp);
-        else if (pl->sp.rows <= 8)
-            v2a::igemm_smallm_kernel<8><<<pl->grid, v2a::kSmallWarps * 32, 0, (cudaStream_t)stream>>>(pl->sp);
-        else if (pl->sp.rows <= 16)
-            v2a::igemm_smallm_kernel<16><<<pl->grid, v2a::kSmallWarps * 32, 0, (cudaStream_t)stream>>>(pl->sp);
-        else
-            v2a::igemm_smallm_kernel<32><<<pl->grid, v2a::kSmallWarps * 32, 0, (cudaStream_t)stream>>>(pl->sp);
+        const int rc = pl->sp.rows <= 4 ? 4 : (pl->sp.rows <= 8 ? 8 : 16);
+        const dim3 blk(v2a::kSmallWarps * 32);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (pl->small_ch == 4) {
+            if (rc == 4) v2a::igemm_smallm_kernel<4, 4><<<pl->grid, blk, 0, st>>>(pl->sp);
+            else if (rc == 8) v2a::igemm_smallm_kernel<8, 4><<<pl->grid, blk, 0, st>>>(pl->sp);
+            else v2a::igemm_smallm_kernel<16, 4><<<pl->grid, blk, 0, st>>>(pl->sp);
+        } else {
+            if (rc == 4) v2a::igemm_smallm_kernel<4, 1><<<pl->grid, blk, 0, st>>>(pl->sp);
+            else if (rc == 8) v2a::igemm_smallm_kernel<8, 1><<<pl->grid, blk, 0, st>>>(pl->sp);
+            else v2a::igemm_smallm_kernel<16, 1><<<pl->grid, blk, 0, st>>>(pl->sp);
+        }
         V2A_CUDA_OK(cudaGetLastError());
         v2a::g_launches.fetch_add(1);
         return 0;

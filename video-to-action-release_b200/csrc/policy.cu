@@ -134,6 +134,93 @@ __global__ void __launch_bounds__(kPolThreads) gn_act_fwd_kernel(const GnActPara
     }
 }
 
+// Small-batch form of the forward (`predict_action`: B = 1 .. 4 between simulator steps): one CTA per (sample, GROUP)
+// instead of one per sample -- at B = 1 the per-sample kernel is a single block walking 16 k values through two
+// shared-memory atomic reductions (~9 us, 200 launches per predict_action call).  Here a block holds T x C/groups
+// values (<= 2 octets per thread), every parameter load is issued before the statistics, and the two reductions are
+// warp shuffles + one barrier each.
+constexpr int kGrpOct = 2;
+__global__ void __launch_bounds__(kPolThreads) gn_act_fwd_group_kernel(const GnActParams p) {
+    __shared__ float red[2][kPolThreads / 32];
+    const int b = blockIdx.x, g = blockIdx.y;
+    const int cpg = p.C / p.groups;
+    const int octs = cpg >> 3;                    // octets per row inside the group; divides the block size
+    const int n_oct = p.T * octs;
+    const int oc = threadIdx.x % octs;
+    const int c0 = g * cpg + oc * 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    float v[kGrpOct][8], ga[8], be[8], fs[8], fb[8], ad[kGrpOct][8];
+    bool on[kGrpOct];
+#pragma unroll
+    for (int k = 0; k < kGrpOct; ++k) {
+        const int i = threadIdx.x + k * blockDim.x;
+        on[k] = i < n_oct;
+        const int64_t row = (int64_t)b * p.T + i / octs;
+        if (on[k]) {
+            load8(p.y + row * p.C + c0, v[k]);
+            if (p.addend) load8(p.addend + row * p.ld_add + c0, ad[k]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[k][j] = 0.0f;
+        }
+    }
+    load8(p.gamma + c0, ga);
+    load8(p.beta + c0, be);
+    if (p.film) {
+        load8(p.film + (int64_t)b * p.ld_film + c0, fs);
+        load8(p.film + (int64_t)b * p.ld_film + p.C + c0, fb);
+    }
+    auto block_sum = [&](float x, float* sh) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) sh[warp] = x;
+        __syncthreads();
+        float t = 0.0f;
+        for (int w = 0; w < nw; ++w) t += sh[w];
+        return t;
+    };
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kGrpOct; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[k][j];
+    const float cnt = (float)(cpg * p.T);
+    const float mean = block_sum(s, red[0]) / cnt;
+    float q = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kGrpOct; ++k)
+        if (on[k]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = v[k][j] - mean; q += d * d; }
+        }
+    const float rstd = rsqrtf(block_sum(q, red[1]) / cnt + p.eps);
+    if (threadIdx.x == 0) {
+        p.mean_rstd[((int64_t)b * p.groups + g) * 2] = mean;
+        p.mean_rstd[((int64_t)b * p.groups + g) * 2 + 1] = rstd;
+    }
+#pragma unroll
+    for (int k = 0; k < kGrpOct; ++k) {
+        if (!on[k]) continue;
+        const int i = threadIdx.x + k * blockDim.x;
+        const int64_t row = (int64_t)b * p.T + i / octs;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float x = mish_f((v[k][j] - mean) * rstd * ga[j] + be[j]);
+            if (p.film) x = fs[j] * x + fb[j];
+            if (p.addend) x += ad[k][j];
+            o[j] = x;
+        }
+        if (p.out_f32) store8(p.out_f32 + row * p.ld_out + c0, o);
+        if (p.out_hi) {
+            uint4 h, l;
+            split8(o, h, l);
+            *reinterpret_cast<uint4*>(p.out_hi + row * p.ld_hl + c0) = h;
+            *reinterpret_cast<uint4*>(p.out_lo + row * p.ld_hl + c0) = l;
+        }
+    }
+}
+
 // backward of  out = film_s * mish(gamma * (y - mean) * rstd + beta) + film_b  (+ addend)
 __global__ void __launch_bounds__(kPolThreads) gn_act_bwd_kernel(const GnActParams p) {
     __shared__ float sh[64];
@@ -582,6 +669,22 @@ extern "C" {
 int v2a_policy_gn_act_fwd(const v2a_policy_gn_desc* d, void* stream) {
     if (int rc = check_gn(d)) return rc;
     V2A_REQUIRE(d->y && d->gamma && d->beta && d->mean_rstd, "policy_gn_fwd: missing pointers");
+    {
+        // small batches: one CTA per (sample, group)  (V2A_POLICY_GN_GROUPS=0: the per-sample kernel, A/B probe)
+        static const bool allow = [] { const char* e = getenv("V2A_POLICY_GN_GROUPS"); return !(e && atoi(e) == 0); }();
+        const int cpg = d->C / d->groups, octs = cpg / 8;
+        if (allow && d->B <= 16 && cpg % 8 == 0 && octs >= 1 && kPolThreads % octs == 0) {
+            const int n_oct = d->T * octs;
+            int threads = ((n_oct + kGrpOct - 1) / kGrpOct + 31) / 32 * 32;
+            while (threads % octs) threads += 32;                     // every thread keeps ONE channel octet
+            if (threads <= kPolThreads && threads * kGrpOct >= n_oct) {
+                gn_act_fwd_group_kernel<<<dim3((unsigned)d->B, (unsigned)d->groups), threads, 0, (cudaStream_t)stream>>>(
+                    to_params(d));
+                POL_LAUNCH_OK();
+                return 0;
+            }
+        }
+    }
     gn_act_fwd_kernel<<<d->B, kPolThreads, 0, (cudaStream_t)stream>>>(to_params(d));
     POL_LAUNCH_OK();
     return 0;
