@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <utility>
 
 namespace v2a {
 
@@ -120,6 +122,14 @@ __device__ __forceinline__ float4 ld_nc_f4(const float* p) {
                  : "l"(p));
     return v;
 }
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// become resident while its predecessor in the stream is still running.  `pdl_trigger` (predecessor side) lets the
+// successor's CTAs be scheduled once every CTA of this grid has called it or exited; `pdl_wait` (successor side) blocks
+// until the predecessor grid has completed and its memory is visible -- everything before it may only touch data no
+// earlier kernel of the chain writes (static weights).  Both are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -366,3 +376,23 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_16(int m, int n, int a_f
 }
 
 }  // namespace v2a
+
+// host: launch `kernel` with the PDL attribute (V2A_PDL=0 -> ordinary launch, A/B probe)
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_maybe_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                           Args&&... args) {
+    static const bool pdl = [] { const char* e = getenv("V2A_PDL"); return !(e && atoi(e) == 0); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif

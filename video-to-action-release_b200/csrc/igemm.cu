@@ -1379,6 +1379,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32) igemm_smallm_kernel(const __
         wh[j] = reinterpret_cast<const uint4*>(p.w_hi + (size_t)n * p.ktot);
         wl[j] = reinterpret_cast<const uint4*>(p.w_lo + (size_t)n * p.ktot);
     }
+    pdl_trigger();       // the next kernel of the chain may start streaming ITS weights while this one computes
     uint4 h[kCh], l[kCh];
     int g = g_begin + lane;
     if (live && g < g_end) {
@@ -1391,6 +1392,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32) igemm_smallm_kernel(const __
     for (int idx = threadIdx.x; idx < kSmallMaxRows * V2A_MAX_TAPS; idx += blockDim.x)
         (&s_off[0][0])[idx] = (&p.off[0][0])[idx];
     __syncthreads();
+    pdl_wait();          // activations / residual come from the previous kernels; the weights above do not
     float acc[kRows][kCh];
 #pragma unroll
     for (int m = 0; m < kRows; ++m)
@@ -2051,15 +2053,17 @@ int v2a_igemm_plan_run(void* plan, void* stream) {
         const int rc = pl->sp.rows <= 4 ? 4 : (pl->sp.rows <= 8 ? 8 : 16);
         const dim3 blk(v2a::kSmallWarps * 32);
         cudaStream_t st = (cudaStream_t)stream;
+        cudaError_t le;
         if (pl->small_ch == 4) {
-            if (rc == 4) v2a::igemm_smallm_kernel<4, 4><<<pl->grid, blk, 0, st>>>(pl->sp);
-            else if (rc == 8) v2a::igemm_smallm_kernel<8, 4><<<pl->grid, blk, 0, st>>>(pl->sp);
-            else v2a::igemm_smallm_kernel<16, 4><<<pl->grid, blk, 0, st>>>(pl->sp);
+            if (rc == 4) le = launch_maybe_pdl(v2a::igemm_smallm_kernel<4, 4>, dim3(pl->grid), blk, 0, st, pl->sp);
+            else if (rc == 8) le = launch_maybe_pdl(v2a::igemm_smallm_kernel<8, 4>, dim3(pl->grid), blk, 0, st, pl->sp);
+            else le = launch_maybe_pdl(v2a::igemm_smallm_kernel<16, 4>, dim3(pl->grid), blk, 0, st, pl->sp);
         } else {
-            if (rc == 4) v2a::igemm_smallm_kernel<4, 1><<<pl->grid, blk, 0, st>>>(pl->sp);
-            else if (rc == 8) v2a::igemm_smallm_kernel<8, 1><<<pl->grid, blk, 0, st>>>(pl->sp);
-            else v2a::igemm_smallm_kernel<16, 1><<<pl->grid, blk, 0, st>>>(pl->sp);
+            if (rc == 4) le = launch_maybe_pdl(v2a::igemm_smallm_kernel<4, 1>, dim3(pl->grid), blk, 0, st, pl->sp);
+            else if (rc == 8) le = launch_maybe_pdl(v2a::igemm_smallm_kernel<8, 1>, dim3(pl->grid), blk, 0, st, pl->sp);
+            else le = launch_maybe_pdl(v2a::igemm_smallm_kernel<16, 1>, dim3(pl->grid), blk, 0, st, pl->sp);
         }
+        V2A_CUDA_OK(le);
         V2A_CUDA_OK(cudaGetLastError());
         v2a::g_launches.fetch_add(1);
         return 0;

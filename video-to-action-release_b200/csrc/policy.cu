@@ -151,6 +151,10 @@ __global__ void __launch_bounds__(kPolThreads) gn_act_fwd_group_kernel(const GnA
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     float v[kGrpOct][8], ga[8], be[8], fs[8], fb[8], ad[kGrpOct][8];
     bool on[kGrpOct];
+    pdl_trigger();
+    load8(p.gamma + c0, ga);       // parameters: not written by any kernel of the chain
+    load8(p.beta + c0, be);
+    pdl_wait();
 #pragma unroll
     for (int k = 0; k < kGrpOct; ++k) {
         const int i = threadIdx.x + k * blockDim.x;
@@ -164,8 +168,6 @@ __global__ void __launch_bounds__(kPolThreads) gn_act_fwd_group_kernel(const GnA
             for (int j = 0; j < 8; ++j) v[k][j] = 0.0f;
         }
     }
-    load8(p.gamma + c0, ga);
-    load8(p.beta + c0, be);
     if (p.film) {
         load8(p.film + (int64_t)b * p.ld_film + c0, fs);
         load8(p.film + (int64_t)b * p.ld_film + p.C + c0, fb);
@@ -678,8 +680,8 @@ int v2a_policy_gn_act_fwd(const v2a_policy_gn_desc* d, void* stream) {
             int threads = ((n_oct + kGrpOct - 1) / kGrpOct + 31) / 32 * 32;
             while (threads % octs) threads += 32;                     // every thread keeps ONE channel octet
             if (threads <= kPolThreads && threads * kGrpOct >= n_oct) {
-                gn_act_fwd_group_kernel<<<dim3((unsigned)d->B, (unsigned)d->groups), threads, 0, (cudaStream_t)stream>>>(
-                    to_params(d));
+                V2A_CUDA_OK(launch_maybe_pdl(gn_act_fwd_group_kernel, dim3((unsigned)d->B, (unsigned)d->groups),
+                                             dim3((unsigned)threads), 0, (cudaStream_t)stream, to_params(d)));
                 POL_LAUNCH_OK();
                 return 0;
             }

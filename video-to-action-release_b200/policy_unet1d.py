@@ -527,12 +527,29 @@ class _PolicyEngine(PackedParams):
             ga1, be1 = self.vec(lambda: gn1.weight, Co), self.vec(lambda: gn1.bias, Co)
             ga2, be2 = self.vec(lambda: gn2.weight, Co), self.vec(lambda: gn2.bias, Co)
             film_ptr = self.film.data_ptr() + 4 * fo
+            has_res = not isinstance(m.residual_conv, nn.Identity)
+            # Small batches (`predict_action`: every launch is latency, not throughput): the 1x1 residual conv reads
+            # only the block input, so it runs on the side lane beside conv1 -> GN -> conv2 and the second GroupNorm
+            # adds its result (same two fp32 values added once, whichever kernel does it): 4 dependent launches per
+            # block instead of 5.
+            side_res = has_res and rows <= 16
+            if side_res:
+                rc = m.residual_conv
+                r_side = self.zeros(rows, Co)
+                self.fwd.lane = 1
+                self.conv_fwd(lambda: rc.weight, lambda: rc.bias, Co, 1, 0, ins, out_f32=r_side)
+                self.fwd.lane = 0
             self.conv_fwd(lambda: c1.weight, lambda: c1.bias, Co, k, pad, ins, out_f32=y1)
             self.gn(self.fwd, False, B=Bn, T=Tn, C=Co, groups=G, eps=gn1.eps, y=y1, gamma=ga1, beta=be1,
                     film=film_ptr, ld_film=ftot, out_hi=hf.hl.hi, out_lo=hf.hl.lo, ld_hl=Co, mean_rstd=mr1)
             self.conv_fwd(lambda: c2.weight, lambda: c2.bias, Co, k, pad, [hf], out_f32=y2)
-            has_res = not isinstance(m.residual_conv, nn.Identity)
-            if has_res:
+            if side_res:
+                self.fwd.lane = 2
+                self.gn(self.fwd, False, B=Bn, T=Tn, C=Co, groups=G, eps=gn2.eps, y=y2, gamma=ga2, beta=be2,
+                        addend=r_side, ld_add=Co, out_f32=out.f32, ld_out=Co, out_hi=out.hl.hi,
+                        out_lo=out.hl.lo, ld_hl=Co, mean_rstd=mr2)
+                self.fwd.lane = 0
+            elif has_res:
                 h2 = self.zeros(rows, Co)
                 self.gn(self.fwd, False, B=Bn, T=Tn, C=Co, groups=G, eps=gn2.eps, y=y2, gamma=ga2, beta=be2,
                         out_f32=h2, ld_out=Co, mean_rstd=mr2)
@@ -750,6 +767,8 @@ class _PolicyEngine(PackedParams):
                         fn()
                     used_side = True
                 else:
+                    if lane == 2 and used_side:      # a main-lane step that consumes what the side lane produced
+                        main.wait_stream(self._side)
                     fn()
             if used_side:
                 main.wait_stream(self._side)
