@@ -552,6 +552,10 @@ class _PredictPlan:
         self.pred_sample = int(sched.config.prediction_type == "sample")
         self.clip = int(bool(sched.config.clip_sample))
         self.out = torch.zeros(B, policy.horizon, policy.action_dim, dtype=torch.float32, device=device)
+        # the timestep MLP (embedding -> Linear -> Mish -> Linear: 5 launches per forward) sees only t and the weights:
+        # its 8 outputs live in a table refreshed with the packed weights, each forward starts after it
+        self.fwd_tail = self.unet.fwd.tail(self.unet.n_temb_steps)
+        self.temb_table = torch.zeros(len(self.steps), *self.unet.temb_out.shape, dtype=torch.float32, device=device)
         self.graph = None
         self._warm = False
         self._params = [p for eng in (*self.enc, self.unet) for p in eng.params if p.numel()]
@@ -586,9 +590,9 @@ class _PredictPlan:
             cur.wait_stream(s)
         assert off == unet.gc_in.shape[1], "global_cond width disagrees with the encoders' features"
         din, rows = unet.x0.C, self.B * unet.T
-        for (t, c1, c2, c3, c4) in self.steps:
-            unet.t_buf.fill_(t)
-            unet._run("fwd", unet.fwd, force_eager=True)
+        for s, (t, c1, c2, c3, c4) in enumerate(self.steps):
+            unet.temb_out.copy_(self.temb_table[s])
+            unet._run("fwd_tail", self.fwd_tail, force_eager=True)
             _lib.check(_lib.load().v2a_policy_ddim_step(unet.x_in_base.data_ptr(), unet.x_in_base.stride(0),
                                                         unet.out16.data_ptr(), unet.out16.stride(0), rows, din,
                                                         c1, c2, c3, c4, self.pred_sample, self.clip, ops._stream()),
@@ -608,6 +612,12 @@ class _PredictPlan:
                 eng._wkey = None
                 eng.refresh_weights()
             self._key = key
+            unet = self.unet
+            for s, step in enumerate(self.steps):          # timestep-MLP table (eager; only when the weights moved)
+                unet.t_buf.fill_(step[0])
+                for fn in list(unet.fwd)[:unet.n_temb_steps]:
+                    fn()
+                self.temb_table[s].copy_(unet.temb_out)
         for k in self.keys:
             self.obs[k].copy_(obs_dict[k][:, :policy.n_obs_steps])
         # RNG order of the reference: the encoders draw nothing in eval mode, then ONE randn for the trajectory

@@ -258,6 +258,13 @@ class _Steps(list):
     def append(self, fn: Callable) -> None:
         self.add(getattr(fn, "__name__", "step"), fn)
 
+    def tail(self, start: int) -> "_Steps":
+        """The same launches from index ``start`` on (tags and lanes kept)."""
+        out = _Steps()
+        for fn, tag, lane in list(zip(self, self.tags, self.lanes))[start:]:
+            out.add(tag, fn, lane)
+        return out
+
 
 class _PolicyEngine(PackedParams):
     def __init__(self, model: ConditionalUnet1D, B, T, device):
@@ -495,6 +502,10 @@ class _PolicyEngine(PackedParams):
         self.gf = self.zeros(Bn, cd)
         self.conv_fwd(lambda: lin3.weight.unsqueeze(-1), lambda: lin3.bias, dsed, 1, 0, [n_m1],
                       out_f32=self.gf[:, :dsed])
+        # everything up to here depends on the timestep and the weights only (not on the observation): the single-graph
+        # predict_action keeps gf[:, :dsed] of its 8 DDIM timesteps in a table and starts each forward after this point
+        self.n_temb_steps = len(self.fwd)
+        self.temb_out = self.gf[:, :dsed]
         self.gc_in = self.gf[:, dsed:]
         mgf_hl = self.hlz(Bn, cd)
         p2 = ops.Prep(x0=self.gf, act=ops.ACT_MISH, out_hl=mgf_hl)
