@@ -1418,35 +1418,60 @@ __global__ void __launch_bounds__(kSmallWarps * 32) igemm_smallm_kernel(const __
             if (c >= p.src_ch[src]) continue;                // zero padding of the last chunk of a tap
             const __nv_bfloat16* ah = p.a_hi[src] + c;
             const __nv_bfloat16* al = p.a_lo[src] + c;
+            // rows in chunks of four, branch-free: the eight activation loads of a chunk are issued back to back (a
+            // `continue` per padded row kept them from being hoisted and made every row a dependent L1 round trip)
 #pragma unroll
-            for (int m = 0; m < kRows; ++m) {
-                if (m >= p.rows) break;
-                const int off = s_off[m][e];
-                if (off < 0) continue;
-                const uint4 xh = __ldg(reinterpret_cast<const uint4*>(ah + off));
-                const uint4 xl = __ldg(reinterpret_cast<const uint4*>(al + off));
-                float x[8];
-                bf16x8_to_f32(xh, xl, x);
+            for (int m0 = 0; m0 < kRows; m0 += 4) {
+                uint4 xh[4], xl[4];
 #pragma unroll
-                for (int j = 0; j < kCh; ++j) {
-                    float a = acc[m][j];
+                for (int r = 0; r < 4; ++r) {
+                    const int off = m0 + r < p.rows ? s_off[m0 + r][e] : -1;
+                    const int o = off < 0 ? 0 : off;
+                    xh[r] = __ldg(reinterpret_cast<const uint4*>(ah + o));
+                    xl[r] = __ldg(reinterpret_cast<const uint4*>(al + o));
+                    if (off < 0) xh[r] = xl[r] = make_uint4(0u, 0u, 0u, 0u);      // a select, not a branch
+                }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) a = fmaf(x[i], w[j][i], a);
-                    acc[m][j] = a;
+                for (int r = 0; r < 4; ++r) {
+                    float x[8];
+                    bf16x8_to_f32(xh[r], xl[r], x);
+#pragma unroll
+                    for (int j = 0; j < kCh; ++j) {
+                        float a = acc[m0 + r][j];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) a = fmaf(x[i], w[j][i], a);
+                        acc[m0 + r][j] = a;
+                    }
                 }
             }
         }
     }
-    // ---- reduce over the lanes, then over the K slices of the channel group ----
+    // ---- reduce over the lanes (recursive halving: lanes trade halves of their value list, 2N instead of 5N
+    // shuffles), then over the K slices of the channel group ----
+    {
+        constexpr int N = kRows * kCh;
+        float* v = &acc[0][0];
+        int n = N, o = 16, k = 0;
 #pragma unroll
-    for (int m = 0; m < kRows; ++m) {
-        if (m >= p.rows) break;
+        for (; o >= 1 && n > 1; o >>= 1, ++k) {
+            n >>= 1;
+            const bool hi = (lane & o) != 0;
 #pragma unroll
-        for (int j = 0; j < kCh; ++j) {
-            float v = acc[m][j];
+            for (int i = 0; i < N / 2; ++i) {
+                if (i < n) {
+                    const float send = hi ? v[i] : v[i + n];
+                    const float recv = __shfl_xor_sync(0xffffffffu, send, o);
+                    v[i] = (hi ? v[i + n] : v[i]) + recv;
+                }
+            }
+        }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) s_part[warp][m][j] = v;
+        for (; o >= 1; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+        // lane L now holds the finished sums of value indices (L >> (5 - k)) * n .. + n - 1   (n = N >> k)
+        if ((lane & ((32 >> k) - 1)) == 0) {
+            const int base = (lane >> (5 - k)) * n;
+#pragma unroll
+            for (int i = 0; i < (N >= 32 ? N / 32 : 1); ++i) (&s_part[warp][0][0])[base + i] = v[i];
         }
     }
     __syncthreads();
