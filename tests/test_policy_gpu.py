@@ -346,7 +346,8 @@ def test_policy_engines_follow_dot_data_updates_and_copy_ema_to():
         with torch.no_grad():
             return p.predict_action(obs, use_ddim=True)["action_pred"].clone()
 
-    a0 = act(pol)
+    for _ in range(4):      # from the third call on the captured graph replays SPECULATIVELY beside the content check:
+        a0 = act(pol)       # the `.data` update below must be caught by that path (re-pack + second replay)
     versions = [p._version for p in pol.parameters()]
     g = torch.Generator().manual_seed(1)
     with torch.no_grad():

@@ -560,6 +560,11 @@ class _PredictPlan:
         self._warm = False
         self._params = [p for eng in (*self.enc, self.unet) for p in eng.params if p.numel()]
         self._key = None
+        self._fp = None
+        self._fp_stream = torch.cuda.Stream(device=device)
+        self._fp_event = torch.cuda.Event()
+        self._entry_event = torch.cuda.Event()
+        self._fp_host = torch.zeros(1, dtype=torch.int64).pin_memory()
 
     def _body(self):
         policy = self.policy()
@@ -600,24 +605,38 @@ class _PredictPlan:
         unet.fwd_token += 1
         self.out.copy_(unet.x_in.reshape(self.B, unet.T, din))
 
+    def _refresh(self, fp):
+        unet = self.unet
+        for eng in (*self.enc, unet):
+            eng._wkey = None
+            eng.refresh_weights()
+        for s, step in enumerate(self.steps):          # timestep-MLP table (eager; only when the weights moved)
+            unet.t_buf.fill_(step[0])
+            for fn in list(unet.fwd)[:unet.n_temb_steps]:
+                fn()
+            self.temb_table[s].copy_(unet.temb_out)
+        self._fp = fp
+
+    def _host_key(self):
+        ptrs = tuple(p.data_ptr() for p in self._params)
+        return ptrs, (ptrs, tuple(p._version for p in self._params))
+
     def run(self, obs_dict):
         policy = self.policy()
-        # ONE content check for the three engines: (data_ptr, _version) of every parameter + one fingerprint launch
-        # over all of them (a `.data` write bumps no version, packing.content_key); the engines re-pack only when
-        # that key moves or one of them was invalidated explicitly (fused optimiser step)
-        ptrs = tuple(p.data_ptr() for p in self._params)
-        key = (ptrs, tuple(p._version for p in self._params), ops.params_fingerprint(self._params, key=ptrs))
-        if key != self._key or any(eng._wkey is None for eng in (*self.enc, self.unet)):
-            for eng in (*self.enc, self.unet):
-                eng._wkey = None
-                eng.refresh_weights()
-            self._key = key
-            unet = self.unet
-            for s, step in enumerate(self.steps):          # timestep-MLP table (eager; only when the weights moved)
-                unet.t_buf.fill_(step[0])
-                for fn in list(unet.fwd)[:unet.n_temb_steps]:
-                    fn()
-                self.temb_table[s].copy_(unet.temb_out)
+        # ONE content check for the three engines: (data_ptr, _version) of every parameter on the host + one
+        # fingerprint launch over all of them (a `.data` write bumps no version, packing.content_key); the engines
+        # re-pack only when that key moves or one of them was invalidated explicitly (fused optimiser step).
+        cur = torch.cuda.current_stream()
+        speculate = self.graph is not None and self._fp is not None and \
+            not any(eng._wkey is None for eng in (*self.enc, self.unet))
+        if speculate:
+            self._entry_event.record(cur)             # parameter writes enqueued before this call end here
+        else:                                         # first calls / explicit invalidation: check first, synchronously
+            ptrs, hostkey = self._host_key()
+            fp = ops.params_fingerprint(self._params, key=ptrs)
+            if hostkey != self._key or fp != self._fp or any(eng._wkey is None for eng in (*self.enc, self.unet)):
+                self._refresh(fp)
+            self._key = hostkey
         for k in self.keys:
             self.obs[k].copy_(obs_dict[k][:, :policy.n_obs_steps])
         # RNG order of the reference: the encoders draw nothing in eval mode, then ONE randn for the trajectory
@@ -630,7 +649,6 @@ class _PredictPlan:
             if self.graph is None:
                 saved = self.unet.x_in_base.clone()
                 g = torch.cuda.CUDAGraph()
-                cur = torch.cuda.current_stream()
                 side = torch.cuda.Stream()
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
@@ -640,6 +658,26 @@ class _PredictPlan:
                 self.unet.x_in_base.copy_(saved)      # capture does not execute, but keep the inputs explicit
                 self.graph = g
             self.graph.replay()
+            if speculate:
+                # Steady state: the whole content check -- the host walk over the parameters, the fingerprint kernel
+                # (0.08 ms) and its read-back -- is off the critical path: issued AFTER the graph, the kernel on a side
+                # stream that only waits for the work queued before this call, so it overlaps the replay, which ran
+                # on the weights packed last time.  Only if the key differs (a `.data` update or an in-place write
+                # since the last call) are the weights re-packed and the graph replayed again; the result is
+                # returned after the check, so a stale answer is never handed out.
+                ptrs, hostkey = self._host_key()
+                self._fp_stream.wait_event(self._entry_event)
+                with torch.cuda.stream(self._fp_stream):
+                    dev_fp = ops.params_fingerprint(self._params, key=ptrs, launch_only=True)
+                    self._fp_host.copy_(dev_fp, non_blocking=True)
+                    self._fp_event.record(self._fp_stream)
+                self._fp_event.synchronize()
+                fp = int(self._fp_host.item())
+                if fp != self._fp or hostkey != self._key:
+                    self._refresh(fp)
+                    self._key = hostkey
+                    self.unet.x_in.copy_(noise.reshape(self.B * self.unet.T, -1))
+                    self.graph.replay()
         return self.out.clone()
 
 

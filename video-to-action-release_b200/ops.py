@@ -592,14 +592,15 @@ _FP_TABLES: dict = {}
 _FP_CHUNK = 1 << 16
 
 
-def params_fingerprint(params: Sequence[torch.Tensor], key=None) -> int:
+def params_fingerprint(params: Sequence[torch.Tensor], key=None, launch_only: bool = False):
     """64-bit fingerprint of the VALUES of ``params`` (CUDA fp32 tensors): one kernel launch over a cached
     device table of (pointer, length, global offset) chunks, then an 8-byte read-back (this synchronises).
     ``key``: any hashable that changes whenever a parameter's storage does (callers that already hold the
-    (data_ptr, _version) tuple pass it to save a second walk over the parameters)."""
+    (data_ptr, _version) tuple pass it to save a second walk over the parameters).  ``launch_only``: enqueue the
+    kernel on the current stream and return the int64[1] device tensor it writes (the caller reads it back later)."""
     ps = [p.detach() for p in params if p.numel()]
     if not ps:
-        return 0
+        return torch.zeros(1, dtype=torch.int64) if launch_only else 0
     _require_cuda(*ps)
     dev = ps[0].device
     key = (str(dev), key) if key is not None else (str(dev),) + tuple((p.data_ptr(), p.numel()) for p in ps)
@@ -619,7 +620,7 @@ def params_fingerprint(params: Sequence[torch.Tensor], key=None) -> int:
         ent = _FP_TABLES[key] = (table, torch.zeros(1, dtype=torch.int64, device=dev), len(rows))
     table, out, n = ent
     _lib.check(_lib.load().v2a_params_fingerprint(table.data_ptr(), n, out.data_ptr(), _stream()), "params_fingerprint")
-    return int(out.item())
+    return out if launch_only else int(out.item())
 
 
 def launch_count() -> int:
