@@ -379,10 +379,16 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_16(int m, int n, int a_f
 
 // host: launch `kernel` with the PDL attribute (V2A_PDL=0 -> ordinary launch, A/B probe)
 #ifdef __CUDACC__
+namespace v2a {
+static inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("V2A_PDL"); return !(e && atoi(e) == 0); }();
+    return on;
+}
+}  // namespace v2a
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_maybe_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                            Args&&... args) {
-    static const bool pdl = [] { const char* e = getenv("V2A_PDL"); return !(e && atoi(e) == 0); }();
+    const bool pdl = v2a::pdl_enabled();
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;

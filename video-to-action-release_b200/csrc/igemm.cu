@@ -204,6 +204,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
     float* warp_add = reinterpret_cast<float*>(bars) + 64;  // 8 epilogue warps x 256 floats, after the 256 B barrier block
     float* stage_slab = warp_add + 8 * 256;   // 8 epilogue warps x [32 rows][kSlabStride] coalescing slabs
 
+    pdl_trigger();
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -230,6 +231,9 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
     __syncthreads();
     if (p.cluster > 1) cluster_sync_all();   // the peer's barriers exist before anything is multicast at them
     tc_fence_after();
+    // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlaps the previous
+    // kernel's tail; nothing below may run before that kernel's results are visible
+    pdl_wait();
     const uint32_t tmem_base = *tmem_slot;
     const int nacc_mask = (1 << p.nacc_log2) - 1;
     const uint32_t acc_stride = kTmemCols >> p.nacc_log2;
@@ -865,6 +869,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
     float* warp_add = reinterpret_cast<float*>(bars) + 64;
     float* stage_slab = warp_add + 8 * 256;
 
+    pdl_trigger();
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -889,6 +894,7 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_dual_kernel(const __grid_co
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
+    pdl_wait();                                        // see igemm_kernel
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t acc_stride = kTmemCols >> 1;       // two accumulators of 256 columns
     const uint32_t crank = cluster_ctarank();
@@ -2045,13 +2051,15 @@ int v2a_igemm_dual_plan_run(void* plan, void* stream) {
     cfg.blockDim = dim3(v2a::kThreads);
     cfg.dynamicSmemBytes = pl->smem;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = v2a::pdl_enabled() ? 2 : 1;
     V2A_CUDA_OK(cudaLaunchKernelEx(&cfg, v2a::igemm_dual_kernel, pl->dp));
     V2A_CUDA_OK(cudaGetLastError());
     v2a::g_launches.fetch_add(1);
@@ -2102,16 +2110,19 @@ int v2a_igemm_plan_run(void* plan, void* stream) {
         cfg.blockDim = dim3(v2a::kThreads);
         cfg.dynamicSmemBytes = pl->smem;
         cfg.stream = (cudaStream_t)stream;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = 2;
-        attr.val.clusterDim.y = 1;
-        attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr;
-        cfg.numAttrs = 1;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = v2a::pdl_enabled() ? 2 : 1;
         V2A_CUDA_OK(cudaLaunchKernelEx(&cfg, v2a::igemm_fn(pl->p.cta2 != 0, pl->epi), pl->p));
     } else {
-        v2a::igemm_fn(false, pl->epi)<<<pl->grid, v2a::kThreads, pl->smem, (cudaStream_t)stream>>>(pl->p);
+        V2A_CUDA_OK(launch_maybe_pdl(v2a::igemm_fn(false, pl->epi), dim3(pl->grid), dim3(v2a::kThreads), pl->smem,
+                                     (cudaStream_t)stream, pl->p));
     }
     V2A_CUDA_OK(cudaGetLastError());
     v2a::g_launches.fetch_add(1);

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     const uint32_t a_plane = 2 * kWgUnitBytes;                 // both units of one plane
     const uint32_t b_plane = (uint32_t)p.nb * kWgUnitBytes;
 
+    pdl_trigger();
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();          // set-up above overlaps the previous kernel's tail (programmatic dependent launch)
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
@@ -364,7 +366,8 @@ int v2a_wgrad_plan_create(const v2a_wgrad_desc* desc, void** plan_out) {
 
 int v2a_wgrad_plan_run(void* plan, void* stream) {
     v2a::WgradPlan* pl = reinterpret_cast<v2a::WgradPlan*>(plan);
-    v2a::wgrad_kernel<<<pl->grid, v2a::kWgThreads, pl->smem, (cudaStream_t)stream>>>(pl->p);
+    V2A_CUDA_OK(launch_maybe_pdl(v2a::wgrad_kernel, dim3(pl->grid), dim3(v2a::kWgThreads), pl->smem, (cudaStream_t)stream,
+                                 pl->p));
     V2A_CUDA_OK(cudaGetLastError());
     v2a::g_launches.fetch_add(1);
     return 0;
