@@ -539,11 +539,11 @@ class _PolicyEngine(PackedParams):
             ga2, be2 = self.vec(lambda: gn2.weight, Co), self.vec(lambda: gn2.bias, Co)
             film_ptr = self.film.data_ptr() + 4 * fo
             has_res = not isinstance(m.residual_conv, nn.Identity)
-            # Small batches (`predict_action`: every launch is latency, not throughput): the 1x1 residual conv reads
-            # only the block input, so it runs on the side lane beside conv1 -> GN -> conv2 and the second GroupNorm
-            # adds its result (same two fp32 values added once, whichever kernel does it): 4 dependent launches per
-            # block instead of 5.
-            side_res = has_res and rows <= 16
+            # The 1x1 residual conv reads only the block input, so it runs on the side lane beside conv1 -> GN -> conv2
+            # and the second GroupNorm adds its result (same two fp32 values added once, whichever kernel does it): 4
+            # dependent launches per block instead of 5.  `predict_action` (every launch is latency): 4.6 -> 4.2 ms per
+            # call; training batch: forward 1.244 -> 1.155 ms (gpurun_out/r2c28_*).  V2A_SIDE_RES=0: the serial form.
+            side_res = has_res and os.environ.get("V2A_SIDE_RES", "1") != "0"
             if side_res:
                 rc = m.residual_conv
                 r_side = self.zeros(rows, Co)
