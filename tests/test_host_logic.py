@@ -276,3 +276,20 @@ def test_dual_conv3d_eligibility_and_contiguous_tilings():
                                   j1 << tl[1]:(j1 + 1) << tl[1], j0 << tl[0]:(j0 + 1) << tl[0]].reshape(-1)
                         assert box.tolist() == list(range(128 * m, 128 * m + 128)), (dims, tl, m)
                         m += 1
+
+
+def test_block_n_small_grid_rule():
+    """ops.choose_block_n with the launch's row count: unchanged where the widest tile already fills the machine
+    (every B = 16 layer), narrower N tiles (>= 64, multiples of 32, no extra padding beyond one 32-column step) on the
+    deep levels at small batch."""
+    from v2a_b200 import ops
+    for cout in (128, 256, 384, 512, 640):
+        assert ops.choose_block_n(cout, 114688) == ops.choose_block_n(cout)        # full resolution, any batch
+        assert ops.choose_block_n(cout, 16 * 7 * 64) == ops.choose_block_n(cout) or cout == 128   # B = 16 at 8 x 8
+    assert ops.choose_block_n(512, 1792) == 64 and ops.choose_block_n(640, 448) == 64     # B = 1 at 16 x 16 / 8 x 8
+    assert ops.choose_block_n(512, 3584) == 128                                          # B = 2: 28 x 4 = 112 tiles
+    assert ops.choose_block_n(1536, 1792) == 192                                         # qkv: 14 x 8 tiles, no padding
+    for cout in (128, 256, 384, 512, 640, 1536, 1920):
+        for rows in (448, 1792, 3584, 7168):
+            bn = ops.choose_block_n(cout, rows)
+            assert bn % 32 == 0 and 64 <= bn <= 256

@@ -97,15 +97,35 @@ def choose_tile(out_dims: Sequence[int], total_log2: int = 7) -> tuple[int, int,
     return best[1]
 
 
-def choose_block_n(cout: int) -> int:
-    """N tile (multiple of 16, <= 256): least padding, then the widest."""
+def choose_block_n(cout: int, rows: Optional[int] = None, sms: int = 148) -> int:
+    """N tile (multiple of 16, <= 256): least padding, then the widest.
+
+    ``rows`` (the launch's output rows) switches on the small-grid rule: when the widest tile leaves fewer than
+    ~0.7 x ``sms`` (M tile, N tile) pairs -- the deep levels of the video UNet at batch 1-8: 1792 or 448 rows against
+    512-640 channels and K ~ 10 k, which ran as 16-28 CTAs walking 160 k-steps each -- the N tile narrows (multiples of
+    32, >= 64, so CTA pairs stay possible) until the grid fills the machine or the floor is reached.  Outputs that
+    are bf16 planes or carry GroupNorm sums cannot use split-K (the epilogue needs the finished sum), so the N
+    dimension is the parallelism there is."""
     best = None
     for n in range(16, 257, 16):
         tiles = -(-cout // n)
         key = (tiles * n - cout, -n)
         if best is None or key < best[0]:
             best = (key, n)
-    return best[1]
+    bn = best[1]
+    if rows is not None:
+        m_tiles = -(-rows // 128)
+        want = int(0.7 * sms)
+        if m_tiles * -(-cout // bn) < want:
+            # floor 64: below it every CTA re-reads the activation tile for too few columns (N = 32: 20 x the A
+            # traffic at 640 channels)
+            cands = [n for n in range(64, bn + 1, 32) if (-(-cout // n)) * n - cout <= best[0][0] + 31]
+            filled = [n for n in cands if m_tiles * -(-cout // n) >= want]
+            if filled:
+                bn = max(filled)
+            elif cands:
+                bn = min(cands)
+    return bn
 
 
 def nchunks(c: int) -> int:
@@ -127,7 +147,8 @@ def pack_weight_taps(per_tap: Sequence[torch.Tensor]) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 def _igemm_desc(*, srcs, taps, w: HL, out_dims, cout, ldc=None, out_f32=None, out_hl=None,
                 bias=None, rowvec=None, rowvec_mul=(0, 0, 0, 0), residual=None, stats=None,
-                stats_mul=(0, 0, 0, 0), block_n=None, passes=3, tile_log2=None, out_pix=None, algo_flops_scale=1.0):
+                stats_mul=(0, 0, 0, 0), block_n=None, passes=3, tile_log2=None, out_pix=None, algo_flops_scale=1.0,
+                fill_sms=False):
     """Fill a `v2a_igemm_desc` from torch tensors.  Returns (desc, keep-alive list, meta dict).
 
     out_pix = ((m0, m1, m2, m3), off): the output row of grid point c is off + sum c[d] * m[d] instead of
@@ -172,7 +193,7 @@ def _igemm_desc(*, srcs, taps, w: HL, out_dims, cout, ldc=None, out_f32=None, ou
         d.tile_log2[k] = tile_log2[k]
         d.rowvec_mul[k] = rowvec_mul[k]
         d.stats_mul[k] = stats_mul[k]
-    d.block_n = block_n or choose_block_n(cout)
+    d.block_n = block_n or choose_block_n(cout, (out_dims[0] * out_dims[1] * out_dims[2] * out_dims[3]) if fill_sms else None)
     d.passes = passes
     d.cout = cout
     rows = out_dims[0] * out_dims[1] * out_dims[2] * out_dims[3]

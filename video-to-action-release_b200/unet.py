@@ -444,7 +444,7 @@ class _UNetEngine:
                 slot[0] = ops.Prep(**args)
             else:
                 args = {k: res(v) for k, v in kw.items()}
-                g = ops.Igemm(passes=self.passes, **args)
+                g = ops.Igemm(passes=self.passes, fill_sms="block_n" not in args, **args)
                 slot[0] = g
                 self.igemms.append(g)
         self._pending = []
