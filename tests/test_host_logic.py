@@ -285,7 +285,8 @@ def test_block_n_small_grid_rule():
     from v2a_b200 import ops
     for cout in (128, 256, 384, 512, 640):
         assert ops.choose_block_n(cout, 114688) == ops.choose_block_n(cout)        # full resolution, any batch
-        assert ops.choose_block_n(cout, 16 * 7 * 64) == ops.choose_block_n(cout) or cout == 128   # B = 16 at 8 x 8
+    for cout in (512, 640):                                                              # the channel counts of that level
+        assert ops.choose_block_n(cout, 16 * 7 * 64) == ops.choose_block_n(cout)         # B = 16 at 8 x 8
     assert ops.choose_block_n(512, 1792) == 64 and ops.choose_block_n(640, 448) == 64     # B = 1 at 16 x 16 / 8 x 8
     assert ops.choose_block_n(512, 3584) == 128                                          # B = 2: 28 x 4 = 112 tiles
     assert ops.choose_block_n(1536, 1792) == 192                                         # qkv: 14 x 8 tiles, no padding
