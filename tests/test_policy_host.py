@@ -82,3 +82,22 @@ def test_train_step_checkpoint_formats_roundtrip_with_stock_adamw():
     TS.import_ema_state(net, segs, ema_sd)
     assert all(torch.equal(a.ema, b) for a, b in zip(segs, kept))
     assert TS.export_optimizer_state(net, segs, 0, lr=1e-4, betas=(0.95, 0.999), eps=1e-8, weight_decay=0)["state"] == {}
+
+
+def test_launch_list_tail_keeps_tags_and_lanes():
+    """`_Steps.tail(k)` (the single-graph predict_action starts each forward after the timestep MLP): same callables,
+    tags and lanes from index k on; lane 1 = side stream, lane 2 = main-lane step that joins the side stream first."""
+    from v2a_b200.policy_unet1d import _Steps
+    s = _Steps()
+    calls = []
+    for i, lane in enumerate([0, 0, 1, 0, 2, 1]):
+        s.add(f"step{i}", (lambda i=i: calls.append(i)), lane=lane)
+    t = s.tail(2)
+    assert len(t) == 4 and t.tags == ["step2", "step3", "step4", "step5"] and t.lanes == [1, 0, 2, 1]
+    for fn in t:
+        fn()
+    assert calls == [2, 3, 4, 5]
+    assert len(s) == 6 and s.lanes == [0, 0, 1, 0, 2, 1]          # the source list is untouched
+    s.lane = 1
+    s.add("default-lane", lambda: None)
+    assert s.lanes[-1] == 1
