@@ -45,6 +45,16 @@ def test_wgrad_3x3_matches_torch(N, H, W, Ci, Co):
     ops.wgrad_scatter(scratch, Co, Ci, 9, dw)
     want = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2), (Co, Ci, 3, 3), dy.permute(0, 3, 1, 2), padding=1)
     assert rel_l2(dw, want) < 1e-5, (g.k_splits, rel_l2(dw, want))
+    # one bf16 product (V2A_WGRAD_PASSES probe): stages then hold no lo planes -- the first version still placed the
+    # dy operand behind two x planes and ran off the stage; result = the bf16-rounded operands' exact product
+    scratch1 = torch.zeros_like(scratch)
+    ops.Wgrad(srcs=[(_planes(x), Ci, (W, H, N, 1))], units=units, dy=_planes(dy), dy_channels=Co,
+              dy_dims=(W, H, N, 1), cout=Co, out=scratch1, passes=1).run()
+    dw1 = torch.zeros(Co, Ci, 3, 3, device="cuda")
+    ops.wgrad_scatter(scratch1, Co, Ci, 9, dw1)
+    want1 = torch.nn.grad.conv2d_weight(x.bfloat16().float().permute(0, 3, 1, 2), (Co, Ci, 3, 3),
+                                        dy.bfloat16().float().permute(0, 3, 1, 2), padding=1)
+    assert rel_l2(dw1, want1) < 1e-5 and rel_l2(dw1, want) < 2e-2
 
 
 def test_wgrad_stride2_phase_split_and_pointwise():

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
                 if (p.passes == 3)
                     tma_load_5d(st + a_plane + u * kWgUnitBytes, &p.a_lo[src], &full_bar[stage], c0, c1, c2, c3, c4);
             }
-            uint8_t* sb = st + 2 * a_plane;
+            uint8_t* sb = st + (p.passes == 3 ? 2 : 1) * a_plane;   // one-pass stages hold no lo planes
             for (int j = 0; j < p.nb; ++j) {
                 tma_load_5d(sb + j * kWgUnitBytes, &p.b_hi, &full_bar[stage], n0 + 64 * j, o[0], o[1], o[2], o[3]);
                 if (p.passes == 3)
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
             mbar_wait(&full_bar[stage], phase, 600 + stage);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-            const uint32_t sb = sa + 2 * a_plane;
+            const uint32_t sb = sa + (p.passes == 3 ? 2 : 1) * a_plane;
             const uint64_t a_hi = umma_desc_mn_sw128(sa, kWgUnitBytes);
             const uint64_t a_lo = umma_desc_mn_sw128(sa + a_plane, kWgUnitBytes);
             const uint64_t b_hi = umma_desc_mn_sw128(sb, kWgUnitBytes);

@@ -20,6 +20,7 @@ Parameter gradients land in one flat slab in ``parameters()`` order (``engine.gs
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import weakref
 from typing import Dict, List, Optional
@@ -248,7 +249,7 @@ class _EncoderEngine(PackedParams):
 
         def make():
             g = ops.Wgrad(srcs=srcs, units=units, dy=dy, dy_channels=dy_channels, dy_dims=dy_dims, cout=cout,
-                          out=sc[0], passes=self.passes)
+                          out=sc[0], passes=ops.wgrad_passes(self.passes, int(math.prod(dy_dims))))
             slot[0] = g
             self.wgrads.append(g)
         self._deferred.append(make)

@@ -345,6 +345,21 @@ class IgemmDual:
             pass
 
 
+def wgrad_passes(default_passes: int, reduction_len: int) -> int:
+    """MMA passes of a weight-gradient GEMM whose reduction runs over ``reduction_len`` pixels / rows.
+
+    V2A_WGRAD_PASSES: unset or "3" -> ``default_passes`` (the engine's class); "1" -> one bf16 product everywhere;
+    "auto" -> one bf16 product where the reduction is at least V2A_WGRAD_MINK terms long (default 4096), the engine's
+    class below that.  (Probe for DESIGN.md: the rounding errors of a long random-sign reduction average out.)"""
+    import os
+    mode = os.environ.get("V2A_WGRAD_PASSES", "3")
+    if mode == "1":
+        return 1
+    if mode == "auto" and reduction_len >= int(os.environ.get("V2A_WGRAD_MINK", "4096")):
+        return 1
+    return default_passes
+
+
 class Wgrad:
     """One planned weight-gradient GEMM (MN-major tcgen05, operands straight from channels-last planes):
     out[(unit, ci), co] += sum_pixels x[pixel + d(unit), 64 * chunk(unit) + ci] * dy[pixel, co]."""

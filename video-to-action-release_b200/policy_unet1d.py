@@ -423,7 +423,7 @@ class _PolicyEngine(PackedParams):
                 # transposed im2col copy (44 launches, 1.8 ms of the 3.5 ms backward before) and no dy^T operand
                 sc = self._wg_scratch(64 * len(units), ld_dy)
                 wg = ops.Wgrad(srcs=[(n.hl, n.ld, (T, Bn, 1, 1))], units=units, dy=dy, dy_channels=ld_dy,
-                               dy_dims=(T, Bn, 1, 1), cout=ld_dy, out=sc, passes=self.passes)
+                               dy_dims=(T, Bn, 1, 1), cout=ld_dy, out=sc, passes=ops.wgrad_passes(self.passes, T * Bn))
                 self.wgrads.append(wg)
                 steps.add(f"wgrad M{64 * len(units)} N{ld_dy}", wg.run)
                 win = wgrad_target[:, off * k:(off + n.C) * k]
