@@ -114,12 +114,14 @@ def choose_block_n(cout: int, rows: Optional[int] = None, sms: int = 148) -> int
             best = (key, n)
     bn = best[1]
     if rows is not None:
+        import os
         m_tiles = -(-rows // 128)
-        want = int(0.7 * sms)
+        want = int(float(os.environ.get("V2A_BN_FILL", "0.7")) * sms)       # env: tuning probes
+        floor = int(os.environ.get("V2A_BN_FLOOR", "64"))
         if m_tiles * -(-cout // bn) < want:
             # floor 64: below it every CTA re-reads the activation tile for too few columns (N = 32: 20 x the A
             # traffic at 640 channels)
-            cands = [n for n in range(64, bn + 1, 32) if (-(-cout // n)) * n - cout <= best[0][0] + 31]
+            cands = [n for n in range(floor, bn + 1, 32) if (-(-cout // n)) * n - cout <= best[0][0] + 31]
             filled = [n for n in cands if m_tiles * -(-cout // n) >= want]
             if filled:
                 bn = max(filled)
