@@ -294,3 +294,17 @@ def test_block_n_small_grid_rule():
         for rows in (448, 1792, 3584, 7168):
             bn = ops.choose_block_n(cout, rows)
             assert 64 <= bn <= 256 and (bn % 32 == 0 or bn == ops.choose_block_n(cout))   # narrowed tiles keep CTA pairs
+
+
+def test_wgrad_passes_switch(monkeypatch):
+    """ops.wgrad_passes: the engine's class by default; V2A_WGRAD_PASSES=1 / auto (+ V2A_WGRAD_MINK) are probes."""
+    from v2a_b200 import ops
+    monkeypatch.delenv("V2A_WGRAD_PASSES", raising=False)
+    monkeypatch.delenv("V2A_WGRAD_MINK", raising=False)
+    assert ops.wgrad_passes(3, 10) == 3 and ops.wgrad_passes(3, 1 << 20) == 3 and ops.wgrad_passes(1, 5) == 1
+    monkeypatch.setenv("V2A_WGRAD_PASSES", "1")
+    assert ops.wgrad_passes(3, 10) == 1
+    monkeypatch.setenv("V2A_WGRAD_PASSES", "auto")
+    assert ops.wgrad_passes(3, 4095) == 3 and ops.wgrad_passes(3, 4096) == 1
+    monkeypatch.setenv("V2A_WGRAD_MINK", "1024")
+    assert ops.wgrad_passes(3, 1024) == 1 and ops.wgrad_passes(3, 1023) == 3
