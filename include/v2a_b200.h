@@ -90,6 +90,11 @@ typedef struct v2a_igemm_desc {
                                sub-pixel phases of `Upsample` (F.interpolate(nearest, x2) -> 3x3 conv,
                                guided_diffusion/unet.py:107-114) are 2x2-tap convs over the LOW-resolution grid whose
                                results interleave on the fine grid */
+    int64_t split_stride;   /* > 0: when the plan splits K (v2a_igemm_plan_k_splits > 1), split s writes its partial sums
+                               with plain stores to out_f32 + s * split_stride (elements) instead of adding them
+                               atomically into out_f32 -- the caller reduces the slices in a fixed order
+                               (v2a_sum_slices_hl), so the result does not depend on the arrival order of the CTAs;
+                               such plans use at most 16 splits */
 } v2a_igemm_desc;
 
 int v2a_igemm_plan_create(const v2a_igemm_desc* desc, void** plan_out);
@@ -257,6 +262,11 @@ int v2a_cfg_step(float* x, const float* v, const float* noise, const float* coef
                  void* stream);
 /* out = clamp((x + 1) / 2, 0, 1)   goal_diffusion.py:598,650 */
 int v2a_unnormalize_clamp(const float* x, float* out, int64_t n, void* stream);
+
+/* out = sum over s < slices of x[s * stride + r * cols + c], summed in slice order, as (hi, lo) bf16 planes
+ * [rows][cols]: the deterministic reduction of a split-K launch made with v2a_igemm_desc.split_stride */
+int v2a_sum_slices_hl(const float* x, int slices, int64_t stride, int64_t rows, int cols, void* out_hi, void* out_lo,
+                      void* stream);
 
 /* fp32 -> (hi, lo) bf16 planes, optional [rows][cols] row-padding to ld */
 int v2a_split_hl(const float* x, int64_t rows, int cols, int ld_out, void* out_hi, void* out_lo,

@@ -321,6 +321,42 @@ def test_igemm_split_k_matches_unsplit(rows, K, cout, T):
     assert _rel(acc[:, :cout], want) < 5e-5
 
 
+@pytest.mark.parametrize("N,H,W,ci,co", [(7, 8, 8, 512, 640), (2, 16, 16, 256, 512)])
+def test_igemm_split_k_slices_reduce_deterministically(N, H, W, ci, co):
+    """`split_stride`: every K split stores its partial sums in its own slice and `v2a_sum_slices_hl` adds the slices
+    in order into bf16 planes (the deep spatial convs of the video UNet at batch 1-2: few tiles, K ~ 5-10 k, planes
+    output).  Same value as float64 within the split product's accuracy, and bit-identical from run to run -- the
+    atomic form of split-K is neither available for planes nor repeatable."""
+    import ctypes as C
+    from v2a_b200 import _lib
+    ops, convs = _ops()
+    torch.manual_seed(N * 100 + co)
+    x = torch.randn(N, H, W, ci, device=DEV)
+    w = torch.randn(co, ci, 3, 3, device=DEV) / math.sqrt(9 * ci)
+    b = torch.randn(co, device=DEV)
+    prog = convs.spatial3x3(ci, N, H, W)
+    rows = N * H * W
+    srcs = [(ops.split_hl(x.reshape(-1, ci)), ci, prog.src_dims[0])]
+    wt = ops.split_hl_torch(convs.spatial3x3_weight(w))
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1).reshape(rows, co)
+    lib = _lib.load()
+    outs = []
+    for _ in range(2):
+        sc = torch.full((16, rows, co), float("nan"), device=DEV)
+        g = ops.Igemm(srcs=srcs, taps=prog.taps, w=wt, out_dims=prog.out_dims, cout=co, out_f32=sc[0], bias=b,
+                      split_stride=rows * co)
+        assert 1 < g.k_splits <= 16
+        g.run()
+        hl = ops.HL.empty(rows, co, DEV)
+        _lib.check(lib.v2a_sum_slices_hl(sc.data_ptr(), g.k_splits, rows * co, rows, co, hl.hi.data_ptr(), hl.lo.data_ptr(),
+                                         ops._stream()), "sum_slices_hl")
+        torch.cuda.synchronize()
+        assert torch.isfinite(sc[:g.k_splits]).all() and torch.isnan(sc[g.k_splits:]).all()   # exactly k_splits slices
+        outs.append(hl.float())
+    assert _rel(outs[0], ref) < 5e-5
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("N,H,W,ci,co", [(7, 16, 16, 64, 128), (3, 32, 32, 128, 256), (5, 16, 8, 64, 64)])
 def test_igemm_cta_pair_multicast_matches_single_cta(N, H, W, ci, co, monkeypatch):
     """Cout <= 256 (one N tile): CTA pairs share every weight tile through TMA multicast; odd tile counts

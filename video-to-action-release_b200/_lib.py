@@ -56,6 +56,7 @@ class IgemmDesc(C.Structure):
         ("b_fp16", C.c_int),
         ("out_pix_mul", C.c_int64 * 4),
         ("out_pix_off", C.c_int64),
+        ("split_stride", C.c_int64),
     ]
 
 
@@ -201,6 +202,7 @@ SIGNATURES = {
     "v2a_cfg_step": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "v2a_unnormalize_clamp": (_i, [_vp, _vp, _i64, _vp]),
     "v2a_split_hl": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "v2a_sum_slices_hl": (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp, _vp]),
     "v2a_params_fingerprint": (_i, [_vp, _i, _vp, _vp]),
     "v2a_gather_split": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "v2a_policy_gn_act_fwd": (_i, [C.POINTER(PolicyGnDesc), _vp]),

@@ -573,6 +573,28 @@ __global__ void __launch_bounds__(256) fingerprint_kernel(const FpItem* __restri
     if ((threadIdx.x & 31) == 0 && h) atomicAdd(out, h);
 }
 
+// deterministic reduction of split-K slices: out[r][c] = x[0][r][c] + x[1][r][c] + ... (slice order) -> bf16 planes
+__global__ void sum_slices_hl_kernel(const float* __restrict__ x, int slices, int64_t stride, int64_t n8,
+                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    float v[8];
+    {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + i * 8));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(x + i * 8) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    for (int s = 1; s < slices; ++s) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + s * stride + i * 8));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(x + s * stride + i * 8) + 1);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    uint4 h, l;
+    split8(v, h, l);
+    *reinterpret_cast<uint4*>(hi + i * 8) = h;
+    *reinterpret_cast<uint4*>(lo + i * 8) = l;
+}
+
 }  // namespace v2a
 
 using namespace v2a;
@@ -830,6 +852,19 @@ int v2a_gather_split_fmt(const float* src, const int32_t* map, int64_t n, void* 
     if (blocks < 1) blocks = 1;
     gather_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         src, map, n, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32, plane_fmt);
+    V2A_LAUNCH_OK();
+    return 0;
+}
+
+int v2a_sum_slices_hl(const float* x, int slices, int64_t stride, int64_t rows, int cols, void* out_hi, void* out_lo,
+                      void* stream) {
+    V2A_REQUIRE(x && out_hi && out_lo && slices >= 1 && rows >= 0 && cols % 8 == 0 && stride % 4 == 0 &&
+                    (slices == 1 || stride >= rows * cols),
+                "sum_slices_hl: cols must be a multiple of 8, slices at least rows * cols apart");
+    const int64_t n8 = rows * cols / 8;
+    if (n8 == 0) return 0;
+    sum_slices_hl_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x, slices, stride, n8, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
     V2A_LAUNCH_OK();
     return 0;
 }

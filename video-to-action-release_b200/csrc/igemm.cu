@@ -96,6 +96,7 @@ struct alignas(64) IgemmParams {
     int cluster;          // 2: CTA pairs share every B (weight) tile through TMA multicast
     int iters_per_cta;    // cluster mode: tile iterations of every CTA (ghost tiles pad the last ones)
     int k_splits;         // >1: the K loop of one output tile is shared by k_splits CTAs (fp32 atomics)
+    long long split_stride;  // > 0 with k_splits > 1: split s stores its partial sums at out_f32 + s * split_stride
     int kps;              // K iterations per split
     int a_fp16, b_fp16;   // operand planes hold fp16 (hi, lo) pairs instead of bf16 ones
     int nacc_log2;        // accumulator ring: 2 x 256 TMEM columns (1) or 4 x 128 (2: block_n <= 128, unfused)
@@ -620,7 +621,9 @@ __global__ void __maxnreg__(V2A_IGEMM_MAXNREG) igemm_kernel(const __grid_constan
                             }
                             if (has_f32 && !(dbg & 2)) {
                                 float4* op = reinterpret_cast<float4*>(p.out_f32 + spix[i] * p.ldc + n) + piece;
-                                if (splitk) atomicAdd(op, x);   // partial sum of this K range
+                                if (splitk && p.split_stride > 0)      // own slice, plain store: the caller reduces
+                                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(op) + split * p.split_stride) = x;
+                                else if (splitk) atomicAdd(op, x);     // partial sum of this K range
                                 else *op = x;
                             }
                             cs[0] += x.x; cs[1] += x.y; cs[2] += x.z; cs[3] += x.w;
@@ -1851,12 +1854,16 @@ static int plan_create(const v2a_igemm_desc* d, IgemmPlan** out, bool force_cta2
             if (want > 16) want = 16;
             if (want > p.k_iters / 4) want = p.k_iters / 4;
             if (env && atoi(env) > 1) want = atoi(env);
+            if (d->split_stride > 0 && want > 16) want = 16;   // callers size their slice buffers for 16
             if (want > 1) {
                 p.kps = ceil_div(p.k_iters, want);
                 p.k_splits = ceil_div(p.k_iters, p.kps);
             }
         }
-        if (p.k_splits > 1) {
+        p.split_stride = p.k_splits > 1 && d->split_stride > 0 ? d->split_stride : 0;
+        if (p.split_stride > 0) {
+            V2A_REQUIRE(!d->residual, "igemm: split_stride slices take no residual (the lead split would hold it alone)");
+        } else if (p.k_splits > 1) {
             // accumulate-in-place (residual aliases the output): the atomics add onto what is there
             const bool in_place = d->residual == d->out_f32 && d->ld_res == d->ldc;
             if (in_place) p.residual = nullptr;

@@ -150,7 +150,7 @@ def pack_weight_taps(per_tap: Sequence[torch.Tensor]) -> torch.Tensor:
 def _igemm_desc(*, srcs, taps, w: HL, out_dims, cout, ldc=None, out_f32=None, out_hl=None,
                 bias=None, rowvec=None, rowvec_mul=(0, 0, 0, 0), residual=None, stats=None,
                 stats_mul=(0, 0, 0, 0), block_n=None, passes=3, tile_log2=None, out_pix=None, algo_flops_scale=1.0,
-                fill_sms=False):
+                fill_sms=False, split_stride=0):
     """Fill a `v2a_igemm_desc` from torch tensors.  Returns (desc, keep-alive list, meta dict).
 
     out_pix = ((m0, m1, m2, m3), off): the output row of grid point c is off + sum c[d] * m[d] instead of
@@ -196,6 +196,7 @@ def _igemm_desc(*, srcs, taps, w: HL, out_dims, cout, ldc=None, out_f32=None, ou
         d.rowvec_mul[k] = rowvec_mul[k]
         d.stats_mul[k] = stats_mul[k]
     d.block_n = block_n or choose_block_n(cout, (out_dims[0] * out_dims[1] * out_dims[2] * out_dims[3]) if fill_sms else None)
+    d.split_stride = split_stride        # > 0: split-K partial sums go to their own slices (deterministic reduction)
     d.passes = passes
     d.cout = cout
     rows = out_dims[0] * out_dims[1] * out_dims[2] * out_dims[3]

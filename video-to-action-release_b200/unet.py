@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import convs, ops, packing
+from . import _lib, convs, ops, packing
 from .ops import HL
 
 # ---------------------------------------------------------------------------
@@ -503,7 +503,31 @@ class _UNetEngine:
             self.add_igemm_dual(dict(block_n=bn, **spatial_kw), dict(block_n=bn, **temporal_kw))
         else:
             if spatial_kw is not None:
-                self.add_igemm(**spatial_kw)
+                # Few output tiles and a long K (the deep levels at batch 1-2: 448 / 1792 rows, K up to 11.5 k): the
+                # planes output rules out split-K, so the spatial GEMM goes to an fp32 scratch WITH split-K (widest N
+                # tile: the activation tile is read once per split, not once per narrow N tile) and one small kernel
+                # splits the finished sums into the planes.  V2A_SPLITK_SPATIAL=0: planes straight from the epilogue.
+                rows_o = N * Ho * Wo
+                bn0 = ops.choose_block_n(cout)
+                tiles = -(-rows_o // 128) * -(-cout // bn0)
+                if os.environ.get("V2A_SPLITK_SPATIAL", "1") != "0" and tiles * 2 <= 148 and \
+                        spatial_kw["w"].hi.shape[1] // 64 >= 32 and cout % 16 == 0:
+                    slices = 16                                   # the plan never splits further (csrc/igemm.cu)
+                    sc_store = self.pool.get(slices * rows_o * cout * 4)
+                    sc = sc_store.view(torch.float32).view(slices, rows_o, cout)
+                    kw = dict(spatial_kw)
+                    kw.pop("out_hl")
+                    # every split stores its partial sums in its own slice and ONE kernel adds the slices in order
+                    # and splits the result into the planes: no atomics, so repeated runs agree bit for bit
+                    slot = self.add_igemm(out_f32=sc[0], block_n=bn0, split_stride=rows_o * cout, **kw)
+                    lib = _lib.load()
+                    self._step(lambda: _lib.check(lib.v2a_sum_slices_hl(sc.data_ptr(), slot[0].k_splits, rows_o * cout,
+                                                                       rows_o, cout, y_hl.hi.data_ptr(),
+                                                                       y_hl.lo.data_ptr(), ops._stream()), "sum_slices_hl"),
+                               "sum_slices_hl")
+                    self.pool.put(sc_store)
+                else:
+                    self.add_igemm(**spatial_kw)
             self.add_igemm(**temporal_kw)
         self.release(y_st)
         return out
